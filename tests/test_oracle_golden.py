@@ -1,0 +1,132 @@
+"""Pins the CPU oracle (oracle/bpl_oracle.c) against the golden vectors that
+tests/golden/make_golden.py produced from the live reference (rfeinman/pyBPL).
+
+The reference's own tests hold no values for this path
+(pybpl/tests/test_vanilla_to_motor.py:47-48 asserts shapes only), so these
+fixtures are the pin.  Tolerances: integer work bit-exact; trajectories
+bit-exact given the reference's basis table; fp32 images/ll/grads to the
+reference's own fp32 noise.
+"""
+import numpy as np
+import pytest
+
+import oracle as O
+from oracle import Oracle
+from tests.util_golden import load, render_cases, token_cases, relinf
+
+
+@pytest.fixture(scope="module")
+def o32():
+    return Oracle(np.float32)
+
+
+def test_basis_tables_close_to_reference(o32):
+    # splines.py:72-93.  torch builds the table with Sleef powf + an MKL dot, which no
+    # portable C sequence reproduces to the bit; the restatement is within 1 ulp-ish.
+    d = load("splines")
+    for nland, neval in d["table_pairs"]:
+        C = o32.basis_table(int(nland), int(neval))
+        ref = d[f"table_{nland}_{neval}"]
+        assert C.shape == ref.shape
+        assert np.abs(C - ref).max() < 1e-6
+        assert np.array_equal(C != 0, ref != 0)
+    C = o32.basis_rows(5, d["s_explicit"])
+    assert np.abs(C - d["table_s_explicit"]).max() < 1e-6
+
+
+def test_spline_eval_bit_exact_given_table(o32):
+    # splines.py:136: torch.matmul(C, Y) == fma chain
+    d = load("splines")
+    assert np.array_equal(o32.spline_eval(d["table_5_200"], d["Y_explicit"]), d["X_200"])
+    assert np.array_equal(o32.spline_eval(d["table_7_200"], d["Y7"]), d["X7_200"])
+    assert np.array_equal(o32.spline_eval(d["table_s_explicit"], d["Y_explicit"]), d["X_explicit"])
+
+
+def test_adaptive_neval_integer_exact(o32):
+    # splines.py:129-133 (integer work)
+    d = load("splines")
+    nev, dist = o32.adaptive_neval(d["table_5_200"], d["Y_adaptive"])
+    assert np.array_equal(nev, d["neval_adaptive"])
+    assert relinf(dist, d["dist_adaptive"]) < 2e-6
+
+
+@pytest.mark.parametrize("case", render_cases(), ids=lambda c: c["name"])
+def test_render_cases(case):
+    # rendering.py:185-229 + image_dist.py:75-78 on raw trajectories
+    o = Oracle(np.float32, O.default_params(hinton=case["hinton"]))
+    m, fl, ce = o.point_indices(case["pts"])
+    assert np.array_equal(m, case["mask_out"])
+    inb = ~m
+    assert np.array_equal(fl[inb], case["floor"][inb]) and np.array_equal(ce[inb], case["ceil"][inb])
+    res = o.render_grad(case["strokes"], case["eps"], case["sigma"], image=case["image"])
+    assert res["off_page"] == case["off"]
+    assert np.abs(res["pimg"] - case["pimg"]).max() <= 3e-6 * max(1.0, np.abs(case["pimg"]).max())
+    assert abs(res["ll"] - case["ll"]) <= 2e-6 * abs(case["ll"])
+    assert relinf(res["g_pts"], case["g_pts"]) < 1e-4
+    assert abs(res["g_eps"] - case["g_eps"]) <= 2e-4 * max(1.0, abs(case["g_eps"]))
+    assert abs(res["g_sigma"] - case["g_sigma"]) <= 2e-3 * max(1.0, abs(case["g_sigma"]))
+    # generic cotangent (render_image drop-in backward)
+    ct = case["ct"]
+    r2 = o.render_grad(case["strokes"], case["eps"], case["sigma"], gP=ct)
+    assert relinf(r2["g_pts"], case["gct_pts"]) < 1e-4
+    assert abs(r2["g_eps"] - case["gct_eps"]) <= 1e-4 * max(1.0, abs(case["gct_eps"]))
+    assert abs(r2["g_sigma"] - case["gct_sigma"]) <= 2e-3 * max(1.0, abs(case["gct_sigma"]))
+
+
+def test_tokens_whole_path(o32):
+    # CharacterImageDist.get_pimg/score_image (image_dist.py:32-42,75-78) incl. vanilla_to_motor + affine
+    d, toks = token_cases()
+    C = d["basis_5_200"]
+    worst = dict(ll=0, gc=0, gi=0, gp=0, gs=0, ge=0, ga=0)
+    for t in toks:
+        res = o32.token(C, t["nsub"], t["ctrl"], t["invscale"], t["position"], t["eps"], t["sigma"],
+                        affine=t["affine"] if t["has_affine"] else None, image=t["image"], grad=True)
+        assert res["off_page"] == t["off_page"], t["name"]
+        if "motor" in t and not t["has_affine"]:
+            assert np.array_equal(res["motor"], t["motor"]), t["name"]     # bit-exact trajectories
+            assert np.abs(res["pimg"] - t["pimg"]).max() < 3e-6
+        if not t["has_affine"]:
+            # integer work: in-bounds counts and floor sums per sub-stroke (bit-exact)
+            m, fl, _ = o32.point_indices(res["motor"].reshape(-1, 2))
+            inb = (~m).reshape(-1, 200)
+            assert np.array_equal(inb.sum(1).astype(np.int32), t["n_inbounds"])
+            fsum = (fl.reshape(-1, 200, 2).astype(np.int64) * inb[..., None]).sum(1)
+            assert np.array_equal(fsum, t["floor_sum"])
+        worst["ll"] = max(worst["ll"], abs(res["ll"] - t["ll"]) / abs(t["ll"]))
+        worst["gc"] = max(worst["gc"], relinf(res["g_ctrl"], t["g_ctrl"]))
+        worst["gi"] = max(worst["gi"], relinf(res["g_invscale"], t["g_invscale"]))
+        worst["gp"] = max(worst["gp"], relinf(res["g_position"], t["g_position"]))
+        worst["gs"] = max(worst["gs"], abs(res["g_sigma"] - t["g_sigma"]) / max(1.0, abs(t["g_sigma"])))
+        worst["ge"] = max(worst["ge"], abs(res["g_eps"] - t["g_eps"]) / max(1.0, abs(t["g_eps"])))
+        if t["has_affine"]:
+            worst["ga"] = max(worst["ga"], relinf(res["g_affine"], t["g_affine"]))
+    print("worst", worst)
+    assert worst["ll"] < 1e-5
+    assert worst["gc"] < 5e-4 and worst["gi"] < 5e-4 and worst["gp"] < 5e-4  # reference fp32 autograd noise (App. B.4)
+    assert worst["gs"] < 1e-2 and worst["ge"] < 2e-3 and worst["ga"] < 2e-3
+
+
+def test_batch_equals_single(o32):
+    d, toks = token_cases()
+    from tests.util_golden import pack_tokens
+    sel = [t for t in toks if not t["has_affine"]][:12]
+    b = pack_tokens(sel)
+    res = o32.token_batch(d["basis_5_200"], b["tok_stroke_off"], b["stroke_sub_off"], b["ctrl"], b["invscale"],
+                          b["position"], b["eps"], b["sigma"], b["images"], img_idx=b["img_idx"])
+    for i, t in enumerate(sel):
+        assert abs(res["ll"][i] - t["ll"]) <= 1e-5 * abs(t["ll"])
+        assert bool(res["off_page"][i]) == t["off_page"]
+
+
+def test_fp64_noise_floor():
+    # the fp64 instantiation only measures how far the fp32 reference is from exact arithmetic
+    d, toks = token_cases()
+    o64 = Oracle(np.float64)
+    C64 = d["basis_5_200"].astype(np.float64)
+    errs = []
+    for t in toks[:16]:
+        if t["has_affine"]:
+            continue
+        r = o64.token(C64, t["nsub"], t["ctrl"], t["invscale"], t["position"], t["eps"], t["sigma"], image=t["image"])
+        errs.append(abs(r["ll"] - t["ll"]) / abs(t["ll"]))
+    assert max(errs) < 2e-4  # reference fp32 ll is itself only ~5e-5 from fp64
