@@ -1,0 +1,169 @@
+/*
+ * pybpl_b200.h -- C ABI of libpybpl_b200.so, the B200 (sm_100a) implementation of
+ * pyBPL's render+score hot path.
+ *
+ * The reference (rfeinman/pyBPL) is pure Python with no FFI of its own: the boundary is
+ * a set of Python call sites.  Each entry point below names the reference
+ * function(s) it replaces (paths relative to the reference root).  Every pointer marked
+ * "dev" is a borrowed CUDA device pointer valid for the duration of the call on `stream`
+ * (a cudaStream_t passed as void*); outputs are caller-allocated; the library never
+ * allocates, frees or synchronises.  Every entry returns 0 on success, a negative
+ * BPL_E* code for a bad argument, or a positive cudaError_t; bpl_last_error() gives text.
+ * Host code binds it with ctypes (pybpl_b200/_lib.py); see INTEGRATION.md.
+ */
+#ifndef PYBPL_B200_H
+#define PYBPL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BPL_IMSIZE 105          /* pybpl/parameters.py:21  imsize = (105,105) */
+#define BPL_FSIZE 11            /* pybpl/parameters.py:41  fsize */
+#define BPL_IMG_WORDS 4         /* 105 pixels of one image row packed LSB-first into 4 u32 */
+#define BPL_MAX_SUBSTROKES 128  /* sub-strokes per token handled by one CTA */
+#define BPL_MAX_STROKES 32      /* strokes per token */
+#define BPL_NCPT 5              /* control points per sub-stroke on the fused path (lib_data shape/mu: 1212x10) */
+#define BPL_MAX_NEVAL 800       /* basis table rows held in shared memory on the fused path */
+
+#define BPL_EINVAL (-1)
+#define BPL_ELIMIT (-2)
+#define BPL_ENODEV (-3)
+
+/* Rendering constants: pybpl/parameters.py:19-41 (class Parameters). */
+typedef struct {
+    int imsize;          /* must be 105 */
+    int fsize;           /* must be 11 */
+    int ink_ncon;        /* :31 */
+    float ink_pp;        /* :25 */
+    float ink_max_dist;  /* :27 */
+    float ink_a, ink_b;  /* :33, :35 */
+    int hinton;          /* broaden_mode == 'Hinton' (:37) */
+} bpl_params;
+
+/* A ragged batch of character tokens in control-point form = what
+ * CharacterImageDist.get_pimg reads from a CharacterToken (pybpl/model/image_dist.py:32-42,
+ * pybpl/objects/concept.py:235-241, pybpl/objects/part.py:214-224). */
+typedef struct {
+    int n_tokens;               /* P */
+    int ncpt;                   /* must be BPL_NCPT */
+    int neval;                  /* points per sub-stroke (vanilla_to_motor neval, default 200) */
+    const int *tok_stroke_off;  /* dev [P+1]   CSR: token -> strokes */
+    const int *stroke_sub_off;  /* dev [K+1]   CSR: stroke -> sub-strokes */
+    const float *ctrl;          /* dev [S][ncpt][2]  StrokeToken.shapes[:, :, i] per sub-stroke */
+    const float *invscale;      /* dev [S]           StrokeToken.invscales */
+    const float *position;      /* dev [K][2]        StrokeToken.position */
+    const float *affine;        /* dev [P][4] or NULL  CharacterToken.affine */
+    const float *eps;           /* dev [P]  CharacterToken.epsilon */
+    const float *sigma;         /* dev [P]  CharacterToken.blur_sigma */
+    const float *basis;         /* dev [neval][ncpt]  coefficient_mat(ncpt, neval) (pybpl/splines.py:72-93) */
+} bpl_token_batch;
+
+/* A ragged batch of characters given as raw motor-space trajectories = the `strokes`
+ * argument of rendering.render_image (pybpl/rendering.py:185-229). */
+typedef struct {
+    int n_tokens;               /* P */
+    const int *tok_sub_off;     /* dev [P+1]  CSR: token -> strokes */
+    const int *sub_pt_off;      /* dev [S+1]  CSR: stroke -> points */
+    const float *pts;           /* dev [N][2] motor space (x right, y negative down) */
+    const float *eps;           /* dev [P] */
+    const float *sigma;         /* dev [P] */
+} bpl_stroke_batch;
+
+/* Target images and where each token's score goes. */
+typedef struct {
+    const uint32_t *image_bits; /* dev [T][105][4] from bpl_pack_images_*; NULL => no scoring */
+    const int *img_idx;         /* dev [P] image per token, or NULL => image 0 */
+    int n_images;               /* T */
+} bpl_targets;
+
+/* Outputs of the forward (any may be NULL). */
+typedef struct {
+    float *ll;                  /* dev [P]  sum Bernoulli(pimg).log_prob(image) (image_dist.py:75-78) */
+    uint8_t *off_page;          /* dev [P]  ink_off_page (rendering.py:85-88,219-220) */
+    float *pimg;                /* dev [P][105][105] probability maps (render_image / get_pimg) */
+} bpl_fwd_out;
+
+/* Gradient outputs of the fused forward+backward.  The cotangent is g_ll[p] on ll[p]
+ * (NULL => 1) or, when g_pimg != NULL, a full cotangent on pimg ([P][105][105]). */
+typedef struct {
+    const float *g_ll;          /* dev [P] or NULL */
+    const float *g_pimg;        /* dev [P][105][105] or NULL */
+    float *g_ctrl;              /* dev [S][ncpt][2]   (token batches) */
+    float *g_invscale;          /* dev [S] */
+    float *g_position;          /* dev [K][2] */
+    float *g_affine;            /* dev [P][4] or NULL */
+    float *g_pts;               /* dev [N][2]  (stroke batches; must be zero-filled by the caller) */
+    float *g_eps;               /* dev [P] */
+    float *g_sigma;             /* dev [P] */
+} bpl_grads;
+
+int bpl_version(void);
+const char *bpl_last_error(void);
+void bpl_default_params(bpl_params *ps);                    /* pybpl/parameters.py:19-41 */
+/* device queries used to size launches (SM count, opt-in shared memory) */
+int bpl_device_info(int *sm_count, int *smem_optin);
+
+/* ---- splines (pybpl/splines.py) -------------------------------------------------- */
+/* bspline_gen_s + coefficient_mat (splines.py:57-93), host arrays. */
+int bpl_basis_table_host(int nland, int neval, float *C);
+int bpl_basis_rows_host(int nland, int n, const float *s, float *C);
+/* get_stk_from_bspline: X[b] = C @ Y[b] (splines.py:136); nspl splines share one table. */
+int bpl_spline_eval(const float *C, int neval, int nland, int nspl, const float *Y, float *X, void *stream);
+/* its backward: gY[b] = C^T @ gX[b] */
+int bpl_spline_eval_bwd(const float *C, int neval, int nland, int nspl, const float *gX, float *gY, void *stream);
+/* adaptive neval (splines.py:129-133): dist along the 200-point trajectory and
+ * clamp(ceil(dist/grain), min_neval, max_neval); C200 is the [max_neval][nland] table. */
+int bpl_spline_adaptive_neval(const float *C200, int max_neval, int nland, int nspl, const float *Y, float grain,
+                              int min_neval, int *neval, float *dist, void *stream);
+/* vanilla_to_motor (pybpl/objects/part.py:290-328) for a batch of strokes:
+ * stroke_sub_off [K+1]; motor [S][neval][2]; motor_spline [S][ncpt][2] (or NULL). */
+int bpl_vanilla_to_motor(const float *C, int neval, int ncpt, int n_strokes, const int *stroke_sub_off,
+                         const float *ctrl, const float *invscale, const float *position, float *motor,
+                         float *motor_spline, void *stream);
+
+/* ---- images ------------------------------------------------------------------------ */
+/* Pack T 105x105 images into bit rows.  `bad` (dev int, zero-filled by the caller) is set
+ * to 1 if any pixel is not exactly 0 or 1 (torch's Bernoulli.log_prob support check). */
+int bpl_pack_images_u8(const uint8_t *img, int T, uint32_t *bits, int *bad, void *stream);
+int bpl_pack_images_f32(const float *img, int T, uint32_t *bits, int *bad, void *stream);
+
+/* ---- render + score ------------------------------------------------------------------
+ * Forward: CharacterImageDist.get_pimg + score_image (pybpl/model/image_dist.py:32-42,60-80)
+ * = vanilla_to_motor (objects/part.py:290-328) -> apply_warp (util/affine.py:29-55) ->
+ * render_image (rendering.py:185-229: add_stroke :58-127, broaden_and_blur :130-182) ->
+ * Bernoulli log_prob.  One CTA per token; the image never leaves shared memory. */
+int bpl_score_tokens(const bpl_params *ps, const bpl_token_batch *b, const bpl_targets *t, const bpl_fwd_out *out,
+                     void *stream);
+/* Same, plus the fused backward (autograd-equivalent gradients). */
+int bpl_score_tokens_grad(const bpl_params *ps, const bpl_token_batch *b, const bpl_targets *t,
+                          const bpl_fwd_out *out, const bpl_grads *g, void *stream);
+/* rendering.render_image on raw trajectories (+ optional scoring). */
+int bpl_render_strokes(const bpl_params *ps, const bpl_stroke_batch *b, const bpl_targets *t,
+                       const bpl_fwd_out *out, void *stream);
+int bpl_render_strokes_grad(const bpl_params *ps, const bpl_stroke_batch *b, const bpl_targets *t,
+                            const bpl_fwd_out *out, const bpl_grads *g, void *stream);
+
+/* Inspection: the path's integer work per point, computed by the same device code as the fused
+ * kernels: motor [S][neval][2] (post-warp motor space = torch.cat(motor) in image_dist.py:34-38),
+ * mask_out [S][neval] (check_bounds, rendering.py:27-31), floor/ceil [S][neval][2] (row, col;
+ * rendering.py:113-116), n_in [S] surviving points per sub-stroke.  Any output may be NULL. */
+int bpl_token_points(const bpl_params *ps, const bpl_token_batch *b, float *motor, uint8_t *mask_out, int *fl, int *ce,
+                     int *n_in, void *stream);
+
+/* ---- particle sweep reduction (per-GPU partial of the final log-sum-exp) ------------- */
+/* out[0] = max_p ll[p], out[1] = sum_p exp(ll[p] - max)   (dev float[2]); one launch. */
+int bpl_logsumexp_partial(const float *ll, int n, float *out2, void *stream);
+
+/* Roofline probe: `blocks` CTAs x 1024 threads x `iters` x 8 FFMA (2 flop each); scratch = 1 dev float. */
+int bpl_fp32_probe(float *scratch, int iters, int blocks, void *stream);
+
+/* number of kernel launches issued by this library in this process (bench.py gpu_launches) */
+long long bpl_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,162 @@
+// bpl_common.cuh -- shared device helpers for the pyBPL render+score kernels (sm_100a).
+//
+// Geometry of one image buffer in shared memory: the 105x105 image sits inside a 115x115
+// frame of zeros (5-pixel border = the half-width of the 11-tap Gaussian, parameters.py:41).
+// The row stride 115 is odd, so a warp whose lanes walk down a column (stride 115) and a warp
+// whose lanes walk along a row (stride 1) are both bank-conflict free, and the zero border
+// implements the zero padding of F.conv2d (pybpl/util/general.py:161-163) with no predicates.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pybpl_b200.h"
+
+namespace bpl {
+
+constexpr int IMG = BPL_IMSIZE;            // 105
+constexpr int PAD = BPL_FSIZE / 2;         // 5
+constexpr int STRIDE = IMG + 2 * PAD;      // 115 (odd)
+constexpr int BUFN = STRIDE * STRIDE;      // 13225 floats
+constexpr int BUFP = (BUFN + 3) / 4 * 4;   // allocation per buffer (16-byte multiple): 13228 floats = 52,912 B
+constexpr int ORIGIN = PAD * STRIDE + PAD; // buffer index of pixel (0,0)
+constexpr int NPIX = IMG * IMG;
+constexpr int MAXS = BPL_MAX_SUBSTROKES;
+constexpr int MAXK = BPL_MAX_STROKES;
+constexpr int NCPT = BPL_NCPT;
+constexpr int MAX_TABLE = 1024;            // floats of basis table kept in shared memory
+constexpr int IMG_WORDS = BPL_IMG_WORDS;
+constexpr float TORCH_EPS = 1.1920928955078125e-07f;  // torch.finfo(float32).eps (clamp_probs)
+
+// Rendering constants pre-digested on the host (pybpl/parameters.py:19-41, rendering.py:151-166).
+struct RenderConsts {
+    int ink_ncon;
+    float ink_pp, ink_max_dist;
+    float ink_f;     // ink_pp / ink_max_dist (d ink / d dist)
+    float c1, c2;    // H_broaden = c1 * (1,2,1)x(1,2,1) + c2 * delta
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Sum NV doubles over the block; result valid in every thread.  scratch: NV*32 doubles.
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double *scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) scratch[i * 32 + warp] = v[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        double x = (lane < nw) ? scratch[i * 32 + lane] : 0.0;
+        v[i] = warp_sum(x);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// One separable stencil pass over the whole image (a "sweep").
+//   VERT : slide down rows (vertical filter), lanes across columns; else slide along a row,
+//          lanes across rows.  Either way lane addresses are conflict free (odd stride).
+//   TAPS : 3 (broaden) or 11 (Gaussian); symmetric taps w[f][d], d = distance from centre.
+//   R    : outputs per work item (IMG % R == 0); an item loads R+TAPS-1 inputs into registers
+//          once and produces R outputs, so shared-memory reads per output are (R+TAPS-1)/R.
+//   NF   : filters evaluated on the same loaded window (the backward needs g and h~ together).
+//   ld   : applied to every loaded input (identity, or min(x,1) = rendering.py:171 on the fly)
+//   epi  : epi(r, c, acc[NF]) consumes each output (store / combine / likelihood).
+// ---------------------------------------------------------------------------------------
+template <int TAPS, int R, bool VERT, int NF, class Load, class Epi>
+__device__ __forceinline__ void sweep(const float *__restrict__ in, const float (&w)[NF][TAPS / 2 + 1], Load ld,
+                                      Epi epi) {
+    static_assert(IMG % R == 0, "bands must tile the image");
+    constexpr int HALF = TAPS / 2;
+    constexpr int NB = IMG / R;
+    constexpr int SA = VERT ? STRIDE : 1;   // stride along the sliding axis
+    constexpr int SL = VERT ? 1 : STRIDE;   // stride across lanes
+    for (int item = threadIdx.x; item < NB * IMG; item += blockDim.x) {
+        const int band = item / IMG;
+        const int line = item - band * IMG;
+        const int a0 = band * R;
+        const float *p = in + ORIGIN + (a0 - HALF) * SA + line * SL;
+        float x[R + TAPS - 1];
+#pragma unroll
+        for (int i = 0; i < R + TAPS - 1; ++i) x[i] = ld(p[i * SA]);
+#pragma unroll
+        for (int o = 0; o < R; ++o) {
+            float acc[NF];
+#pragma unroll
+            for (int f = 0; f < NF; ++f) acc[f] = w[f][0] * x[o + HALF];
+#pragma unroll
+            for (int d = 1; d <= HALF; ++d) {
+                const float s = x[o + HALF - d] + x[o + HALF + d];
+#pragma unroll
+                for (int f = 0; f < NF; ++f) acc[f] = fmaf(w[f][d], s, acc[f]);
+            }
+            if (VERT) epi(a0 + o, line, acc); else epi(line, a0 + o, acc);
+        }
+    }
+}
+
+struct LoadId { __device__ __forceinline__ float operator()(float v) const { return v; } };
+struct LoadMin1 { __device__ __forceinline__ float operator()(float v) const { return fminf(v, 1.0f); } };
+
+// ---------------------------------------------------------------------------------------
+// Per-pixel Bernoulli log-likelihood in torch's formulation (pybpl/model/image_dist.py:75-78;
+// torch/distributions/utils.py clamp_probs + probs_to_logits, bernoulli.py log_prob =
+// -binary_cross_entropy_with_logits):
+//   pt = clamp(p, eps32, 1-eps32);  l = log(pt) - log1p(-pt)
+//   lp = -((1-x) * l - (min(l,0) - log1p(exp(-|l|))))
+// The operation order is kept (the catastrophic cancellation in it is part of the reference's
+// result).  dlp is what autograd returns for d lp / d p.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void pixel_lp(float p, bool x, bool want_grad, float &lp, float &dlp) {
+    const float pt = fminf(fmaxf(p, TORCH_EPS), 1.0f - TORCH_EPS);
+    const float l = logf(pt) - log1pf(-pt);
+    const float ex = expf(-fabsf(l));
+    const float lg = log1pf(ex);
+    const float ls = fminf(l, 0.0f) - lg;
+    const float t = x ? 0.0f * l : l;
+    lp = -(t - ls);
+    if (want_grad) {
+        if (p < TORCH_EPS || p > 1.0f - TORCH_EPS) {
+            dlp = 0.0f;
+        } else {
+            const float sg = (l >= 0.0f) ? 1.0f / (1.0f + ex) : ex / (1.0f + ex);
+            dlp = ((x ? 1.0f : 0.0f) - sg) * (1.0f / p + 1.0f / (1.0f - p));
+        }
+    }
+}
+
+// The same in double, each libm result rounded to float (= correctly rounded fp32 libm), used
+// once per token for the background value shared by ~90% of the pixels: a 1-ulp wobble there
+// would be multiplied by ~10^4 pixels.
+__device__ inline void pixel_lp_exact(float p, bool x, float &lp, float &dlp) {
+    const float pt = fminf(fmaxf(p, TORCH_EPS), 1.0f - TORCH_EPS);
+    const float l1 = (float)log((double)pt);
+    const float l2 = (float)log1p(-(double)pt);
+    const float l = l1 - l2;
+    const float ex = (float)exp(-(double)fabsf(l));
+    const float lg = (float)log1p((double)ex);
+    const float ls = fminf(l, 0.0f) - lg;
+    const float t = x ? 0.0f * l : l;
+    lp = -(t - ls);
+    if (p < TORCH_EPS || p > 1.0f - TORCH_EPS) {
+        dlp = 0.0f;
+    } else {
+        const float sg = (float)(1.0 / (1.0 + exp(-(double)l)));
+        dlp = ((x ? 1.0f : 0.0f) - sg) * (1.0f / p + 1.0f / (1.0f - p));
+    }
+}
+
+}  // namespace bpl

@@ -1,0 +1,1119 @@
+// bpl_render.cu -- fused render+score kernels for pyBPL's P(Image | Token) on B200 (sm_100a).
+//
+// One CTA renders one token: spline evaluation + sub-stroke chaining (objects/part.py:290-328),
+// optional affine warp (util/affine.py:29-55), bounds check / compaction / ink / bilinear splat
+// with shared-memory atomics (rendering.py:58-127), 2x broaden + clamp + 2x Gaussian + clamp
+// (rendering.py:130-182), epsilon mix (:226-227) and the Bernoulli log-likelihood
+// (model/image_dist.py:75-78).  The image lives in shared memory from the first splat to the
+// final warp-shuffle reduction; HBM sees ~0.2 KB of control points in and 5 bytes out.
+// The *_grad kernel recomputes the forward and runs the adjoint in the same CTA.
+//
+// No tensor cores: nothing here is a dense contraction.  FP32 issue and
+// shared-memory bandwidth bound it; see DESIGN.md for the roofline.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+
+#include <atomic>
+
+#include "bpl_common.cuh"
+
+namespace bpl {
+
+// ------------------------------------------------------------------------------------------
+// kernel arguments
+// ------------------------------------------------------------------------------------------
+struct KArgs {
+    RenderConsts rc;
+    int n_tokens;
+    // token (control point) mode
+    int neval;
+    const int *tok_stroke_off, *stroke_sub_off;
+    const float *ctrl, *invscale, *position, *affine, *basis;
+    // raw stroke mode
+    const int *tok_sub_off, *sub_pt_off;
+    const float *pts;
+    // common
+    const float *eps, *sigma;
+    const uint32_t *image_bits;
+    const int *img_idx;
+    int n_images;
+    float *ll;
+    uint8_t *off_page;
+    float *pimg;
+    // gradients
+    const float *g_ll, *g_pimg;
+    float *g_ctrl, *g_invscale, *g_position, *g_affine, *g_pts, *g_eps, *g_sigma;
+};
+
+// Per-CTA bookkeeping in shared memory.
+struct Misc {
+    double red[4 * 32];      // block_sum scratch
+    float4 sub[MAXS];        // per sub-stroke: (t0x,t0y,tlastx,tlasty) then (offx,offy,-,-)
+    float g[8], ht[8];       // Gaussian half kernel g[d], and h~[d] = (d^2 - mu2) g[d]
+    float lp_bg[2], dlp_bg[2];
+    float affB[4], com[2];
+    float colsum[8];         // column sums of the basis table (affine backward)
+    double aff_acc[4];       // sum gx*prex, sum gy*prey, sum gx, sum gy
+    int off_page;
+    int cur_img;
+    uint32_t bits[IMG * IMG_WORDS];
+};
+
+enum : int { BR_NONE = 0, BR_SINGLE = 1, BR_FILL = 2, BR_RESCALE = 3, BR_NORMAL = 4 };
+
+// ------------------------------------------------------------------------------------------
+// point sources
+// ------------------------------------------------------------------------------------------
+struct CtrlSrc {   // X = C @ (invscale * shapes) - offset   (splines.py:136, part.py:318-323)
+    const float *tab;
+    float yx[NCPT], yy[NCPT];
+    float offx, offy;
+    bool aff;
+    float b0, b1, b2, b3;
+    __device__ __forceinline__ void pre(int j, float &x, float &y) const {
+        float ax = 0.0f, ay = 0.0f;
+        const float *row = tab + j * NCPT;
+#pragma unroll
+        for (int k = 0; k < NCPT; ++k) {          // sequential fma chain == torch.matmul here (App. B.1)
+            const float c = row[k];
+            ax = __fmaf_rn(c, yx[k], ax);
+            ay = __fmaf_rn(c, yy[k], ay);
+        }
+        x = __fsub_rn(ax, offx);
+        y = __fsub_rn(ay, offy);
+    }
+    __device__ __forceinline__ void point(int j, float &x, float &y) const {
+        pre(j, x, y);
+        if (aff) {                                  // stk * B[:2] + B[2:]  (affine.py:26)
+            x = __fadd_rn(__fmul_rn(x, b0), b2);
+            y = __fadd_rn(__fmul_rn(y, b1), b3);
+        }
+    }
+};
+
+struct RawSrc {
+    const float2 *p;
+    __device__ __forceinline__ void point(int j, float &x, float &y) const {
+        const float2 v = p[j];
+        x = v.x; y = v.y;
+    }
+    __device__ __forceinline__ void pre(int j, float &x, float &y) const { point(j, x, y); }
+};
+
+// ------------------------------------------------------------------------------------------
+// Sub-stroke walk: 32 points per round, one per lane.  Out-of-bounds points are dropped
+// BEFORE distances are taken (rendering.py:85-98), so each surviving point needs its previous
+// surviving neighbour: inside a round that is the nearest lower lane whose ballot bit is set,
+// across rounds it is carried in warp-uniform registers.
+// ------------------------------------------------------------------------------------------
+struct Walk {
+    int cnt;          // survivors so far
+    float cr, cc;     // last survivor (row, col)
+    int cj;           // its point index
+};
+
+struct Pt {
+    bool valid, inb;
+    int j, idx, pj;           // point index, survivor rank, previous survivor's point index
+    float r, c, pr, pc;       // image coords (row = -y, col = x) and previous survivor's
+    float dr, dc, dist, ink0; // segment to the previous survivor; ink0 = ink_pp*min(dist,max)/max
+};
+
+template <class Src>
+__device__ __forceinline__ Pt walk_round(const Src &src, int n, int base, int lane, const RenderConsts &rc, Walk &w) {
+    Pt p;
+    p.j = base + lane;
+    p.valid = p.j < n;
+    float x = 0.0f, y = 0.0f;
+    if (p.valid) src.point(p.j, x, y);
+    p.r = -y;   // space_motor_to_img (rendering.py:52-53): flip, times (-1, 1)
+    p.c = x;
+    // check_bounds (rendering.py:27-31): floor<0 | ceil>=105  <=>  not (0 <= v <= 104)
+    p.inb = p.valid && (p.r >= 0.0f) && (p.r <= (float)(IMG - 1)) && (p.c >= 0.0f) && (p.c <= (float)(IMG - 1));
+    const unsigned m = __ballot_sync(0xffffffffu, p.inb);
+    const unsigned lower = m & ((1u << lane) - 1u);
+    const int srcl = lower ? (31 - __clz(lower)) : 0;
+    p.pr = __shfl_sync(0xffffffffu, p.r, srcl);
+    p.pc = __shfl_sync(0xffffffffu, p.c, srcl);
+    p.pj = base + srcl;
+    if (!lower) { p.pr = w.cr; p.pc = w.cc; p.pj = w.cj; }
+    p.idx = w.cnt + __popc(lower);
+    p.dr = 0.0f; p.dc = 0.0f; p.dist = 0.0f; p.ink0 = 0.0f;
+    if (p.inb && p.idx >= 1) {
+        p.dr = __fsub_rn(p.r, p.pr);
+        p.dc = __fsub_rn(p.c, p.pc);
+        p.dist = __fsqrt_rn(__fadd_rn(__fmul_rn(p.dr, p.dr), __fmul_rn(p.dc, p.dc)));   // torch.norm (:96)
+        const float d = fminf(p.dist, rc.ink_max_dist);                                   // clamp (:97)
+        p.ink0 = __fdiv_rn(__fmul_rn(rc.ink_pp, d), rc.ink_max_dist);                      // (:99)
+    }
+    if (m) {
+        const int last = 31 - __clz(m);
+        w.cr = __shfl_sync(0xffffffffu, p.r, last);
+        w.cc = __shfl_sync(0xffffffffu, p.c, last);
+        w.cj = base + last;
+        w.cnt += __popc(m);
+    }
+    return p;
+}
+
+struct Stats {
+    int cnt;        // surviving points
+    int branch;
+    float sum;      // sum of ink before the min-ink fix-up (rendering.py:103)
+    float first;    // ink of survivor 0 (= ink of survivor 1, rendering.py:98)
+    float scale;    // rescale factor ink_pp / sum
+    float fill;     // ink_pp / n
+    bool any_out;
+};
+
+template <class Src>
+__device__ __forceinline__ Stats substroke_stats(const Src &src, int n, int lane, const RenderConsts &rc) {
+    Walk w{0, 0.0f, 0.0f, 0};
+    float psum = 0.0f, first = 0.0f;
+    bool any_out = false;
+    for (int base = 0; base < n; base += 32) {
+        const Pt p = walk_round(src, n, base, lane, rc, w);
+        any_out |= (p.valid && !p.inb);
+        if (p.inb && p.idx >= 1) psum += p.ink0;
+        const unsigned b1 = __ballot_sync(0xffffffffu, p.inb && p.idx == 1);
+        if (b1) first = __shfl_sync(0xffffffffu, p.ink0, __ffs(b1) - 1);
+    }
+    Stats s;
+    s.cnt = w.cnt;
+    s.any_out = __any_sync(0xffffffffu, any_out);
+    s.first = first;
+    s.sum = warp_sum(psum) + first;
+    s.scale = 1.0f;
+    s.fill = 0.0f;
+    if (s.cnt == 0) {
+        s.branch = BR_NONE;
+    } else if (s.cnt == 1) {                       // myink = [ink_pp]  (:93-94)
+        s.branch = BR_SINGLE;
+        s.first = rc.ink_pp;
+        s.sum = rc.ink_pp;
+    } else if (s.sum < 2.22e-6f) {                 // (:104-105)
+        s.branch = BR_FILL;
+        s.fill = (float)((double)rc.ink_pp / (double)s.cnt);
+    } else if (s.sum < rc.ink_pp) {                // (:106-107)
+        s.branch = BR_RESCALE;
+        s.scale = __fdiv_rn(rc.ink_pp, s.sum);
+    } else {
+        s.branch = BR_NORMAL;
+    }
+    return s;
+}
+
+__device__ __forceinline__ float final_ink(const Pt &p, const Stats &s) {
+    float ink = (p.idx == 0) ? s.first : p.ink0;
+    if (s.branch == BR_FILL) ink = s.fill;
+    else if (s.branch == BR_RESCALE) ink = __fmul_rn(s.scale, ink);
+    return ink;
+}
+
+// bilinear splat with shared-memory atomics (rendering.py:111-125)
+template <class Src>
+__device__ __forceinline__ void substroke_splat(const Src &src, int n, int lane, const RenderConsts &rc,
+                                                const Stats &s, float *img) {
+    Walk w{0, 0.0f, 0.0f, 0};
+    for (int base = 0; base < n; base += 32) {
+        const Pt p = walk_round(src, n, base, lane, rc, w);
+        if (!p.inb) continue;
+        const float ink = final_ink(p, s);
+        const float rf = floorf(p.r), cf = floorf(p.c), rce = ceilf(p.r), cce = ceilf(p.c);
+        const float fr = __fsub_rn(p.r, rf), fc = __fsub_rn(p.c, cf);
+        const float gr = __fsub_rn(1.0f, fr), gc = __fsub_rn(1.0f, fc);
+        const int r0 = (int)rf, c0 = (int)cf, r1 = (int)rce, c1 = (int)cce;
+        atomicAdd(img + ORIGIN + r0 * STRIDE + c0, __fmul_rn(__fmul_rn(ink, gr), gc));
+        atomicAdd(img + ORIGIN + r1 * STRIDE + c0, __fmul_rn(__fmul_rn(ink, fr), gc));
+        atomicAdd(img + ORIGIN + r0 * STRIDE + c1, __fmul_rn(__fmul_rn(ink, gr), fc));
+        atomicAdd(img + ORIGIN + r1 * STRIDE + c1, __fmul_rn(__fmul_rn(ink, fr), fc));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// token geometry shared by forward and backward
+// ------------------------------------------------------------------------------------------
+struct TokGeom {
+    int k0, K;      // strokes [k0, k0+K)
+    int s0, S;      // sub-strokes [s0, s0+S)   (raw mode: strokes)
+};
+
+template <bool RAW>
+__device__ __forceinline__ TokGeom token_geom(const KArgs &a, int p) {
+    TokGeom t;
+    if (RAW) {
+        t.k0 = 0; t.K = 0;
+        t.s0 = a.tok_sub_off[p];
+        t.S = a.tok_sub_off[p + 1] - t.s0;
+    } else {
+        t.k0 = a.tok_stroke_off[p];
+        t.K = a.tok_stroke_off[p + 1] - t.k0;
+        t.s0 = a.stroke_sub_off[t.k0];
+        t.S = a.stroke_sub_off[t.k0 + t.K] - t.s0;
+    }
+    return t;
+}
+
+// Sub-stroke chaining (part.py:316-326): offset_i = traj_i[0] - prev_i, prev_{i+1} = traj_i[-1] - offset_i.
+// Phase 1 (one thread per sub-stroke): first and last trajectory points.  Phase 2 (one thread
+// per stroke): the serial recurrence, two subtractions per sub-stroke and coordinate.
+__device__ __forceinline__ void chain_offsets(const KArgs &a, const TokGeom &t, const float *tab, Misc *ms) {
+    for (int s = threadIdx.x; s < t.S; s += blockDim.x) {
+        const float inv = a.invscale[t.s0 + s];
+        const float *cp = a.ctrl + (size_t)(t.s0 + s) * NCPT * 2;
+        float ax = 0.0f, ay = 0.0f, bx = 0.0f, by = 0.0f;
+        const float *r0 = tab, *r1 = tab + (a.neval - 1) * NCPT;
+#pragma unroll
+        for (int k = 0; k < NCPT; ++k) {
+            const float yx = __fmul_rn(inv, cp[2 * k]), yy = __fmul_rn(inv, cp[2 * k + 1]);
+            ax = __fmaf_rn(r0[k], yx, ax); ay = __fmaf_rn(r0[k], yy, ay);
+            bx = __fmaf_rn(r1[k], yx, bx); by = __fmaf_rn(r1[k], yy, by);
+        }
+        ms->sub[s] = make_float4(ax, ay, bx, by);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < t.K; k += blockDim.x) {
+        float px = a.position[2 * (t.k0 + k)], py = a.position[2 * (t.k0 + k) + 1];
+        const int b = a.stroke_sub_off[t.k0 + k] - t.s0, e = a.stroke_sub_off[t.k0 + k + 1] - t.s0;
+        for (int s = b; s < e; ++s) {
+            const float4 v = ms->sub[s];
+            const float ox = __fsub_rn(v.x, px), oy = __fsub_rn(v.y, py);
+            px = __fsub_rn(v.z, ox); py = __fsub_rn(v.w, oy);
+            ms->sub[s] = make_float4(ox, oy, 0.0f, 0.0f);
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ CtrlSrc make_ctrl_src(const KArgs &a, const TokGeom &t, int s, const float *tab,
+                                                 const Misc *ms, bool aff) {
+    CtrlSrc src;
+    src.tab = tab;
+    const float inv = a.invscale[t.s0 + s];
+    const float *cp = a.ctrl + (size_t)(t.s0 + s) * NCPT * 2;
+#pragma unroll
+    for (int k = 0; k < NCPT; ++k) {
+        src.yx[k] = __fmul_rn(inv, cp[2 * k]);        // invscales[i] * shapes[:,:,i]  (part.py:318)
+        src.yy[k] = __fmul_rn(inv, cp[2 * k + 1]);
+    }
+    const float4 o = ms->sub[s];
+    src.offx = o.x; src.offy = o.y;
+    src.aff = aff;
+    src.b0 = ms->affB[0]; src.b1 = ms->affB[1]; src.b2 = ms->affB[2]; src.b3 = ms->affB[3];
+    return src;
+}
+
+// com_char (util/stroke.py:134-135) and B (affine.py:48-53).  All S*neval points, in-bounds or not.
+__device__ __forceinline__ void affine_setup(const KArgs &a, const TokGeom &t, int p, const float *tab, Misc *ms) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    double sx = 0.0, sy = 0.0;
+    for (int s = warp; s < t.S; s += nw) {
+        const CtrlSrc src = make_ctrl_src(a, t, s, tab, ms, false);
+        for (int j = lane; j < a.neval; j += 32) {
+            float x, y;
+            src.pre(j, x, y);
+            sx += (double)x; sy += (double)y;
+        }
+    }
+    double v[2] = {sx, sy};
+    block_sum<2>(v, ms->red);
+    if (threadIdx.x == 0) {
+        const double npts = (double)t.S * (double)a.neval;
+        const float cx = (float)(v[0] / npts), cy = (float)(v[1] / npts);
+        const float *A = a.affine + 4 * (size_t)p;
+        ms->com[0] = cx; ms->com[1] = cy;
+        ms->affB[0] = A[0]; ms->affB[1] = A[1];
+        ms->affB[2] = __fsub_rn(A[2], __fmul_rn(__fsub_rn(A[0], 1.0f), cx));
+        ms->affB[3] = __fsub_rn(A[3], __fmul_rn(__fsub_rn(A[1], 1.0f), cy));
+    }
+    __syncthreads();
+}
+
+// Per-token constants computed by a few lanes of the last warp while the others zero buffers:
+// the 1-D Gaussian g (K = g (x) g exactly: fspecial normalises by sum(E) = (sum e)^2,
+// util/general.py:196-207), h~ for d/dsigma, and the background log-prob constants.
+__device__ __forceinline__ void token_consts(float eps, float sigma, bool grad, Misc *ms) {
+    const int lane = threadIdx.x & 31;
+    if ((int)(threadIdx.x >> 5) != (int)(blockDim.x >> 5) - 1) return;
+    // lanes 0..5: e[d] = exp(-0.5 (d/sigma)^2)
+    double e = 0.0;
+    if (lane <= PAD && sigma > 0.0f) {
+        const double q = (double)lane / (double)sigma;
+        e = exp(-0.5 * q * q);
+    }
+    double tot = (lane == 0) ? e : 2.0 * e;
+    double m2 = (lane == 0) ? 0.0 : 2.0 * e * (double)(lane * lane);
+    tot = warp_sum(tot);
+    m2 = warp_sum(m2);
+    if (lane <= PAD && sigma > 0.0f) {
+        const double g = e / tot;
+        const double mu2 = m2 / tot;      // sum_u u^2 g_u
+        ms->g[lane] = (float)g;
+        ms->ht[lane] = (float)(((double)(lane * lane) - mu2) * g);
+    }
+    // lanes 8,9: background pixel (pimg == eps after the mix, or 0 when eps <= 0)
+    if (lane == 8 || lane == 9) {
+        const bool x = (lane == 9);
+        const float bg = eps > 0.0f ? eps : 0.0f;
+        float lp, dlp;
+        pixel_lp_exact(bg, x, lp, dlp);
+        ms->lp_bg[x] = lp;
+        ms->dlp_bg[x] = dlp;
+    }
+    (void)grad;
+}
+
+__device__ __forceinline__ void load_image_bits(const KArgs &a, int p, Misc *ms) {
+    if (!a.image_bits) return;
+    const int t = a.img_idx ? a.img_idx[p] : 0;
+    if (t == ms->cur_img) return;      // cur_img is only written after the barrier below, read before it
+    for (int i = threadIdx.x; i < IMG * IMG_WORDS; i += blockDim.x)
+        ms->bits[i] = a.image_bits[(size_t)t * IMG * IMG_WORDS + i];
+}
+
+__device__ __forceinline__ void zero_floats(float *p, int n) {
+    float4 *p4 = reinterpret_cast<float4 *>(p);
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = threadIdx.x; i < n / 4; i += blockDim.x) p4[i] = z;
+    for (int i = (n / 4) * 4 + threadIdx.x; i < n; i += blockDim.x) p[i] = 0.0f;
+}
+
+// broaden (rendering.py:160-171): ncon x [ c1 * S_h S_v + c2 ], then min(.,1) if CLAMP.
+// A holds the image and receives the result; T is scratch.
+template <int R3, bool CLAMP>
+__device__ __forceinline__ void broaden(float *A, float *T, const RenderConsts &rc) {
+    const float w3[1][2] = {{2.0f, 1.0f}};
+    for (int it = 0; it < rc.ink_ncon; ++it) {
+        sweep<3, R3, true, 1>(A, w3, LoadId(), [&](int r, int c, const float (&acc)[1]) {
+            T[ORIGIN + r * STRIDE + c] = acc[0];
+        });
+        __syncthreads();
+        const bool last = CLAMP && (it == rc.ink_ncon - 1);
+        sweep<3, R3, false, 1>(T, w3, LoadId(), [&](int r, int c, const float (&acc)[1]) {
+            float *q = A + ORIGIN + r * STRIDE + c;
+            float v = fmaf(rc.c1, acc[0], rc.c2 * (*q));
+            if (last) v = fminf(v, 1.0f);
+            *q = v;
+        });
+        __syncthreads();
+    }
+    if (CLAMP && rc.ink_ncon == 0) {
+        for (int i = threadIdx.x; i < BUFN; i += blockDim.x) A[i] = fminf(A[i], 1.0f);
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// forward kernel
+// ------------------------------------------------------------------------------------------
+constexpr int FWD_THREADS = 256;
+constexpr int FWD_R = 15;       // outputs per sweep item (Gaussian); 7 bands x 105 lines = 735 items
+constexpr int FWD_R3 = 15;
+
+struct FwdSmem {
+    float A[BUFP];
+    float B[BUFP];
+    float tab[MAX_TABLE];
+    Misc ms;
+};
+
+template <bool RAW>
+__global__ void __launch_bounds__(FWD_THREADS, 2) bpl_forward_kernel(const KArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FwdSmem &sm = *reinterpret_cast<FwdSmem *>(smem_raw);
+    float *A = sm.A, *B = sm.B;
+    Misc *ms = &sm.ms;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+
+    zero_floats(B, BUFP);
+    if (!RAW)
+        for (int i = threadIdx.x; i < a.neval * NCPT; i += blockDim.x) sm.tab[i] = a.basis[i];
+    if (threadIdx.x == 0) ms->cur_img = -1;
+    __syncthreads();
+
+    for (int p = blockIdx.x; p < a.n_tokens; p += gridDim.x) {
+        const TokGeom t = token_geom<RAW>(a, p);
+        const float eps = a.eps[p], sigma = a.sigma[p];
+        if (!RAW && (t.S > MAXS || t.K > MAXK)) {      // beyond the per-CTA tables: flag, do not guess
+            if (threadIdx.x == 0) {
+                if (a.ll) a.ll[p] = nanf("");
+                if (a.off_page) a.off_page[p] = 255;
+            }
+            continue;
+        }
+        const bool aff = !RAW && a.affine != nullptr;
+        zero_floats(A, BUFP);
+        load_image_bits(a, p, ms);
+        token_consts(eps, sigma, false, ms);
+        if (threadIdx.x == 0) ms->off_page = 0;
+        if (!RAW) {
+            chain_offsets(a, t, sm.tab, ms);
+            if (aff) affine_setup(a, t, p, sm.tab, ms);
+        } else {
+            __syncthreads();
+        }
+        if (threadIdx.x == 0 && a.image_bits) ms->cur_img = a.img_idx ? a.img_idx[p] : 0;
+
+        // ---- add_stroke over sub-strokes: one warp each ----
+        bool any_out = false;
+        for (int s = warp; s < t.S; s += nw) {
+            if (RAW) {
+                const int o = a.sub_pt_off[t.s0 + s], n = a.sub_pt_off[t.s0 + s + 1] - o;
+                const RawSrc src{reinterpret_cast<const float2 *>(a.pts) + o};
+                const Stats st = substroke_stats(src, n, lane, a.rc);
+                any_out |= st.any_out;
+                if (st.cnt > 0) substroke_splat(src, n, lane, a.rc, st, A);
+            } else {
+                const CtrlSrc src = make_ctrl_src(a, t, s, sm.tab, ms, aff);
+                const Stats st = substroke_stats(src, a.neval, lane, a.rc);
+                any_out |= st.any_out;
+                if (st.cnt > 0) substroke_splat(src, a.neval, lane, a.rc, st, A);
+            }
+        }
+        if (any_out && lane == 0) atomicOr(&ms->off_page, 1);
+        __syncthreads();
+
+        // ---- broaden + clamp ----
+        broaden<FWD_R3, true>(A, B, a.rc);
+
+        // ---- blur, clamp, mix, likelihood ----
+        const float bgv = eps > 0.0f ? eps : 0.0f;
+        const float om = 1.0f - eps;
+        const float lp_bg0 = ms->lp_bg[0], lp_bg1 = ms->lp_bg[1];
+        const bool score = a.image_bits != nullptr;
+        const bool want_pimg = a.pimg != nullptr;
+        float acc_ll = 0.0f;
+        auto finish = [&](int r, int c, float v, float *dst) {
+            v = fminf(fmaxf(v, 0.0f), 1.0f);                               // clamp_(0,1)  (:180)
+            if (eps > 0.0f) v = __fadd_rn(__fmul_rn(om, v), __fmul_rn(eps, __fsub_rn(1.0f, v)));   // (:227)
+            if (want_pimg) dst[ORIGIN + r * STRIDE + c] = v;
+            if (score) {
+                const bool x = (ms->bits[r * IMG_WORDS + (c >> 5)] >> (c & 31)) & 1u;
+                if (v == bgv) {
+                    acc_ll += x ? lp_bg1 : lp_bg0;
+                } else {
+                    float lp, d;
+                    pixel_lp(v, x, false, lp, d);
+                    acc_ll += lp;
+                }
+            }
+        };
+        if (sigma > 0.0f) {
+            float wg[1][PAD + 1];
+#pragma unroll
+            for (int d = 0; d <= PAD; ++d) wg[0][d] = ms->g[d];
+            auto store_B = [&](int r, int c, const float (&acc)[1]) { B[ORIGIN + r * STRIDE + c] = acc[0]; };
+            auto store_A = [&](int r, int c, const float (&acc)[1]) { A[ORIGIN + r * STRIDE + c] = acc[0]; };
+            sweep<BPL_FSIZE, FWD_R, true, 1>(A, wg, LoadId(), store_B);
+            __syncthreads();
+            sweep<BPL_FSIZE, FWD_R, false, 1>(B, wg, LoadId(), store_A);
+            __syncthreads();
+            sweep<BPL_FSIZE, FWD_R, true, 1>(A, wg, LoadId(), store_B);
+            __syncthreads();
+            sweep<BPL_FSIZE, FWD_R, false, 1>(B, wg, LoadId(),
+                                              [&](int r, int c, const float (&acc)[1]) { finish(r, c, acc[0], A); });
+        } else {
+            for (int i = threadIdx.x; i < NPIX; i += blockDim.x) {
+                const int r = i / IMG, c = i - r * IMG;
+                finish(r, c, A[ORIGIN + r * STRIDE + c], A);
+            }
+        }
+        double v[1] = {(double)acc_ll};
+        block_sum<1>(v, ms->red);      // contains the barriers that order the pimg stores below
+        if (threadIdx.x == 0) {
+            if (a.ll) a.ll[p] = score ? (float)v[0] : 0.0f;
+            if (a.off_page) a.off_page[p] = (uint8_t)(ms->off_page != 0);
+        }
+        if (want_pimg) {
+            float *dst = a.pimg + (size_t)p * NPIX;
+            for (int i = threadIdx.x; i < NPIX; i += blockDim.x) {
+                const int r = i / IMG, c = i - r * IMG;
+                dst[i] = A[ORIGIN + r * STRIDE + c];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// fused forward + backward kernel (4 image buffers, one CTA per SM)
+// ------------------------------------------------------------------------------------------
+constexpr int BWD_THREADS = 544;   // 17 warps: 5 bands x 105 lines = 525 sweep items in one round
+constexpr int BWD_R = 21;
+constexpr int BWD_R3 = 21;
+constexpr int NACC = 2 * NCPT + 2; // per sub-stroke: W[k].x, W[k].y, Gsum.x, Gsum.y
+
+struct BwdSmem {
+    float A[BUFP];
+    float B[BUFP];
+    float C[BUFP];
+    float D[BUFP];
+    float tab[MAX_TABLE];
+    Misc ms;
+};
+
+// gather the image gradient at the four splat corners (adjoint of rendering.py:111-125)
+struct Corner {
+    float gink, gr, gc;     // d/d ink, d/d row, d/d col (for ink weight 1)
+};
+__device__ __forceinline__ Corner gather_corners(const float *G, float r, float c) {
+    const float rf = floorf(r), cf = floorf(c), rce = ceilf(r), cce = ceilf(c);
+    const float fr = r - rf, fc = c - cf, gr = 1.0f - fr, gc = 1.0f - fc;
+    const int r0 = (int)rf, c0 = (int)cf, r1 = (int)rce, c1 = (int)cce;
+    const float G00 = G[ORIGIN + r0 * STRIDE + c0], G10 = G[ORIGIN + r1 * STRIDE + c0];
+    const float G01 = G[ORIGIN + r0 * STRIDE + c1], G11 = G[ORIGIN + r1 * STRIDE + c1];
+    Corner k;
+    k.gink = gr * gc * G00 + fr * gc * G10 + gr * fc * G01 + fr * fc * G11;
+    k.gr = gc * (G10 - G00) + fc * (G11 - G01);
+    k.gc = gr * (G01 - G00) + fr * (G11 - G10);
+    return k;
+}
+
+// Backward of add_stroke for one sub-stroke.  `emit(j, gx, gy)` receives motor-space (post-warp)
+// point gradients; a point may be emitted more than once (own splat, own segment, next segment).
+template <class Src, class Emit>
+__device__ __forceinline__ void substroke_backward(const Src &src, int n, int lane, const RenderConsts &rc,
+                                                   const Stats &st, const float *G, Emit emit) {
+    if (st.cnt == 0) return;
+    const bool use_dist = (st.branch == BR_NORMAL || st.branch == BR_RESCALE);
+    float sc = 1.0f, gsum = 0.0f;
+    if (st.branch == BR_RESCALE) {      // ink' = ink * (ink_pp / sum)   (rendering.py:106-107)
+        Walk w{0, 0.0f, 0.0f, 0};
+        float dot = 0.0f;
+        for (int base = 0; base < n; base += 32) {
+            const Pt p = walk_round(src, n, base, lane, rc, w);
+            if (p.inb) {
+                const Corner k = gather_corners(G, p.r, p.c);
+                dot += k.gink * ((p.idx == 0) ? st.first : p.ink0);
+            }
+        }
+        dot = warp_sum(dot);
+        sc = st.scale;
+        gsum = -dot * rc.ink_pp / (st.sum * st.sum);
+    }
+    Walk w{0, 0.0f, 0.0f, 0};
+    float cgink = 0.0f;      // d/d ink0 of the last survivor of earlier rounds
+    for (int base = 0; base < n; base += 32) {
+        const Pt p = walk_round(src, n, base, lane, rc, w);
+        float ginkp = 0.0f, g_r = 0.0f, g_c = 0.0f;
+        if (p.inb) {
+            const Corner k = gather_corners(G, p.r, p.c);
+            const float ink = final_ink(p, st);
+            g_r = ink * k.gr;
+            g_c = ink * k.gc;
+            ginkp = use_dist ? fmaf(k.gink, sc, gsum) : 0.0f;
+        }
+        // d/d ink0 of the previous survivor (needed only by survivor 1: ink0[0] = ink0[1])
+        const unsigned m = __ballot_sync(0xffffffffu, p.inb);
+        const unsigned lower = m & ((1u << lane) - 1u);
+        float pgink = __shfl_sync(0xffffffffu, ginkp, lower ? (31 - __clz(lower)) : 0);
+        if (!lower) pgink = cgink;
+        if (m) cgink = __shfl_sync(0xffffffffu, ginkp, 31 - __clz(m));
+        if (p.inb) {
+            float ur = 0.0f, uc = 0.0f;
+            if (use_dist && p.idx >= 1 && p.dist <= rc.ink_max_dist && p.dist != 0.0f) {
+                const float gd = rc.ink_f * (ginkp + (p.idx == 1 ? pgink : 0.0f));
+                ur = gd * (p.dr / p.dist);
+                uc = gd * (p.dc / p.dist);
+            }
+            // un-flip: row = -y, col = x
+            emit(p.j, g_c + uc, -(g_r + ur));
+            if (ur != 0.0f || uc != 0.0f) emit(p.pj, -uc, ur);
+        }
+    }
+}
+
+template <bool RAW>
+__global__ void __launch_bounds__(BWD_THREADS, 1) bpl_backward_kernel(const KArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BwdSmem &sm = *reinterpret_cast<BwdSmem *>(smem_raw);
+    float *A = sm.A, *B = sm.B, *C = sm.C, *D = sm.D;
+    Misc *ms = &sm.ms;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+
+    zero_floats(B, 3 * BUFP);    // B, C, D are contiguous
+    if (!RAW) {
+        for (int i = threadIdx.x; i < a.neval * NCPT; i += blockDim.x) sm.tab[i] = a.basis[i];
+    }
+    if (threadIdx.x == 0) ms->cur_img = -1;
+    __syncthreads();
+    if (!RAW && warp == 0) {     // column sums of the table (d com / d control points)
+        float cs[NCPT];
+#pragma unroll
+        for (int k = 0; k < NCPT; ++k) cs[k] = 0.0f;
+        for (int j = lane; j < a.neval; j += 32)
+#pragma unroll
+            for (int k = 0; k < NCPT; ++k) cs[k] += sm.tab[j * NCPT + k];
+#pragma unroll
+        for (int k = 0; k < NCPT; ++k) {
+            const float s = warp_sum(cs[k]);
+            if (lane == 0) ms->colsum[k] = s;
+        }
+    }
+
+    for (int p = blockIdx.x; p < a.n_tokens; p += gridDim.x) {
+        const TokGeom t = token_geom<RAW>(a, p);
+        const float eps = a.eps[p], sigma = a.sigma[p];
+        if (!RAW && (t.S > MAXS || t.K > MAXK)) {      // beyond the per-CTA tables: flag, do not guess
+            if (threadIdx.x == 0) {
+                if (a.ll) a.ll[p] = nanf("");
+                if (a.off_page) a.off_page[p] = 255;
+            }
+            continue;
+        }
+        const bool aff = !RAW && a.affine != nullptr;
+        zero_floats(A, BUFP);
+        load_image_bits(a, p, ms);
+        token_consts(eps, sigma, true, ms);
+        if (threadIdx.x == 0) {
+            ms->off_page = 0;
+            ms->aff_acc[0] = ms->aff_acc[1] = ms->aff_acc[2] = ms->aff_acc[3] = 0.0;
+        }
+        if (!RAW) {
+            chain_offsets(a, t, sm.tab, ms);
+            if (aff) affine_setup(a, t, p, sm.tab, ms);
+        } else {
+            __syncthreads();
+        }
+        if (threadIdx.x == 0 && a.image_bits) ms->cur_img = a.img_idx ? a.img_idx[p] : 0;
+
+        // ---- forward: splat ----
+        bool any_out = false;
+        for (int s = warp; s < t.S; s += nw) {
+            if (RAW) {
+                const int o = a.sub_pt_off[t.s0 + s], n = a.sub_pt_off[t.s0 + s + 1] - o;
+                const RawSrc src{reinterpret_cast<const float2 *>(a.pts) + o};
+                const Stats st = substroke_stats(src, n, lane, a.rc);
+                any_out |= st.any_out;
+                if (st.cnt > 0) substroke_splat(src, n, lane, a.rc, st, A);
+            } else {
+                const CtrlSrc src = make_ctrl_src(a, t, s, sm.tab, ms, aff);
+                const Stats st = substroke_stats(src, a.neval, lane, a.rc);
+                any_out |= st.any_out;
+                if (st.cnt > 0) substroke_splat(src, a.neval, lane, a.rc, st, A);
+            }
+        }
+        if (any_out && lane == 0) atomicOr(&ms->off_page, 1);
+        __syncthreads();
+
+        // ---- forward: broaden; A keeps I2 (pre-clamp); consumers apply min(.,1) on load ----
+        broaden<BWD_R3, false>(A, B, a.rc);
+
+        const float bgv = eps > 0.0f ? eps : 0.0f;
+        const float om = 1.0f - eps;
+        const float mixd = eps > 0.0f ? (1.0f - 2.0f * eps) : 1.0f;     // d mix / d I6
+        const float lp_bg0 = ms->lp_bg[0], lp_bg1 = ms->lp_bg[1];
+        const float dlp_bg0 = ms->dlp_bg[0], dlp_bg1 = ms->dlp_bg[1];
+        const bool score = a.image_bits != nullptr;
+        const float *gP_ext = a.g_pimg ? a.g_pimg + (size_t)p * NPIX : nullptr;
+        const float gscale = (!gP_ext && a.g_ll) ? a.g_ll[p] : 1.0f;
+        float acc_ll = 0.0f, acc_eps = 0.0f, acc_sig = 0.0f;
+
+        // pointwise tail of the forward + head of the backward for pixel (r,c) with blurred value v:
+        // returns d L / d I5 (cotangent entering the second blur pass).
+        auto tail = [&](int r, int c, float v) -> float {
+            const bool pass5 = (v >= 0.0f) && (v <= 1.0f);                  // clamp_(0,1) passes gradient on [0,1]
+            const float i6 = fminf(fmaxf(v, 0.0f), 1.0f);
+            float pm = i6;
+            if (eps > 0.0f) pm = __fadd_rn(__fmul_rn(om, i6), __fmul_rn(eps, __fsub_rn(1.0f, i6)));
+            float gp;
+            if (gP_ext) {
+                gp = gP_ext[r * IMG + c];
+            } else {
+                const bool x = score && ((ms->bits[r * IMG_WORDS + (c >> 5)] >> (c & 31)) & 1u);
+                float lp, d;
+                if (pm == bgv) { lp = x ? lp_bg1 : lp_bg0; d = x ? dlp_bg1 : dlp_bg0; }
+                else pixel_lp(pm, x, true, lp, d);
+                acc_ll += lp;
+                gp = d * gscale;
+            }
+            if (eps > 0.0f) acc_eps += gp * (1.0f - 2.0f * i6);              // d/d eps of (1-eps) p + eps (1-p)
+            return pass5 ? gp * mixd : 0.0f;
+        };
+
+        if (sigma > 0.0f) {
+            float wg[1][PAD + 1], wgh[2][PAD + 1];
+#pragma unroll
+            for (int d = 0; d <= PAD; ++d) { wg[0][d] = ms->g[d]; wgh[0][d] = ms->g[d]; wgh[1][d] = ms->ht[d]; }
+            // blur A forward: I3 = min(A,1) -V-> B -H-> C = I4
+            sweep<BPL_FSIZE, BWD_R, true, 1>(A, wg, LoadMin1(), [&](int r, int c, const float (&acc)[1]) {
+                B[ORIGIN + r * STRIDE + c] = acc[0]; });
+            __syncthreads();
+            sweep<BPL_FSIZE, BWD_R, false, 1>(B, wg, LoadId(), [&](int r, int c, const float (&acc)[1]) {
+                C[ORIGIN + r * STRIDE + c] = acc[0]; });
+            __syncthreads();
+            // blur B forward, first axis with both filters: U = g_v * I4 -> B, W = h~_v * I4 -> D
+            sweep<BPL_FSIZE, BWD_R, true, 2>(C, wgh, LoadId(), [&](int r, int c, const float (&acc)[2]) {
+                B[ORIGIN + r * STRIDE + c] = acc[0];
+                D[ORIGIN + r * STRIDE + c] = acc[1]; });
+            __syncthreads();
+            // second axis: I5 = g_h * U; pointwise tail; G_B -> C
+            sweep<BPL_FSIZE, BWD_R, false, 1>(B, wg, LoadId(), [&](int r, int c, const float (&acc)[1]) {
+                C[ORIGIN + r * STRIDE + c] = tail(r, c, acc[0]); });
+            __syncthreads();
+            // adjoint of blur B along h, reduced against U, W for d/d sigma; t_g -> D (in place of W)
+            sweep<BPL_FSIZE, BWD_R, false, 2>(C, wgh, LoadId(), [&](int r, int c, const float (&acc)[2]) {
+                const int q = ORIGIN + r * STRIDE + c;
+                acc_sig = fmaf(acc[0], D[q], fmaf(acc[1], B[q], acc_sig));
+                D[q] = acc[0]; });
+            __syncthreads();
+            // adjoint along v: G_A = d L / d I4 -> C
+            sweep<BPL_FSIZE, BWD_R, true, 1>(D, wg, LoadId(), [&](int r, int c, const float (&acc)[1]) {
+                C[ORIGIN + r * STRIDE + c] = acc[0]; });
+            __syncthreads();
+            // recompute U_A, W_A from I3 = min(A,1)
+            sweep<BPL_FSIZE, BWD_R, true, 2>(A, wgh, LoadMin1(), [&](int r, int c, const float (&acc)[2]) {
+                B[ORIGIN + r * STRIDE + c] = acc[0];
+                D[ORIGIN + r * STRIDE + c] = acc[1]; });
+            __syncthreads();
+            sweep<BPL_FSIZE, BWD_R, false, 2>(C, wgh, LoadId(), [&](int r, int c, const float (&acc)[2]) {
+                const int q = ORIGIN + r * STRIDE + c;
+                acc_sig = fmaf(acc[0], D[q], fmaf(acc[1], B[q], acc_sig));
+                D[q] = acc[0]; });
+            __syncthreads();
+            // G_3 = d L / d I3, masked by clamp_(max=1) (:171) -> A (pointwise in place over I2)
+            sweep<BPL_FSIZE, BWD_R, true, 1>(D, wg, LoadId(), [&](int r, int c, const float (&acc)[1]) {
+                float *q = A + ORIGIN + r * STRIDE + c;
+                *q = (*q <= 1.0f) ? acc[0] : 0.0f; });
+            __syncthreads();
+        } else {
+            for (int i = threadIdx.x; i < NPIX; i += blockDim.x) {
+                const int r = i / IMG, c = i - r * IMG;
+                float *q = A + ORIGIN + r * STRIDE + c;
+                const float i2 = *q;
+                const float g = tail(r, c, fminf(i2, 1.0f));
+                *q = (i2 <= 1.0f) ? g : 0.0f;
+            }
+            __syncthreads();
+        }
+        // adjoint broaden (symmetric kernel, zero padding): A -> A
+        broaden<BWD_R3, false>(A, B, a.rc);
+
+        // ---- scalar outputs ----
+        {
+            double v[3] = {(double)acc_ll, (double)acc_eps, (double)acc_sig};
+            block_sum<3>(v, ms->red);
+            if (threadIdx.x == 0) {
+                if (a.ll) a.ll[p] = (score && !gP_ext) ? (float)v[0] : 0.0f;
+                if (a.off_page) a.off_page[p] = (uint8_t)(ms->off_page != 0);
+                if (a.g_eps) a.g_eps[p] = (float)v[1];
+                if (a.g_sigma) {
+                    const double s3 = (double)sigma * (double)sigma * (double)sigma;
+                    a.g_sigma[p] = sigma > 0.0f ? (float)(v[2] / s3) : 0.0f;
+                }
+            }
+        }
+
+        // ---- add_stroke backward: gather at the splat points ----
+        float *accs = B;       // [S][NACC] warp-reduced sums per sub-stroke (B is free; interior only)
+        for (int s = warp; s < t.S; s += nw) {
+            if (RAW) {
+                const int o = a.sub_pt_off[t.s0 + s], n = a.sub_pt_off[t.s0 + s + 1] - o;
+                const RawSrc src{reinterpret_cast<const float2 *>(a.pts) + o};
+                const Stats st = substroke_stats(src, n, lane, a.rc);
+                float *gp = a.g_pts + 2 * (size_t)o;
+                substroke_backward(src, n, lane, a.rc, st, A, [&](int j, float gx, float gy) {
+                    atomicAdd(gp + 2 * j, gx);
+                    atomicAdd(gp + 2 * j + 1, gy);
+                });
+            } else {
+                const CtrlSrc src = make_ctrl_src(a, t, s, sm.tab, ms, aff);
+                const Stats st = substroke_stats(src, a.neval, lane, a.rc);
+                float wx[NCPT], wy[NCPT], sx = 0.0f, sy = 0.0f, ax = 0.0f, ay = 0.0f;
+#pragma unroll
+                for (int k = 0; k < NCPT; ++k) { wx[k] = 0.0f; wy[k] = 0.0f; }
+                substroke_backward(src, a.neval, lane, a.rc, st, A, [&](int j, float gx, float gy) {
+                    const float *row = sm.tab + j * NCPT;
+#pragma unroll
+                    for (int k = 0; k < NCPT; ++k) { wx[k] = fmaf(row[k], gx, wx[k]); wy[k] = fmaf(row[k], gy, wy[k]); }
+                    sx += gx; sy += gy;
+                    if (aff) {
+                        float px, py;
+                        src.pre(j, px, py);
+                        ax = fmaf(gx, px, ax); ay = fmaf(gy, py, ay);
+                    }
+                });
+                float *o = accs + ORIGIN + s * NACC;      // inside B's interior rows? no: plain scratch, re-zeroed below
+#pragma unroll
+                for (int k = 0; k < NCPT; ++k) {
+                    const float a0 = warp_sum(wx[k]), a1 = warp_sum(wy[k]);
+                    if (lane == 0) { o[2 * k] = a0; o[2 * k + 1] = a1; }
+                }
+                sx = warp_sum(sx); sy = warp_sum(sy);
+                if (lane == 0) { o[2 * NCPT] = sx; o[2 * NCPT + 1] = sy; }
+                if (aff) {
+                    ax = warp_sum(ax); ay = warp_sum(ay);
+                    if (lane == 0) {
+                        atomicAdd(&ms->aff_acc[0], (double)ax); atomicAdd(&ms->aff_acc[1], (double)ay);
+                        atomicAdd(&ms->aff_acc[2], (double)sx); atomicAdd(&ms->aff_acc[3], (double)sy);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- chain backward (part.py:316-326) and control-point gradients ----
+        if (!RAW) {
+            float gcx = 0.0f, gcy = 0.0f, b0 = 1.0f, b1 = 1.0f;
+            if (aff) {      // p' = p * B[:2] + B[2:], B[2:] = A[2:] - (A[:2]-1) com, com = mean(p)
+                const float *Aa = a.affine + 4 * (size_t)p;
+                const double npts = (double)t.S * (double)a.neval;
+                b0 = ms->affB[0]; b1 = ms->affB[1];
+                gcx = (float)(-((double)Aa[0] - 1.0) * ms->aff_acc[2] / npts);
+                gcy = (float)(-((double)Aa[1] - 1.0) * ms->aff_acc[3] / npts);
+                if (threadIdx.x == 0 && a.g_affine) {
+                    float *ga = a.g_affine + 4 * (size_t)p;
+                    ga[0] = (float)(ms->aff_acc[0] - (double)ms->com[0] * ms->aff_acc[2]);
+                    ga[1] = (float)(ms->aff_acc[1] - (double)ms->com[1] * ms->aff_acc[3]);
+                    ga[2] = (float)ms->aff_acc[2];
+                    ga[3] = (float)ms->aff_acc[3];
+                }
+            } else if (threadIdx.x == 0 && a.g_affine) {
+                float *ga = a.g_affine + 4 * (size_t)p;
+                ga[0] = ga[1] = ga[2] = ga[3] = 0.0f;
+            }
+            const float *rfirst = sm.tab, *rlast = sm.tab + (a.neval - 1) * NCPT;
+            for (int k = threadIdx.x; k < t.K; k += blockDim.x) {
+                const int b = a.stroke_sub_off[t.k0 + k] - t.s0, e = a.stroke_sub_off[t.k0 + k + 1] - t.s0;
+                float cx = 0.0f, cy = 0.0f;       // gradient w.r.t. previous_pos of the following sub-stroke
+                for (int s = e - 1; s >= b; --s) {
+                    const float *o = accs + ORIGIN + s * NACC;
+                    const float sx = fmaf(b0, o[2 * NCPT], (float)a.neval * gcx);
+                    const float sy = fmaf(b1, o[2 * NCPT + 1], (float)a.neval * gcy);
+                    const float tx = sx + cx, ty = sy + cy;
+                    const float inv = a.invscale[t.s0 + s];
+                    const float *cp = a.ctrl + (size_t)(t.s0 + s) * NCPT * 2;
+                    float *gc = a.g_ctrl + (size_t)(t.s0 + s) * NCPT * 2;
+                    float gi = 0.0f;
+#pragma unroll
+                    for (int q = 0; q < NCPT; ++q) {
+                        const float wx = fmaf(b0, o[2 * q], gcx * ms->colsum[q]);
+                        const float wy = fmaf(b1, o[2 * q + 1], gcy * ms->colsum[q]);
+                        const float gyx = wx + rlast[q] * cx - rfirst[q] * tx;
+                        const float gyy = wy + rlast[q] * cy - rfirst[q] * ty;
+                        gc[2 * q] = inv * gyx;
+                        gc[2 * q + 1] = inv * gyy;
+                        gi = fmaf(cp[2 * q], gyx, fmaf(cp[2 * q + 1], gyy, gi));
+                    }
+                    a.g_invscale[t.s0 + s] = gi;
+                    cx = tx; cy = ty;
+                }
+                a.g_position[2 * (t.k0 + k)] = cx;
+                a.g_position[2 * (t.k0 + k) + 1] = cy;
+            }
+            __syncthreads();
+            // B's interior was used as scratch: restore zeros (its border was never touched)
+            for (int i = threadIdx.x; i < t.S * NACC; i += blockDim.x) accs[ORIGIN + i] = 0.0f;
+        }
+        __syncthreads();
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Inspection kernel: the integer work of the path, per point, through the very same device
+// functions the fused kernels use (chain_offsets / affine_setup / CtrlSrc / walk_round):
+// motor-space points, out-of-bounds mask (rendering.py:27-31), floor/ceil pixel indices
+// (rendering.py:113-116) and surviving-point count per sub-stroke.  Used by the parity tests and by
+// StrokeToken.motor-style consumers that want all trajectories of a batch.
+// ------------------------------------------------------------------------------------------
+struct PtsSmem {
+    float tab[MAX_TABLE];
+    Misc ms;
+};
+
+__global__ void __launch_bounds__(256) bpl_points_kernel(const KArgs a, float *__restrict__ motor,
+                                                          uint8_t *__restrict__ mask_out, int *__restrict__ fl,
+                                                          int *__restrict__ ce, int *__restrict__ n_in) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PtsSmem &sm = *reinterpret_cast<PtsSmem *>(smem_raw);
+    Misc *ms = &sm.ms;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int i = threadIdx.x; i < a.neval * NCPT; i += blockDim.x) sm.tab[i] = a.basis[i];
+    __syncthreads();
+    for (int p = blockIdx.x; p < a.n_tokens; p += gridDim.x) {
+        const TokGeom t = token_geom<false>(a, p);
+        if (t.S > MAXS || t.K > MAXK) continue;
+        const bool aff = a.affine != nullptr;
+        chain_offsets(a, t, sm.tab, ms);
+        if (aff) affine_setup(a, t, p, sm.tab, ms);
+        for (int s = warp; s < t.S; s += nw) {
+            const CtrlSrc src = make_ctrl_src(a, t, s, sm.tab, ms, aff);
+            Walk w{0, 0.0f, 0.0f, 0};
+            const size_t o = (size_t)(t.s0 + s) * a.neval;
+            for (int base = 0; base < a.neval; base += 32) {
+                const Pt q = walk_round(src, a.neval, base, lane, a.rc, w);
+                if (!q.valid) continue;
+                if (motor) { motor[2 * (o + q.j)] = q.c; motor[2 * (o + q.j) + 1] = -q.r; }
+                if (mask_out) mask_out[o + q.j] = (uint8_t)(!q.inb);
+                if (fl) { fl[2 * (o + q.j)] = (int)floorf(q.r); fl[2 * (o + q.j) + 1] = (int)floorf(q.c); }
+                if (ce) { ce[2 * (o + q.j)] = (int)ceilf(q.r); ce[2 * (o + q.j) + 1] = (int)ceilf(q.c); }
+            }
+            if (n_in && lane == 0) n_in[t.s0 + s] = w.cnt;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char *fmt, const char *detail) { snprintf(g_err, sizeof(g_err), fmt, detail); }
+const char *last_error() { return g_err; }
+void count_launch(int n) { g_launches += n; }
+long long launch_count() { return g_launches.load(); }
+
+static int make_consts(const bpl_params *ps, RenderConsts *rc) {
+    if (!ps) { set_error("%s", "params is NULL"); return BPL_EINVAL; }
+    if (ps->imsize != BPL_IMSIZE || ps->fsize != BPL_FSIZE) {
+        set_error("%s", "only imsize=105 and fsize=11 are built (pybpl/parameters.py:21,41)");
+        return BPL_EINVAL;
+    }
+    if (ps->ink_ncon < 0 || ps->ink_ncon > 16) { set_error("%s", "ink_ncon out of range"); return BPL_EINVAL; }
+    const double a = ps->ink_a, b = ps->ink_b;
+    const double hs = ps->hinton ? b * (1.0 + a) : b;      // rendering.py:153-156
+    rc->ink_ncon = ps->ink_ncon;
+    rc->ink_pp = ps->ink_pp;
+    rc->ink_max_dist = ps->ink_max_dist;
+    rc->ink_f = ps->ink_pp / ps->ink_max_dist;
+    rc->c1 = (float)(hs * a / 12.0);
+    rc->c2 = (float)(hs * (1.0 - 4.0 * a / 3.0));
+    return 0;
+}
+
+struct DevInfo { int sm_count; int smem_optin; bool ok; };
+static DevInfo dev_info() {
+    static thread_local int cached_dev = -1;
+    static thread_local DevInfo info{0, 0, false};
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) return DevInfo{0, 0, false};
+    if (dev != cached_dev) {
+        info.ok = cudaDeviceGetAttribute(&info.sm_count, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
+                  cudaDeviceGetAttribute(&info.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess;
+        cached_dev = dev;
+    }
+    return info;
+}
+
+template <class K>
+static int launch(K kernel, int threads, size_t smem, int ctas_per_sm, const KArgs &ka, cudaStream_t st) {
+    const DevInfo di = dev_info();
+    if (!di.ok) { set_error("%s", "no CUDA device"); return BPL_ENODEV; }
+    if ((size_t)di.smem_optin < smem) { set_error("%s", "device lacks the shared memory this kernel needs (built for sm_100a)"); return BPL_ENODEV; }
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    int grid = di.sm_count * ctas_per_sm;
+    if (grid > ka.n_tokens) grid = ka.n_tokens;
+    if (grid <= 0) return 0;
+    kernel<<<grid, threads, smem, st>>>(ka);
+    count_launch(1);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("kernel launch: %s", cudaGetErrorString(e)); return (int)e; }
+    return 0;
+}
+
+static int fill_common(KArgs &ka, const bpl_params *ps, const bpl_targets *t, const bpl_fwd_out *out,
+                       const bpl_grads *g) {
+    int rcode = make_consts(ps, &ka.rc);
+    if (rcode) return rcode;
+    if (t) { ka.image_bits = t->image_bits; ka.img_idx = t->img_idx; ka.n_images = t->n_images; }
+    if (out) { ka.ll = out->ll; ka.off_page = out->off_page; ka.pimg = out->pimg; }
+    if (g) {
+        ka.g_ll = g->g_ll; ka.g_pimg = g->g_pimg; ka.g_ctrl = g->g_ctrl; ka.g_invscale = g->g_invscale;
+        ka.g_position = g->g_position; ka.g_affine = g->g_affine; ka.g_pts = g->g_pts; ka.g_eps = g->g_eps;
+        ka.g_sigma = g->g_sigma;
+    }
+    return 0;
+}
+
+static int fill_tokens(KArgs &ka, const bpl_token_batch *b) {
+    if (!b) { set_error("%s", "batch is NULL"); return BPL_EINVAL; }
+    if (b->ncpt != NCPT) { set_error("%s", "fused path is built for ncpt=5 (use bpl_vanilla_to_motor + bpl_render_strokes otherwise)"); return BPL_ELIMIT; }
+    if (b->neval < 1 || b->neval * NCPT > MAX_TABLE) { set_error("%s", "neval*ncpt exceeds the shared-memory basis table (use bpl_vanilla_to_motor + bpl_render_strokes)"); return BPL_ELIMIT; }
+    if (!b->tok_stroke_off || !b->stroke_sub_off || !b->ctrl || !b->invscale || !b->position || !b->eps || !b->sigma || !b->basis) {
+        set_error("%s", "token batch has a NULL array"); return BPL_EINVAL;
+    }
+    ka.n_tokens = b->n_tokens; ka.neval = b->neval;
+    ka.tok_stroke_off = b->tok_stroke_off; ka.stroke_sub_off = b->stroke_sub_off;
+    ka.ctrl = b->ctrl; ka.invscale = b->invscale; ka.position = b->position; ka.affine = b->affine;
+    ka.basis = b->basis; ka.eps = b->eps; ka.sigma = b->sigma;
+    return 0;
+}
+
+static int fill_strokes(KArgs &ka, const bpl_stroke_batch *b) {
+    if (!b) { set_error("%s", "batch is NULL"); return BPL_EINVAL; }
+    if (!b->tok_sub_off || !b->sub_pt_off || !b->pts || !b->eps || !b->sigma) {
+        set_error("%s", "stroke batch has a NULL array"); return BPL_EINVAL;
+    }
+    ka.n_tokens = b->n_tokens;
+    ka.tok_sub_off = b->tok_sub_off; ka.sub_pt_off = b->sub_pt_off; ka.pts = b->pts;
+    ka.eps = b->eps; ka.sigma = b->sigma;
+    return 0;
+}
+
+}  // namespace bpl
+
+using namespace bpl;
+
+extern "C" {
+
+int bpl_score_tokens(const bpl_params *ps, const bpl_token_batch *b, const bpl_targets *t, const bpl_fwd_out *out,
+                     void *stream) {
+    KArgs ka{};
+    int r = fill_common(ka, ps, t, out, nullptr);
+    if (r) return r;
+    if ((r = fill_tokens(ka, b))) return r;
+    return launch(bpl_forward_kernel<false>, FWD_THREADS, sizeof(FwdSmem), 2, ka, (cudaStream_t)stream);
+}
+
+int bpl_render_strokes(const bpl_params *ps, const bpl_stroke_batch *b, const bpl_targets *t, const bpl_fwd_out *out,
+                       void *stream) {
+    KArgs ka{};
+    int r = fill_common(ka, ps, t, out, nullptr);
+    if (r) return r;
+    if ((r = fill_strokes(ka, b))) return r;
+    return launch(bpl_forward_kernel<true>, FWD_THREADS, sizeof(FwdSmem), 2, ka, (cudaStream_t)stream);
+}
+
+int bpl_score_tokens_grad(const bpl_params *ps, const bpl_token_batch *b, const bpl_targets *t,
+                          const bpl_fwd_out *out, const bpl_grads *g, void *stream) {
+    KArgs ka{};
+    int r = fill_common(ka, ps, t, out, g);
+    if (r) return r;
+    if ((r = fill_tokens(ka, b))) return r;
+    if (!g || !g->g_ctrl || !g->g_invscale || !g->g_position) { set_error("%s", "g_ctrl/g_invscale/g_position required"); return BPL_EINVAL; }
+    if (!ka.image_bits && !ka.g_pimg) { set_error("%s", "need target images or a pimg cotangent"); return BPL_EINVAL; }
+    return launch(bpl_backward_kernel<false>, BWD_THREADS, sizeof(BwdSmem), 1, ka, (cudaStream_t)stream);
+}
+
+int bpl_token_points(const bpl_params *ps, const bpl_token_batch *b, float *motor, uint8_t *mask_out, int *fl, int *ce,
+                      int *n_in, void *stream) {
+    KArgs ka{};
+    int r = fill_common(ka, ps, nullptr, nullptr, nullptr);
+    if (r) return r;
+    if ((r = fill_tokens(ka, b))) return r;
+    if (ka.n_tokens <= 0) return 0;
+    int grid = ka.n_tokens < 148 * 8 ? ka.n_tokens : 148 * 8;
+    bpl_points_kernel<<<grid, 256, sizeof(PtsSmem), (cudaStream_t)stream>>>(ka, motor, mask_out, fl, ce, n_in);
+    count_launch(1);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("kernel launch: %s", cudaGetErrorString(e)); return (int)e; }
+    return 0;
+}
+
+int bpl_render_strokes_grad(const bpl_params *ps, const bpl_stroke_batch *b, const bpl_targets *t,
+                            const bpl_fwd_out *out, const bpl_grads *g, void *stream) {
+    KArgs ka{};
+    int r = fill_common(ka, ps, t, out, g);
+    if (r) return r;
+    if ((r = fill_strokes(ka, b))) return r;
+    if (!g || !g->g_pts) { set_error("%s", "g_pts required"); return BPL_EINVAL; }
+    if (!ka.image_bits && !ka.g_pimg) { set_error("%s", "need target images or a pimg cotangent"); return BPL_EINVAL; }
+    return launch(bpl_backward_kernel<true>, BWD_THREADS, sizeof(BwdSmem), 1, ka, (cudaStream_t)stream);
+}
+
+}  // extern "C"

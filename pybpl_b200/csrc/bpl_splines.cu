@@ -1,0 +1,352 @@
+// bpl_splines.cu -- B-spline basis tables (host), batched spline evaluation, vanilla_to_motor,
+// image bit-packing and the per-GPU log-sum-exp partial.  Small kernels around the fused
+// render+score kernels in bpl_render.cu; all HBM-bound or latency-bound, no tensor cores.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdlib.h>
+
+#include "bpl_common.cuh"
+
+namespace bpl {
+void set_error(const char *fmt, const char *detail);
+const char *last_error();
+void count_launch(int n);
+long long launch_count();
+
+// ---- host: basis table (pybpl/splines.py:19-93) ----------------------------------------------
+// Uniform cubic B-spline weights of control point i at time s, divided by 6, then each row
+// normalised by its sum (splines.py:91; matters at the ends where s is in [2,3) or (nland,nland+1]).
+static void basis_row(int nland, float s, float *row) {
+    float sum = 0.0f;
+    for (int i = 0; i < nland; ++i) {
+        const float vi = (float)i;
+        float c = 0.0f;
+        if (s >= vi && s < vi + 1.0f) {
+            const float d = s - vi;
+            c = d * d * d;
+        } else if (s >= vi + 1.0f && s < vi + 2.0f) {
+            const float d = s - vi - 1.0f;
+            c = ((-3.0f * (d * d * d) + 3.0f * (d * d)) + 3.0f * d) + 1.0f;
+        } else if (s >= vi + 2.0f && s < vi + 3.0f) {
+            const float d = s - vi - 2.0f;
+            c = (3.0f * (d * d * d) - 6.0f * (d * d)) + 4.0f;
+        } else if (s >= vi + 3.0f && s < vi + 4.0f) {
+            const float e = 1.0f - (s - vi - 3.0f);
+            c = e * e * e;
+        }
+        c = c / 6.0f;
+        row[i] = c;
+        sum += c;
+    }
+    for (int i = 0; i < nland; ++i) row[i] = row[i] / sum;
+}
+
+// torch.linspace(2, nland+1, neval) (splines.py:66-67): filled from both ends.
+static void gen_s(int nland, int neval, float *s) {
+    const float lo = 2.0f, hi = (float)(nland + 1);
+    if (neval == 1) { s[0] = lo; return; }
+    const float step = (hi - lo) / (float)(neval - 1);
+    for (int j = 0; j < neval; ++j)
+        s[j] = (j < neval / 2) ? lo + step * (float)j : hi - step * (float)(neval - 1 - j);
+}
+
+// ---- device kernels ------------------------------------------------------------------------------
+
+// X[b][j][:] = sum_k C[j][k] Y[b][k][:], sequential fma chain from 0 (== torch.matmul, App. B.1)
+__global__ void spline_eval_kernel(const float *__restrict__ C, int neval, int nland, int nspl,
+                                   const float *__restrict__ Y, float *__restrict__ X) {
+    const long long total = (long long)nspl * neval;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(i / neval), j = (int)(i - (long long)b * neval);
+        const float *y = Y + (size_t)b * nland * 2;
+        const float *row = C + (size_t)j * nland;
+        float ax = 0.0f, ay = 0.0f;
+        for (int k = 0; k < nland; ++k) {
+            const float c = row[k];
+            ax = __fmaf_rn(c, y[2 * k], ax);
+            ay = __fmaf_rn(c, y[2 * k + 1], ay);
+        }
+        reinterpret_cast<float2 *>(X)[i] = make_float2(ax, ay);
+    }
+}
+
+// gY[b][k][:] = sum_j C[j][k] gX[b][j][:]; one warp per (spline, control point)
+__global__ void spline_eval_bwd_kernel(const float *__restrict__ C, int neval, int nland, int nspl,
+                                       const float *__restrict__ gX, float *__restrict__ gY) {
+    const int lane = threadIdx.x & 31;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long total = (long long)nspl * nland;
+    for (long long wi = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; wi < total; wi += nwarps) {
+        const int b = (int)(wi / nland), k = (int)(wi - (long long)b * nland);
+        const float2 *g = reinterpret_cast<const float2 *>(gX) + (size_t)b * neval;
+        float ax = 0.0f, ay = 0.0f;
+        for (int j = lane; j < neval; j += 32) {
+            const float c = C[(size_t)j * nland + k];
+            const float2 v = g[j];
+            ax = fmaf(c, v.x, ax);
+            ay = fmaf(c, v.y, ay);
+        }
+        ax = warp_sum(ax); ay = warp_sum(ay);
+        if (lane == 0) reinterpret_cast<float2 *>(gY)[wi] = make_float2(ax, ay);
+    }
+}
+
+// dist_along_traj (util/stroke.py:22-28) over the max_neval-point trajectory, then
+// clamp(ceil(dist / grain), min_neval, max_neval) (splines.py:129-133).  One warp per spline;
+// the segment lengths are summed in index order by lane 0 so that the integer result does not
+// depend on a reduction tree.
+__global__ void adaptive_neval_kernel(const float *__restrict__ C, int max_neval, int nland, int nspl,
+                                      const float *__restrict__ Y, float grain, int min_neval,
+                                      int *__restrict__ neval, float *__restrict__ dist) {
+    extern __shared__ float seg[];      // [warps][max_neval]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    float *my = seg + (size_t)warp * max_neval;
+    for (int b = blockIdx.x * wpb + warp; b < nspl; b += gridDim.x * wpb) {
+        const float *y = Y + (size_t)b * nland * 2;
+        for (int j = lane; j < max_neval - 1; j += 32) {
+            float ax = 0.0f, ay = 0.0f, bx = 0.0f, by = 0.0f;
+            for (int k = 0; k < nland; ++k) {
+                const float c0 = C[(size_t)j * nland + k], c1 = C[(size_t)(j + 1) * nland + k];
+                ax = __fmaf_rn(c0, y[2 * k], ax); ay = __fmaf_rn(c0, y[2 * k + 1], ay);
+                bx = __fmaf_rn(c1, y[2 * k], bx); by = __fmaf_rn(c1, y[2 * k + 1], by);
+            }
+            const float dx = __fsub_rn(bx, ax), dy = __fsub_rn(by, ay);
+            my[j] = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+        }
+        __syncwarp();
+        if (lane == 0) {
+            float tot = 0.0f;
+            for (int j = 0; j < max_neval - 1; ++j) tot = __fadd_rn(tot, my[j]);
+            float q = ceilf(__fdiv_rn(tot, grain));
+            q = fminf(fmaxf(q, (float)min_neval), (float)max_neval);
+            neval[b] = (int)q;
+            if (dist) dist[b] = tot;
+        }
+        __syncwarp();
+    }
+}
+
+// vanilla_to_motor (objects/part.py:316-326): one warp per stroke, sub-strokes in sequence.
+__global__ void vanilla_to_motor_kernel(const float *__restrict__ C, int neval, int ncpt, int n_strokes,
+                                        const int *__restrict__ stroke_sub_off, const float *__restrict__ ctrl,
+                                        const float *__restrict__ invscale, const float *__restrict__ position,
+                                        float *__restrict__ motor, float *__restrict__ mspline) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int k = blockIdx.x * wpb + (threadIdx.x >> 5); k < n_strokes; k += gridDim.x * wpb) {
+        float px = position[2 * k], py = position[2 * k + 1];
+        for (int s = stroke_sub_off[k]; s < stroke_sub_off[k + 1]; ++s) {
+            const float inv = invscale[s];
+            const float *cp = ctrl + (size_t)s * ncpt * 2;
+            // first and last points give the offset and the next start (all lanes, redundantly)
+            float ax = 0.0f, ay = 0.0f, bx = 0.0f, by = 0.0f;
+            for (int q = 0; q < ncpt; ++q) {
+                const float yx = __fmul_rn(inv, cp[2 * q]), yy = __fmul_rn(inv, cp[2 * q + 1]);
+                const float c0 = C[q], c1 = C[(size_t)(neval - 1) * ncpt + q];
+                ax = __fmaf_rn(c0, yx, ax); ay = __fmaf_rn(c0, yy, ay);
+                bx = __fmaf_rn(c1, yx, bx); by = __fmaf_rn(c1, yy, by);
+            }
+            const float ox = __fsub_rn(ax, px), oy = __fsub_rn(ay, py);
+            for (int j = lane; j < neval; j += 32) {
+                float tx = 0.0f, ty = 0.0f;
+                for (int q = 0; q < ncpt; ++q) {
+                    const float c = C[(size_t)j * ncpt + q];
+                    tx = __fmaf_rn(c, __fmul_rn(inv, cp[2 * q]), tx);
+                    ty = __fmaf_rn(c, __fmul_rn(inv, cp[2 * q + 1]), ty);
+                }
+                reinterpret_cast<float2 *>(motor)[(size_t)s * neval + j] =
+                    make_float2(__fsub_rn(tx, ox), __fsub_rn(ty, oy));
+            }
+            if (mspline)
+                for (int q = lane; q < ncpt; q += 32)
+                    reinterpret_cast<float2 *>(mspline)[(size_t)s * ncpt + q] =
+                        make_float2(__fsub_rn(__fmul_rn(inv, cp[2 * q]), ox), __fsub_rn(__fmul_rn(inv, cp[2 * q + 1]), oy));
+            px = __fsub_rn(bx, ox); py = __fsub_rn(by, oy);
+        }
+    }
+}
+
+// One warp packs one image row: 105 pixels -> 4 words, LSB first.
+template <class T>
+__global__ void pack_images_kernel(const T *__restrict__ img, int n_img, uint32_t *__restrict__ bits,
+                                   int *__restrict__ bad) {
+    const int lane = threadIdx.x & 31;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long rows = (long long)n_img * IMG;
+    for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += nwarps) {
+        const T *src = img + row * IMG;
+        bool any_bad = false;
+#pragma unroll
+        for (int w = 0; w < IMG_WORDS; ++w) {
+            const int c = w * 32 + lane;
+            bool one = false;
+            if (c < IMG) {
+                const T v = src[c];
+                one = (v == (T)1);
+                any_bad |= !(v == (T)0 || v == (T)1);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, one);
+            if (lane == 0) bits[row * IMG_WORDS + w] = m;
+        }
+        if (any_bad && bad) atomicOr(bad, 1);
+    }
+}
+
+// out[0] = max ll, out[1] = sum exp(ll - max): one CTA, one pass held in registers where possible.
+__global__ void logsumexp_partial_kernel(const float *__restrict__ ll, int n, float *__restrict__ out2) {
+    __shared__ float red[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    float m = -INFINITY;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, ll[i]);
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) red[warp] = m;
+    __syncthreads();
+    m = (lane < nw) ? red[lane] : -INFINITY;
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __syncthreads();
+    double s = 0.0;
+    if (m > -INFINITY)
+        for (int i = threadIdx.x; i < n; i += blockDim.x) s += (double)expf(ll[i] - m);
+    s = warp_sum(s);
+    __shared__ double reds[32];
+    if (lane == 0) reds[warp] = s;
+    __syncthreads();
+    if (warp == 0) {
+        s = (lane < nw) ? reds[lane] : 0.0;
+        s = warp_sum(s);
+        if (lane == 0) { out2[0] = m; out2[1] = (float)s; }
+    }
+}
+
+// Live FP32 peak probe for the roofline denominator (MEASURED_PEAKS.json has HBM and bf16-tensor
+// figures but no CUDA-core FP32 one): 8 independent FFMA chains per thread, `iters` rounds.
+__global__ void fp32_probe_kernel(float *out, int iters, float a, float b) {
+    float x0 = threadIdx.x, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f,
+          x7 = x0 + 7.f;
+    for (int i = 0; i < iters; ++i) {
+        x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+        x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+    }
+    const float s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 123.456f) out[0] = s;      // never true in practice; keeps the chains alive
+}
+
+static int check_launch(const char *what) {
+    count_launch(1);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("%s", cudaGetErrorString(e)); (void)what; return (int)e; }
+    return 0;
+}
+
+static int grid_for(long long work_items, int per_block) {
+    long long g = (work_items + per_block - 1) / per_block;
+    if (g < 1) g = 1;
+    if (g > 148 * 16) g = 148 * 16;
+    return (int)g;
+}
+
+}  // namespace bpl
+
+using namespace bpl;
+
+extern "C" {
+
+int bpl_version(void) { return 1; }
+const char *bpl_last_error(void) { return last_error(); }
+long long bpl_launch_count(void) { return launch_count(); }
+
+void bpl_default_params(bpl_params *ps) {      // pybpl/parameters.py:19-41
+    ps->imsize = BPL_IMSIZE; ps->fsize = BPL_FSIZE; ps->ink_ncon = 2;
+    ps->ink_pp = 2.0f; ps->ink_max_dist = 2.0f; ps->ink_a = 0.5f; ps->ink_b = 6.0f; ps->hinton = 0;
+}
+
+int bpl_device_info(int *sm_count, int *smem_optin) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) { set_error("%s", cudaGetErrorString(e)); return BPL_ENODEV; }
+    if (sm_count) cudaDeviceGetAttribute(sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (smem_optin) cudaDeviceGetAttribute(smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    return 0;
+}
+
+int bpl_basis_rows_host(int nland, int n, const float *s, float *C) {
+    if (nland < 1 || n < 0 || !s || !C) { set_error("%s", "bad basis_rows arguments"); return BPL_EINVAL; }
+    for (int j = 0; j < n; ++j) basis_row(nland, s[j], C + (size_t)j * nland);
+    return 0;
+}
+
+int bpl_basis_table_host(int nland, int neval, float *C) {
+    if (nland < 1 || neval < 1 || !C) { set_error("%s", "bad basis_table arguments"); return BPL_EINVAL; }
+    float *s = (float *)malloc(sizeof(float) * (size_t)neval);
+    if (!s) { set_error("%s", "out of host memory"); return BPL_EINVAL; }
+    gen_s(nland, neval, s);
+    for (int j = 0; j < neval; ++j) basis_row(nland, s[j], C + (size_t)j * nland);
+    free(s);
+    return 0;
+}
+
+int bpl_spline_eval(const float *C, int neval, int nland, int nspl, const float *Y, float *X, void *stream) {
+    if (!C || !Y || !X || neval < 1 || nland < 1 || nspl < 0) { set_error("%s", "bad spline_eval arguments"); return BPL_EINVAL; }
+    if (nspl == 0) return 0;
+    spline_eval_kernel<<<grid_for((long long)nspl * neval, 256), 256, 0, (cudaStream_t)stream>>>(C, neval, nland, nspl, Y, X);
+    return check_launch("spline_eval");
+}
+
+int bpl_spline_eval_bwd(const float *C, int neval, int nland, int nspl, const float *gX, float *gY, void *stream) {
+    if (!C || !gX || !gY || neval < 1 || nland < 1 || nspl < 0) { set_error("%s", "bad spline_eval_bwd arguments"); return BPL_EINVAL; }
+    if (nspl == 0) return 0;
+    spline_eval_bwd_kernel<<<grid_for((long long)nspl * nland * 32, 256), 256, 0, (cudaStream_t)stream>>>(C, neval, nland, nspl, gX, gY);
+    return check_launch("spline_eval_bwd");
+}
+
+int bpl_spline_adaptive_neval(const float *C200, int max_neval, int nland, int nspl, const float *Y, float grain,
+                              int min_neval, int *neval, float *dist, void *stream) {
+    if (!C200 || !Y || !neval || max_neval < 2 || max_neval > 2048 || nland < 1 || nspl < 0 || !(grain > 0.0f)) {
+        set_error("%s", "bad adaptive_neval arguments"); return BPL_EINVAL;
+    }
+    if (nspl == 0) return 0;
+    const int wpb = 4;
+    adaptive_neval_kernel<<<grid_for(nspl, wpb), wpb * 32, sizeof(float) * wpb * max_neval, (cudaStream_t)stream>>>(
+        C200, max_neval, nland, nspl, Y, grain, min_neval, neval, dist);
+    return check_launch("adaptive_neval");
+}
+
+int bpl_vanilla_to_motor(const float *C, int neval, int ncpt, int n_strokes, const int *stroke_sub_off,
+                         const float *ctrl, const float *invscale, const float *position, float *motor,
+                         float *motor_spline, void *stream) {
+    if (!C || !stroke_sub_off || !ctrl || !invscale || !position || !motor || neval < 1 || ncpt < 1 || n_strokes < 0) {
+        set_error("%s", "bad vanilla_to_motor arguments"); return BPL_EINVAL;
+    }
+    if (n_strokes == 0) return 0;
+    vanilla_to_motor_kernel<<<grid_for(n_strokes, 4), 128, 0, (cudaStream_t)stream>>>(
+        C, neval, ncpt, n_strokes, stroke_sub_off, ctrl, invscale, position, motor, motor_spline);
+    return check_launch("vanilla_to_motor");
+}
+
+int bpl_pack_images_u8(const uint8_t *img, int T, uint32_t *bits, int *bad, void *stream) {
+    if (!img || !bits || T < 0) { set_error("%s", "bad pack_images arguments"); return BPL_EINVAL; }
+    if (T == 0) return 0;
+    pack_images_kernel<uint8_t><<<grid_for((long long)T * IMG * 32, 256), 256, 0, (cudaStream_t)stream>>>(img, T, bits, bad);
+    return check_launch("pack_images_u8");
+}
+
+int bpl_pack_images_f32(const float *img, int T, uint32_t *bits, int *bad, void *stream) {
+    if (!img || !bits || T < 0) { set_error("%s", "bad pack_images arguments"); return BPL_EINVAL; }
+    if (T == 0) return 0;
+    pack_images_kernel<float><<<grid_for((long long)T * IMG * 32, 256), 256, 0, (cudaStream_t)stream>>>(img, T, bits, bad);
+    return check_launch("pack_images_f32");
+}
+
+int bpl_fp32_probe(float *scratch, int iters, int blocks, void *stream) {
+    if (!scratch || iters < 1 || blocks < 1) { set_error("%s", "bad fp32_probe arguments"); return BPL_EINVAL; }
+    fp32_probe_kernel<<<blocks, 1024, 0, (cudaStream_t)stream>>>(scratch, iters, 0.999f, 0.001f);
+    return check_launch("fp32_probe");
+}
+
+int bpl_logsumexp_partial(const float *ll, int n, float *out2, void *stream) {
+    if (!ll || !out2 || n < 0) { set_error("%s", "bad logsumexp arguments"); return BPL_EINVAL; }
+    logsumexp_partial_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(ll, n, out2);
+    return check_launch("logsumexp_partial");
+}
+
+}  // extern "C"

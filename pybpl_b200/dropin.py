@@ -1,0 +1,53 @@
+"""Rebinds the reference's hot-path call sites to the CUDA implementation.
+
+    import pybpl, pybpl_b200.dropin
+    pybpl_b200.dropin.install()          # pybpl.* now renders and scores on the GPU
+    pybpl_b200.dropin.uninstall()
+
+Patched names (each bound by-name in the reference, so both the defining module and its importers):
+  pybpl.rendering.render_image, pybpl.model.image_dist.render_image          (rendering.py:185)
+  pybpl.splines.get_stk_from_bspline (+ new alias pybpl.splines.bspline_eval),
+  pybpl.objects.relation.get_stk_from_bspline                                 (splines.py:108, relation.py:9)
+  pybpl.objects.part.vanilla_to_motor                                         (part.py:290)
+  CharacterImageDist.get_pimg / sample_image / score_image                    (image_dist.py:32-80)
+"""
+import importlib
+
+from . import model, objects, rendering, splines
+
+_saved = []
+
+
+def _patch(mod, name, new):
+    _saved.append((mod, name, getattr(mod, name, None)))
+    setattr(mod, name, new)
+
+
+def install(pybpl_module=None):
+    if _saved:
+        return
+    if pybpl_module is None:
+        pybpl_module = importlib.import_module("pybpl")
+    R = importlib.import_module("pybpl.rendering")
+    S = importlib.import_module("pybpl.splines")
+    P = importlib.import_module("pybpl.objects.part")
+    REL = importlib.import_module("pybpl.objects.relation")
+    ID = importlib.import_module("pybpl.model.image_dist")
+    _patch(R, "render_image", rendering.render_image)
+    _patch(ID, "render_image", rendering.render_image)
+    _patch(S, "get_stk_from_bspline", splines.get_stk_from_bspline)
+    _patch(S, "bspline_eval", splines.bspline_eval)
+    _patch(REL, "get_stk_from_bspline", splines.get_stk_from_bspline)
+    _patch(P, "vanilla_to_motor", objects.vanilla_to_motor)
+    mirror = model.CharacterImageDist
+    for meth in ("get_pimg", "sample_image", "score_image"):
+        _patch(ID.CharacterImageDist, meth, getattr(mirror, meth))
+
+
+def uninstall():
+    while _saved:
+        mod, name, old = _saved.pop()
+        if old is None:
+            delattr(mod, name)
+        else:
+            setattr(mod, name, old)

@@ -1,0 +1,98 @@
+"""Host-side mirror of the reference's image distribution (pybpl/model/image_dist.py:24-80) and the
+three CharacterModel methods on the hot path (pybpl/model/model.py:32-39).
+
+The tokens are duck-typed: anything with `.part_tokens[i].{shapes (ncpt,2,nsub), invscales (nsub,),
+position (2,)}`, `.affine` (None or (4,)), `.epsilon`, `.blur_sigma` works -- the reference's
+CharacterToken/StrokeToken (pybpl/objects/concept.py:217-241, part.py:188-249) or the light containers
+in pybpl_b200.objects."""
+import torch
+
+from . import ops
+from .parameters import Parameters
+
+
+def _compute_device(t):
+    return t.device if t.is_cuda else torch.device("cuda", torch.cuda.current_device())
+
+
+def token_batch_from(ctokens, device=None, neval=200):
+    """Pack a list of character tokens into one ops.TokenBatch (keeps the autograd graph to the leaves)."""
+    ctrl, inv, pos, tso, sso, eps, sig, aff = [], [], [], [0], [0], [], [], []
+    any_aff = any(getattr(t, "affine", None) is not None for t in ctokens)
+    if device is None:
+        device = _compute_device(ctokens[0].part_tokens[0].shapes)
+    for t in ctokens:
+        for p in t.part_tokens:
+            sh = p.shapes
+            assert sh.dim() == 3 and sh.shape[1] == 2
+            ctrl.append(sh.permute(2, 0, 1))
+            inv.append(p.invscales.reshape(-1))
+            pos.append(p.position.reshape(1, 2))
+            sso.append(sso[-1] + sh.shape[2])
+        tso.append(tso[-1] + len(t.part_tokens))
+        eps.append(torch.as_tensor(t.epsilon, dtype=torch.float32).reshape(1))
+        sig.append(torch.as_tensor(t.blur_sigma, dtype=torch.float32).reshape(1))
+        if any_aff:
+            a = getattr(t, "affine", None)
+            aff.append((torch.tensor([1., 1., 0., 0.]) if a is None else a).reshape(1, 4))
+    to = lambda xs: torch.cat([x.to(device, torch.float32) for x in xs])
+    return ops.TokenBatch(tso, sso, to(ctrl).contiguous(), to(inv), to(pos), to(eps), to(sig),
+                          affine=to(aff) if any_aff else None, neval=neval)
+
+
+class CharacterImageDist:
+    """P(Image | Token) (pybpl/model/image_dist.py:24-80)."""
+
+    def __init__(self, lib=None):
+        self.lib = lib
+        self.ps = Parameters()
+
+    def get_pimg(self, ctoken):
+        src = ctoken.part_tokens[0].shapes.device
+        batch = token_batch_from([ctoken])
+        pimg, _ = ops.render_tokens(batch, ps=self.ps)
+        return pimg[0].to(src)
+
+    def sample_image(self, ctoken):
+        """Binary image sample (image_dist.py:44-58); torch's global RNG, no gradient."""
+        with torch.no_grad():
+            pimg = self.get_pimg(ctoken)
+            return torch.bernoulli(pimg)
+
+    def score_image(self, ctoken, image):
+        """Log-likelihood of a binary image (image_dist.py:60-80): 0-d float32 tensor."""
+        src = ctoken.part_tokens[0].shapes.device
+        batch = token_batch_from([ctoken])
+        imgs = ops.pack_images(image.detach().to(batch.device), validate=True)
+        ll, _ = ops.score_tokens(batch, imgs, ps=self.ps)
+        return ll[0].to(src)
+
+
+class CharacterModel:
+    """The hot-path third of pybpl/model/model.py:8-39.  Type and token priors are out of scope
+    (SURVEY.md 8): pass `type_dist`/`token_dist` objects (e.g. the reference's) to get the full façade."""
+
+    def __init__(self, lib=None, type_dist=None, token_dist=None):
+        self.type_dist = type_dist
+        self.token_dist = token_dist
+        self.image_dist = CharacterImageDist(lib)
+
+    def sample_image(self, ctoken):
+        return self.image_dist.sample_image(ctoken)
+
+    def score_image(self, ctoken, image):
+        return self.image_dist.score_image(ctoken, image)
+
+    def get_pimg(self, ctoken):
+        return self.image_dist.get_pimg(ctoken)
+
+    def __getattr__(self, name):
+        # sample_type/score_type/sample_token/score_token delegate to the supplied prior objects
+        for prefix, d in (("sample_type", "type_dist"), ("score_type", "type_dist"),
+                          ("sample_token", "token_dist"), ("score_token", "token_dist")):
+            if name == prefix:
+                dist = self.__dict__.get(d)
+                if dist is None:
+                    raise AttributeError(f"{name}: no {d} supplied (priors are outside pybpl_b200's scope)")
+                return getattr(dist, name)
+        raise AttributeError(name)

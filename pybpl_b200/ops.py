@@ -1,0 +1,559 @@
+"""Batched operators over the C-ABI library: packed ragged batches, autograd.Functions.
+
+torch is plumbing here (device memory, streams, autograd graph); every number is produced by
+the CUDA kernels in pybpl_b200/csrc through libpybpl_b200.so.
+"""
+import ctypes
+import functools
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import IMSIZE, IMG_WORDS, NCPT, check, lib
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+# ---------------------------------------------------------------------------------------------
+# helpers
+# ---------------------------------------------------------------------------------------------
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _need_cuda(t, name):
+    if not t.is_cuda:
+        raise _lib.BplError(f"{name} must be a CUDA tensor: pybpl_b200 has no CPU path")
+
+
+def _f32(t, device):
+    return torch.as_tensor(t, dtype=torch.float32, device=device).contiguous()
+
+
+def _i32(t, device):
+    return torch.as_tensor(t, dtype=torch.int32, device=device).contiguous()
+
+
+def make_params(ps=None):
+    """bpl_params from None or a reference-style Parameters object (pybpl/parameters.py:19-41)."""
+    p = _lib.default_params()
+    if ps is not None:
+        imsize = tuple(int(v) for v in getattr(ps, "imsize", (IMSIZE, IMSIZE)))
+        if imsize != (IMSIZE, IMSIZE) or int(getattr(ps, "fsize", 11)) != 11:
+            raise NotImplementedError("pybpl_b200 kernels are built for imsize=(105,105), fsize=11")
+        p.ink_ncon = int(getattr(ps, "ink_ncon", p.ink_ncon))
+        p.ink_pp = float(getattr(ps, "ink_pp", p.ink_pp))
+        p.ink_max_dist = float(getattr(ps, "ink_max_dist", p.ink_max_dist))
+        p.ink_a = float(getattr(ps, "ink_a", p.ink_a))
+        p.ink_b = float(getattr(ps, "ink_b", p.ink_b))
+        mode = getattr(ps, "broaden_mode", "Lake")
+        if mode not in ("Lake", "Hinton"):
+            raise Exception("'broaden_mode' must be either 'Lake' or 'Hinton'")     # rendering.py:157-158
+        p.hinton = int(mode == "Hinton")
+    return p
+
+
+@functools.lru_cache(maxsize=None)
+def _basis_host(nland, neval):
+    """coefficient_mat(nland, neval) (pybpl/splines.py:72-93) as a numpy array.
+
+    (5, 200) -- the only table on the render path -- is the reference's own output shipped as data
+    (pybpl_b200/data/basis_5_200.npy, see tests/golden/make_golden.py:make_assets); all others are
+    computed by the library and agree with torch's to ~4e-7."""
+    asset = os.path.join(_HERE, "data", f"basis_{nland}_{neval}.npy")
+    if os.path.exists(asset):
+        return np.load(asset).astype(np.float32)
+    C = np.empty((neval, nland), np.float32)
+    check(lib().bpl_basis_table_host(nland, neval, C.ctypes.data_as(ctypes.c_void_p)))
+    return C
+
+
+_basis_dev = {}
+
+
+def basis_table(nland, neval, device):
+    key = (nland, neval, str(device))
+    t = _basis_dev.get(key)
+    if t is None:
+        t = torch.from_numpy(_basis_host(nland, neval)).to(device)
+        _basis_dev[key] = t
+    return t
+
+
+def basis_rows(nland, s):
+    """Rows of the coefficient matrix at explicit times s (1-D tensor); host computation, result on s.device."""
+    sh = s.detach().to("cpu", torch.float32).contiguous().numpy()
+    C = np.empty((len(sh), nland), np.float32)
+    check(lib().bpl_basis_rows_host(nland, len(sh), sh.ctypes.data_as(ctypes.c_void_p),
+                                    C.ctypes.data_as(ctypes.c_void_p)))
+    return torch.from_numpy(C).to(s.device)
+
+
+# ---------------------------------------------------------------------------------------------
+# target images
+# ---------------------------------------------------------------------------------------------
+class PackedImages:
+    """T binary 105x105 images packed to bit rows on the device ([T,105,4] int32 words, LSB first)."""
+
+    def __init__(self, bits, bad):
+        self.bits = bits
+        self._bad = bad
+        self.n = bits.shape[0]
+        self.device = bits.device
+
+    def validate(self):
+        # torch's Bernoulli.log_prob raises ValueError for values outside {0,1} (image_dist.py:76-77)
+        if int(self._bad.item()) != 0:
+            raise ValueError("Expected value argument to be within the support (Boolean()) of the "
+                             "distribution Bernoulli(), but found invalid values")
+        return self
+
+
+def pack_images(images, validate=True):
+    """images: [T,105,105] or [105,105], uint8/bool/float on a CUDA device."""
+    _need_cuda(images, "images")
+    if images.dim() == 2:
+        images = images.unsqueeze(0)
+    if images.shape[-2:] != (IMSIZE, IMSIZE):
+        raise ValueError("images must be 105x105")
+    T = images.shape[0]
+    dev = images.device
+    bits = torch.empty((T, IMSIZE, IMG_WORDS), dtype=torch.int32, device=dev)
+    bad = torch.zeros((), dtype=torch.int32, device=dev)
+    if images.dtype in (torch.uint8, torch.bool):
+        src = images.contiguous().view(torch.uint8)
+        check(lib().bpl_pack_images_u8(_ptr(src), T, _ptr(bits), _ptr(bad), _stream(dev)))
+    else:
+        src = images.to(torch.float32).contiguous()
+        check(lib().bpl_pack_images_f32(_ptr(src), T, _ptr(bits), _ptr(bad), _stream(dev)))
+    out = PackedImages(bits, bad)
+    return out.validate() if validate else out
+
+
+# ---------------------------------------------------------------------------------------------
+# packed ragged batches
+# ---------------------------------------------------------------------------------------------
+class TokenBatch:
+    """P character tokens in control-point form (what CharacterImageDist.get_pimg reads).
+
+    tok_stroke_off [P+1], stroke_sub_off [K+1] int32 CSR offsets; ctrl [S,5,2]; invscale [S];
+    position [K,2]; affine [P,4] or None; eps [P]; sigma [P].  All on one CUDA device.
+    """
+
+    def __init__(self, tok_stroke_off, stroke_sub_off, ctrl, invscale, position, eps, sigma, affine=None, neval=200,
+                 check_limits=True):
+        dev = ctrl.device
+        _need_cuda(ctrl, "ctrl")
+        if check_limits:
+            tso = torch.as_tensor(tok_stroke_off).cpu().numpy().astype(np.int64)
+            sso = torch.as_tensor(stroke_sub_off).cpu().numpy().astype(np.int64)
+            if len(tso) > 1:
+                if np.diff(tso).max() > _lib.MAX_STROKES or np.diff(sso[tso]).max() > _lib.MAX_SUBSTROKES:
+                    raise _lib.BplError("a token exceeds 32 strokes / 128 sub-strokes (BPL_MAX_*)")
+        self.tok_stroke_off = _i32(tok_stroke_off, dev)
+        self.stroke_sub_off = _i32(stroke_sub_off, dev)
+        self.ctrl = ctrl if ctrl.dtype == torch.float32 and ctrl.is_contiguous() else _f32(ctrl, dev)
+        self.invscale = _f32(invscale, dev) if not isinstance(invscale, torch.Tensor) else invscale
+        self.position = position
+        self.eps = eps
+        self.sigma = sigma
+        self.affine = affine
+        self.neval = int(neval)
+        self.P = self.tok_stroke_off.numel() - 1
+        self.K = self.stroke_sub_off.numel() - 1
+        self.S = self.ctrl.shape[0]
+        if self.ctrl.shape[1:] != (NCPT, 2):
+            raise _lib.BplError("fused path takes ncpt=5 control points per sub-stroke")
+        self.device = dev
+        self._sub_token = None
+        self._stroke_token = None
+
+    # token index of every sub-stroke / stroke (for scaling gradients by the per-token cotangent)
+    @property
+    def sub_token(self):
+        if self._sub_token is None:
+            tso = self.tok_stroke_off.long()
+            sub_off = self.stroke_sub_off.long()[tso]          # [P+1] token -> sub-strokes
+            self._sub_token = torch.repeat_interleave(torch.arange(self.P, device=self.device),
+                                                      sub_off[1:] - sub_off[:-1], output_size=self.S)
+        return self._sub_token
+
+    @property
+    def stroke_token(self):
+        if self._stroke_token is None:
+            tso = self.tok_stroke_off.long()
+            self._stroke_token = torch.repeat_interleave(torch.arange(self.P, device=self.device),
+                                                         tso[1:] - tso[:-1], output_size=self.K)
+        return self._stroke_token
+
+    def c_struct(self, ctrl, invscale, position, affine, eps, sigma):
+        b = _lib.TokenBatchC()
+        b.n_tokens = self.P; b.ncpt = NCPT; b.neval = self.neval
+        b.tok_stroke_off = self.tok_stroke_off.data_ptr(); b.stroke_sub_off = self.stroke_sub_off.data_ptr()
+        b.ctrl = ctrl.data_ptr(); b.invscale = invscale.data_ptr(); b.position = position.data_ptr()
+        b.affine = None if affine is None else affine.data_ptr()
+        b.eps = eps.data_ptr(); b.sigma = sigma.data_ptr()
+        b.basis = basis_table(NCPT, self.neval, self.device).data_ptr()
+        return b
+
+
+def _targets(images, img_idx):
+    t = _lib.Targets()
+    if images is not None:
+        t.image_bits = images.bits.data_ptr()
+        t.img_idx = None if img_idx is None else img_idx.data_ptr()
+        t.n_images = images.n
+    return t
+
+
+def _c32(t):
+    return t.detach().to(torch.float32).contiguous()
+
+
+class _ScoreTokens(torch.autograd.Function):
+    """ll[p] = score_image(token p, image[img_idx[p]]) with the fused backward.
+
+    When any input needs a gradient the forward runs the fused forward+backward kernel once and keeps
+    d ll / d inputs; backward() only scales them by the incoming cotangent (one scalar per token)."""
+
+    @staticmethod
+    def forward(ctx, ctrl, invscale, position, affine, eps, sigma, batch, images, img_idx, ps):
+        dev = batch.device
+        P = batch.P
+        ctrl_c, inv_c, pos_c = _c32(ctrl), _c32(invscale), _c32(position)
+        aff_c = None if affine is None else _c32(affine)
+        eps_c, sig_c = _c32(eps), _c32(sigma)
+        ll = torch.empty(P, dtype=torch.float32, device=dev)
+        off = torch.empty(P, dtype=torch.uint8, device=dev)
+        out = _lib.FwdOut(ll.data_ptr(), off.data_ptr(), None)
+        b = batch.c_struct(ctrl_c, inv_c, pos_c, aff_c, eps_c, sig_c)
+        t = _targets(images, img_idx)
+        need = any(ctx.needs_input_grad[:6])
+        if need:
+            g_ctrl = torch.empty_like(ctrl_c); g_inv = torch.empty_like(inv_c); g_pos = torch.empty_like(pos_c)
+            g_aff = None if aff_c is None else torch.empty_like(aff_c)
+            g_eps = torch.empty(P, dtype=torch.float32, device=dev); g_sig = torch.empty_like(g_eps)
+            g = _lib.Grads(None, None, g_ctrl.data_ptr(), g_inv.data_ptr(), g_pos.data_ptr(),
+                           None if g_aff is None else g_aff.data_ptr(), None, g_eps.data_ptr(), g_sig.data_ptr())
+            check(lib().bpl_score_tokens_grad(ctypes.byref(ps), ctypes.byref(b), ctypes.byref(t), ctypes.byref(out),
+                                              ctypes.byref(g), _stream(dev)))
+            ctx.batch = batch
+            ctx.has_aff = g_aff is not None
+            ctx.save_for_backward(g_ctrl, g_inv, g_pos, g_eps, g_sig, *([g_aff] if g_aff is not None else []))
+        else:
+            check(lib().bpl_score_tokens(ctypes.byref(ps), ctypes.byref(b), ctypes.byref(t), ctypes.byref(out),
+                                         _stream(dev)))
+        ctx.mark_non_differentiable(off)
+        return ll, off
+
+    @staticmethod
+    def backward(ctx, g_ll, _g_off):
+        saved = ctx.saved_tensors
+        g_ctrl, g_inv, g_pos, g_eps, g_sig = saved[:5]
+        g_aff = saved[5] if ctx.has_aff else None
+        b = ctx.batch
+        gs = g_ll.to(torch.float32)
+        st, kt = b.sub_token, b.stroke_token
+        return (g_ctrl * gs[st].view(-1, 1, 1), g_inv * gs[st], g_pos * gs[kt].view(-1, 1),
+                None if g_aff is None else g_aff * gs.view(-1, 1), g_eps * gs, g_sig * gs, None, None, None, None)
+
+
+class _RenderTokens(torch.autograd.Function):
+    """pimg[p] = get_pimg(token p); backward takes a full cotangent on pimg and re-runs the fused kernel."""
+
+    @staticmethod
+    def forward(ctx, ctrl, invscale, position, affine, eps, sigma, batch, ps):
+        dev = batch.device
+        P = batch.P
+        tens = [_c32(ctrl), _c32(invscale), _c32(position), None if affine is None else _c32(affine), _c32(eps),
+                _c32(sigma)]
+        pimg = torch.empty((P, IMSIZE, IMSIZE), dtype=torch.float32, device=dev)
+        off = torch.empty(P, dtype=torch.uint8, device=dev)
+        out = _lib.FwdOut(None, off.data_ptr(), pimg.data_ptr())
+        b = batch.c_struct(*tens)
+        t = _lib.Targets()
+        check(lib().bpl_score_tokens(ctypes.byref(ps), ctypes.byref(b), ctypes.byref(t), ctypes.byref(out),
+                                     _stream(dev)))
+        ctx.batch = batch; ctx.ps = ps; ctx.has_aff = affine is not None
+        ctx.save_for_backward(*[x for x in tens if x is not None])
+        ctx.mark_non_differentiable(off)
+        return pimg, off
+
+    @staticmethod
+    def backward(ctx, g_pimg, _g_off):
+        saved = list(ctx.saved_tensors)
+        ctrl, inv, pos = saved[:3]
+        aff = saved[3] if ctx.has_aff else None
+        eps, sig = saved[-2], saved[-1]
+        batch = ctx.batch
+        dev = batch.device
+        P = batch.P
+        gp = g_pimg.to(torch.float32).contiguous()
+        g_ctrl = torch.empty_like(ctrl); g_inv = torch.empty_like(inv); g_pos = torch.empty_like(pos)
+        g_aff = None if aff is None else torch.empty_like(aff)
+        g_eps = torch.empty(P, dtype=torch.float32, device=dev); g_sig = torch.empty_like(g_eps)
+        g = _lib.Grads(None, gp.data_ptr(), g_ctrl.data_ptr(), g_inv.data_ptr(), g_pos.data_ptr(),
+                       None if g_aff is None else g_aff.data_ptr(), None, g_eps.data_ptr(), g_sig.data_ptr())
+        b = batch.c_struct(ctrl, inv, pos, aff, eps, sig)
+        t = _lib.Targets()
+        out = _lib.FwdOut(None, None, None)
+        check(lib().bpl_score_tokens_grad(ctypes.byref(ctx.ps), ctypes.byref(b), ctypes.byref(t), ctypes.byref(out),
+                                          ctypes.byref(g), _stream(dev)))
+        return g_ctrl, g_inv, g_pos, g_aff, g_eps, g_sig, None, None
+
+
+def score_tokens(batch, images, img_idx=None, ps=None):
+    """Render and score a TokenBatch.  images: PackedImages; img_idx: int32 [P] or None (image 0).
+    Returns (ll [P] float32, ink_off_page [P] bool).  Differentiable w.r.t. batch.ctrl / invscale /
+    position / affine / eps / sigma."""
+    if not isinstance(ps, _lib.Params):
+        ps = make_params(ps)
+    if img_idx is not None:
+        img_idx = _i32(img_idx, batch.device)
+    ll, off = _ScoreTokens.apply(batch.ctrl, batch.invscale, batch.position, batch.affine, batch.eps, batch.sigma,
+                                 batch, images, img_idx, ps)
+    return ll, off.bool()
+
+
+def render_tokens(batch, ps=None):
+    """Probability maps of a TokenBatch: (pimg [P,105,105], ink_off_page [P] bool)."""
+    if not isinstance(ps, _lib.Params):
+        ps = make_params(ps)
+    pimg, off = _RenderTokens.apply(batch.ctrl, batch.invscale, batch.position, batch.affine, batch.eps, batch.sigma,
+                                    batch, ps)
+    return pimg, off.bool()
+
+
+def token_points(batch, ps=None):
+    """Per-point integer work of a TokenBatch via the fused kernels' own device code: dict with
+    motor [S,neval,2], mask_out [S,neval] bool, floor/ceil [S,neval,2] int32 (row, col), n_in [S] int32."""
+    if not isinstance(ps, _lib.Params):
+        ps = make_params(ps)
+    dev = batch.device
+    S, n = batch.S, batch.neval
+    motor = torch.empty((S, n, 2), dtype=torch.float32, device=dev)
+    mask = torch.empty((S, n), dtype=torch.uint8, device=dev)
+    fl = torch.empty((S, n, 2), dtype=torch.int32, device=dev)
+    ce = torch.empty((S, n, 2), dtype=torch.int32, device=dev)
+    n_in = torch.empty(S, dtype=torch.int32, device=dev)
+    tens = [_c32(batch.ctrl), _c32(batch.invscale), _c32(batch.position),
+            None if batch.affine is None else _c32(batch.affine), _c32(batch.eps), _c32(batch.sigma)]
+    b = batch.c_struct(*tens)
+    check(lib().bpl_token_points(ctypes.byref(ps), ctypes.byref(b), _ptr(motor), _ptr(mask), _ptr(fl), _ptr(ce),
+                                 _ptr(n_in), _stream(dev)))
+    return dict(motor=motor, mask_out=mask.bool(), floor=fl, ceil=ce, n_in=n_in)
+
+
+# ---------------------------------------------------------------------------------------------
+# raw trajectories (rendering.render_image)
+# ---------------------------------------------------------------------------------------------
+class StrokeBatch:
+    """P characters given as ragged motor-space trajectories: tok_sub_off [P+1], sub_pt_off [S+1], pts [N,2]."""
+
+    def __init__(self, tok_sub_off, sub_pt_off, pts, eps, sigma):
+        _need_cuda(pts, "pts")
+        dev = pts.device
+        self.tok_sub_off = _i32(tok_sub_off, dev)
+        self.sub_pt_off = _i32(sub_pt_off, dev)
+        self.pts = pts
+        self.eps = eps
+        self.sigma = sigma
+        self.P = self.tok_sub_off.numel() - 1
+        self.device = dev
+
+    def c_struct(self, pts, eps, sigma):
+        b = _lib.StrokeBatchC()
+        b.n_tokens = self.P
+        b.tok_sub_off = self.tok_sub_off.data_ptr(); b.sub_pt_off = self.sub_pt_off.data_ptr()
+        b.pts = pts.data_ptr(); b.eps = eps.data_ptr(); b.sigma = sigma.data_ptr()
+        return b
+
+
+class _RenderStrokes(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pts, eps, sigma, batch, images, img_idx, want_pimg, ps):
+        dev = batch.device
+        P = batch.P
+        pts_c, eps_c, sig_c = _c32(pts), _c32(eps), _c32(sigma)
+        pimg = torch.empty((P, IMSIZE, IMSIZE), dtype=torch.float32, device=dev) if want_pimg else None
+        ll = torch.empty(P, dtype=torch.float32, device=dev) if images is not None else None
+        off = torch.empty(P, dtype=torch.uint8, device=dev)
+        out = _lib.FwdOut(None if ll is None else ll.data_ptr(), off.data_ptr(),
+                          None if pimg is None else pimg.data_ptr())
+        b = batch.c_struct(pts_c, eps_c, sig_c)
+        t = _targets(images, img_idx)
+        check(lib().bpl_render_strokes(ctypes.byref(ps), ctypes.byref(b), ctypes.byref(t), ctypes.byref(out),
+                                       _stream(dev)))
+        ctx.batch = batch; ctx.ps = ps; ctx.images = images; ctx.img_idx = img_idx
+        ctx.save_for_backward(pts_c, eps_c, sig_c)
+        ctx.mark_non_differentiable(off)
+        if pimg is None:
+            pimg = torch.empty(0, device=dev)
+        if ll is None:
+            ll = torch.zeros(P, dtype=torch.float32, device=dev)
+        return pimg, ll, off
+
+    @staticmethod
+    def backward(ctx, g_pimg, g_ll, _g_off):
+        pts, eps, sig = ctx.saved_tensors
+        batch = ctx.batch
+        dev = batch.device
+        P = batch.P
+
+        def run(gp, gl, images):
+            g_pts = torch.zeros_like(pts)
+            g_eps = torch.empty(P, dtype=torch.float32, device=dev); g_sig = torch.empty_like(g_eps)
+            g = _lib.Grads(None if gl is None else gl.data_ptr(), None if gp is None else gp.data_ptr(), None, None,
+                           None, None, g_pts.data_ptr(), g_eps.data_ptr(), g_sig.data_ptr())
+            b = batch.c_struct(pts, eps, sig)
+            t = _targets(images, ctx.img_idx)
+            out = _lib.FwdOut(None, None, None)
+            check(lib().bpl_render_strokes_grad(ctypes.byref(ctx.ps), ctypes.byref(b), ctypes.byref(t),
+                                                ctypes.byref(out), ctypes.byref(g), _stream(dev)))
+            return g_pts, g_eps, g_sig
+
+        tot = None
+        if g_pimg is not None and g_pimg.numel() > 0:
+            tot = run(g_pimg.to(torch.float32).contiguous(), None, None)
+        if ctx.images is not None and g_ll is not None:
+            r = run(None, g_ll.to(torch.float32).contiguous(), ctx.images)
+            tot = r if tot is None else tuple(a + b for a, b in zip(tot, r))
+        if tot is None:
+            tot = (torch.zeros_like(pts), torch.zeros(P, device=dev), torch.zeros(P, device=dev))
+        return tot[0], tot[1], tot[2], None, None, None, None, None
+
+
+def render_strokes(batch, images=None, img_idx=None, want_pimg=True, ps=None):
+    """render_image over a StrokeBatch: returns (pimg [P,105,105] or None, ll [P] or None, off_page [P] bool)."""
+    if not isinstance(ps, _lib.Params):
+        ps = make_params(ps)
+    if img_idx is not None:
+        img_idx = _i32(img_idx, batch.device)
+    pimg, ll, off = _RenderStrokes.apply(batch.pts, batch.eps, batch.sigma, batch, images, img_idx, want_pimg, ps)
+    return (pimg if want_pimg else None), (ll if images is not None else None), off.bool()
+
+
+# ---------------------------------------------------------------------------------------------
+# splines
+# ---------------------------------------------------------------------------------------------
+class _SplineEval(torch.autograd.Function):
+    """X[b] = C @ Y[b] (pybpl/splines.py:136); gradients to Y and to C (C carries d/ds when s needs grad)."""
+
+    @staticmethod
+    def forward(ctx, C, Y):
+        dev = Y.device
+        Cc, Yc = _c32(C), _c32(Y)
+        nspl, nland = Yc.shape[0], Yc.shape[1]
+        neval = Cc.shape[0]
+        X = torch.empty((nspl, neval, 2), dtype=torch.float32, device=dev)
+        check(lib().bpl_spline_eval(_ptr(Cc), neval, nland, nspl, _ptr(Yc), _ptr(X), _stream(dev)))
+        ctx.save_for_backward(Cc, Yc)
+        return X
+
+    @staticmethod
+    def backward(ctx, gX):
+        Cc, Yc = ctx.saved_tensors
+        dev = Yc.device
+        nspl, nland = Yc.shape[0], Yc.shape[1]
+        neval = Cc.shape[0]
+        gXc = gX.to(torch.float32).contiguous()
+        gY = None
+        if ctx.needs_input_grad[1]:
+            gY = torch.empty_like(Yc)
+            check(lib().bpl_spline_eval_bwd(_ptr(Cc), neval, nland, nspl, _ptr(gXc), _ptr(gY), _stream(dev)))
+        gC = None
+        if ctx.needs_input_grad[0]:
+            gC = torch.einsum("bjc,bkc->jk", gXc, Yc)     # only when the time points s carry a gradient
+        return gC, gY
+
+
+def spline_eval(C, Y):
+    """Y: [nspl, nland, 2] CUDA; C: [neval, nland] CUDA -> X [nspl, neval, 2]."""
+    _need_cuda(Y, "Y")
+    return _SplineEval.apply(C, Y)
+
+
+def adaptive_neval(Y, grain=1.5, min_neval=10, max_neval=200):
+    """Integer neval per spline (pybpl/splines.py:129-133) and the trajectory lengths."""
+    _need_cuda(Y, "Y")
+    Yc = _c32(Y)
+    nspl, nland = Yc.shape[0], Yc.shape[1]
+    C = basis_table(nland, max_neval, Y.device)
+    nev = torch.empty(nspl, dtype=torch.int32, device=Y.device)
+    dist = torch.empty(nspl, dtype=torch.float32, device=Y.device)
+    check(lib().bpl_spline_adaptive_neval(_ptr(C), max_neval, nland, nspl, _ptr(Yc), float(grain), int(min_neval),
+                                          _ptr(nev), _ptr(dist), _stream(Y.device)))
+    return nev, dist
+
+
+class _VanillaToMotor(torch.autograd.Function):
+    """Batched vanilla_to_motor (pybpl/objects/part.py:290-328): ctrl [S,ncpt,2], invscale [S], position [K,2],
+    stroke_sub_off [K+1] -> motor [S,neval,2], motor_spline [S,ncpt,2]."""
+
+    @staticmethod
+    def forward(ctx, ctrl, invscale, position, stroke_sub_off, neval):
+        dev = ctrl.device
+        c, i, p = _c32(ctrl), _c32(invscale), _c32(position)
+        S, ncpt = c.shape[0], c.shape[1]
+        K = p.shape[0]
+        C = basis_table(ncpt, neval, dev)
+        motor = torch.empty((S, neval, 2), dtype=torch.float32, device=dev)
+        ms = torch.empty((S, ncpt, 2), dtype=torch.float32, device=dev)
+        check(lib().bpl_vanilla_to_motor(_ptr(C), neval, ncpt, K, _ptr(stroke_sub_off), _ptr(c), _ptr(i), _ptr(p),
+                                         _ptr(motor), _ptr(ms), _stream(dev)))
+        ctx.save_for_backward(c, i, C, stroke_sub_off)
+        ctx.neval = neval
+        return motor, ms
+
+    @staticmethod
+    def backward(ctx, g_motor, g_ms):
+        # motor_i = C @ Y_i - off_i, ms_i = Y_i - off_i, off_i = (C[0] @ Y_i) - prev_i, prev_{i+1} = motor_i[-1];
+        # a short chain of tiny tensor ops on the device -- this standalone operator is not on the hot path
+        # (the fused kernels differentiate the chain themselves).
+        c, inv, C, sso = ctx.saved_tensors
+        dev = c.device
+        S, ncpt = c.shape[0], c.shape[1]
+        neval = ctx.neval
+        gm = torch.zeros((S, neval, 2), device=dev) if g_motor is None else g_motor.to(torch.float32).clone()
+        gs = torch.zeros((S, ncpt, 2), device=dev) if g_ms is None else g_ms.to(torch.float32)
+        off = sso.tolist()
+        K = len(off) - 1
+        g_off_tot = -(gm.sum(1) + gs.sum(1))                     # d/d off_i from the direct uses
+        g_prev = torch.zeros((S, 2), device=dev)
+        g_pos = torch.zeros((K, 2), device=dev)
+        for k in range(K):
+            carry = torch.zeros(2, device=dev)
+            for s in range(off[k + 1] - 1, off[k] - 1, -1):
+                gm[s, -1] += carry
+                g_off = g_off_tot[s] - carry                      # the carry also flows through -off_s
+                g_prev[s] = -g_off
+                gm[s, 0] += g_off                                # off_s = traj_s[0] - prev_s
+                carry = g_prev[s]
+            g_pos[k] = carry
+        gY = torch.empty((S, ncpt, 2), dtype=torch.float32, device=dev)
+        check(lib().bpl_spline_eval_bwd(_ptr(C), neval, ncpt, S, _ptr(gm.contiguous()), _ptr(gY), _stream(dev)))
+        gY = gY + gs
+        return gY * inv.view(-1, 1, 1), (gY * c).sum((1, 2)), g_pos, None, None
+
+
+def vanilla_to_motor_batch(ctrl, invscale, position, stroke_sub_off, neval=200):
+    _need_cuda(ctrl, "ctrl")
+    return _VanillaToMotor.apply(ctrl, invscale, position, _i32(stroke_sub_off, ctrl.device), int(neval))
+
+
+# ---------------------------------------------------------------------------------------------
+# particle-sweep reduction
+# ---------------------------------------------------------------------------------------------
+def logsumexp_partial(ll):
+    """(max, sum exp(ll - max)) of a CUDA float32 vector as a 2-element tensor (one kernel)."""
+    _need_cuda(ll, "ll")
+    llc = _c32(ll)
+    out = torch.empty(2, dtype=torch.float32, device=ll.device)
+    check(lib().bpl_logsumexp_partial(_ptr(llc), llc.numel(), _ptr(out), _stream(ll.device)))
+    return out

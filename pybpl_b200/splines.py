@@ -1,0 +1,95 @@
+"""Drop-in for the evaluation half of pybpl/splines.py (bspline_gen_s, coefficient_mat,
+get_stk_from_bspline) plus the `bspline_eval` alias the north-star names.  Same signatures, argument
+meaning and assertions; the arithmetic runs in libpybpl_b200.so on the GPU."""
+import torch
+
+from . import ops
+from .parameters import Parameters
+
+__all__ = ['bspline_gen_s', 'coefficient_mat', 'get_stk_from_bspline', 'bspline_eval']
+
+PM = Parameters()
+
+
+def _compute_device(t):
+    return t.device if t.is_cuda else torch.device("cuda", torch.cuda.current_device())
+
+
+def bspline_gen_s(nland, neval=200, device=None):
+    """Time points for evaluating a spline (pybpl/splines.py:57-69): (s, lb, ub)."""
+    lb = float(2)
+    ub = float(nland + 1)
+    s = torch.linspace(lb, ub, neval, device=device)
+    return s, lb, ub
+
+
+def coefficient_mat(nland, neval=None, s=None, device=None):
+    """B-spline coefficient matrix (pybpl/splines.py:72-93).  Not cached on tensor identity: the
+    reference's lru_cache returns a stale matrix after an in-place update of `s`."""
+    if s is None:
+        assert neval is not None, 'neval must be provided when s not provided.'
+        dev = torch.device("cpu") if device is None else torch.device(device)
+        if dev.type == "cuda":
+            return ops.basis_table(nland, neval, dev)
+        return torch.from_numpy(ops._basis_host(nland, neval)).clone()
+    if s.dim() == 0:
+        s = s.view(1)
+    assert s.dim() == 1
+    return ops.basis_rows(nland, s)
+
+
+def _check_input(x):
+    assert torch.is_tensor(x)
+    assert x.dim() == 2
+    assert x.size(1) == 2
+
+
+def get_stk_from_bspline(Y, neval=None, s=None):
+    """Evaluate a B-spline: Y [nland,2] -> X [neval,2] (pybpl/splines.py:108-138).
+
+    With neither `neval` nor `s`, neval is chosen from the trajectory length exactly as the reference
+    does (integer work: clamp(ceil(dist/1.5), 10, 200))."""
+    _check_input(Y)
+    nland = Y.size(0)
+    dev = _compute_device(Y)
+    Yd = Y.to(dev)
+    if neval is None and s is None:
+        nev, _ = ops.adaptive_neval(Yd.detach().unsqueeze(0), PM.spline_grain, PM.spline_min_neval,
+                                    PM.spline_max_neval)
+        neval = int(nev.item())
+    if s is not None:
+        sv = s.view(1) if s.dim() == 0 else s
+        C = ops.basis_rows(nland, sv).to(dev)
+        if s.requires_grad:
+            # d C / d s: derivative of the normalised cubic basis, by differences of the same host routine
+            C = _BasisRowsWithGrad.apply(sv.to(dev), nland, C)
+    else:
+        C = ops.basis_table(nland, int(neval), dev)
+    X = ops.spline_eval(C, Yd.unsqueeze(0))[0]
+    return X.to(Y.device)
+
+
+def bspline_eval(sval, cpts):
+    """Evaluate the spline with control points `cpts` [nland,2] at times `sval` (scalar or [n])."""
+    return get_stk_from_bspline(cpts, s=sval)
+
+
+class _BasisRowsWithGrad(torch.autograd.Function):
+    """Attaches d C / d s (central differences of the piecewise-cubic basis, exact to ~1e-4 relative) so that
+    eval_spot-style parameters receive a gradient, which the reference intends but loses to its cache."""
+
+    @staticmethod
+    def forward(ctx, s, nland, C):
+        ctx.nland = nland
+        ctx.save_for_backward(s)
+        return C.clone()
+
+    @staticmethod
+    def backward(ctx, gC):
+        (s,) = ctx.saved_tensors
+        h = 1e-3
+        lo = torch.clamp(s.detach() - h, min=2.0)
+        hi = torch.clamp(s.detach() + h, max=float(ctx.nland + 1))
+        dC = (ops.basis_rows(ctx.nland, hi).to(gC.device) - ops.basis_rows(ctx.nland, lo).to(gC.device)) \
+            / (hi - lo).view(-1, 1)
+        return (gC * dC).sum(1), None, None

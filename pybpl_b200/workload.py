@@ -1,0 +1,141 @@
+"""Seeded synthetic token batches for the bench configs and the parity tests.
+
+Tokens are drawn the way the reference's prior shapes them, without running the reference's
+(28 ms/type) sampler: K strokes, nsub sub-strokes per stroke from pmat_nsub, primitive ids uniform over
+the 1212 library primitives, control points ~ N(mu[id], sd[id]) + token noise, scales ~ Gamma(theta[id]) +
+token noise, first stroke position uniform over the canvas, later strokes attached to the start or end of
+an earlier stroke.  The hyper-parameter tables (pybpl_b200/data/workload_lib.npz) are data exported from
+the reference's lib_data by tests/golden/make_golden.py:make_assets.  Everything is numpy on the host:
+this is input generation, not the hot path.
+"""
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = dict(np.load(os.path.join(_HERE, "data", "workload_lib.npz")))
+    return _LIB
+
+
+def synth_tokens(P, seed=1234, max_strokes=5, kappa="uniform", sigma_mode="uniform", eps=1e-4, neval=200):
+    """Packed ragged batch of P tokens as numpy arrays (the layout of include/pybpl_b200.h).
+
+    kappa: "uniform" (K ~ U{1..max_strokes}, config 2) or "prior" (K ~ pkappa truncated at max_strokes, config 5).
+    sigma_mode: "uniform" (blur_sigma ~ U(0.5,16)), "fixed" (0.5) or a float.
+    """
+    L = _lib()
+    rng = np.random.default_rng(seed)
+    nprim = L["mu"].shape[0]
+    if kappa == "prior":
+        pk = L["pkappa"][:max_strokes].astype(np.float64)
+        K = rng.choice(np.arange(1, max_strokes + 1), size=P, p=pk / pk.sum())
+    else:
+        K = rng.integers(1, max_strokes + 1, size=P)
+    Ktot = int(K.sum())
+    tok_of_stroke = np.repeat(np.arange(P), K)
+    # sub-strokes per stroke ~ pmat_nsub[K-1]
+    pm = L["pmat_nsub"].astype(np.float64)
+    pm = pm / pm.sum(1, keepdims=True)
+    u = rng.random(Ktot)
+    cdf = np.cumsum(pm[K[tok_of_stroke] - 1], axis=1)
+    nsub = 1 + (u[:, None] > cdf).sum(1)
+    nsub = np.minimum(nsub, pm.shape[1]).astype(np.int64)
+    Stot = int(nsub.sum())
+    ids = rng.integers(0, nprim, size=Stot)
+    ctrl = L["mu"][ids] + L["sd"][ids] * rng.standard_normal((Stot, 10)).astype(np.float32)
+    ctrl = ctrl + float(L["sigma_shape"]) * rng.standard_normal((Stot, 10)).astype(np.float32)
+    th = L["theta"][ids].astype(np.float64)
+    inv = rng.gamma(th[:, 0], th[:, 1])
+    for _ in range(50):                                   # token noise, resampled until positive
+        noisy = inv + float(L["sigma_invscale"]) * rng.standard_normal(Stot)
+        bad = noisy <= 0
+        if not bad.any():
+            break
+        noisy[bad] = inv[bad]
+    inv = np.maximum(noisy, 1e-3)
+    ctrl = ctrl.reshape(Stot, 5, 2).astype(np.float32)
+    inv = inv.astype(np.float32)
+    tso = np.zeros(P + 1, np.int64); tso[1:] = np.cumsum(K)
+    sso = np.zeros(Ktot + 1, np.int64); sso[1:] = np.cumsum(nsub)
+    # positions: stroke 0 uniform on the canvas; later strokes at the start/end of a random earlier stroke
+    # (+ N(0, rel_sigma)); end points are estimated from the control polygons, which is all the attachment
+    # needs to look Omniglot-shaped.
+    pos = np.zeros((Ktot, 2), np.float32)
+    span = (ctrl[:, -1, :] - ctrl[:, 0, :]) * inv[:, None]      # approx. start->end displacement per sub-stroke
+    stroke_span = np.add.reduceat(span, sso[:-1], axis=0) if Stot else np.zeros((0, 2), np.float32)
+    first = np.zeros(Ktot, bool); first[tso[:-1][K > 0]] = True
+    pos[first, 0] = rng.random(first.sum()) * 104.0
+    pos[first, 1] = -rng.random(first.sum()) * 104.0
+    rel = L["rel_sigma"]
+    kk = np.arange(Ktot) - tso[tok_of_stroke]                  # stroke rank inside its token
+    for rank in range(1, max_strokes):
+        sel = np.nonzero(kk == rank)[0]
+        if sel.size == 0:
+            continue
+        prev = tso[tok_of_stroke[sel]] + (rng.random(sel.size) * rank).astype(np.int64)
+        at_end = rng.random(sel.size) < 0.5
+        base = pos[prev] + np.where(at_end[:, None], stroke_span[prev], 0.0)
+        pos[sel] = base + rel * rng.standard_normal((sel.size, 2)).astype(np.float32)
+    if sigma_mode == "uniform":
+        sigma = rng.uniform(0.5, 16.0, size=P)
+    elif sigma_mode == "fixed":
+        sigma = np.full(P, 0.5)
+    else:
+        sigma = np.full(P, float(sigma_mode))
+    return dict(P=P, tok_stroke_off=tso.astype(np.int32), stroke_sub_off=sso.astype(np.int32), ctrl=ctrl, invscale=inv,
+                position=pos.astype(np.float32), eps=np.full(P, eps, np.float32), sigma=sigma.astype(np.float32),
+                neval=neval)
+
+
+def permute(w, perm):
+    """The same batch with tokens reordered / subset by `perm` (token indices)."""
+    tso, sso = w["tok_stroke_off"].astype(np.int64), w["stroke_sub_off"].astype(np.int64)
+    strokes = np.concatenate([np.arange(tso[p], tso[p + 1]) for p in perm]) if len(perm) else np.zeros(0, np.int64)
+    subs = np.concatenate([np.arange(sso[k], sso[k + 1]) for k in strokes]) if len(strokes) else np.zeros(0, np.int64)
+    K = (tso[1:] - tso[:-1])[perm]
+    ns = (sso[1:] - sso[:-1])[strokes]
+    tso2 = np.zeros(len(perm) + 1, np.int64); tso2[1:] = np.cumsum(K)
+    sso2 = np.zeros(len(strokes) + 1, np.int64); sso2[1:] = np.cumsum(ns)
+    return dict(P=len(perm), tok_stroke_off=tso2.astype(np.int32), stroke_sub_off=sso2.astype(np.int32),
+                ctrl=w["ctrl"][subs], invscale=w["invscale"][subs], position=w["position"][strokes],
+                eps=w["eps"][perm], sigma=w["sigma"][perm], neval=w["neval"])
+
+
+def shard(w, rank, world):
+    """Contiguous block of ceil(P/world) tokens for `rank`."""
+    P = w["P"]
+    per = (P + world - 1) // world
+    lo, hi = min(P, rank * per), min(P, (rank + 1) * per)
+    return permute(w, np.arange(lo, hi))
+
+
+def to_device(w, device, requires_grad=False, pin=False):
+    """ops.TokenBatch on `device` from the numpy batch."""
+    import torch
+    from . import ops
+
+    def f(a):
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        if pin:
+            t = t.pin_memory()
+        t = t.to(device, non_blocking=pin)
+        return t.requires_grad_(True) if requires_grad and t.is_floating_point() else t
+    return ops.TokenBatch(f(w["tok_stroke_off"]), f(w["stroke_sub_off"]), f(w["ctrl"]), f(w["invscale"]),
+                          f(w["position"]), f(w["eps"]), f(w["sigma"]), neval=w["neval"], check_limits=False)
+
+
+def target_image_for(w, oracle, C, token=0, seed=99):
+    """Binary target = Bernoulli sample of one token's probability map, rendered by the CPU oracle
+    (tests only: the product never imports oracle/)."""
+    sub = permute(w, np.array([token]))
+    nsub = np.diff(sub["stroke_sub_off"])
+    r = oracle.token(C, nsub, sub["ctrl"], sub["invscale"], sub["position"], float(sub["eps"][0]),
+                     float(sub["sigma"][0]))
+    rng = np.random.default_rng(seed)
+    return (rng.random((105, 105)) < r["pimg"]).astype(np.uint8)

@@ -414,14 +414,40 @@ def make_tokens(n_prior=96, n_full=24):
           "off_page frac", np.mean(off_all), "ll range", min(ll_all), max(ll_all))
 
 
+def make_assets():
+    """pybpl_b200/data/basis_5_200.npy: coefficient_mat(5, 200) exactly as the reference's torch builds it
+    (splines.py:72-93).  torch assembles it with Sleef powf and an MKL dot, which portable C cannot
+    reproduce to the bit, and bit-exact integer work (floor/ceil/in-bounds) needs bit-exact trajectories,
+    so the product ships this one table as data; every other (nland, neval) is computed by the library."""
+    S.coefficient_mat.cache_clear()
+    C = S.coefficient_mat(5, 200).numpy().astype(f32)
+    dst = os.path.join(os.path.dirname(os.path.dirname(OUT)), "pybpl_b200", "data")
+    os.makedirs(dst, exist_ok=True)
+    np.save(os.path.join(dst, "basis_5_200.npy"), C)
+    print("asset basis_5_200.npy", C.shape)
+    # Hyper-parameter tables the synthetic workload generator draws from (SURVEY.md 8d / App. D): data, not code.
+    lib = Library(use_hist=True)
+    Sig = lib.shape['Sigma'].numpy()
+    np.savez_compressed(os.path.join(dst, "workload_lib.npz"),
+                        mu=lib.shape['mu'].numpy().astype(f32),
+                        sd=np.sqrt(np.stack([np.diag(Sig[i]) for i in range(Sig.shape[0])])).astype(f32),
+                        theta=lib.scale['theta'].numpy().astype(f32),
+                        pmat_nsub=lib.pmat_nsub.numpy().astype(f32), pkappa=lib.pkappa.numpy().astype(f32),
+                        sigma_shape=f32(lib.tokenvar['sigma_shape']), sigma_invscale=f32(lib.tokenvar['sigma_invscale']),
+                        rel_sigma=np.array([float(lib.rel['sigma_x']), float(lib.rel['sigma_y'])], f32))
+    print("asset workload_lib.npz")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["splines", "render", "tokens"]
+    which = sys.argv[1:] or ["splines", "render", "tokens", "assets"]
     if "splines" in which:
         make_splines()
     if "render" in which:
         make_render()
     if "tokens" in which:
         make_tokens()
+    if "assets" in which:
+        make_assets()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")

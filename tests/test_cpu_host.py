@@ -1,0 +1,136 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol include/pybpl_b200.h declares,
+host-side basis tables, the workload generator, and the multi-rank combine logic under gloo."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_builds_and_exports_header_symbols():
+    import __graft_entry__ as ge
+    ge.build()
+    from pybpl_b200 import _lib
+    L = _lib.lib()
+    hdr = open(os.path.join(ROOT, "include", "pybpl_b200.h")).read()
+    declared = set(re.findall(r"\b(bpl_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations found"
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in the header but not exported"
+    assert set(_lib.EXPORTS) <= declared
+    assert L.bpl_version() == 1
+    ps = _lib.default_params()
+    assert (ps.imsize, ps.fsize, ps.ink_ncon) == (105, 11, 2) and ps.ink_b == 6.0
+
+
+def test_sass_is_sm100a():
+    from pybpl_b200 import _lib
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.SO_PATH], stdout=subprocess.PIPE, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_host_basis_tables_close_to_reference():
+    from pybpl_b200 import ops
+    from tests.util_golden import load
+    d = load("splines")
+    assert np.array_equal(ops._basis_host(5, 200), d["table_5_200"])       # shipped reference table
+    for nland, neval in d["table_pairs"]:
+        C = ops._basis_host(int(nland), int(neval))
+        assert np.abs(C - d[f"table_{nland}_{neval}"]).max() < 1e-6
+    import torch
+    C = ops.basis_rows(5, torch.from_numpy(d["s_explicit"])).numpy()
+    assert np.abs(C - d["table_s_explicit"]).max() < 1e-6
+
+
+def test_no_cpu_fallback():
+    import torch
+    from pybpl_b200 import _lib, ops
+    with pytest.raises(_lib.BplError):
+        ops.pack_images(torch.zeros(105, 105))
+    with pytest.raises(_lib.BplError):
+        ops.spline_eval(torch.zeros(200, 5), torch.zeros(1, 5, 2))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "pybpl_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                if f == "workload.py":
+                    src = src.replace("def target_image_for(w, oracle, C", "")
+                assert "import oracle" not in src and "from oracle" not in src and "bpl_oracle" not in src, f
+
+
+def test_workload_generator_is_seeded_and_shardable():
+    from pybpl_b200 import workload
+    a = workload.synth_tokens(512, seed=3)
+    b = workload.synth_tokens(512, seed=3)
+    assert all(np.array_equal(a[k], b[k]) for k in a if isinstance(a[k], np.ndarray))
+    tso = a["tok_stroke_off"]; sso = a["stroke_sub_off"]
+    K = np.diff(tso); S = np.diff(sso[tso])
+    assert K.min() >= 1 and K.max() <= 5 and S.max() <= 50 and (a["invscale"] > 0).all()
+    parts = [workload.shard(a, r, 3) for r in range(3)]
+    assert sum(p["P"] for p in parts) == 512
+    assert np.array_equal(np.concatenate([p["ctrl"] for p in parts]), a["ctrl"])
+    assert np.array_equal(np.concatenate([p["sigma"] for p in parts]), a["sigma"])
+
+
+def test_oracle_runs_workload():
+    from oracle import Oracle
+    from pybpl_b200 import workload
+    w = workload.synth_tokens(16, seed=11)
+    o = Oracle(np.float32)
+    C = np.load(os.path.join(ROOT, "pybpl_b200", "data", "basis_5_200.npy"))
+    img = workload.target_image_for(w, o, C)
+    r = o.token_batch(C, w["tok_stroke_off"], w["stroke_sub_off"], w["ctrl"], w["invscale"], w["position"], w["eps"],
+                      w["sigma"], img[None])
+    assert np.isfinite(r["ll"]).all() and (r["ll"] < 0).all()
+
+
+_GLOO = r'''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, {root!r})
+from pybpl_b200 import sweep
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+g = torch.Generator().manual_seed(0)
+ll = -50 - 2000 * torch.rand(1001, generator=g)
+per = (1001 + world - 1) // world
+mine = ll[rank * per:(rank + 1) * per]
+part = sweep.partial_from_scores(mine)
+tot = sweep.combine_partials(part, group=None)
+want = torch.logsumexp(ll.double(), 0).item()
+assert abs(tot - want) < 1e-6 * abs(want), (tot, want)
+# empty shard
+tot2 = sweep.combine_partials(sweep.partial_from_scores(mine if rank == 0 else mine[:0]), group=None)
+want2 = torch.logsumexp(ll[:per].double(), 0).item()
+assert abs(tot2 - want2) < 1e-6 * abs(want2)
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_sweep_combine_world2_gloo(tmp_path):
+    script = tmp_path / "gloo_sweep.py"
+    script.write_text(_GLOO.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29611", str(script)],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, timeout=240)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert r.stdout.count("ok") >= 2
+
+
+def test_bench_reference_arm_runs():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "1"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    import json
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"

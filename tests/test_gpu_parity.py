@@ -1,0 +1,412 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the golden vectors generated from the
+live reference and against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): integer work bit-exact; fp32 pimg / ll within 1e-5 relative;
+gradients per tensor in inf-norm-relative terms, stated below next to the reference's own fp32 noise
+(the reference's autograd is 7e-5 (points) .. 5e-3 (d/d sigma) from fp64)."""
+import numpy as np
+import pytest
+import torch
+
+from tests.util_golden import load, render_cases, token_cases, pack_tokens, relinf
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from pybpl_b200 import ops as _ops
+    return _ops
+
+
+def T(a, dtype=torch.float32):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype, device=DEV)
+
+
+def make_token_batch(ops, toks, grad=False, with_affine=None):
+    b = pack_tokens(toks)
+    use_aff = bool(b["has_affine"].any()) if with_affine is None else with_affine
+    aff = b["affine"].copy()
+    aff[~b["has_affine"]] = [1, 1, 0, 0]
+    ctrl, inv, pos = T(b["ctrl"]), T(b["invscale"]), T(b["position"])
+    eps, sig = T(b["eps"]), T(b["sigma"])
+    affine = T(aff) if use_aff else None
+    if grad:
+        for t in (ctrl, inv, pos, eps, sig):
+            t.requires_grad_(True)
+        if affine is not None:
+            affine.requires_grad_(True)
+    batch = ops.TokenBatch(b["tok_stroke_off"], b["stroke_sub_off"], ctrl, inv, pos, eps, sig, affine=affine)
+    imgs = ops.pack_images(T(b["images"], torch.uint8))
+    return batch, imgs, T(b["img_idx"], torch.int32), b
+
+
+# ---------------------------------------------------------------------------------------------
+# splines
+# ---------------------------------------------------------------------------------------------
+def test_spline_eval_bit_exact(ops):
+    d = load("splines")
+    X = ops.spline_eval(T(d["table_5_200"]), T(d["Y_explicit"]))
+    assert np.array_equal(X.cpu().numpy(), d["X_200"])
+    X7 = ops.spline_eval(T(d["table_7_200"]), T(d["Y7"]))
+    assert np.array_equal(X7.cpu().numpy(), d["X7_200"])
+    Xe = ops.spline_eval(T(d["table_s_explicit"]), T(d["Y_explicit"]))
+    assert np.array_equal(Xe.cpu().numpy(), d["X_explicit"])
+
+
+def test_shipped_table_is_the_references(ops):
+    d = load("splines")
+    assert np.array_equal(ops.basis_table(5, 200, DEV).cpu().numpy(), d["table_5_200"])
+    for nland, neval in d["table_pairs"]:
+        C = ops.basis_table(int(nland), int(neval), DEV).cpu().numpy()
+        assert np.abs(C - d[f"table_{nland}_{neval}"]).max() < 1e-6
+
+
+def test_spline_eval_backward(ops):
+    d = load("splines")
+    Y = T(d["Y_explicit"]).requires_grad_(True)
+    X = ops.spline_eval(T(d["table_5_200"]), Y)
+    (X * T(d["ct_200"])).sum().backward()
+    assert relinf(Y.grad.cpu().numpy(), d["gY_200"]) < 2e-6
+
+
+def test_adaptive_neval_integer_exact(ops):
+    d = load("splines")
+    nev, dist = ops.adaptive_neval(T(d["Y_adaptive"]))
+    assert np.array_equal(nev.cpu().numpy(), d["neval_adaptive"])
+    assert relinf(dist.cpu().numpy(), d["dist_adaptive"]) < 2e-6
+
+
+def test_get_stk_from_bspline_dropin():
+    from pybpl_b200 import splines
+    d = load("splines")
+    Y = torch.from_numpy(d["Y_adaptive"][:8])
+    outs = [splines.get_stk_from_bspline(y) for y in Y]              # adaptive neval, CPU tensors in/out
+    assert [o.shape[0] for o in outs] == list(d["neval_adaptive"][:8])
+    assert all(o.device.type == "cpu" for o in outs)
+    got = torch.cat(outs).numpy()
+    assert np.abs(got - d["X_adaptive_first8"]).max() < 2e-4          # non-(5,200) tables: ~4e-7 coefficient diffs
+    Ye = torch.from_numpy(d["Y_explicit"][0])
+    X = splines.bspline_eval(torch.tensor(4.5), Ye)
+    assert X.shape == (1, 2) and np.abs(X.numpy() - d["X_scalar_s"][0]).max() < 1e-4
+    X200 = splines.get_stk_from_bspline(Ye, neval=200)
+    assert np.array_equal(X200.numpy(), d["X_200"][0])
+
+
+# ---------------------------------------------------------------------------------------------
+# vanilla_to_motor + integer work
+# ---------------------------------------------------------------------------------------------
+def test_vanilla_to_motor_bit_exact(ops):
+    d, toks = token_cases()
+    from pybpl_b200 import objects
+    for t in toks[: int(d["n_full"])]:
+        if t["has_affine"]:
+            continue
+        s0 = 0
+        for k, n in enumerate(t["nsub"]):
+            shapes = torch.from_numpy(t["ctrl"][s0:s0 + n]).permute(1, 2, 0).contiguous()   # (ncpt,2,nsub)
+            motor, ms = objects.vanilla_to_motor(shapes, torch.from_numpy(t["invscale"][s0:s0 + n]),
+                                                 torch.from_numpy(t["position"][k]))
+            assert motor.shape == (n, 200, 2) and ms.shape == (5, 2, n)    # the reference test's own assertion
+            assert np.array_equal(motor.numpy(), t["motor"][s0:s0 + n]), t["name"]
+            s0 += n
+
+
+def test_integer_work_bit_exact(ops):
+    """In-bounds masks, surviving-point counts and pixel indices, from the fused kernels' own device code."""
+    d, toks = token_cases()
+    sel = [t for t in toks if not t["has_affine"]]
+    batch, _, _, b = make_token_batch(ops, sel, with_affine=False)
+    r = ops.token_points(batch)
+    mask = r["mask_out"].cpu().numpy()
+    fl = r["floor"].cpu().numpy().astype(np.int64)
+    n_in = r["n_in"].cpu().numpy()
+    s0 = 0
+    for t in sel:
+        S = len(t["invscale"])
+        m = mask[s0:s0 + S]
+        assert np.array_equal(m, t["mask_out"]), t["name"]
+        assert np.array_equal(n_in[s0:s0 + S], t["n_inbounds"])
+        fsum = (fl[s0:s0 + S] * (~m)[..., None]).sum(1)
+        assert np.array_equal(fsum, t["floor_sum"])
+        if "motor" in t:
+            assert np.array_equal(r["motor"][s0:s0 + S].cpu().numpy(), t["motor"])
+        s0 += S
+
+
+# ---------------------------------------------------------------------------------------------
+# render_image on raw trajectories (edge cases)
+# ---------------------------------------------------------------------------------------------
+class _PS:
+    def __init__(self, hinton):
+        self.broaden_mode = "Hinton" if hinton else "Lake"
+
+
+@pytest.mark.parametrize("case", render_cases(), ids=lambda c: c["name"])
+def test_render_image_cases(ops, case):
+    from pybpl_b200 import rendering
+    strokes = [torch.from_numpy(s.copy()).requires_grad_(True) for s in case["strokes"]]
+    eps = torch.tensor(case["eps"], requires_grad=case["eps"] > 0)
+    sig = torch.tensor(case["sigma"], requires_grad=case["sigma"] > 0)
+    pimg, off = rendering.render_image(strokes, eps, sig, _PS(case["hinton"]))
+    assert pimg.shape == (105, 105) and pimg.dtype == torch.float32 and pimg.device.type == "cpu"
+    assert bool(off) == case["off"]
+    ref = case["pimg"]
+    err = np.abs(pimg.detach().numpy() - ref).max()
+    assert err <= 1e-5 * max(1.0, np.abs(ref).max()), err
+    # generic cotangent on pimg (render_image's autograd)
+    (pimg * torch.from_numpy(case["ct"])).sum().backward()
+    g = torch.cat([s.grad for s in strokes]).numpy()
+    assert relinf(g, case["gct_pts"]) < 2e-4
+    if case["eps"] > 0:
+        assert abs(eps.grad.item() - case["gct_eps"]) <= 2e-4 * max(1.0, abs(case["gct_eps"]))
+    if case["sigma"] > 0:
+        assert abs(sig.grad.item() - case["gct_sigma"]) <= 5e-3 * max(1.0, abs(case["gct_sigma"]))
+
+
+@pytest.mark.parametrize("case", render_cases(), ids=lambda c: c["name"])
+def test_render_and_score_cases(ops, case):
+    """Raw trajectories scored in-kernel: ll and d ll / d (points, eps, sigma)."""
+    lens = case["lens"]
+    off = np.zeros(len(lens) + 1, np.int32); off[1:] = np.cumsum(lens)
+    pts = T(case["pts"]).requires_grad_(True)
+    eps = T([case["eps"]]).requires_grad_(True)
+    sig = T([case["sigma"]]).requires_grad_(True)
+    batch = ops.StrokeBatch([0, len(lens)], off, pts, eps, sig)
+    imgs = ops.pack_images(T(case["image"], torch.uint8))
+    _, ll, offp = ops.render_strokes(batch, images=imgs, want_pimg=False, ps=_PS(case["hinton"]))
+    assert bool(offp[0]) == case["off"]
+    assert abs(ll.item() - case["ll"]) <= 1e-5 * abs(case["ll"]), (ll.item(), case["ll"])
+    ll.sum().backward()
+    assert relinf(pts.grad.cpu().numpy(), case["g_pts"]) < 2e-4
+    assert abs(eps.grad.item() - case["g_eps"]) <= 5e-4 * max(1.0, abs(case["g_eps"]))
+    assert abs(sig.grad.item() - case["g_sigma"]) <= 5e-3 * max(1.0, abs(case["g_sigma"]))
+
+
+# ---------------------------------------------------------------------------------------------
+# whole path on tokens (CharacterImageDist.get_pimg / score_image)
+# ---------------------------------------------------------------------------------------------
+def test_tokens_forward(ops):
+    d, toks = token_cases()
+    batch, imgs, idx, b = make_token_batch(ops, toks)
+    ll, off = ops.score_tokens(batch, imgs, idx)
+    ll = ll.cpu().numpy(); off = off.cpu().numpy()
+    ref = np.array([t["ll"] for t in toks])
+    assert np.array_equal(off, np.array([t["off_page"] for t in toks]))
+    rel = np.abs(ll - ref) / np.abs(ref)
+    print("tokens ll max rel", rel.max())
+    assert rel.max() < 1e-5
+    pimg, off2 = ops.render_tokens(batch)
+    pimg = pimg.cpu().numpy()
+    for i, t in enumerate(toks):
+        if "pimg" in t:
+            assert np.abs(pimg[i] - t["pimg"]).max() < 1e-5, t["name"]
+
+
+def test_tokens_gradients(ops):
+    d, toks = token_cases()
+    batch, imgs, idx, b = make_token_batch(ops, toks, grad=True)
+    ll, _ = ops.score_tokens(batch, imgs, idx)
+    ll.sum().backward()
+    gc = batch.ctrl.grad.cpu().numpy(); gi = batch.invscale.grad.cpu().numpy(); gp = batch.position.grad.cpu().numpy()
+    ge = batch.eps.grad.cpu().numpy(); gs = batch.sigma.grad.cpu().numpy(); ga = batch.affine.grad.cpu().numpy()
+    ref_ll = np.array([t["ll"] for t in toks])
+    assert (np.abs(ll.detach().cpu().numpy() - ref_ll) / np.abs(ref_ll)).max() < 1e-5
+    worst = dict(gc=0, gi=0, gp=0, gs=0, ge=0, ga=0)
+    s0 = k0 = 0
+    for i, t in enumerate(toks):
+        S, K = len(t["invscale"]), len(t["nsub"])
+        worst["gc"] = max(worst["gc"], relinf(gc[s0:s0 + S], t["g_ctrl"]))
+        worst["gi"] = max(worst["gi"], relinf(gi[s0:s0 + S], t["g_invscale"]))
+        worst["gp"] = max(worst["gp"], relinf(gp[k0:k0 + K], t["g_position"]))
+        worst["gs"] = max(worst["gs"], abs(gs[i] - t["g_sigma"]) / max(1.0, abs(t["g_sigma"])))
+        worst["ge"] = max(worst["ge"], abs(ge[i] - t["g_eps"]) / max(1.0, abs(t["g_eps"])))
+        if t["has_affine"]:
+            worst["ga"] = max(worst["ga"], relinf(ga[i], t["g_affine"]))
+        s0 += S; k0 += K
+    print("worst grad errors vs reference fp32 autograd", worst)
+    assert worst["gc"] < 5e-4 and worst["gi"] < 5e-4 and worst["gp"] < 5e-4
+    assert worst["gs"] < 1e-2 and worst["ge"] < 2e-3 and worst["ga"] < 2e-3
+
+
+def test_gradients_no_worse_than_reference_vs_fp64(ops):
+    """|g_cuda - g_fp64| <= |g_ref - g_fp64| (+ slack) per tensor: the build is as accurate as the reference."""
+    from oracle import Oracle
+    d, toks = token_cases()
+    sel = [t for t in toks if not t["has_affine"]][:24]
+    batch, imgs, idx, b = make_token_batch(ops, sel, grad=True, with_affine=False)
+    ll, _ = ops.score_tokens(batch, imgs, idx)
+    ll.sum().backward()
+    gc = batch.ctrl.grad.cpu().numpy(); gs = batch.sigma.grad.cpu().numpy()
+    o64 = Oracle(np.float64)
+    C64 = d["basis_5_200"].astype(np.float64)
+    s0 = 0
+    ours, refs = [], []
+    for i, t in enumerate(sel):
+        S = len(t["invscale"])
+        r = o64.token(C64, t["nsub"], t["ctrl"], t["invscale"], t["position"], t["eps"], t["sigma"],
+                      image=t["image"], grad=True)
+        ours.append(relinf(gc[s0:s0 + S], r["g_ctrl"])); refs.append(relinf(t["g_ctrl"], r["g_ctrl"]))
+        s0 += S
+    print("g_ctrl vs fp64: ours max %.2e median %.2e | reference max %.2e median %.2e" %
+          (max(ours), np.median(ours), max(refs), np.median(refs)))
+    assert max(ours) <= max(3 * max(refs), 2e-4)
+
+
+def test_score_matches_oracle_on_random_batch(ops):
+    """Seeded synthetic batch (the bench workload generator) against the CPU oracle, forward and backward."""
+    from oracle import Oracle
+    from pybpl_b200 import workload
+    w = workload.synth_tokens(96, seed=1234, sigma_mode="uniform")
+    o = Oracle(np.float32)
+    C = load("tokens")["basis_5_200"]
+    img = workload.target_image_for(w, o, C)
+    ref = o.token_batch(C, w["tok_stroke_off"], w["stroke_sub_off"], w["ctrl"], w["invscale"], w["position"],
+                        w["eps"], w["sigma"], img[None], grad=True)
+    ctrl, inv, pos = T(w["ctrl"]).requires_grad_(True), T(w["invscale"]).requires_grad_(True), T(w["position"]).requires_grad_(True)
+    eps, sig = T(w["eps"]).requires_grad_(True), T(w["sigma"]).requires_grad_(True)
+    batch = ops.TokenBatch(w["tok_stroke_off"], w["stroke_sub_off"], ctrl, inv, pos, eps, sig)
+    imgs = ops.pack_images(T(img, torch.uint8))
+    ll, off = ops.score_tokens(batch, imgs)
+    ll.sum().backward()
+    assert np.array_equal(off.cpu().numpy(), ref["off_page"])
+    rel = np.abs(ll.detach().cpu().numpy() - ref["ll"]) / np.abs(ref["ll"])
+    assert rel.max() < 1e-5, rel.max()
+    assert relinf(ctrl.grad.cpu().numpy(), ref["g_ctrl"]) < 2e-4
+    assert relinf(inv.grad.cpu().numpy(), ref["g_invscale"]) < 2e-4
+    assert relinf(pos.grad.cpu().numpy(), ref["g_position"]) < 2e-4
+    assert relinf(eps.grad.cpu().numpy(), ref["g_eps"]) < 5e-4
+    assert relinf(sig.grad.cpu().numpy(), ref["g_sigma"]) < 5e-3
+
+
+# ---------------------------------------------------------------------------------------------
+# mirror of the reference API
+# ---------------------------------------------------------------------------------------------
+def test_character_model_api(ops):
+    from pybpl_b200.model import CharacterModel
+    from pybpl_b200.objects import CharacterToken, StrokeToken
+    d, toks = token_cases()
+    model = CharacterModel()
+    for t in toks[:6]:
+        parts, s0 = [], 0
+        for k, n in enumerate(t["nsub"]):
+            shapes = torch.from_numpy(t["ctrl"][s0:s0 + n]).permute(1, 2, 0).contiguous().requires_grad_(True)
+            parts.append(StrokeToken(shapes, torch.from_numpy(t["invscale"][s0:s0 + n]).requires_grad_(True),
+                                     torch.from_numpy(t["position"][k]).requires_grad_(True)))
+            s0 += n
+        ctok = CharacterToken(parts, torch.from_numpy(t["affine"]) if t["has_affine"] else None,
+                              torch.tensor(t["eps"]), torch.tensor(t["sigma"], requires_grad=True))
+        image = torch.from_numpy(t["image"]).float()
+        ll = model.score_image(ctok, image)
+        assert ll.dim() == 0 and ll.device.type == "cpu"
+        assert abs(ll.item() - t["ll"]) <= 1e-5 * abs(t["ll"])
+        ll.backward()
+        g = torch.cat([p.shapes.grad.permute(2, 0, 1) for p in parts]).numpy()
+        assert relinf(g, t["g_ctrl"]) < 5e-4
+        assert abs(ctok.blur_sigma.grad.item() - t["g_sigma"]) <= 1e-2 * max(1.0, abs(t["g_sigma"]))
+        if "pimg" in t:
+            pimg = model.get_pimg(ctok)
+            assert np.abs(pimg.detach().numpy() - t["pimg"]).max() < 1e-5
+        torch.manual_seed(0)
+        img = model.sample_image(ctok)
+        assert img.shape == (105, 105) and set(np.unique(img.numpy())) <= {0.0, 1.0}
+    with pytest.raises(ValueError):
+        model.score_image(ctok, image * 0.5)        # torch's Bernoulli support check
+
+
+def test_sample_image_statistics(ops):
+    from pybpl_b200.model import CharacterModel
+    from pybpl_b200.objects import CharacterToken, StrokeToken
+    d, toks = token_cases()
+    t = toks[1]
+    parts, s0 = [], 0
+    for k, n in enumerate(t["nsub"]):
+        parts.append(StrokeToken(torch.from_numpy(t["ctrl"][s0:s0 + n]).permute(1, 2, 0).contiguous(),
+                                 torch.from_numpy(t["invscale"][s0:s0 + n]), torch.from_numpy(t["position"][k])))
+        s0 += n
+    ctok = CharacterToken(parts, None, t["eps"], t["sigma"])
+    model = CharacterModel()
+    torch.manual_seed(3)
+    mean = torch.stack([model.sample_image(ctok) for _ in range(64)]).mean(0).numpy()
+    assert abs(mean.mean() - t["pimg"].mean()) < 0.01
+
+
+# ---------------------------------------------------------------------------------------------
+# size-independent properties at the bench size
+# ---------------------------------------------------------------------------------------------
+def test_full_size_properties(ops):
+    from pybpl_b200 import workload
+    P = 4096
+    w = workload.synth_tokens(P, seed=1234, sigma_mode="uniform")
+    batch = workload.to_device(w, DEV)
+    img = torch.zeros((105, 105), dtype=torch.uint8, device=DEV)
+    imgs0 = ops.pack_images(img)
+    imgs1 = ops.pack_images(1 - img)
+    ll0, off0 = ops.score_tokens(batch, imgs0)
+    ll1, _ = ops.score_tokens(batch, imgs1)
+    # determinism of everything but the atomics' summation order
+    ll0b, off0b = ops.score_tokens(batch, imgs0)
+    assert torch.equal(off0, off0b)
+    assert ((ll0 - ll0b).abs() <= 2e-5 * ll0.abs()).all()
+    # permutation equivariance: scoring a permuted batch permutes the scores
+    perm = torch.randperm(P, generator=torch.Generator().manual_seed(0))
+    wp = workload.permute(w, perm.numpy())
+    llp, offp = ops.score_tokens(workload.to_device(wp, DEV), imgs0)
+    assert torch.equal(offp.cpu(), off0.cpu()[perm])
+    assert ((llp.cpu() - ll0.cpu()[perm]).abs() <= 2e-5 * ll0.cpu()[perm].abs()).all()
+    # ll(all-zero image) + ll(all-one image) = sum over pixels of [log p + log(1-p)]: check against pimg
+    pimg, _ = ops.render_tokens(workload.to_device(workload.permute(w, np.arange(64)), DEV))
+    p = pimg.double().clamp(1.1920929e-7, 1 - 1.1920929e-7)
+    want = (p.log() + (-p).log1p()).sum((1, 2))
+    got = (ll0[:64] + ll1[:64]).double()
+    assert ((got - want).abs() <= 2e-5 * want.abs()).all()
+    assert torch.isfinite(ll0).all() and (ll0 < 0).all()
+
+
+def test_multi_image_indexing(ops):
+    from pybpl_b200 import workload
+    w = workload.synth_tokens(64, seed=5, sigma_mode="fixed")
+    batch = workload.to_device(w, DEV)
+    g = torch.Generator().manual_seed(1)
+    imgs = (torch.rand((5, 105, 105), generator=g) < 0.1).to(torch.uint8).to(DEV)
+    packed = ops.pack_images(imgs)
+    idx = torch.arange(64, dtype=torch.int32, device=DEV) % 5
+    ll, _ = ops.score_tokens(batch, packed, idx)
+    for t in range(5):
+        llt, _ = ops.score_tokens(batch, ops.pack_images(imgs[t]))
+        sel = (idx == t)
+        assert ((ll[sel] - llt[sel]).abs() <= 2e-5 * llt[sel].abs()).all()
+
+
+def test_empty_and_ragged(ops):
+    # empty batch
+    z = torch.zeros
+    batch = ops.TokenBatch([0], [0], z((0, 5, 2), device=DEV), z(0, device=DEV), z((0, 2), device=DEV),
+                           z(0, device=DEV), z(0, device=DEV))
+    imgs = ops.pack_images(z((105, 105), dtype=torch.uint8, device=DEV))
+    ll, off = ops.score_tokens(batch, imgs)
+    assert ll.numel() == 0 and off.numel() == 0
+    # a token with zero strokes renders the empty image: ll = 11025 * lp(eps, 0)
+    batch = ops.TokenBatch([0, 0], [0], z((0, 5, 2), device=DEV), z(0, device=DEV), z((0, 2), device=DEV),
+                           torch.tensor([1e-4], device=DEV), torch.tensor([0.5], device=DEV))
+    ll, off = ops.score_tokens(batch, imgs)
+    want = torch.distributions.Bernoulli(probs=torch.full((105, 105), 1e-4)).log_prob(torch.zeros(105, 105)).sum()
+    assert abs(ll.item() - want.item()) <= 1e-5 * abs(want.item())
+    assert not bool(off[0])
+
+
+def test_logsumexp_partial(ops):
+    g = torch.Generator().manual_seed(0)
+    ll = (-2000 * torch.rand(100000, generator=g) - 50).to(DEV)
+    out = ops.logsumexp_partial(ll)
+    got = out[0].item() + np.log(out[1].item())
+    assert abs(got - torch.logsumexp(ll.double(), 0).item()) < 1e-4
+
+
+def test_library_fails_loudly_without_cuda_tensors(ops):
+    from pybpl_b200 import _lib
+    with pytest.raises(_lib.BplError):
+        ops.TokenBatch([0, 0], [0], torch.zeros((0, 5, 2)), torch.zeros(0), torch.zeros((0, 2)), torch.zeros(1),
+                       torch.zeros(1))
