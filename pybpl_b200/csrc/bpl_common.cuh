@@ -122,19 +122,20 @@ struct LoadMin1 { __device__ __forceinline__ float operator()(float v) const { r
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void pixel_lp(float p, bool x, bool want_grad, float &lp, float &dlp) {
     const float pt = fminf(fmaxf(p, TORCH_EPS), 1.0f - TORCH_EPS);
-    const float l = logf(pt) - log1pf(-pt);
-    const float ex = expf(-fabsf(l));
-    const float lg = log1pf(ex);
+    const float L1 = logf(pt), L2 = log1pf(-pt);
+    const float l = L1 - L2;
+    // log1p(exp(-|l|)) equals -log(1-p) for l < 0 and -log(p) for l >= 0 (exp(l) = p/(1-p)); using the
+    // two logs already at hand instead of exp+log1p moves individual pixels by <= 1 ulp(l), with no
+    // common sign (only values repeated across thousands of pixels can bias the sum, and the one such
+    // value -- the background -- is handled exactly by pixel_lp_exact).
+    const float lg = (l < 0.0f) ? -L2 : -L1;
     const float ls = fminf(l, 0.0f) - lg;
-    const float t = x ? 0.0f * l : l;
+    const float t = x ? 0.0f : l;
     lp = -(t - ls);
     if (want_grad) {
-        if (p < TORCH_EPS || p > 1.0f - TORCH_EPS) {
-            dlp = 0.0f;
-        } else {
-            const float sg = (l >= 0.0f) ? 1.0f / (1.0f + ex) : ex / (1.0f + ex);
-            dlp = ((x ? 1.0f : 0.0f) - sg) * (1.0f / p + 1.0f / (1.0f - p));
-        }
+        // autograd: (x - sigmoid(l)) (1/p + 1/(1-p)) = 1/p for x = 1, -1/(1-p) for x = 0; zero outside clamp_probs
+        if (p < TORCH_EPS || p > 1.0f - TORCH_EPS) dlp = 0.0f;
+        else dlp = x ? __frcp_rn(p) : -__frcp_rn(1.0f - p);
     }
 }
 

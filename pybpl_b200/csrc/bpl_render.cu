@@ -212,7 +212,7 @@ __device__ __forceinline__ float final_ink(const Pt &p, const Stats &s) {
 }
 
 // bilinear splat with shared-memory atomics (rendering.py:111-125)
-template <class Src>
+template <int ORG, int STR, class Src>
 __device__ __forceinline__ void substroke_splat(const Src &src, int n, int lane, const RenderConsts &rc,
                                                 const Stats &s, float *img) {
     Walk w{0, 0.0f, 0.0f, 0};
@@ -224,10 +224,10 @@ __device__ __forceinline__ void substroke_splat(const Src &src, int n, int lane,
         const float fr = __fsub_rn(p.r, rf), fc = __fsub_rn(p.c, cf);
         const float gr = __fsub_rn(1.0f, fr), gc = __fsub_rn(1.0f, fc);
         const int r0 = (int)rf, c0 = (int)cf, r1 = (int)rce, c1 = (int)cce;
-        atomicAdd(img + ORIGIN + r0 * STRIDE + c0, __fmul_rn(__fmul_rn(ink, gr), gc));
-        atomicAdd(img + ORIGIN + r1 * STRIDE + c0, __fmul_rn(__fmul_rn(ink, fr), gc));
-        atomicAdd(img + ORIGIN + r0 * STRIDE + c1, __fmul_rn(__fmul_rn(ink, gr), fc));
-        atomicAdd(img + ORIGIN + r1 * STRIDE + c1, __fmul_rn(__fmul_rn(ink, fr), fc));
+        atomicAdd(img + ORG + r0 * STR + c0, __fmul_rn(__fmul_rn(ink, gr), gc));
+        atomicAdd(img + ORG + r1 * STR + c0, __fmul_rn(__fmul_rn(ink, fr), gc));
+        atomicAdd(img + ORG + r0 * STR + c1, __fmul_rn(__fmul_rn(ink, gr), fc));
+        atomicAdd(img + ORG + r1 * STR + c1, __fmul_rn(__fmul_rn(ink, fr), fc));
     }
 }
 
@@ -404,137 +404,11 @@ __device__ __forceinline__ void broaden(float *A, float *T, const RenderConsts &
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// forward kernel
-// ------------------------------------------------------------------------------------------
-constexpr int FWD_THREADS = 256;
-constexpr int FWD_R = 15;       // outputs per sweep item (Gaussian); 7 bands x 105 lines = 735 items
-constexpr int FWD_R3 = 15;
+}  // namespace bpl
 
-struct FwdSmem {
-    float A[BUFP];
-    float B[BUFP];
-    float tab[MAX_TABLE];
-    Misc ms;
-};
+#include "bpl_forward.cuh"
 
-template <bool RAW>
-__global__ void __launch_bounds__(FWD_THREADS, 2) bpl_forward_kernel(const KArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    FwdSmem &sm = *reinterpret_cast<FwdSmem *>(smem_raw);
-    float *A = sm.A, *B = sm.B;
-    Misc *ms = &sm.ms;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-
-    zero_floats(B, BUFP);
-    if (!RAW)
-        for (int i = threadIdx.x; i < a.neval * NCPT; i += blockDim.x) sm.tab[i] = a.basis[i];
-    if (threadIdx.x == 0) ms->cur_img = -1;
-    __syncthreads();
-
-    for (int p = blockIdx.x; p < a.n_tokens; p += gridDim.x) {
-        const TokGeom t = token_geom<RAW>(a, p);
-        const float eps = a.eps[p], sigma = a.sigma[p];
-        if (!RAW && (t.S > MAXS || t.K > MAXK)) {      // beyond the per-CTA tables: flag, do not guess
-            if (threadIdx.x == 0) {
-                if (a.ll) a.ll[p] = nanf("");
-                if (a.off_page) a.off_page[p] = 255;
-            }
-            continue;
-        }
-        const bool aff = !RAW && a.affine != nullptr;
-        zero_floats(A, BUFP);
-        load_image_bits(a, p, ms);
-        token_consts(eps, sigma, false, ms);
-        if (threadIdx.x == 0) ms->off_page = 0;
-        if (!RAW) {
-            chain_offsets(a, t, sm.tab, ms);
-            if (aff) affine_setup(a, t, p, sm.tab, ms);
-        } else {
-            __syncthreads();
-        }
-        if (threadIdx.x == 0 && a.image_bits) ms->cur_img = a.img_idx ? a.img_idx[p] : 0;
-
-        // ---- add_stroke over sub-strokes: one warp each ----
-        bool any_out = false;
-        for (int s = warp; s < t.S; s += nw) {
-            if (RAW) {
-                const int o = a.sub_pt_off[t.s0 + s], n = a.sub_pt_off[t.s0 + s + 1] - o;
-                const RawSrc src{reinterpret_cast<const float2 *>(a.pts) + o};
-                const Stats st = substroke_stats(src, n, lane, a.rc);
-                any_out |= st.any_out;
-                if (st.cnt > 0) substroke_splat(src, n, lane, a.rc, st, A);
-            } else {
-                const CtrlSrc src = make_ctrl_src(a, t, s, sm.tab, ms, aff);
-                const Stats st = substroke_stats(src, a.neval, lane, a.rc);
-                any_out |= st.any_out;
-                if (st.cnt > 0) substroke_splat(src, a.neval, lane, a.rc, st, A);
-            }
-        }
-        if (any_out && lane == 0) atomicOr(&ms->off_page, 1);
-        __syncthreads();
-
-        // ---- broaden + clamp ----
-        broaden<FWD_R3, true>(A, B, a.rc);
-
-        // ---- blur, clamp, mix, likelihood ----
-        const float bgv = eps > 0.0f ? eps : 0.0f;
-        const float om = 1.0f - eps;
-        const float lp_bg0 = ms->lp_bg[0], lp_bg1 = ms->lp_bg[1];
-        const bool score = a.image_bits != nullptr;
-        const bool want_pimg = a.pimg != nullptr;
-        float acc_ll = 0.0f;
-        auto finish = [&](int r, int c, float v, float *dst) {
-            v = fminf(fmaxf(v, 0.0f), 1.0f);                               // clamp_(0,1)  (:180)
-            if (eps > 0.0f) v = __fadd_rn(__fmul_rn(om, v), __fmul_rn(eps, __fsub_rn(1.0f, v)));   // (:227)
-            if (want_pimg) dst[ORIGIN + r * STRIDE + c] = v;
-            if (score) {
-                const bool x = (ms->bits[r * IMG_WORDS + (c >> 5)] >> (c & 31)) & 1u;
-                if (v == bgv) {
-                    acc_ll += x ? lp_bg1 : lp_bg0;
-                } else {
-                    float lp, d;
-                    pixel_lp(v, x, false, lp, d);
-                    acc_ll += lp;
-                }
-            }
-        };
-        if (sigma > 0.0f) {
-            float wg[1][PAD + 1];
-#pragma unroll
-            for (int d = 0; d <= PAD; ++d) wg[0][d] = ms->g[d];
-            auto store_B = [&](int r, int c, const float (&acc)[1]) { B[ORIGIN + r * STRIDE + c] = acc[0]; };
-            auto store_A = [&](int r, int c, const float (&acc)[1]) { A[ORIGIN + r * STRIDE + c] = acc[0]; };
-            sweep<BPL_FSIZE, FWD_R, true, 1>(A, wg, LoadId(), store_B);
-            __syncthreads();
-            sweep<BPL_FSIZE, FWD_R, false, 1>(B, wg, LoadId(), store_A);
-            __syncthreads();
-            sweep<BPL_FSIZE, FWD_R, true, 1>(A, wg, LoadId(), store_B);
-            __syncthreads();
-            sweep<BPL_FSIZE, FWD_R, false, 1>(B, wg, LoadId(),
-                                              [&](int r, int c, const float (&acc)[1]) { finish(r, c, acc[0], A); });
-        } else {
-            for (int i = threadIdx.x; i < NPIX; i += blockDim.x) {
-                const int r = i / IMG, c = i - r * IMG;
-                finish(r, c, A[ORIGIN + r * STRIDE + c], A);
-            }
-        }
-        double v[1] = {(double)acc_ll};
-        block_sum<1>(v, ms->red);      // contains the barriers that order the pimg stores below
-        if (threadIdx.x == 0) {
-            if (a.ll) a.ll[p] = score ? (float)v[0] : 0.0f;
-            if (a.off_page) a.off_page[p] = (uint8_t)(ms->off_page != 0);
-        }
-        if (want_pimg) {
-            float *dst = a.pimg + (size_t)p * NPIX;
-            for (int i = threadIdx.x; i < NPIX; i += blockDim.x) {
-                const int r = i / IMG, c = i - r * IMG;
-                dst[i] = A[ORIGIN + r * STRIDE + c];
-            }
-        }
-        __syncthreads();
-    }
-}
+namespace bpl {
 
 // ------------------------------------------------------------------------------------------
 // fused forward + backward kernel (4 image buffers, one CTA per SM)
@@ -686,12 +560,12 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) bpl_backward_kernel(const KArg
                 const RawSrc src{reinterpret_cast<const float2 *>(a.pts) + o};
                 const Stats st = substroke_stats(src, n, lane, a.rc);
                 any_out |= st.any_out;
-                if (st.cnt > 0) substroke_splat(src, n, lane, a.rc, st, A);
+                if (st.cnt > 0) substroke_splat<ORIGIN, STRIDE>(src, n, lane, a.rc, st, A);
             } else {
                 const CtrlSrc src = make_ctrl_src(a, t, s, sm.tab, ms, aff);
                 const Stats st = substroke_stats(src, a.neval, lane, a.rc);
                 any_out |= st.any_out;
-                if (st.cnt > 0) substroke_splat(src, a.neval, lane, a.rc, st, A);
+                if (st.cnt > 0) substroke_splat<ORIGIN, STRIDE>(src, a.neval, lane, a.rc, st, A);
             }
         }
         if (any_out && lane == 0) atomicOr(&ms->off_page, 1);
@@ -1034,7 +908,7 @@ static int fill_tokens(KArgs &ka, const bpl_token_batch *b) {
     if (!b) { set_error("%s", "batch is NULL"); return BPL_EINVAL; }
     if (b->ncpt != NCPT) { set_error("%s", "fused path is built for ncpt=5 (use bpl_vanilla_to_motor + bpl_render_strokes otherwise)"); return BPL_ELIMIT; }
     if (b->neval < 1 || b->neval * NCPT > MAX_TABLE) { set_error("%s", "neval*ncpt exceeds the shared-memory basis table (use bpl_vanilla_to_motor + bpl_render_strokes)"); return BPL_ELIMIT; }
-    if (!b->tok_stroke_off || !b->stroke_sub_off || !b->ctrl || !b->invscale || !b->position || !b->eps || !b->sigma || !b->basis) {
+    if (!b->tok_stroke_off || !b->stroke_sub_off || !b->eps || !b->sigma || !b->basis) {   // ctrl etc. may be NULL when no token has a stroke
         set_error("%s", "token batch has a NULL array"); return BPL_EINVAL;
     }
     ka.n_tokens = b->n_tokens; ka.neval = b->neval;
@@ -1046,7 +920,7 @@ static int fill_tokens(KArgs &ka, const bpl_token_batch *b) {
 
 static int fill_strokes(KArgs &ka, const bpl_stroke_batch *b) {
     if (!b) { set_error("%s", "batch is NULL"); return BPL_EINVAL; }
-    if (!b->tok_sub_off || !b->sub_pt_off || !b->pts || !b->eps || !b->sigma) {
+    if (!b->tok_sub_off || !b->sub_pt_off || !b->eps || !b->sigma) {
         set_error("%s", "stroke batch has a NULL array"); return BPL_EINVAL;
     }
     ka.n_tokens = b->n_tokens;
@@ -1063,24 +937,27 @@ extern "C" {
 
 int bpl_score_tokens(const bpl_params *ps, const bpl_token_batch *b, const bpl_targets *t, const bpl_fwd_out *out,
                      void *stream) {
+    if (b && b->n_tokens == 0) return 0;
     KArgs ka{};
     int r = fill_common(ka, ps, t, out, nullptr);
     if (r) return r;
     if ((r = fill_tokens(ka, b))) return r;
-    return launch(bpl_forward_kernel<false>, FWD_THREADS, sizeof(FwdSmem), 2, ka, (cudaStream_t)stream);
+    return launch(bpl_forward_kernel<false>, FWD_THREADS, sizeof(FwdSmem), FWD_CTAS_PER_SM, ka, (cudaStream_t)stream);
 }
 
 int bpl_render_strokes(const bpl_params *ps, const bpl_stroke_batch *b, const bpl_targets *t, const bpl_fwd_out *out,
                        void *stream) {
+    if (b && b->n_tokens == 0) return 0;
     KArgs ka{};
     int r = fill_common(ka, ps, t, out, nullptr);
     if (r) return r;
     if ((r = fill_strokes(ka, b))) return r;
-    return launch(bpl_forward_kernel<true>, FWD_THREADS, sizeof(FwdSmem), 2, ka, (cudaStream_t)stream);
+    return launch(bpl_forward_kernel<true>, FWD_THREADS, sizeof(FwdSmem), FWD_CTAS_PER_SM, ka, (cudaStream_t)stream);
 }
 
 int bpl_score_tokens_grad(const bpl_params *ps, const bpl_token_batch *b, const bpl_targets *t,
                           const bpl_fwd_out *out, const bpl_grads *g, void *stream) {
+    if (b && b->n_tokens == 0) return 0;
     KArgs ka{};
     int r = fill_common(ka, ps, t, out, g);
     if (r) return r;
@@ -1092,6 +969,7 @@ int bpl_score_tokens_grad(const bpl_params *ps, const bpl_token_batch *b, const 
 
 int bpl_token_points(const bpl_params *ps, const bpl_token_batch *b, float *motor, uint8_t *mask_out, int *fl, int *ce,
                       int *n_in, void *stream) {
+    if (b && b->n_tokens == 0) return 0;
     KArgs ka{};
     int r = fill_common(ka, ps, nullptr, nullptr, nullptr);
     if (r) return r;
@@ -1107,6 +985,7 @@ int bpl_token_points(const bpl_params *ps, const bpl_token_batch *b, float *moto
 
 int bpl_render_strokes_grad(const bpl_params *ps, const bpl_stroke_batch *b, const bpl_targets *t,
                             const bpl_fwd_out *out, const bpl_grads *g, void *stream) {
+    if (b && b->n_tokens == 0) return 0;
     KArgs ka{};
     int r = fill_common(ka, ps, t, out, g);
     if (r) return r;
