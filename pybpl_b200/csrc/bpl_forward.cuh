@@ -19,12 +19,10 @@ constexpr int FWD_CTAS_PER_SM = 3;
 constexpr int GR = 35;                      // outputs per Gaussian sweep item
 constexpr int GNB = IMG / GR;               // 3 bands
 constexpr int FBUF = (NPIX + 3) / 4 * 4;    // 11028 floats
-constexpr int BR_SPLIT = 53;                // broaden: band 0 = rows [0,53), band 1 = rows [53,105)
-constexpr int NSIDE = 6;                    // warp-boundary columns 31|32, 63|64, 95|96
 
 struct FwdSmem {
     float A[FBUF];
-    float side[NSIDE * IMG];                // copies of the warp-boundary columns for the in-place broaden
+    float side[2 * IMG + 2];                // copies of columns 63 and 64 for the in-place broaden
     float tab[MAX_TABLE];
     Misc ms;
 };
@@ -68,55 +66,68 @@ __device__ __forceinline__ void gauss_inplace(float *buf, const float (&g)[PAD +
 }
 
 // ---- in-place 3x3 broaden (rendering.py:160-168) --------------------------------------------------
-// out = c1 * (1,2,1)x(1,2,1) * in + c2 * in.  Thread = one column of one row band; horizontal
-// neighbours come from the adjacent lanes by shuffle (no shared-memory hazard inside a warp) and, at
-// warp boundaries, from `side` (copied before the pass).  Two bands x four warps.
+// out = c1 * (1,2,1)x(1,2,1) * in + c2 * in.  A thread owns TWO adjacent columns of a 21-row band
+// (5 bands x 2 warps = all 10 warps); the horizontal neighbours of its column pair come from the
+// adjacent lanes by shuffle, so nothing inside a warp is read from shared memory after a neighbour may
+// have overwritten it.  The single warp boundary (columns 63|64) is served from `side`, a copy taken
+// before the pass; band halo rows are preloaded before the barrier.
+constexpr int BR = 21;                      // rows per broaden band
+constexpr int NSIDE = 2;                    // copies of columns 63 and 64
+
 template <bool CLAMP>
 __device__ __forceinline__ void broaden_inplace(float *A, float *side, const RenderConsts &rc) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const bool in_pass = warp < 8;
-    const int band = warp >> 2, wq = warp & 3;
-    const int c = wq * 32 + lane;
-    const bool col_ok = in_pass && c < IMG;
-    const int r0 = band ? BR_SPLIT : 0, r1 = band ? IMG : BR_SPLIT;
-    // side column slots: for warp wq, left neighbour column (32wq-1) is slot 2wq-2, right (32wq+32) is slot 2wq+1
-    const float *sl = side + (wq > 0 ? 2 * wq - 2 : 0) * IMG, *sr = side + (wq < 3 ? 2 * wq + 1 : 0) * IMG;
+    const int band = warp >> 1, half = warp & 1;
+    const int i2 = half * 32 + lane;            // column pair index
+    const int c0 = 2 * i2, c1 = c0 + 1;
+    const bool ok0 = c0 < IMG, ok1 = c1 < IMG;
+    const int a0 = band * BR;
+    const float *side63 = side, *side64 = side + IMG;
+    const float c1w = rc.c1, c2w = rc.c2;
     for (int it = 0; it < rc.ink_ncon; ++it) {
-        // (a) copy warp-boundary columns; preload the halo rows' horizontal sums straight from the image
         for (int i = threadIdx.x; i < NSIDE * IMG; i += blockDim.x) {
-            const int s = i / IMG, r = i - s * IMG;
-            side[i] = A[r * IMG + ((s >> 1) * 32 + 31 + (s & 1))];      // slots 0..5 -> columns 31,32,63,64,95,96
+            const int sidx = i / IMG, r = i - sidx * IMG;
+            side[i] = A[r * IMG + 63 + sidx];
         }
-        float h_prev = 0.0f, h_cur = 0.0f, x_cur = 0.0f, h_trail = 0.0f;
-        auto hsum_direct = [&](int r) -> float {
+        // halo rows (a0-1 and a0+BR): horizontal sums straight from the image (nothing is being written yet)
+        float hp0 = 0.0f, hp1 = 0.0f, ht0 = 0.0f, ht1 = 0.0f;
+        auto hdirect = [&](int r, float &h0, float &h1) {
             const float *row = A + r * IMG;
-            const float xl = (c > 0) ? row[c - 1] : 0.0f, xr = (c < IMG - 1) ? row[c + 1] : 0.0f;
-            return xl + 2.0f * row[c] + xr;
+            const float xl = (ok0 && c0 > 0) ? row[c0 - 1] : 0.0f;
+            const float x0 = ok0 ? row[c0] : 0.0f, x1 = ok1 ? row[c1] : 0.0f;
+            const float xr = (c1 + 1 < IMG) ? row[c1 + 1] : 0.0f;
+            h0 = xl + 2.0f * x0 + x1;
+            h1 = x0 + 2.0f * x1 + xr;
         };
-        if (col_ok) {
-            if (r0 > 0) h_prev = hsum_direct(r0 - 1);
-            if (r1 < IMG) h_trail = hsum_direct(r1);
-        }
+        if (band > 0) hdirect(a0 - 1, hp0, hp1);
+        if (band < IMG / BR - 1) hdirect(a0 + BR, ht0, ht1);
         __syncthreads();
-        if (in_pass) {
-            auto hsum = [&](int r, float &x) -> float {
-                x = col_ok ? A[r * IMG + c] : 0.0f;
-                float xl = __shfl_up_sync(0xffffffffu, x, 1);
-                float xr = __shfl_down_sync(0xffffffffu, x, 1);
-                if (lane == 0) xl = (wq > 0) ? sl[r] : 0.0f;
-                if (lane == 31) xr = (wq < 3) ? sr[r] : 0.0f;      // c = 104 is lane 8 of warp 3: its right lane holds 0
-                return xl + 2.0f * x + xr;
-            };
-            const bool last = CLAMP && (it == rc.ink_ncon - 1);
-            h_cur = hsum(r0, x_cur);
-            for (int r = r0; r < r1; ++r) {
-                float x_next = 0.0f;
-                const float h_next = (r + 1 < r1) ? hsum(r + 1, x_next) : h_trail;
-                float v = fmaf(rc.c1, h_prev + 2.0f * h_cur + h_next, rc.c2 * x_cur);
-                if (last) v = fminf(v, 1.0f);                          // clamp_(max=1)  (:171)
-                if (col_ok) A[r * IMG + c] = v;
-                h_prev = h_cur; h_cur = h_next; x_cur = x_next;
-            }
+        const bool last = CLAMP && (it == rc.ink_ncon - 1);
+        auto hrow = [&](int r, float &x0, float &x1, float &h0, float &h1) {
+            const float *row = A + r * IMG;
+            x0 = ok0 ? row[c0] : 0.0f;
+            x1 = ok1 ? row[c1] : 0.0f;
+            float xl = __shfl_up_sync(0xffffffffu, x1, 1);
+            float xr = __shfl_down_sync(0xffffffffu, x0, 1);
+            const float s63 = side63[r], s64 = side64[r];       // broadcast loads
+            if (lane == 0) xl = half ? s63 : 0.0f;
+            if (lane == 31) xr = half ? 0.0f : s64;
+            h0 = xl + 2.0f * x0 + x1;
+            h1 = x0 + 2.0f * x1 + xr;
+        };
+        float xc0, xc1, hc0, hc1;
+        hrow(a0, xc0, xc1, hc0, hc1);
+#pragma unroll
+        for (int o = 0; o < BR; ++o) {
+            float xn0 = 0.0f, xn1 = 0.0f, hn0 = ht0, hn1 = ht1;
+            if (o + 1 < BR) hrow(a0 + o + 1, xn0, xn1, hn0, hn1);
+            float v0 = fmaf(c1w, hp0 + 2.0f * hc0 + hn0, c2w * xc0);
+            float v1 = fmaf(c1w, hp1 + 2.0f * hc1 + hn1, c2w * xc1);
+            if (last) { v0 = fminf(v0, 1.0f); v1 = fminf(v1, 1.0f); }      // clamp_(max=1)  (:171)
+            float *row = A + (a0 + o) * IMG;
+            if (ok0) row[c0] = v0;
+            if (ok1) row[c1] = v1;
+            hp0 = hc0; hp1 = hc1; hc0 = hn0; hc1 = hn1; xc0 = xn0; xc1 = xn1;
         }
         __syncthreads();
     }
@@ -124,6 +135,116 @@ __device__ __forceinline__ void broaden_inplace(float *A, float *side, const Ren
         for (int i = threadIdx.x; i < NPIX; i += blockDim.x) A[i] = fminf(A[i], 1.0f);
         __syncthreads();
     }
+}
+
+// ---- flat point phase (control-point mode) ---------------------------------------------------------
+// Work item = 32 consecutive points of one sub-stroke, spread over ALL warps of the CTA.  A point's
+// ink is the clamped distance to its previous surviving neighbour (rendering.py:95-99); inside a chunk
+// that neighbour comes by shuffle, before the chunk it is found by a cooperative backward scan (one
+// extra 32-point evaluation in the common case).  The first survivor of a sub-stroke has no
+// predecessor and takes the distance to its successor (= dist[:1], rendering.py:98).  Ink is splatted
+// at once assuming the common branch; the rare min-ink branches (:104-107) need the sub-stroke's
+// total, accumulated in shared memory, and are patched by a second, normally empty, pass.
+struct PEval { float r, c; bool inb; };
+
+__device__ __forceinline__ PEval eval_pt(const CtrlSrc &src, int j, bool valid) {
+    PEval e;
+    float x = 0.0f, y = 0.0f;
+    if (valid) src.point(j, x, y);
+    e.r = -y; e.c = x;
+    e.inb = valid && (e.r >= 0.0f) && (e.r <= (float)(IMG - 1)) && (e.c >= 0.0f) && (e.c <= (float)(IMG - 1));
+    return e;
+}
+
+__device__ __forceinline__ float ink_from(float r, float c, float qr, float qc, const RenderConsts &rc) {
+    const float dr = __fsub_rn(r, qr), dc = __fsub_rn(c, qc);
+    const float dist = __fsqrt_rn(__fadd_rn(__fmul_rn(dr, dr), __fmul_rn(dc, dc)));
+    return __fdiv_rn(__fmul_rn(rc.ink_pp, fminf(dist, rc.ink_max_dist)), rc.ink_max_dist);
+}
+
+__device__ __forceinline__ void splat4(float *img, float r, float c, float ink) {
+    const float rf = floorf(r), cf = floorf(c), rce = ceilf(r), cce = ceilf(c);
+    const float fr = __fsub_rn(r, rf), fc = __fsub_rn(c, cf);
+    const float gr = __fsub_rn(1.0f, fr), gc = __fsub_rn(1.0f, fc);
+    const int r0 = (int)rf, c0 = (int)cf, r1 = (int)rce, c1 = (int)cce;
+    atomicAdd(img + r0 * IMG + c0, __fmul_rn(__fmul_rn(ink, gr), gc));
+    atomicAdd(img + r1 * IMG + c0, __fmul_rn(__fmul_rn(ink, fr), gc));
+    atomicAdd(img + r0 * IMG + c1, __fmul_rn(__fmul_rn(ink, gr), fc));
+    atomicAdd(img + r1 * IMG + c1, __fmul_rn(__fmul_rn(ink, fr), fc));
+}
+
+// FIX = false: splat with the common-branch ink and accumulate (sum, count) into rec->z / rec->w.
+// FIX = true : rec holds the totals; splat (final - common) for the min-ink branches.
+template <bool FIX>
+__device__ __forceinline__ bool chunk_points(const CtrlSrc &src, int n, int base, int lane, const RenderConsts &rc,
+                                             float *img, float4 *rec) {
+    const PEval e = eval_pt(src, base + lane, base + lane < n);
+    const bool out = (base + lane < n) && !e.inb;
+    const unsigned m = __ballot_sync(0xffffffffu, e.inb);
+    if (m == 0u) return out;
+    // predecessor inside the chunk
+    const unsigned lower = m & ((1u << lane) - 1u);
+    const int pl = lower ? (31 - __clz(lower)) : 0;
+    float pr = __shfl_sync(0xffffffffu, e.r, pl), pc = __shfl_sync(0xffffffffu, e.c, pl);
+    // last survivor before the chunk (warp-uniform)
+    bool has_carry = false;
+    float cr = 0.0f, cc = 0.0f;
+    for (int hi = base; hi > 0 && !has_carry; hi -= 32) {
+        const int j = hi - 32 + lane;
+        const PEval q = eval_pt(src, j, j >= 0);
+        const unsigned mq = __ballot_sync(0xffffffffu, q.inb);
+        if (mq) {
+            const int l = 31 - __clz(mq);
+            cr = __shfl_sync(0xffffffffu, q.r, l); cc = __shfl_sync(0xffffffffu, q.c, l);
+            has_carry = true;
+        }
+    }
+    if (!lower) { pr = cr; pc = cc; }
+    const bool has_pred = lower || has_carry;
+    // the sub-stroke's first survivor (no predecessor at all) looks forward instead
+    bool has_succ = false;
+    float nr = 0.0f, nc = 0.0f;
+    if (!has_carry) {
+        const int first = __ffs(m) - 1;
+        const unsigned higher = (first < 31) ? (m & ~((2u << first) - 1u)) : 0u;
+        if (higher) {
+            const int l = __ffs(higher) - 1;
+            nr = __shfl_sync(0xffffffffu, e.r, l); nc = __shfl_sync(0xffffffffu, e.c, l);
+            has_succ = true;
+        } else {
+            for (int lo = base + 32; lo < n && !has_succ; lo += 32) {
+                const PEval q = eval_pt(src, lo + lane, lo + lane < n);
+                const unsigned mq = __ballot_sync(0xffffffffu, q.inb);
+                if (mq) {
+                    const int l = __ffs(mq) - 1;
+                    nr = __shfl_sync(0xffffffffu, q.r, l); nc = __shfl_sync(0xffffffffu, q.c, l);
+                    has_succ = true;
+                }
+            }
+        }
+    }
+    float ink0 = 0.0f;
+    if (e.inb) {
+        if (has_pred) ink0 = ink_from(e.r, e.c, pr, pc, rc);
+        else if (has_succ) ink0 = ink_from(nr, nc, e.r, e.c, rc);
+        else ink0 = rc.ink_pp;                                     // the only survivor  (:93-94)
+    }
+    if (!FIX) {
+        const float tot = warp_sum(ink0);
+        if (lane == 0) {
+            atomicAdd(&rec->z, tot);
+            atomicAdd(reinterpret_cast<int *>(&rec->w), __popc(m));
+        }
+        if (e.inb) splat4(img, e.r, e.c, ink0);
+    } else {
+        const float sum = rec->z;
+        const int cnt = *reinterpret_cast<const int *>(&rec->w);
+        float fin = ink0;
+        if (sum < 2.22e-6f) fin = (float)((double)rc.ink_pp / (double)cnt);      // (:104-105)
+        else fin = __fmul_rn(__fdiv_rn(rc.ink_pp, sum), ink0);                  // (:106-107)
+        if (e.inb) splat4(img, e.r, e.c, fin - ink0);
+    }
+    return out;
 }
 
 template <bool RAW>
@@ -162,24 +283,40 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) bpl_forward_kern
         }
         if (threadIdx.x == 0 && a.image_bits) ms->cur_img = a.img_idx ? a.img_idx[p] : 0;
 
-        // ---- add_stroke over sub-strokes: one warp each ----
+        // ---- add_stroke ----
         bool any_out = false;
-        for (int s = warp; s < t.S; s += nw) {
-            if (RAW) {
+        if (RAW) {          // ragged raw trajectories: one warp per stroke, two passes (not the hot path)
+            for (int s = warp; s < t.S; s += nw) {
                 const int o = a.sub_pt_off[t.s0 + s], n = a.sub_pt_off[t.s0 + s + 1] - o;
                 const RawSrc src{reinterpret_cast<const float2 *>(a.pts) + o};
                 const Stats st = substroke_stats(src, n, lane, a.rc);
                 any_out |= st.any_out;
                 if (st.cnt > 0) substroke_splat<0, IMG>(src, n, lane, a.rc, st, A);
-            } else {
-                const CtrlSrc src = make_ctrl_src(a, t, s, sm.tab, ms, aff);
-                const Stats st = substroke_stats(src, a.neval, lane, a.rc);
-                any_out |= st.any_out;
-                if (st.cnt > 0) substroke_splat<0, IMG>(src, a.neval, lane, a.rc, st, A);
             }
+            any_out = __any_sync(0xffffffffu, any_out);
+            if (any_out && lane == 0) atomicOr(&ms->off_page, 1);
+            __syncthreads();
+        } else {
+            const int per = (a.neval + 31) >> 5, total = t.S * per;
+            for (int ch = warp; ch < total; ch += nw) {
+                const int s = ch / per, base = (ch - s * per) << 5;
+                const CtrlSrc src = make_ctrl_src(a, t, s, sm.tab, ms, aff);
+                any_out |= chunk_points<false>(src, a.neval, base, lane, a.rc, A, &ms->sub[s]);
+            }
+            any_out = __any_sync(0xffffffffu, any_out);
+            if (any_out && lane == 0) atomicOr(&ms->off_page, 1);
+            __syncthreads();
+            for (int ch = warp; ch < total; ch += nw) {          // min-ink branches: normally nothing to do
+                const int s = ch / per, base = (ch - s * per) << 5;
+                const float sum = ms->sub[s].z;
+                const int cnt = __float_as_int(ms->sub[s].w);
+                if (cnt >= 2 && sum < a.rc.ink_pp) {
+                    const CtrlSrc src = make_ctrl_src(a, t, s, sm.tab, ms, aff);
+                    chunk_points<true>(src, a.neval, base, lane, a.rc, A, &ms->sub[s]);
+                }
+            }
+            __syncthreads();
         }
-        if (any_out && lane == 0) atomicOr(&ms->off_page, 1);
-        __syncthreads();
 
         // ---- broaden + clamp ----
         broaden_inplace<true>(A, sm.side, a.rc);
