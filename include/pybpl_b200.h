@@ -22,7 +22,7 @@ extern "C" {
 
 #define BPL_IMSIZE 105          /* pybpl/parameters.py:21  imsize = (105,105) */
 #define BPL_FSIZE 11            /* pybpl/parameters.py:41  fsize */
-#define BPL_IMG_WORDS 4         /* 105 pixels of one image row packed LSB-first into 4 u32 */
+#define BPL_IMG_WORDS 345       /* 11025 pixels, row-major, packed LSB-first: pixel i is bit (i & 31) of word (i >> 5) */
 #define BPL_MAX_SUBSTROKES 128  /* sub-strokes per token handled by one CTA */
 #define BPL_MAX_STROKES 32      /* strokes per token */
 #define BPL_NCPT 5              /* control points per sub-stroke on the fused path (lib_data shape/mu: 1212x10) */
@@ -74,7 +74,7 @@ typedef struct {
 
 /* Target images and where each token's score goes. */
 typedef struct {
-    const uint32_t *image_bits; /* dev [T][105][4] from bpl_pack_images_*; NULL => no scoring */
+    const uint32_t *image_bits; /* dev [T][345] from bpl_pack_images_*; NULL => no scoring */
     const int *img_idx;         /* dev [P] image per token, or NULL => image 0 */
     int n_images;               /* T */
 } bpl_targets;

@@ -14,7 +14,7 @@ c_float_p = ctypes.POINTER(ctypes.c_float)
 vp = ctypes.c_void_p
 
 IMSIZE = 105
-IMG_WORDS = 4
+IMG_WORDS = 345
 NCPT = 5
 MAX_SUBSTROKES = 128
 MAX_STROKES = 32

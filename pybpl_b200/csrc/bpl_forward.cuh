@@ -28,41 +28,56 @@ struct FwdSmem {
 };
 
 // ---- in-place 11-tap pass ---------------------------------------------------------------------------
-// epi(r, c, value, ptr): consumes the output for pixel (r,c); ptr is its location in the buffer.
-template <bool VERT, class Epi>
-__device__ __forceinline__ void gauss_inplace(float *buf, const float (&g)[PAD + 1], Epi epi) {
+// Partially unrolled (blocks of 7 outputs) so that the loop body stays inside the instruction cache:
+// three CTAs in different phases share one SM's instruction fetch, and a fully unrolled 35-output
+// body per pass thrashed it (ncu: stall_no_instruction was the top stall reason).
+constexpr int GU = 7;                       // outputs per unrolled block, GR = 5 * GU
+
+template <bool VERT>
+__device__ __forceinline__ void gauss_inplace(float *buf, const float (&g)[PAD + 1]) {
+    static_assert(GR % GU == 0 && GU > PAD, "block structure");
     constexpr int SA = VERT ? IMG : 1;
     constexpr int SL = VERT ? 1 : IMG;
     const int item = threadIdx.x;
     const bool active = item < GNB * IMG;
     const int band = item / IMG;
     const int line = item - band * IMG;
-    const int a0 = band * GR;
-    float *p = buf + a0 * SA + line * SL;
-    float w[BPL_FSIZE];     // sliding window: w[k] = in[a0 + o - 5 + k]
+    float *p = buf + band * GR * SA + line * SL;
+    float W[GU + 2 * PAD];      // W[0..9]: the ten inputs before the block's first new one; W[10..16]: new inputs
     float trail[PAD];
     if (active) {
 #pragma unroll
         for (int i = 0; i < PAD; ++i) {
-            w[i] = (band > 0) ? p[(i - PAD) * SA] : 0.0f;
+            W[i] = (band > 0) ? p[(i - PAD) * SA] : 0.0f;
             trail[i] = (band < GNB - 1) ? p[(GR + i) * SA] : 0.0f;
         }
     }
     __syncthreads();        // every halo is in registers: runs may now be overwritten
-    if (active) {
+    if (!active) return;
 #pragma unroll
-        for (int i = 0; i < PAD; ++i) w[PAD + i] = p[i * SA];
+    for (int i = 0; i < PAD; ++i) W[PAD + i] = p[i * SA];
+    auto block = [&](float *q) {
 #pragma unroll
-        for (int o = 0; o < GR; ++o) {
-            w[2 * PAD] = (o + PAD < GR) ? p[(o + PAD) * SA] : trail[o + PAD - GR];
-            float acc = g[0] * w[PAD];
+        for (int u = 0; u < GU; ++u) {
+            float acc = g[0] * W[u + PAD];
 #pragma unroll
-            for (int d = 1; d <= PAD; ++d) acc = fmaf(g[d], w[PAD - d] + w[PAD + d], acc);
-            if (VERT) epi(a0 + o, line, acc, p + o * SA); else epi(line, a0 + o, acc, p + o * SA);
-#pragma unroll
-            for (int k = 0; k < 2 * PAD; ++k) w[k] = w[k + 1];
+            for (int d = 1; d <= PAD; ++d) acc = fmaf(g[d], W[u + PAD - d] + W[u + PAD + d], acc);
+            q[u * SA] = acc;
         }
+    };
+#pragma unroll 1
+    for (int ob = 0; ob < GR - GU; ob += GU) {
+        float *q = p + ob * SA;
+#pragma unroll
+        for (int u = 0; u < GU; ++u) W[2 * PAD + u] = q[(u + PAD) * SA];
+        block(q);
+#pragma unroll
+        for (int k = 0; k < 2 * PAD; ++k) W[k] = W[k + GU];
     }
+    float *q = p + (GR - GU) * SA;
+#pragma unroll
+    for (int u = 0; u < GU; ++u) W[2 * PAD + u] = (u + PAD < GU) ? q[(u + PAD) * SA] : trail[u + PAD - GU];
+    block(q);
 }
 
 // ---- in-place 3x3 broaden (rendering.py:160-168) --------------------------------------------------
@@ -346,29 +361,18 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) bpl_forward_kern
             float g[PAD + 1];
 #pragma unroll
             for (int d = 0; d <= PAD; ++d) g[d] = ms->g[d];
-            auto store = [&](int, int, float v, float *q) { *q = v; };
-            gauss_inplace<true>(A, g, store);
-            __syncthreads();
-            gauss_inplace<false>(A, g, store);
-            __syncthreads();
-            gauss_inplace<true>(A, g, store);
-            __syncthreads();
-            // last pass: thread = (row, 35-column band); its target bits sit in two 32-bit words
-            const int item = threadIdx.x, band = item / IMG, row = item - band * IMG, c0 = band * GR;
-            unsigned long long xbits = 0ull;
-            if (score && item < GNB * IMG) {
-                const uint32_t *bw = ms->bits + row * IMG_WORDS + (c0 >> 5);
-                const unsigned long long lo = bw[0], hi = ((c0 >> 5) + 1 < IMG_WORDS) ? bw[1] : 0u;
-                xbits = (lo | (hi << 32)) >> (c0 & 31);
+#pragma unroll 1
+            for (int rep = 0; rep < 2; ++rep) {          // imfilter twice (rendering.py:176-177); one code copy
+                gauss_inplace<true>(A, g);
+                __syncthreads();
+                gauss_inplace<false>(A, g);
+                __syncthreads();
             }
-            gauss_inplace<false>(A, g, [&](int, int c, float v, float *q) {
-                finish(v, (xbits >> (c - c0)) & 1ull, q); });
-        } else {
-            for (int i = threadIdx.x; i < NPIX; i += blockDim.x) {
-                const int r = i / IMG, c = i - r * IMG;
-                const bool x = score && ((ms->bits[r * IMG_WORDS + (c >> 5)] >> (c & 31)) & 1u);
-                finish(A[i], x, A + i);
-            }
+        }
+        // pointwise tail: lanes on consecutive pixels, the 32 target bits of a warp are one broadcast word
+        for (int i = threadIdx.x; i < NPIX; i += blockDim.x) {
+            const bool x = score && ((ms->bits[i >> 5] >> (i & 31)) & 1u);
+            finish(A[i], x, A + i);
         }
         double v[1] = {(double)acc_ll};
         block_sum<1>(v, ms->red);      // contains the barriers that order the pimg stores below

@@ -57,7 +57,7 @@ struct Misc {
     double aff_acc[4];       // sum gx*prex, sum gy*prey, sum gx, sum gy
     int off_page;
     int cur_img;
-    uint32_t bits[IMG * IMG_WORDS];
+    uint32_t bits[IMG_WORDS + 1];
 };
 
 enum : int { BR_NONE = 0, BR_SINGLE = 1, BR_FILL = 2, BR_RESCALE = 3, BR_NORMAL = 4 };
@@ -368,8 +368,8 @@ __device__ __forceinline__ void load_image_bits(const KArgs &a, int p, Misc *ms)
     if (!a.image_bits) return;
     const int t = a.img_idx ? a.img_idx[p] : 0;
     if (t == ms->cur_img) return;      // cur_img is only written after the barrier below, read before it
-    for (int i = threadIdx.x; i < IMG * IMG_WORDS; i += blockDim.x)
-        ms->bits[i] = a.image_bits[(size_t)t * IMG * IMG_WORDS + i];
+    for (int i = threadIdx.x; i < IMG_WORDS; i += blockDim.x)
+        ms->bits[i] = a.image_bits[(size_t)t * IMG_WORDS + i];
 }
 
 __device__ __forceinline__ void zero_floats(float *p, int n) {
@@ -595,7 +595,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) bpl_backward_kernel(const KArg
             if (gP_ext) {
                 gp = gP_ext[r * IMG + c];
             } else {
-                const bool x = score && ((ms->bits[r * IMG_WORDS + (c >> 5)] >> (c & 31)) & 1u);
+                const bool x = score && ((ms->bits[(r * IMG + c) >> 5] >> ((r * IMG + c) & 31)) & 1u);
                 float lp, d;
                 if (pm == bgv) { lp = x ? lp_bg1 : lp_bg0; d = x ? dlp_bg1 : dlp_bg0; }
                 else pixel_lp(pm, x, true, lp, d);

@@ -166,28 +166,25 @@ __global__ void vanilla_to_motor_kernel(const float *__restrict__ C, int neval, 
     }
 }
 
-// One warp packs one image row: 105 pixels -> 4 words, LSB first.
+// One warp packs 32 consecutive pixels (row-major) into one word, LSB first.
 template <class T>
 __global__ void pack_images_kernel(const T *__restrict__ img, int n_img, uint32_t *__restrict__ bits,
                                    int *__restrict__ bad) {
     const int lane = threadIdx.x & 31;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const long long rows = (long long)n_img * IMG;
-    for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += nwarps) {
-        const T *src = img + row * IMG;
-        bool any_bad = false;
-#pragma unroll
-        for (int w = 0; w < IMG_WORDS; ++w) {
-            const int c = w * 32 + lane;
-            bool one = false;
-            if (c < IMG) {
-                const T v = src[c];
-                one = (v == (T)1);
-                any_bad |= !(v == (T)0 || v == (T)1);
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, one);
-            if (lane == 0) bits[row * IMG_WORDS + w] = m;
+    const long long words = (long long)n_img * IMG_WORDS;
+    for (long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < words; w += nwarps) {
+        const long long t = w / IMG_WORDS;
+        const int k = (int)(w - t * IMG_WORDS);
+        const int i = k * 32 + lane;
+        bool one = false, any_bad = false;
+        if (i < NPIX) {
+            const T v = img[t * NPIX + i];
+            one = (v == (T)1);
+            any_bad = !(v == (T)0 || v == (T)1);
         }
+        const unsigned m = __ballot_sync(0xffffffffu, one);
+        if (lane == 0) bits[w] = m;
         if (any_bad && bad) atomicOr(bad, 1);
     }
 }
@@ -326,14 +323,14 @@ int bpl_vanilla_to_motor(const float *C, int neval, int ncpt, int n_strokes, con
 int bpl_pack_images_u8(const uint8_t *img, int T, uint32_t *bits, int *bad, void *stream) {
     if (!img || !bits || T < 0) { set_error("%s", "bad pack_images arguments"); return BPL_EINVAL; }
     if (T == 0) return 0;
-    pack_images_kernel<uint8_t><<<grid_for((long long)T * IMG * 32, 256), 256, 0, (cudaStream_t)stream>>>(img, T, bits, bad);
+    pack_images_kernel<uint8_t><<<grid_for((long long)T * IMG_WORDS * 32, 256), 256, 0, (cudaStream_t)stream>>>(img, T, bits, bad);
     return check_launch("pack_images_u8");
 }
 
 int bpl_pack_images_f32(const float *img, int T, uint32_t *bits, int *bad, void *stream) {
     if (!img || !bits || T < 0) { set_error("%s", "bad pack_images arguments"); return BPL_EINVAL; }
     if (T == 0) return 0;
-    pack_images_kernel<float><<<grid_for((long long)T * IMG * 32, 256), 256, 0, (cudaStream_t)stream>>>(img, T, bits, bad);
+    pack_images_kernel<float><<<grid_for((long long)T * IMG_WORDS * 32, 256), 256, 0, (cudaStream_t)stream>>>(img, T, bits, bad);
     return check_launch("pack_images_f32");
 }
 

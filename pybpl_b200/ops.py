@@ -99,7 +99,7 @@ def basis_rows(nland, s):
 # target images
 # ---------------------------------------------------------------------------------------------
 class PackedImages:
-    """T binary 105x105 images packed to bit rows on the device ([T,105,4] int32 words, LSB first)."""
+    """T binary 105x105 images bit-packed on the device ([T,345] int32 words; pixel i = bit i&31 of word i>>5)."""
 
     def __init__(self, bits, bad):
         self.bits = bits
@@ -124,7 +124,7 @@ def pack_images(images, validate=True):
         raise ValueError("images must be 105x105")
     T = images.shape[0]
     dev = images.device
-    bits = torch.empty((T, IMSIZE, IMG_WORDS), dtype=torch.int32, device=dev)
+    bits = torch.empty((T, IMG_WORDS), dtype=torch.int32, device=dev)
     bad = torch.zeros((), dtype=torch.int32, device=dev)
     if images.dtype in (torch.uint8, torch.bool):
         src = images.contiguous().view(torch.uint8)
