@@ -122,7 +122,11 @@ struct LoadMin1 { __device__ __forceinline__ float operator()(float v) const { r
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void pixel_lp(float p, bool x, bool want_grad, float &lp, float &dlp) {
     const float pt = fminf(fmaxf(p, TORCH_EPS), 1.0f - TORCH_EPS);
-    const float L1 = logf(pt), L2 = log1pf(-pt);
+    // The log that is large in magnitude may be the 3-ulp hardware one (MUFU.LG2); the one that is
+    // close to zero keeps libm accuracy through log1p.  (1 - pt is exact for pt >= 0.5.)
+    float L1, L2;
+    if (pt < 0.5f) { L1 = __logf(pt); L2 = log1pf(-pt); }
+    else { const float q = 1.0f - pt; L2 = __logf(q); L1 = log1pf(-q); }
     const float l = L1 - L2;
     // log1p(exp(-|l|)) equals -log(1-p) for l < 0 and -log(p) for l >= 0 (exp(l) = p/(1-p)); using the
     // two logs already at hand instead of exp+log1p moves individual pixels by <= 1 ulp(l), with no

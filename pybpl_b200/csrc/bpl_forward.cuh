@@ -370,9 +370,20 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) bpl_forward_kern
             }
         }
         // pointwise tail: lanes on consecutive pixels, the 32 target bits of a warp are one broadcast word
-        for (int i = threadIdx.x; i < NPIX; i += blockDim.x) {
-            const bool x = score && ((ms->bits[i >> 5] >> (i & 31)) & 1u);
-            finish(A[i], x, A + i);
+        if (score && !want_pimg && eps > 0.0f) {        // the scoring hot path, conditions hoisted
+            for (int i = threadIdx.x; i < NPIX; i += blockDim.x) {
+                const bool x = (ms->bits[i >> 5] >> (i & 31)) & 1u;
+                float v = fminf(fmaxf(A[i], 0.0f), 1.0f);
+                v = __fadd_rn(__fmul_rn(om, v), __fmul_rn(eps, __fsub_rn(1.0f, v)));
+                float lp = x ? lp_bg1 : lp_bg0, d;
+                if (v != bgv) pixel_lp(v, x, false, lp, d);
+                acc_ll += lp;
+            }
+        } else {
+            for (int i = threadIdx.x; i < NPIX; i += blockDim.x) {
+                const bool x = score && ((ms->bits[i >> 5] >> (i & 31)) & 1u);
+                finish(A[i], x, A + i);
+            }
         }
         double v[1] = {(double)acc_ll};
         block_sum<1>(v, ms->red);      // contains the barriers that order the pimg stores below
