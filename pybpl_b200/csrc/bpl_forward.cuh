@@ -12,6 +12,8 @@
 // halo of the first/last band being zero.
 #pragma once
 
+#include "bpl_points.cuh"
+
 namespace bpl {
 
 constexpr int FWD_THREADS = 320;            // 3 bands x 105 lines = 315 sweep items, one per thread
@@ -152,116 +154,6 @@ __device__ __forceinline__ void broaden_inplace(float *A, float *side, const Ren
     }
 }
 
-// ---- flat point phase (control-point mode) ---------------------------------------------------------
-// Work item = 32 consecutive points of one sub-stroke, spread over ALL warps of the CTA.  A point's
-// ink is the clamped distance to its previous surviving neighbour (rendering.py:95-99); inside a chunk
-// that neighbour comes by shuffle, before the chunk it is found by a cooperative backward scan (one
-// extra 32-point evaluation in the common case).  The first survivor of a sub-stroke has no
-// predecessor and takes the distance to its successor (= dist[:1], rendering.py:98).  Ink is splatted
-// at once assuming the common branch; the rare min-ink branches (:104-107) need the sub-stroke's
-// total, accumulated in shared memory, and are patched by a second, normally empty, pass.
-struct PEval { float r, c; bool inb; };
-
-__device__ __forceinline__ PEval eval_pt(const CtrlSrc &src, int j, bool valid) {
-    PEval e;
-    float x = 0.0f, y = 0.0f;
-    if (valid) src.point(j, x, y);
-    e.r = -y; e.c = x;
-    e.inb = valid && (e.r >= 0.0f) && (e.r <= (float)(IMG - 1)) && (e.c >= 0.0f) && (e.c <= (float)(IMG - 1));
-    return e;
-}
-
-__device__ __forceinline__ float ink_from(float r, float c, float qr, float qc, const RenderConsts &rc) {
-    const float dr = __fsub_rn(r, qr), dc = __fsub_rn(c, qc);
-    const float dist = __fsqrt_rn(__fadd_rn(__fmul_rn(dr, dr), __fmul_rn(dc, dc)));
-    return __fdiv_rn(__fmul_rn(rc.ink_pp, fminf(dist, rc.ink_max_dist)), rc.ink_max_dist);
-}
-
-__device__ __forceinline__ void splat4(float *img, float r, float c, float ink) {
-    const float rf = floorf(r), cf = floorf(c), rce = ceilf(r), cce = ceilf(c);
-    const float fr = __fsub_rn(r, rf), fc = __fsub_rn(c, cf);
-    const float gr = __fsub_rn(1.0f, fr), gc = __fsub_rn(1.0f, fc);
-    const int r0 = (int)rf, c0 = (int)cf, r1 = (int)rce, c1 = (int)cce;
-    atomicAdd(img + r0 * IMG + c0, __fmul_rn(__fmul_rn(ink, gr), gc));
-    atomicAdd(img + r1 * IMG + c0, __fmul_rn(__fmul_rn(ink, fr), gc));
-    atomicAdd(img + r0 * IMG + c1, __fmul_rn(__fmul_rn(ink, gr), fc));
-    atomicAdd(img + r1 * IMG + c1, __fmul_rn(__fmul_rn(ink, fr), fc));
-}
-
-// FIX = false: splat with the common-branch ink and accumulate (sum, count) into rec->z / rec->w.
-// FIX = true : rec holds the totals; splat (final - common) for the min-ink branches.
-template <bool FIX>
-__device__ __forceinline__ bool chunk_points(const CtrlSrc &src, int n, int base, int lane, const RenderConsts &rc,
-                                             float *img, float4 *rec) {
-    const PEval e = eval_pt(src, base + lane, base + lane < n);
-    const bool out = (base + lane < n) && !e.inb;
-    const unsigned m = __ballot_sync(0xffffffffu, e.inb);
-    if (m == 0u) return out;
-    // predecessor inside the chunk
-    const unsigned lower = m & ((1u << lane) - 1u);
-    const int pl = lower ? (31 - __clz(lower)) : 0;
-    float pr = __shfl_sync(0xffffffffu, e.r, pl), pc = __shfl_sync(0xffffffffu, e.c, pl);
-    // last survivor before the chunk (warp-uniform)
-    bool has_carry = false;
-    float cr = 0.0f, cc = 0.0f;
-    for (int hi = base; hi > 0 && !has_carry; hi -= 32) {
-        const int j = hi - 32 + lane;
-        const PEval q = eval_pt(src, j, j >= 0);
-        const unsigned mq = __ballot_sync(0xffffffffu, q.inb);
-        if (mq) {
-            const int l = 31 - __clz(mq);
-            cr = __shfl_sync(0xffffffffu, q.r, l); cc = __shfl_sync(0xffffffffu, q.c, l);
-            has_carry = true;
-        }
-    }
-    if (!lower) { pr = cr; pc = cc; }
-    const bool has_pred = lower || has_carry;
-    // the sub-stroke's first survivor (no predecessor at all) looks forward instead
-    bool has_succ = false;
-    float nr = 0.0f, nc = 0.0f;
-    if (!has_carry) {
-        const int first = __ffs(m) - 1;
-        const unsigned higher = (first < 31) ? (m & ~((2u << first) - 1u)) : 0u;
-        if (higher) {
-            const int l = __ffs(higher) - 1;
-            nr = __shfl_sync(0xffffffffu, e.r, l); nc = __shfl_sync(0xffffffffu, e.c, l);
-            has_succ = true;
-        } else {
-            for (int lo = base + 32; lo < n && !has_succ; lo += 32) {
-                const PEval q = eval_pt(src, lo + lane, lo + lane < n);
-                const unsigned mq = __ballot_sync(0xffffffffu, q.inb);
-                if (mq) {
-                    const int l = __ffs(mq) - 1;
-                    nr = __shfl_sync(0xffffffffu, q.r, l); nc = __shfl_sync(0xffffffffu, q.c, l);
-                    has_succ = true;
-                }
-            }
-        }
-    }
-    float ink0 = 0.0f;
-    if (e.inb) {
-        if (has_pred) ink0 = ink_from(e.r, e.c, pr, pc, rc);
-        else if (has_succ) ink0 = ink_from(nr, nc, e.r, e.c, rc);
-        else ink0 = rc.ink_pp;                                     // the only survivor  (:93-94)
-    }
-    if (!FIX) {
-        const float tot = warp_sum(ink0);
-        if (lane == 0) {
-            atomicAdd(&rec->z, tot);
-            atomicAdd(reinterpret_cast<int *>(&rec->w), __popc(m));
-        }
-        if (e.inb) splat4(img, e.r, e.c, ink0);
-    } else {
-        const float sum = rec->z;
-        const int cnt = *reinterpret_cast<const int *>(&rec->w);
-        float fin = ink0;
-        if (sum < 2.22e-6f) fin = (float)((double)rc.ink_pp / (double)cnt);      // (:104-105)
-        else fin = __fmul_rn(__fdiv_rn(rc.ink_pp, sum), ink0);                  // (:106-107)
-        if (e.inb) splat4(img, e.r, e.c, fin - ink0);
-    }
-    return out;
-}
-
 template <bool RAW>
 __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) bpl_forward_kernel(const KArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -312,25 +204,43 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) bpl_forward_kern
             if (any_out && lane == 0) atomicOr(&ms->off_page, 1);
             __syncthreads();
         } else {
-            const int per = (a.neval + 31) >> 5, total = t.S * per;
-            for (int ch = warp; ch < total; ch += nw) {
-                const int s = ch / per, base = (ch - s * per) << 5;
-                const CtrlSrc src = make_ctrl_src(a, t, s, sm.tab, ms, aff);
-                any_out |= chunk_points<false>(src, a.neval, base, lane, a.rc, A, &ms->sub[s]);
+            const int QN = (a.neval + PPL - 1) / PPL, items = t.S * QN;
+            for (int base = 0; base < items; base += blockDim.x) {
+                const int item = base + threadIdx.x;
+                const bool active = item < items;
+                const int s = active ? item / QN : 0x7fffffff;
+                CtrlSrc src{};
+                if (active) src = make_ctrl_src(a, t, s, sm.tab, ms, aff);
+                const LaneAcc acc = warp_points<false, 1>(active, src, sm.tab, s, a.neval, active ? item - s * QN : 0, lane,
+                                                          a.rc, A, 0.0f, 0);
+                any_out |= acc.any_out;
+                reduce_by_substroke(active, s, acc.sum, acc.cnt, ms->sub, lane);
             }
             any_out = __any_sync(0xffffffffu, any_out);
             if (any_out && lane == 0) atomicOr(&ms->off_page, 1);
             __syncthreads();
-            for (int ch = warp; ch < total; ch += nw) {          // min-ink branches: normally nothing to do
-                const int s = ch / per, base = (ch - s * per) << 5;
-                const float sum = ms->sub[s].z;
-                const int cnt = __float_as_int(ms->sub[s].w);
-                if (cnt >= 2 && sum < a.rc.ink_pp) {
-                    const CtrlSrc src = make_ctrl_src(a, t, s, sm.tab, ms, aff);
-                    chunk_points<true>(src, a.neval, base, lane, a.rc, A, &ms->sub[s]);
-                }
+            // min-ink branches (rendering.py:104-107): every thread reaches the same verdict from the totals
+            bool need_fix = false;
+            for (int s = 0; s < t.S; ++s) {
+                const float4 v = ms->sub[s];
+                need_fix |= (__float_as_int(v.w) >= 2 && v.z < a.rc.ink_pp);
             }
-            __syncthreads();
+            if (need_fix) {
+                for (int base = 0; base < items; base += blockDim.x) {
+                    const int item = base + threadIdx.x;
+                    bool active = item < items;
+                    const int s = active ? item / QN : 0x7fffffff;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (active) v = ms->sub[s];
+                    active = active && (__float_as_int(v.w) >= 2 && v.z < a.rc.ink_pp);
+                    CtrlSrc src{};
+                    if (active) src = make_ctrl_src(a, t, s, sm.tab, ms, aff);
+                    // inactive lanes keep their sub-stroke id so that the segmented scan still sees run order
+                    warp_points<true, 1>(active, src, sm.tab, s, a.neval, item < items ? item - s * QN : 0, lane, a.rc, A, v.z,
+                                         __float_as_int(v.w));
+                }
+                __syncthreads();
+            }
         }
 
         // ---- broaden + clamp ----

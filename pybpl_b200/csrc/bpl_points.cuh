@@ -1,0 +1,197 @@
+// bpl_points.cuh -- add_stroke (rendering.py:58-127) for control-point tokens, lane-serial layout.
+//
+// A thread owns PPL = 7 CONSECUTIVE points of one sub-stroke and walks them serially, so a point's
+// previous surviving neighbour (out-of-bounds points are dropped before distances are taken,
+// rendering.py:85-98) is simply the thread's own previous iteration; only the neighbour before the
+// run is re-evaluated (one extra spline evaluation, a short backward scan if that one is off the page).
+// The 32 lanes of one shared-memory atomic instruction therefore hold points 7 apart along the stroke:
+// with the earlier one-point-per-lane layout six or more lanes hit the same pixel and the CAS loop that
+// implements a shared-memory float atomicAdd (there is no native one) replayed that many times -- ncu
+// showed it as the top stall and 23 % of all shared-memory wavefronts.
+//
+// Ink is splatted at once assuming the common branch while (sum of ink, survivor count) accumulate per
+// sub-stroke; the rare min-ink branches (rendering.py:104-107) are patched by a second pass with
+// FIX = true that adds (final - common) ink.
+#pragma once
+
+namespace bpl {
+
+constexpr int PPL = 7;      // points per lane
+
+struct PEval { float r, c; bool inb; };
+
+// one trajectory point in image space: spline + chain offset (+ affine), flip (rendering.py:52-53), check_bounds (:27-31)
+__device__ __forceinline__ PEval eval_pt(const CtrlSrc &src, int j, bool valid) {
+    PEval e;
+    float x = 0.0f, y = 0.0f;
+    if (valid) src.point(j, x, y);
+    e.r = -y; e.c = x;
+    e.inb = valid && (e.r >= 0.0f) && (e.r <= (float)(IMG - 1)) && (e.c >= 0.0f) && (e.c <= (float)(IMG - 1));
+    return e;
+}
+
+// ink of a point from the clamped distance to its neighbour (rendering.py:96-99)
+__device__ __forceinline__ float ink_from(float r, float c, float qr, float qc, const RenderConsts &rc) {
+    const float dr = __fsub_rn(r, qr), dc = __fsub_rn(c, qc);
+    const float dist = __fsqrt_rn(__fadd_rn(__fmul_rn(dr, dr), __fmul_rn(dc, dc)));
+    return __fdiv_rn(__fmul_rn(rc.ink_pp, fminf(dist, rc.ink_max_dist)), rc.ink_max_dist);
+}
+
+template <int PIXSTRIDE>
+__device__ __forceinline__ void splat_px(float *img, float r, float c, float ink) {     // rendering.py:111-125
+    const float rf = floorf(r), cf = floorf(c), rce = ceilf(r), cce = ceilf(c);
+    const float fr = __fsub_rn(r, rf), fc = __fsub_rn(c, cf);
+    const float gr = __fsub_rn(1.0f, fr), gc = __fsub_rn(1.0f, fc);
+    const int r0 = (int)rf, c0 = (int)cf, r1 = (int)rce, c1 = (int)cce;
+    atomicAdd(img + PIXSTRIDE * (r0 * IMG + c0), __fmul_rn(__fmul_rn(ink, gr), gc));
+    atomicAdd(img + PIXSTRIDE * (r1 * IMG + c0), __fmul_rn(__fmul_rn(ink, fr), gc));
+    atomicAdd(img + PIXSTRIDE * (r0 * IMG + c1), __fmul_rn(__fmul_rn(ink, gr), fc));
+    atomicAdd(img + PIXSTRIDE * (r1 * IMG + c1), __fmul_rn(__fmul_rn(ink, fr), fc));
+}
+
+struct LaneAcc {
+    float sum;      // sum of common-branch ink of this thread's survivors
+    int cnt;        // survivors
+    bool any_out;
+};
+
+__device__ __forceinline__ CtrlSrc shfl_src(const CtrlSrc &s, int from, const float *tab) {
+    CtrlSrc o;
+    o.tab = tab;        // not s.tab: inactive lanes hold no source at all
+#pragma unroll
+    for (int k = 0; k < NCPT; ++k) {
+        o.yx[k] = __shfl_sync(0xffffffffu, s.yx[k], from);
+        o.yy[k] = __shfl_sync(0xffffffffu, s.yy[k], from);
+    }
+    o.offx = __shfl_sync(0xffffffffu, s.offx, from); o.offy = __shfl_sync(0xffffffffu, s.offy, from);
+    o.aff = __shfl_sync(0xffffffffu, (int)s.aff, from) != 0;
+    o.b0 = __shfl_sync(0xffffffffu, s.b0, from); o.b1 = __shfl_sync(0xffffffffu, s.b1, from);
+    o.b2 = __shfl_sync(0xffffffffu, s.b2, from); o.b3 = __shfl_sync(0xffffffffu, s.b3, from);
+    return o;
+}
+
+// Warp-collective (all 32 lanes call; `active` lanes own run q of sub-stroke `sid`; lanes of a warp hold
+// consecutive runs, so sid is non-decreasing across lanes).  Three steps:
+//  A. every lane evaluates its PPL points and notes its last survivor;
+//  B. a segmented shuffle scan hands every lane the last survivor of the earlier lanes of its sub-stroke;
+//     the part of the warp's first sub-stroke that lies before the warp is searched cooperatively,
+//     32 points per step (a sub-stroke that is entirely off the page costs 7 such steps, not 200);
+//  C. every lane walks its points: ink from the distance to the previous survivor, splat.
+// FIX: fix_sum / fix_cnt are the sub-stroke totals; ink becomes fill or scale*ink and only the
+// difference to the common-branch ink is splatted.
+template <bool FIX, int PIXSTRIDE>
+__device__ __forceinline__ LaneAcc warp_points(bool active, const CtrlSrc &src, const float *tab, int sid, int n, int q,
+                                               int lane, const RenderConsts &rc, float *img, float fix_sum, int fix_cnt) {
+    LaneAcc acc{0.0f, 0, false};
+    const int j0 = q * PPL;
+    // ---- A ----
+    float pr_[PPL], pc_[PPL];
+    unsigned inbm = 0u;
+    bool hv = false;
+    float lr = 0.0f, lc = 0.0f;
+#pragma unroll
+    for (int k = 0; k < PPL; ++k) {
+        const int j = j0 + k;
+        const PEval e = eval_pt(src, j, active && j < n);
+        pr_[k] = e.r; pc_[k] = e.c;
+        acc.any_out |= active && (j < n) && !e.inb;
+        if (e.inb) { inbm |= 1u << k; hv = true; lr = e.r; lc = e.c; }
+    }
+    // ---- B ----
+    bool iv = hv;
+    float ir = lr, ic = lc;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const bool ov = __shfl_up_sync(0xffffffffu, (int)iv, d) != 0;
+        const float orr = __shfl_up_sync(0xffffffffu, ir, d), oc = __shfl_up_sync(0xffffffffu, ic, d);
+        const int os = __shfl_up_sync(0xffffffffu, sid, d);
+        if (lane >= d && os == sid && !iv && ov) { iv = true; ir = orr; ic = oc; }
+    }
+    bool has_prev = __shfl_up_sync(0xffffffffu, (int)iv, 1) != 0;
+    float pr = __shfl_up_sync(0xffffffffu, ir, 1), pc = __shfl_up_sync(0xffffffffu, ic, 1);
+    {
+        const int ps = __shfl_up_sync(0xffffffffu, sid, 1);
+        if (lane == 0 || ps != sid) has_prev = false;
+    }
+    // carry from before the warp, for lanes of the warp's first sub-stroke that still have no predecessor
+    const int sid0 = __shfl_sync(0xffffffffu, sid, 0);
+    const int q0 = __shfl_sync(0xffffffffu, q, 0);
+    const bool act0 = __shfl_sync(0xffffffffu, (int)active, 0) != 0;
+    const bool want = active && hv && !has_prev && sid == sid0;
+    if (act0 && q0 > 0 && __any_sync(0xffffffffu, want)) {
+        const CtrlSrc s0 = shfl_src(src, 0, tab);
+        bool found = false;
+        float cr = 0.0f, cc = 0.0f;
+        for (int hi = q0 * PPL; hi > 0 && !found; hi -= 32) {
+            const int j = hi - 32 + lane;
+            const PEval e = eval_pt(s0, j, j >= 0);
+            const unsigned m = __ballot_sync(0xffffffffu, e.inb);
+            if (m) {
+                const int l = 31 - __clz(m);
+                cr = __shfl_sync(0xffffffffu, e.r, l); cc = __shfl_sync(0xffffffffu, e.c, l);
+                found = true;
+            }
+        }
+        if (found && sid == sid0 && !has_prev) { has_prev = true; pr = cr; pc = cc; }
+    }
+    // ---- C ----
+    float fill = 0.0f, scale = 1.0f;
+    if (FIX) {
+        if (fix_sum < 2.22e-6f) fill = (float)((double)rc.ink_pp / (double)fix_cnt);      // (:104-105)
+        else scale = __fdiv_rn(rc.ink_pp, fix_sum);                                     // (:106-107)
+    }
+    auto emit = [&](float r, float c, float ink0) {
+        if (!FIX) {
+            acc.sum += ink0;
+            splat_px<PIXSTRIDE>(img, r, c, ink0);
+        } else {
+            const float fin = (fix_sum < 2.22e-6f) ? fill : __fmul_rn(scale, ink0);
+            splat_px<PIXSTRIDE>(img, r, c, fin - ink0);
+        }
+    };
+    bool pend = false;          // the sub-stroke's first survivor waits for its successor (dist[:1], :98)
+    float fr = 0.0f, fc = 0.0f;
+#pragma unroll
+    for (int k = 0; k < PPL; ++k) {
+        if (inbm & (1u << k)) {
+            ++acc.cnt;
+            if (has_prev) {
+                const float ink0 = ink_from(pr_[k], pc_[k], pr, pc, rc);
+                emit(pr_[k], pc_[k], ink0);
+                if (pend) { emit(fr, fc, ink0); pend = false; }
+            } else {
+                pend = true; fr = pr_[k]; fc = pc_[k];
+            }
+            has_prev = true; pr = pr_[k]; pc = pc_[k];
+        }
+    }
+    if (pend) {                 // successor beyond the run, or none at all: the only survivor gets ink_pp (:93-94)
+        float ink0 = rc.ink_pp;
+        for (int j = j0 + PPL; j < n; ++j) {
+            const PEval e = eval_pt(src, j, true);
+            if (e.inb) { ink0 = ink_from(e.r, e.c, fr, fc, rc); break; }
+        }
+        emit(fr, fc, ink0);
+    }
+    return acc;
+}
+
+// Add each lane's (sum, cnt) into rec[sid].z / .w, combining the lanes of a warp that share a sub-stroke
+// first (a warp spans at most a few sub-strokes).  All 32 lanes must call this.
+__device__ __forceinline__ void reduce_by_substroke(bool active, int sid, float sum, int cnt, float4 *rec, int lane) {
+    unsigned todo = __ballot_sync(0xffffffffu, active);
+    while (todo) {
+        const int leader = __ffs(todo) - 1;
+        const int cur = __shfl_sync(0xffffffffu, sid, leader);
+        const bool mine = active && sid == cur;
+        const float v = warp_sum(mine ? sum : 0.0f);
+        const int c = __reduce_add_sync(0xffffffffu, mine ? cnt : 0);
+        if (lane == leader) {
+            atomicAdd(&rec[cur].z, v);
+            atomicAdd(reinterpret_cast<int *>(&rec[cur].w), c);
+        }
+        todo &= ~__ballot_sync(0xffffffffu, mine);
+    }
+}
+
+}  // namespace bpl

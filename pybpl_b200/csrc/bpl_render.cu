@@ -304,6 +304,23 @@ __device__ __forceinline__ CtrlSrc make_ctrl_src(const KArgs &a, const TokGeom &
     return src;
 }
 
+__device__ __forceinline__ CtrlSrc make_ctrl_src_p(const KArgs &a, const TokGeom &t, int s, const float *tab,
+                                                   const float4 off, const float *affB, bool aff) {
+    CtrlSrc src;
+    src.tab = tab;
+    const float inv = a.invscale[t.s0 + s];
+    const float *cp = a.ctrl + (size_t)(t.s0 + s) * NCPT * 2;
+#pragma unroll
+    for (int k = 0; k < NCPT; ++k) {
+        src.yx[k] = __fmul_rn(inv, cp[2 * k]);
+        src.yy[k] = __fmul_rn(inv, cp[2 * k + 1]);
+    }
+    src.offx = off.x; src.offy = off.y;
+    src.aff = aff;
+    src.b0 = affB[0]; src.b1 = affB[1]; src.b2 = affB[2]; src.b3 = affB[3];
+    return src;
+}
+
 // com_char (util/stroke.py:134-135) and B (affine.py:48-53).  All S*neval points, in-bounds or not.
 __device__ __forceinline__ void affine_setup(const KArgs &a, const TokGeom &t, int p, const float *tab, Misc *ms) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -333,9 +350,9 @@ __device__ __forceinline__ void affine_setup(const KArgs &a, const TokGeom &t, i
 // Per-token constants computed by a few lanes of the last warp while the others zero buffers:
 // the 1-D Gaussian g (K = g (x) g exactly: fspecial normalises by sum(E) = (sum e)^2,
 // util/general.py:196-207), h~ for d/dsigma, and the background log-prob constants.
-__device__ __forceinline__ void token_consts(float eps, float sigma, bool grad, Misc *ms) {
+__device__ __forceinline__ void token_consts(float eps, float sigma, bool grad, Misc *ms, int wsel = 0) {
     const int lane = threadIdx.x & 31;
-    if ((int)(threadIdx.x >> 5) != (int)(blockDim.x >> 5) - 1) return;
+    if ((int)(threadIdx.x >> 5) != (int)(blockDim.x >> 5) - 1 - wsel) return;     // wsel-th warp from the end
     // lanes 0..5: e[d] = exp(-0.5 (d/sigma)^2)
     double e = 0.0;
     if (lane <= PAD && sigma > 0.0f) {
@@ -407,6 +424,7 @@ __device__ __forceinline__ void broaden(float *A, float *T, const RenderConsts &
 }  // namespace bpl
 
 #include "bpl_forward.cuh"
+#include "bpl_forward2.cuh"
 
 namespace bpl {
 
@@ -874,14 +892,16 @@ static DevInfo dev_info() {
 }
 
 template <class K>
-static int launch(K kernel, int threads, size_t smem, int ctas_per_sm, const KArgs &ka, cudaStream_t st) {
+static int launch(K kernel, int threads, size_t smem, int ctas_per_sm, const KArgs &ka, cudaStream_t st,
+                  int work_items = -1) {
     const DevInfo di = dev_info();
     if (!di.ok) { set_error("%s", "no CUDA device"); return BPL_ENODEV; }
     if ((size_t)di.smem_optin < smem) { set_error("%s", "device lacks the shared memory this kernel needs (built for sm_100a)"); return BPL_ENODEV; }
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     int grid = di.sm_count * ctas_per_sm;
-    if (grid > ka.n_tokens) grid = ka.n_tokens;
+    if (work_items < 0) work_items = ka.n_tokens;
+    if (grid > work_items) grid = work_items;
     if (grid <= 0) return 0;
     kernel<<<grid, threads, smem, st>>>(ka);
     count_launch(1);
@@ -942,6 +962,9 @@ int bpl_score_tokens(const bpl_params *ps, const bpl_token_batch *b, const bpl_t
     int r = fill_common(ka, ps, t, out, nullptr);
     if (r) return r;
     if ((r = fill_tokens(ka, b))) return r;
+    if (ka.image_bits && !ka.pimg)      // scoring hot path: two tokens per CTA, packed FP32 stencils
+        return launch(bpl_forward2_kernel, F2_THREADS, sizeof(Fwd2Smem), F2_CTAS_PER_SM, ka, (cudaStream_t)stream,
+                      (ka.n_tokens + 1) / 2);
     return launch(bpl_forward_kernel<false>, FWD_THREADS, sizeof(FwdSmem), FWD_CTAS_PER_SM, ka, (cudaStream_t)stream);
 }
 
