@@ -140,14 +140,35 @@ __device__ __forceinline__ LaneAcc warp_points(bool active, const CtrlSrc &src, 
         if (fix_sum < 2.22e-6f) fill = (float)((double)rc.ink_pp / (double)fix_cnt);      // (:104-105)
         else scale = __fdiv_rn(rc.ink_pp, fix_sum);                                     // (:106-107)
     }
-    auto emit = [&](float r, float c, float ink0) {
-        if (!FIX) {
-            acc.sum += ink0;
-            splat_px<PIXSTRIDE>(img, r, c, ink0);
-        } else {
-            const float fin = (fix_sum < 2.22e-6f) ? fill : __fmul_rn(scale, ink0);
-            splat_px<PIXSTRIDE>(img, r, c, fin - ink0);
+    // Consecutive points of a run mostly fall into the same pixel cell: their four corner contributions are
+    // summed in registers and flushed with one set of atomics when the cell changes (2-4x fewer atomics).
+    int cell = -1;
+    float a00 = 0.0f, a10 = 0.0f, a01 = 0.0f, a11 = 0.0f;
+    auto flush = [&]() {
+        if (cell >= 0) {
+            const int r0 = cell & 127, c0 = (cell >> 7) & 127, r1 = r0 + ((cell >> 14) & 1), c1 = c0 + ((cell >> 15) & 1);
+            atomicAdd(img + PIXSTRIDE * (r0 * IMG + c0), a00);
+            atomicAdd(img + PIXSTRIDE * (r1 * IMG + c0), a10);
+            atomicAdd(img + PIXSTRIDE * (r0 * IMG + c1), a01);
+            atomicAdd(img + PIXSTRIDE * (r1 * IMG + c1), a11);
         }
+    };
+    auto emit = [&](float r, float c, float ink0) {
+        float ink = ink0;
+        if (!FIX) acc.sum += ink0;
+        else ink = ((fix_sum < 2.22e-6f) ? fill : __fmul_rn(scale, ink0)) - ink0;
+        const float rf = floorf(r), cf = floorf(c), rce = ceilf(r), cce = ceilf(c);      // rendering.py:111-125
+        const float fr_ = __fsub_rn(r, rf), fc_ = __fsub_rn(c, cf);
+        const float gr = __fsub_rn(1.0f, fr_), gc = __fsub_rn(1.0f, fc_);
+        const int key = (int)rf | ((int)cf << 7) | ((int)(rce - rf) << 14) | ((int)(cce - cf) << 15);
+        if (key != cell) {
+            flush();
+            cell = key; a00 = a10 = a01 = a11 = 0.0f;
+        }
+        a00 += __fmul_rn(__fmul_rn(ink, gr), gc);
+        a10 += __fmul_rn(__fmul_rn(ink, fr_), gc);
+        a01 += __fmul_rn(__fmul_rn(ink, gr), fc_);
+        a11 += __fmul_rn(__fmul_rn(ink, fr_), fc_);
     };
     bool pend = false;          // the sub-stroke's first survivor waits for its successor (dist[:1], :98)
     float fr = 0.0f, fc = 0.0f;
@@ -157,8 +178,8 @@ __device__ __forceinline__ LaneAcc warp_points(bool active, const CtrlSrc &src, 
             ++acc.cnt;
             if (has_prev) {
                 const float ink0 = ink_from(pr_[k], pc_[k], pr, pc, rc);
-                emit(pr_[k], pc_[k], ink0);
                 if (pend) { emit(fr, fc, ink0); pend = false; }
+                emit(pr_[k], pc_[k], ink0);
             } else {
                 pend = true; fr = pr_[k]; fc = pc_[k];
             }
@@ -173,6 +194,7 @@ __device__ __forceinline__ LaneAcc warp_points(bool active, const CtrlSrc &src, 
         }
         emit(fr, fc, ink0);
     }
+    flush();
     return acc;
 }
 
