@@ -84,26 +84,36 @@ __device__ __forceinline__ void sweep(const float *__restrict__ in, const float 
     constexpr int NB = IMG / R;
     constexpr int SA = VERT ? STRIDE : 1;   // stride along the sliding axis
     constexpr int SL = VERT ? 1 : STRIDE;   // stride across lanes
+    constexpr int U = 7;                    // outputs per unrolled block (keeps the loop body inside the I-cache)
+    static_assert(R % U == 0, "block structure");
     for (int item = threadIdx.x; item < NB * IMG; item += blockDim.x) {
         const int band = item / IMG;
         const int line = item - band * IMG;
         const int a0 = band * R;
         const float *p = in + ORIGIN + (a0 - HALF) * SA + line * SL;
-        float x[R + TAPS - 1];
+        float x[U + TAPS - 1];              // x[0 .. TAPS-2]: inputs before the block's first new one
 #pragma unroll
-        for (int i = 0; i < R + TAPS - 1; ++i) x[i] = ld(p[i * SA]);
+        for (int i = 0; i < TAPS - 1; ++i) x[i] = ld(p[i * SA]);
+#pragma unroll 1
+        for (int ob = 0; ob < R; ob += U) {
+            const float *q = p + (ob + TAPS - 1) * SA;
 #pragma unroll
-        for (int o = 0; o < R; ++o) {
-            float acc[NF];
+            for (int u = 0; u < U; ++u) x[TAPS - 1 + u] = ld(q[u * SA]);
 #pragma unroll
-            for (int f = 0; f < NF; ++f) acc[f] = w[f][0] * x[o + HALF];
+            for (int u = 0; u < U; ++u) {
+                float acc[NF];
 #pragma unroll
-            for (int d = 1; d <= HALF; ++d) {
-                const float s = x[o + HALF - d] + x[o + HALF + d];
+                for (int f = 0; f < NF; ++f) acc[f] = w[f][0] * x[u + HALF];
 #pragma unroll
-                for (int f = 0; f < NF; ++f) acc[f] = fmaf(w[f][d], s, acc[f]);
+                for (int d = 1; d <= HALF; ++d) {
+                    const float s = x[u + HALF - d] + x[u + HALF + d];
+#pragma unroll
+                    for (int f = 0; f < NF; ++f) acc[f] = fmaf(w[f][d], s, acc[f]);
+                }
+                if (VERT) epi(a0 + ob + u, line, acc); else epi(line, a0 + ob + u, acc);
             }
-            if (VERT) epi(a0 + o, line, acc); else epi(line, a0 + o, acc);
+#pragma unroll
+            for (int k = 0; k < TAPS - 1; ++k) x[k] = x[k + U];
         }
     }
 }

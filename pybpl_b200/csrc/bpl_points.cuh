@@ -79,13 +79,12 @@ __device__ __forceinline__ CtrlSrc shfl_src(const CtrlSrc &s, int from, const fl
 //  C. every lane walks its points: ink from the distance to the previous survivor, splat.
 // FIX: fix_sum / fix_cnt are the sub-stroke totals; ink becomes fill or scale*ink and only the
 // difference to the common-branch ink is splatted.
-template <bool FIX, int PIXSTRIDE>
+template <bool FIX, int PIXSTRIDE, int ROWSTRIDE = IMG, int ORG = 0>
 __device__ __forceinline__ LaneAcc warp_points(bool active, const CtrlSrc &src, const float *tab, int sid, int n, int q,
                                                int lane, const RenderConsts &rc, float *img, float fix_sum, int fix_cnt) {
     LaneAcc acc{0.0f, 0, false};
     const int j0 = q * PPL;
     // ---- A ----
-    float pr_[PPL], pc_[PPL];
     unsigned inbm = 0u;
     bool hv = false;
     float lr = 0.0f, lc = 0.0f;
@@ -93,7 +92,6 @@ __device__ __forceinline__ LaneAcc warp_points(bool active, const CtrlSrc &src, 
     for (int k = 0; k < PPL; ++k) {
         const int j = j0 + k;
         const PEval e = eval_pt(src, j, active && j < n);
-        pr_[k] = e.r; pc_[k] = e.c;
         acc.any_out |= active && (j < n) && !e.inb;
         if (e.inb) { inbm |= 1u << k; hv = true; lr = e.r; lc = e.c; }
     }
@@ -147,10 +145,10 @@ __device__ __forceinline__ LaneAcc warp_points(bool active, const CtrlSrc &src, 
     auto flush = [&]() {
         if (cell >= 0) {
             const int r0 = cell & 127, c0 = (cell >> 7) & 127, r1 = r0 + ((cell >> 14) & 1), c1 = c0 + ((cell >> 15) & 1);
-            atomicAdd(img + PIXSTRIDE * (r0 * IMG + c0), a00);
-            atomicAdd(img + PIXSTRIDE * (r1 * IMG + c0), a10);
-            atomicAdd(img + PIXSTRIDE * (r0 * IMG + c1), a01);
-            atomicAdd(img + PIXSTRIDE * (r1 * IMG + c1), a11);
+            atomicAdd(img + ORG + PIXSTRIDE * (r0 * ROWSTRIDE + c0), a00);
+            atomicAdd(img + ORG + PIXSTRIDE * (r1 * ROWSTRIDE + c0), a10);
+            atomicAdd(img + ORG + PIXSTRIDE * (r0 * ROWSTRIDE + c1), a01);
+            atomicAdd(img + ORG + PIXSTRIDE * (r1 * ROWSTRIDE + c1), a11);
         }
     };
     auto emit = [&](float r, float c, float ink0) {
@@ -170,30 +168,34 @@ __device__ __forceinline__ LaneAcc warp_points(bool active, const CtrlSrc &src, 
         a01 += __fmul_rn(__fmul_rn(ink, gr), fc_);
         a11 += __fmul_rn(__fmul_rn(ink, fr_), fc_);
     };
+    // The walk is a rolled loop that re-evaluates each surviving point (14 instructions) instead of keeping
+    // seven positions in registers: one copy of the splat code, fewer registers, no spills.
     bool pend = false;          // the sub-stroke's first survivor waits for its successor (dist[:1], :98)
-    float fr = 0.0f, fc = 0.0f;
-#pragma unroll
-    for (int k = 0; k < PPL; ++k) {
-        if (inbm & (1u << k)) {
-            ++acc.cnt;
-            if (has_prev) {
-                const float ink0 = ink_from(pr_[k], pc_[k], pr, pc, rc);
-                if (pend) { emit(fr, fc, ink0); pend = false; }
-                emit(pr_[k], pc_[k], ink0);
-            } else {
-                pend = true; fr = pr_[k]; fc = pc_[k];
-            }
-            has_prev = true; pr = pr_[k]; pc = pc_[k];
+    bool have_first = false;    // ... and is splatted last, with that successor's ink
+    float fr = 0.0f, fc = 0.0f, first_ink = 0.0f;
+#pragma unroll 1
+    for (unsigned rest = inbm; rest; rest &= rest - 1u) {
+        const int k = __ffs(rest) - 1;
+        const PEval e = eval_pt(src, j0 + k, true);
+        ++acc.cnt;
+        if (has_prev) {
+            const float ink0 = ink_from(e.r, e.c, pr, pc, rc);
+            if (pend) { first_ink = ink0; have_first = true; pend = false; }
+            emit(e.r, e.c, ink0);
+        } else {
+            pend = true; fr = e.r; fc = e.c;
         }
+        has_prev = true; pr = e.r; pc = e.c;
     }
     if (pend) {                 // successor beyond the run, or none at all: the only survivor gets ink_pp (:93-94)
-        float ink0 = rc.ink_pp;
+        first_ink = rc.ink_pp;
         for (int j = j0 + PPL; j < n; ++j) {
             const PEval e = eval_pt(src, j, true);
-            if (e.inb) { ink0 = ink_from(e.r, e.c, fr, fc, rc); break; }
+            if (e.inb) { first_ink = ink_from(e.r, e.c, fr, fc, rc); break; }
         }
-        emit(fr, fc, ink0);
+        have_first = true;
     }
+    if (have_first) emit(fr, fc, first_ink);
     flush();
     return acc;
 }

@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -572,22 +573,54 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) bpl_backward_kernel(const KArg
 
         // ---- forward: splat ----
         bool any_out = false;
-        for (int s = warp; s < t.S; s += nw) {
-            if (RAW) {
+        if (RAW) {
+            for (int s = warp; s < t.S; s += nw) {
                 const int o = a.sub_pt_off[t.s0 + s], n = a.sub_pt_off[t.s0 + s + 1] - o;
                 const RawSrc src{reinterpret_cast<const float2 *>(a.pts) + o};
                 const Stats st = substroke_stats(src, n, lane, a.rc);
                 any_out |= st.any_out;
                 if (st.cnt > 0) substroke_splat<ORIGIN, STRIDE>(src, n, lane, a.rc, st, A);
-            } else {
-                const CtrlSrc src = make_ctrl_src(a, t, s, sm.tab, ms, aff);
-                const Stats st = substroke_stats(src, a.neval, lane, a.rc);
-                any_out |= st.any_out;
-                if (st.cnt > 0) substroke_splat<ORIGIN, STRIDE>(src, a.neval, lane, a.rc, st, A);
+            }
+            any_out = __any_sync(0xffffffffu, any_out);
+            if (any_out && lane == 0) atomicOr(&ms->off_page, 1);
+            __syncthreads();
+        } else {
+            const int QN = (a.neval + PPL - 1) / PPL, items = t.S * QN;
+            for (int base = 0; base < items; base += blockDim.x) {
+                const int item = base + threadIdx.x;
+                const bool active = item < items;
+                const int s = active ? item / QN : 0x7fffffff;
+                CtrlSrc src{};
+                if (active) src = make_ctrl_src(a, t, s, sm.tab, ms, aff);
+                const LaneAcc acc = warp_points<false, 1, STRIDE, ORIGIN>(active, src, sm.tab, s, a.neval,
+                                                                          active ? item - s * QN : 0, lane, a.rc, A, 0.0f, 0);
+                any_out |= acc.any_out;
+                reduce_by_substroke(active, s, acc.sum, acc.cnt, ms->sub, lane);
+            }
+            any_out = __any_sync(0xffffffffu, any_out);
+            if (any_out && lane == 0) atomicOr(&ms->off_page, 1);
+            __syncthreads();
+            bool need_fix = false;
+            for (int s = 0; s < t.S; ++s) {
+                const float4 v = ms->sub[s];
+                need_fix |= (__float_as_int(v.w) >= 2 && v.z < a.rc.ink_pp);
+            }
+            if (need_fix) {
+                for (int base = 0; base < items; base += blockDim.x) {
+                    const int item = base + threadIdx.x;
+                    bool active = item < items;
+                    const int s = active ? item / QN : 0x7fffffff;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (active) v = ms->sub[s];
+                    active = active && (__float_as_int(v.w) >= 2 && v.z < a.rc.ink_pp);
+                    CtrlSrc src{};
+                    if (active) src = make_ctrl_src(a, t, s, sm.tab, ms, aff);
+                    warp_points<true, 1, STRIDE, ORIGIN>(active, src, sm.tab, s, a.neval, item < items ? item - s * QN : 0,
+                                                         lane, a.rc, A, v.z, __float_as_int(v.w));
+                }
+                __syncthreads();
             }
         }
-        if (any_out && lane == 0) atomicOr(&ms->off_page, 1);
-        __syncthreads();
 
         // ---- forward: broaden; A keeps I2 (pre-clamp); consumers apply min(.,1) on load ----
         broaden<BWD_R3, false>(A, B, a.rc);
@@ -962,7 +995,8 @@ int bpl_score_tokens(const bpl_params *ps, const bpl_token_batch *b, const bpl_t
     int r = fill_common(ka, ps, t, out, nullptr);
     if (r) return r;
     if ((r = fill_tokens(ka, b))) return r;
-    if (ka.image_bits && !ka.pimg)      // scoring hot path: two tokens per CTA, packed FP32 stencils
+    static const bool force_single = getenv("BPL_FORCE_SINGLE") != nullptr;     // profiling aid: one token per CTA
+    if (ka.image_bits && !ka.pimg && !force_single)      // scoring hot path: two tokens per CTA, packed FP32 stencils
         return launch(bpl_forward2_kernel, F2_THREADS, sizeof(Fwd2Smem), F2_CTAS_PER_SM, ka, (cudaStream_t)stream,
                       (ka.n_tokens + 1) / 2);
     return launch(bpl_forward_kernel<false>, FWD_THREADS, sizeof(FwdSmem), FWD_CTAS_PER_SM, ka, (cudaStream_t)stream);
