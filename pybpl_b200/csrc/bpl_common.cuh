@@ -153,6 +153,19 @@ __device__ __forceinline__ void pixel_lp(float p, bool x, bool want_grad, float 
     }
 }
 
+// Forward-only score of one non-background pixel with a single logarithm: lp = log p (x = 1) or
+// log(1 - p) (x = 0).  torch's formulation (above) equals this up to a rounding term of at most ulp(l)/2
+// per pixel with no common sign, i.e. ~1e-7 of |ll| after summation; the one value that is repeated
+// over thousands of pixels (the background) never comes here.  The logarithm's argument a and its
+// complement b = 1 - a are both exact: a < 0.5 takes the hardware log (3 ulp of a value >= 0.69),
+// a >= 0.5 takes log1p(-b), accurate where the result is close to zero.
+__device__ __forceinline__ float pixel_lp_fwd(float p, bool x) {
+    const float pt = fminf(fmaxf(p, TORCH_EPS), 1.0f - TORCH_EPS);
+    const float q = 1.0f - pt;
+    const float a = x ? pt : q, b = x ? q : pt;
+    return (a < 0.5f) ? __logf(a) : log1pf(-b);
+}
+
 // The same in double, each libm result rounded to float (= correctly rounded fp32 libm), used
 // once per token for the background value shared by ~90% of the pixels: a 1-ulp wobble there
 // would be multiplied by ~10^4 pixels.

@@ -15,6 +15,14 @@
 
 namespace bpl {
 
+// Optional per-phase cycle counters (build with -DBPL_PHASE_TIMING; thread 0 of every CTA accumulates
+// clock64() deltas into a.g_pts[blockIdx.x*16 + phase], used only by tools/phase_timing.py).
+#ifdef BPL_PHASE_TIMING
+#define BPL_PT(n) do { if (threadIdx.x == 0) { const long long t1_ = clock64(); pt_acc[n] += t1_ - pt_t0; pt_t0 = t1_; } } while (0)
+#else
+#define BPL_PT(n) do { } while (0)
+#endif
+
 constexpr int F2_THREADS = 320;
 constexpr int F2_CTAS_PER_SM = 2;
 
@@ -154,8 +162,14 @@ __global__ void __launch_bounds__(F2_THREADS, F2_CTAS_PER_SM) bpl_forward2_kerne
 
     for (int i = threadIdx.x; i < a.neval * NCPT; i += blockDim.x) sm.tab[i] = a.basis[i];
     if (threadIdx.x < 2) sm.ms[threadIdx.x].cur_img = -1;
+    zero_floats(reinterpret_cast<float *>(A), 2 * NPIX);      // afterwards the tail of every pair re-zeroes what it reads
     __syncthreads();
 
+#ifdef BPL_PHASE_TIMING
+    long long pt_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long pt_acc2[3] = {0, 0, 0};
+    long long pt_t0 = clock64();
+#endif
     const int npairs = (a.n_tokens + 1) >> 1;
     for (int q = blockIdx.x; q < npairs; q += gridDim.x) {
         const int p0 = 2 * q;
@@ -174,13 +188,13 @@ __global__ void __launch_bounds__(F2_THREADS, F2_CTAS_PER_SM) bpl_forward2_kerne
             eps[k] = a.eps[pt[k]];
             sigma[k] = a.sigma[pt[k]];
         }
-        zero_floats(reinterpret_cast<float *>(A), 2 * NPIX);
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             load_image_bits(a, pt[k], &sm.ms[k]);
             token_consts(eps[k], sigma[k], false, &sm.ms[k], k);
             if (threadIdx.x == 0) sm.ms[k].off_page = 0;
         }
+        BPL_PT(0);      // geometry loads, zeroing, constants (no barrier yet)
         // ---- chain offsets for both tokens (one pair of barriers) ----
         for (int s = threadIdx.x; s < t[0].S + t[1].S; s += blockDim.x) {
             const int k = s >= t[0].S, sl = k ? s - t[0].S : s;
@@ -222,6 +236,7 @@ __global__ void __launch_bounds__(F2_THREADS, F2_CTAS_PER_SM) bpl_forward2_kerne
         }
         if (threadIdx.x < 2 && a.image_bits) sm.ms[threadIdx.x].cur_img = a.img_idx ? a.img_idx[pt[threadIdx.x]] : 0;
 
+        BPL_PT(1);      // chain offsets
         // ---- add_stroke: a thread owns 7 consecutive points of a sub-stroke of either token ----
         const int QN = (a.neval + PPL - 1) / PPL;
         const int it0 = t[0].S * QN, items = it0 + t[1].S * QN;
@@ -242,8 +257,12 @@ __global__ void __launch_bounds__(F2_THREADS, F2_CTAS_PER_SM) bpl_forward2_kerne
             const LaneAcc acc = warp_points<false, 2>(active, src, sm.tab, sid, a.neval, qq, lane, a.rc,
                                                       reinterpret_cast<float *>(A) + k, 0.0f, 0);
             if (k) any1 |= acc.any_out; else any0 |= acc.any_out;
+#ifdef BPL_PHASE_TIMING
+            if (threadIdx.x == 0) { pt_acc2[0] += acc.tA; pt_acc2[1] += acc.tB; pt_acc2[2] += acc.tC; }
+#endif
             reduce_by_substroke(active, sid, acc.sum, acc.cnt, sm.sub, lane);
         }
+        BPL_PT(6);      // (timing) thread 0's own share of the point phase
         any0 = __any_sync(0xffffffffu, any0);
         any1 = __any_sync(0xffffffffu, any1);
         if (lane == 0) {
@@ -251,6 +270,7 @@ __global__ void __launch_bounds__(F2_THREADS, F2_CTAS_PER_SM) bpl_forward2_kerne
             if (any1) atomicOr(&sm.ms[1].off_page, 1);
         }
         __syncthreads();
+        BPL_PT(7);      // (timing) waiting for the slowest warp of the point phase
         // min-ink branches (rendering.py:104-107): every thread reaches the same verdict from the totals
         bool need_fix = false;
         for (int s = 0; s < t[0].S + t[1].S; ++s) {
@@ -280,6 +300,7 @@ __global__ void __launch_bounds__(F2_THREADS, F2_CTAS_PER_SM) bpl_forward2_kerne
             __syncthreads();
         }
 
+        BPL_PT(2);      // point phase
         // ---- broaden + clamp ----
         broaden_inplace2(A, sm.side, a.rc);
         if (a.rc.ink_ncon == 0) {
@@ -290,6 +311,7 @@ __global__ void __launch_bounds__(F2_THREADS, F2_CTAS_PER_SM) bpl_forward2_kerne
             __syncthreads();
         }
 
+        BPL_PT(3);      // broaden
         // ---- blur (a token without blur gets the identity kernel: 1*x + 0*(...) = x exactly) ----
         if (sigma[0] > 0.0f || sigma[1] > 0.0f) {
             float2 g[PAD + 1];
@@ -307,6 +329,7 @@ __global__ void __launch_bounds__(F2_THREADS, F2_CTAS_PER_SM) bpl_forward2_kerne
             }
         }
 
+        BPL_PT(4);      // blur
         // ---- clamp, mix, likelihood ----
         float acc[2] = {0.0f, 0.0f};
         {
@@ -314,16 +337,18 @@ __global__ void __launch_bounds__(F2_THREADS, F2_CTAS_PER_SM) bpl_forward2_kerne
             const float om0 = 1.0f - eps[0], om1 = 1.0f - eps[1];
             const float l00 = sm.ms[0].lp_bg[0], l01 = sm.ms[0].lp_bg[1];
             const float l10 = sm.ms[1].lp_bg[0], l11 = sm.ms[1].lp_bg[1];
+            const float2 zz = make_float2(0.0f, 0.0f);
             for (int i = threadIdx.x; i < NPIX; i += blockDim.x) {
                 const float2 v = A[i];
+                A[i] = zz;                                               // leaves the buffer zeroed for the next pair
                 const bool x0 = (sm.ms[0].bits[i >> 5] >> (i & 31)) & 1u;
                 const bool x1 = (sm.ms[1].bits[i >> 5] >> (i & 31)) & 1u;
                 float u0 = fminf(fmaxf(v.x, 0.0f), 1.0f), u1 = fminf(fmaxf(v.y, 0.0f), 1.0f);      // clamp_(0,1) (:180)
                 if (eps[0] > 0.0f) u0 = __fadd_rn(__fmul_rn(om0, u0), __fmul_rn(eps[0], __fsub_rn(1.0f, u0)));
                 if (eps[1] > 0.0f) u1 = __fadd_rn(__fmul_rn(om1, u1), __fmul_rn(eps[1], __fsub_rn(1.0f, u1)));
-                float lp0 = x0 ? l01 : l00, lp1 = x1 ? l11 : l10, d;
-                if (u0 != bg0) pixel_lp(u0, x0, false, lp0, d);
-                if (u1 != bg1) pixel_lp(u1, x1, false, lp1, d);
+                float lp0 = x0 ? l01 : l00, lp1 = x1 ? l11 : l10;
+                if (u0 != bg0) lp0 = pixel_lp_fwd(u0, x0);
+                if (u1 != bg1) lp1 = pixel_lp_fwd(u1, x1);
                 acc[0] += lp0; acc[1] += lp1;
             }
         }
@@ -337,7 +362,14 @@ __global__ void __launch_bounds__(F2_THREADS, F2_CTAS_PER_SM) bpl_forward2_kerne
             }
         }
         __syncthreads();
+        BPL_PT(5);      // tail + reduction
     }
+#ifdef BPL_PHASE_TIMING
+    if (threadIdx.x == 0 && a.g_pts)
+        for (int i = 0; i < 8; ++i) a.g_pts[blockIdx.x * 16 + i] = (float)pt_acc[i];
+    if (threadIdx.x == 0 && a.g_pts)
+        for (int i = 0; i < 3; ++i) a.g_pts[blockIdx.x * 16 + 8 + i] = (float)pt_acc2[i];
+#endif
 }
 
 }  // namespace bpl

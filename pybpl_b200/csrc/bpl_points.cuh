@@ -53,6 +53,9 @@ struct LaneAcc {
     float sum;      // sum of common-branch ink of this thread's survivors
     int cnt;        // survivors
     bool any_out;
+#ifdef BPL_PHASE_TIMING
+    long long tA, tB, tC;
+#endif
 };
 
 __device__ __forceinline__ CtrlSrc shfl_src(const CtrlSrc &s, int from, const float *tab) {
@@ -82,8 +85,11 @@ __device__ __forceinline__ CtrlSrc shfl_src(const CtrlSrc &s, int from, const fl
 template <bool FIX, int PIXSTRIDE, int ROWSTRIDE = IMG, int ORG = 0>
 __device__ __forceinline__ LaneAcc warp_points(bool active, const CtrlSrc &src, const float *tab, int sid, int n, int q,
                                                int lane, const RenderConsts &rc, float *img, float fix_sum, int fix_cnt) {
-    LaneAcc acc{0.0f, 0, false};
+    LaneAcc acc{};
     const int j0 = q * PPL;
+#ifdef BPL_PHASE_TIMING
+    long long tt0 = clock64();
+#endif
     // ---- A ----
     unsigned inbm = 0u;
     bool hv = false;
@@ -95,6 +101,9 @@ __device__ __forceinline__ LaneAcc warp_points(bool active, const CtrlSrc &src, 
         acc.any_out |= active && (j < n) && !e.inb;
         if (e.inb) { inbm |= 1u << k; hv = true; lr = e.r; lc = e.c; }
     }
+#ifdef BPL_PHASE_TIMING
+    { const long long t1 = clock64(); acc.tA = t1 - tt0; tt0 = t1; }
+#endif
     // ---- B ----
     bool iv = hv;
     float ir = lr, ic = lc;
@@ -132,6 +141,9 @@ __device__ __forceinline__ LaneAcc warp_points(bool active, const CtrlSrc &src, 
         }
         if (found && sid == sid0 && !has_prev) { has_prev = true; pr = cr; pc = cc; }
     }
+#ifdef BPL_PHASE_TIMING
+    { const long long t1 = clock64(); acc.tB = t1 - tt0; tt0 = t1; }
+#endif
     // ---- C ----
     float fill = 0.0f, scale = 1.0f;
     if (FIX) {
@@ -197,6 +209,9 @@ __device__ __forceinline__ LaneAcc warp_points(bool active, const CtrlSrc &src, 
     }
     if (have_first) emit(fr, fc, first_ink);
     flush();
+#ifdef BPL_PHASE_TIMING
+    { const long long t1 = clock64(); acc.tC = t1 - tt0; tt0 = t1; }
+#endif
     return acc;
 }
 

@@ -996,6 +996,9 @@ int bpl_score_tokens(const bpl_params *ps, const bpl_token_batch *b, const bpl_t
     if (r) return r;
     if ((r = fill_tokens(ka, b))) return r;
     static const bool force_single = getenv("BPL_FORCE_SINGLE") != nullptr;     // profiling aid: one token per CTA
+#ifdef BPL_PHASE_TIMING
+    if (const char *pb = getenv("BPL_PT_BUF")) ka.g_pts = reinterpret_cast<float *>(strtoull(pb, nullptr, 10));
+#endif
     if (ka.image_bits && !ka.pimg && !force_single)      // scoring hot path: two tokens per CTA, packed FP32 stencils
         return launch(bpl_forward2_kernel, F2_THREADS, sizeof(Fwd2Smem), F2_CTAS_PER_SM, ka, (cudaStream_t)stream,
                       (ka.n_tokens + 1) / 2);
