@@ -11,6 +11,14 @@
 
 #include "../../include/pybpl_b200.h"
 
+// Optional per-phase cycle counters (build with -DBPL_PHASE_TIMING; thread 0 of every CTA accumulates clock64()
+// deltas, written to a.g_pts[blockIdx.x*16 + phase]; used only by tools/phase_timing.py).
+#ifdef BPL_PHASE_TIMING
+#define BPL_PT(n) do { if (threadIdx.x == 0) { const long long t1_ = clock64(); pt_acc[n] += t1_ - pt_t0; pt_t0 = t1_; } } while (0)
+#else
+#define BPL_PT(n) do { } while (0)
+#endif
+
 namespace bpl {
 
 constexpr int IMG = BPL_IMSIZE;            // 105
@@ -84,7 +92,7 @@ __device__ __forceinline__ void sweep(const float *__restrict__ in, const float 
     constexpr int NB = IMG / R;
     constexpr int SA = VERT ? STRIDE : 1;   // stride along the sliding axis
     constexpr int SL = VERT ? 1 : STRIDE;   // stride across lanes
-    constexpr int U = 7;                    // outputs per unrolled block (keeps the loop body inside the I-cache)
+    constexpr int U = (R % 7 == 0) ? 7 : 5;  // outputs per unrolled block (keeps the loop body inside the I-cache)
     static_assert(R % U == 0, "block structure");
     for (int item = threadIdx.x; item < NB * IMG; item += blockDim.x) {
         const int band = item / IMG;

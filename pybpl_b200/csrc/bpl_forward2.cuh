@@ -15,14 +15,6 @@
 
 namespace bpl {
 
-// Optional per-phase cycle counters (build with -DBPL_PHASE_TIMING; thread 0 of every CTA accumulates
-// clock64() deltas into a.g_pts[blockIdx.x*16 + phase], used only by tools/phase_timing.py).
-#ifdef BPL_PHASE_TIMING
-#define BPL_PT(n) do { if (threadIdx.x == 0) { const long long t1_ = clock64(); pt_acc[n] += t1_ - pt_t0; pt_t0 = t1_; } } while (0)
-#else
-#define BPL_PT(n) do { } while (0)
-#endif
-
 constexpr int F2_THREADS = 320;
 constexpr int F2_CTAS_PER_SM = 2;
 
@@ -133,7 +125,7 @@ __device__ __forceinline__ void broaden_inplace2(float2 *A, float2 *side, const 
         };
         float2 xc0, xc1, hc0, hc1;
         hrow(a0, xc0, xc1, hc0, hc1);
-#pragma unroll 7
+#pragma unroll 21
         for (int o = 0; o < BR; ++o) {
             float2 xn0 = z, xn1 = z, hn0 = ht0, hn1 = ht1;
             if (o + 1 < BR) hrow(a0 + o + 1, xn0, xn1, hn0, hn1);
@@ -365,10 +357,10 @@ __global__ void __launch_bounds__(F2_THREADS, F2_CTAS_PER_SM) bpl_forward2_kerne
         BPL_PT(5);      // tail + reduction
     }
 #ifdef BPL_PHASE_TIMING
-    if (threadIdx.x == 0 && a.g_pts)
-        for (int i = 0; i < 8; ++i) a.g_pts[blockIdx.x * 16 + i] = (float)pt_acc[i];
-    if (threadIdx.x == 0 && a.g_pts)
-        for (int i = 0; i < 3; ++i) a.g_pts[blockIdx.x * 16 + 8 + i] = (float)pt_acc2[i];
+    if (threadIdx.x == 0 && a.pt_buf)
+        for (int i = 0; i < 8; ++i) a.pt_buf[blockIdx.x * 16 + i] = (float)pt_acc[i];
+    if (threadIdx.x == 0 && a.pt_buf)
+        for (int i = 0; i < 3; ++i) a.pt_buf[blockIdx.x * 16 + 8 + i] = (float)pt_acc2[i];
 #endif
 }
 

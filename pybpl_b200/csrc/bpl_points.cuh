@@ -16,7 +16,8 @@
 
 namespace bpl {
 
-constexpr int PPL = 7;      // points per lane
+constexpr int PPL_DEFAULT = 7;      // points per lane (forward kernels)
+constexpr int PPL = PPL_DEFAULT;
 
 struct PEval { float r, c; bool inb; };
 
@@ -82,7 +83,7 @@ __device__ __forceinline__ CtrlSrc shfl_src(const CtrlSrc &s, int from, const fl
 //  C. every lane walks its points: ink from the distance to the previous survivor, splat.
 // FIX: fix_sum / fix_cnt are the sub-stroke totals; ink becomes fill or scale*ink and only the
 // difference to the common-branch ink is splatted.
-template <bool FIX, int PIXSTRIDE, int ROWSTRIDE = IMG, int ORG = 0>
+template <bool FIX, int PIXSTRIDE, int ROWSTRIDE = IMG, int ORG = 0, int PPL = PPL_DEFAULT>
 __device__ __forceinline__ LaneAcc warp_points(bool active, const CtrlSrc &src, const float *tab, int sid, int n, int q,
                                                int lane, const RenderConsts &rc, float *img, float fix_sum, int fix_cnt) {
     LaneAcc acc{};
@@ -213,6 +214,159 @@ __device__ __forceinline__ LaneAcc warp_points(bool active, const CtrlSrc &src, 
     { const long long t1 = clock64(); acc.tC = t1 - tt0; tt0 = t1; }
 #endif
     return acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward of add_stroke in the same lane-serial layout (control-point tokens).
+//   G        image gradient d L / d I0 in the padded layout of the backward kernel (ORG/ROWSTRIDE)
+//   branch   decided from the sub-stroke totals (sum, cnt) the forward pass accumulated
+//   DOT      pre-pass for the rescale branch: only dot = sum_k gink[k] * ink0[k] is accumulated
+// emit(j, gx, gy) receives motor-space (post-warp) point gradients; a point may be emitted several
+// times (own splat, own segment, the next segment).  The sub-stroke's first survivor has the ink of the
+// second (dist[:1], rendering.py:98): its lane looks up its successor and differentiates that copy itself.
+// ------------------------------------------------------------------------------------------------
+struct Corner2 { float gink, gr, gc; };
+
+template <int ROWSTRIDE, int ORG>
+__device__ __forceinline__ Corner2 gather_px(const float *G, float r, float c) {
+    const float rf = floorf(r), cf = floorf(c), rce = ceilf(r), cce = ceilf(c);
+    const float fr = r - rf, fc = c - cf, gr = 1.0f - fr, gc = 1.0f - fc;
+    const int r0 = (int)rf, c0 = (int)cf, r1 = (int)rce, c1 = (int)cce;
+    const float G00 = G[ORG + r0 * ROWSTRIDE + c0], G10 = G[ORG + r1 * ROWSTRIDE + c0];
+    const float G01 = G[ORG + r0 * ROWSTRIDE + c1], G11 = G[ORG + r1 * ROWSTRIDE + c1];
+    Corner2 k;
+    k.gink = gr * gc * G00 + fr * gc * G10 + gr * fc * G01 + fr * fc * G11;
+    k.gr = gc * (G10 - G00) + fc * (G11 - G01);
+    k.gc = gr * (G01 - G00) + fr * (G11 - G10);
+    return k;
+}
+
+template <bool DOT, int ROWSTRIDE, int ORG, int PPL, class Emit>
+__device__ __forceinline__ float warp_points_bwd(bool active, const CtrlSrc &src, const float *tab, int sid, int n, int q,
+                                                 int lane, const RenderConsts &rc, const float *G, float sum, int cnt,
+                                                 float dot_in, Emit emit) {
+    const int j0 = q * PPL;
+    // ---- A: own points ----
+    unsigned inbm = 0u;
+    bool hv = false;
+    float lr = 0.0f, lc = 0.0f;
+    int lj = 0;
+#pragma unroll
+    for (int k = 0; k < PPL; ++k) {
+        const int j = j0 + k;
+        const PEval e = eval_pt(src, j, active && j < n);
+        if (e.inb) { inbm |= 1u << k; hv = true; lr = e.r; lc = e.c; lj = j; }
+    }
+    // ---- B: last survivor before the run (position and point index) ----
+    bool iv = hv;
+    float ir = lr, ic = lc;
+    int ij = lj;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const bool ov = __shfl_up_sync(0xffffffffu, (int)iv, d) != 0;
+        const float orr = __shfl_up_sync(0xffffffffu, ir, d), oc = __shfl_up_sync(0xffffffffu, ic, d);
+        const int oj = __shfl_up_sync(0xffffffffu, ij, d), os = __shfl_up_sync(0xffffffffu, sid, d);
+        if (lane >= d && os == sid && !iv && ov) { iv = true; ir = orr; ic = oc; ij = oj; }
+    }
+    bool has_prev = __shfl_up_sync(0xffffffffu, (int)iv, 1) != 0;
+    float pr = __shfl_up_sync(0xffffffffu, ir, 1), pc = __shfl_up_sync(0xffffffffu, ic, 1);
+    int pj = __shfl_up_sync(0xffffffffu, ij, 1);
+    {
+        const int ps = __shfl_up_sync(0xffffffffu, sid, 1);
+        if (lane == 0 || ps != sid) has_prev = false;
+    }
+    const int sid0 = __shfl_sync(0xffffffffu, sid, 0);
+    const int q0 = __shfl_sync(0xffffffffu, q, 0);
+    const bool act0 = __shfl_sync(0xffffffffu, (int)active, 0) != 0;
+    const bool want = active && hv && !has_prev && sid == sid0;
+    if (act0 && q0 > 0 && __any_sync(0xffffffffu, want)) {
+        const CtrlSrc s0 = shfl_src(src, 0, tab);
+        bool found = false;
+        float cr = 0.0f, cc = 0.0f;
+        int cj = 0;
+        for (int hi = q0 * PPL; hi > 0 && !found; hi -= 32) {
+            const int j = hi - 32 + lane;
+            const PEval e = eval_pt(s0, j, j >= 0);
+            const unsigned m = __ballot_sync(0xffffffffu, e.inb);
+            if (m) {
+                const int l = 31 - __clz(m);
+                cr = __shfl_sync(0xffffffffu, e.r, l); cc = __shfl_sync(0xffffffffu, e.c, l);
+                cj = hi - 32 + l;
+                found = true;
+            }
+        }
+        if (found && sid == sid0 && !has_prev) { has_prev = true; pr = cr; pc = cc; pj = cj; }
+    }
+    // ---- C: walk ----
+    const bool fill = sum < 2.22e-6f;                               // (:104-105): constant ink, no distance gradient
+    const bool rescale = !fill && sum < rc.ink_pp;                  // (:106-107)
+    const float sc = rescale ? __fdiv_rn(rc.ink_pp, sum) : 1.0f;
+    const float gsum = rescale ? -dot_in * rc.ink_pp / (sum * sum) : 0.0f;
+    const float fillv = fill ? (float)((double)rc.ink_pp / (double)(cnt > 0 ? cnt : 1)) : 0.0f;
+    float dot = 0.0f;
+    bool pend = false;
+    float fr = 0.0f, fc = 0.0f;
+    int fj = 0;
+    // one segment (earlier point e, later point l): ink0 of the point(s) whose ink it defines, with d L / d ink0 = gi
+    auto segment = [&](float er, float ec, int ej, float lr_, float lc_, int lj_, float gi) {
+        const float dr = __fsub_rn(lr_, er), dc = __fsub_rn(lc_, ec);
+        const float dist = __fsqrt_rn(__fadd_rn(__fmul_rn(dr, dr), __fmul_rn(dc, dc)));
+        if (!fill && dist <= rc.ink_max_dist && dist != 0.0f) {         // clamp passes at the bound; norm' = 0 at 0
+            const float gd = rc.ink_f * gi;
+            const float ur = gd * (dr / dist), uc = gd * (dc / dist);
+            emit(lj_, uc, -ur);        // un-flip: row = -y, col = x
+            emit(ej, -uc, ur);
+        }
+    };
+#pragma unroll 1
+    for (unsigned rest = active ? inbm : 0u; rest; rest &= rest - 1u) {
+        const int j = j0 + __ffs(rest) - 1;
+        const PEval e = eval_pt(src, j, true);
+        const Corner2 K = gather_px<ROWSTRIDE, ORG>(G, e.r, e.c);
+        if (has_prev) {
+            const float ink0 = ink_from(e.r, e.c, pr, pc, rc);
+            if (DOT) {
+                dot = fmaf(K.gink, ink0, dot);
+                if (pend) dot = fmaf(gather_px<ROWSTRIDE, ORG>(G, fr, fc).gink, ink0, dot);
+            } else {
+                const float ink = fill ? fillv : __fmul_rn(sc, ink0);
+                emit(j, ink * K.gc, -(ink * K.gr));
+                segment(pr, pc, pj, e.r, e.c, j, fmaf(K.gink, sc, gsum));
+                if (pend) {             // the first survivor carries a copy of this ink
+                    const Corner2 Kf = gather_px<ROWSTRIDE, ORG>(G, fr, fc);
+                    emit(fj, ink * Kf.gc, -(ink * Kf.gr));
+                    segment(fr, fc, fj, e.r, e.c, j, fmaf(Kf.gink, sc, gsum));
+                }
+            }
+            pend = false;
+        } else {
+            pend = true; fr = e.r; fc = e.c; fj = j;
+        }
+        has_prev = true; pr = e.r; pc = e.c; pj = j;
+    }
+    if (pend) {                 // successor beyond the run, or the only survivor (ink_pp, :93-94)
+        bool found = false;
+        float nr = 0.0f, nc = 0.0f;
+        int nj = 0;
+        for (int j = j0 + PPL; j < n; ++j) {
+            const PEval e = eval_pt(src, j, true);
+            if (e.inb) { found = true; nr = e.r; nc = e.c; nj = j; break; }
+        }
+        const Corner2 Kf = gather_px<ROWSTRIDE, ORG>(G, fr, fc);
+        if (found) {
+            const float ink0 = ink_from(nr, nc, fr, fc, rc);
+            if (DOT) {
+                dot = fmaf(Kf.gink, ink0, dot);
+            } else {
+                const float ink = fill ? fillv : __fmul_rn(sc, ink0);
+                emit(fj, ink * Kf.gc, -(ink * Kf.gr));
+                segment(fr, fc, fj, nr, nc, nj, fmaf(Kf.gink, sc, gsum));
+            }
+        } else if (!DOT) {
+            emit(fj, rc.ink_pp * Kf.gc, -(rc.ink_pp * Kf.gr));
+        }
+    }
+    return dot;
 }
 
 // Add each lane's (sum, cnt) into rec[sid].z / .w, combining the lanes of a warp that share a sub-stroke

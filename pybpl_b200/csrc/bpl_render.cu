@@ -45,12 +45,14 @@ struct KArgs {
     // gradients
     const float *g_ll, *g_pimg;
     float *g_ctrl, *g_invscale, *g_position, *g_affine, *g_pts, *g_eps, *g_sigma;
+    float *pt_buf;           // phase-timing counters (only read by -DBPL_PHASE_TIMING builds)
 };
 
 // Per-CTA bookkeeping in shared memory.
 struct Misc {
     double red[4 * 32];      // block_sum scratch
-    float4 sub[MAXS];        // per sub-stroke: (t0x,t0y,tlastx,tlasty) then (offx,offy,-,-)
+    float4 sub[MAXS];        // per sub-stroke: (t0x,t0y,tlastx,tlasty) then (offx, offy, sum ink, survivors)
+    float dot[MAXS];         // rescale branch: sum_k gink[k] ink0[k] (backward)
     float g[8], ht[8];       // Gaussian half kernel g[d], and h~[d] = (d^2 - mu2) g[d]
     float lp_bg[2], dlp_bg[2];
     float affB[4], com[2];
@@ -432,9 +434,11 @@ namespace bpl {
 // ------------------------------------------------------------------------------------------
 // fused forward + backward kernel (4 image buffers, one CTA per SM)
 // ------------------------------------------------------------------------------------------
-constexpr int BWD_THREADS = 544;   // 17 warps: 5 bands x 105 lines = 525 sweep items in one round
-constexpr int BWD_R = 21;
-constexpr int BWD_R3 = 21;
+constexpr int BWD_THREADS = 768;   // 24 warps: 7 bands x 105 lines = 735 sweep items in one round
+constexpr int BWD_R = 15;
+constexpr int BWD_R3 = 15;
+constexpr int BWD_PPL = 3;         // points per lane in the backward kernel's point stages: the CTA has the SM to
+                                   // itself, so shorter runs (more lanes busy) beat fewer atomic collisions
 constexpr int NACC = 2 * NCPT + 2; // per sub-stroke: W[k].x, W[k].y, Gsum.x, Gsum.y
 
 struct BwdSmem {
@@ -545,6 +549,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) bpl_backward_kernel(const KArg
         }
     }
 
+#ifdef BPL_PHASE_TIMING
+    long long pt_acc[12] = {0};
+    long long pt_t0 = clock64();
+#endif
     for (int p = blockIdx.x; p < a.n_tokens; p += gridDim.x) {
         const TokGeom t = token_geom<RAW>(a, p);
         const float eps = a.eps[p], sigma = a.sigma[p];
@@ -571,6 +579,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) bpl_backward_kernel(const KArg
         }
         if (threadIdx.x == 0 && a.image_bits) ms->cur_img = a.img_idx ? a.img_idx[p] : 0;
 
+        BPL_PT(0);      // setup + chain offsets
         // ---- forward: splat ----
         bool any_out = false;
         if (RAW) {
@@ -585,14 +594,14 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) bpl_backward_kernel(const KArg
             if (any_out && lane == 0) atomicOr(&ms->off_page, 1);
             __syncthreads();
         } else {
-            const int QN = (a.neval + PPL - 1) / PPL, items = t.S * QN;
+            const int QN = (a.neval + BWD_PPL - 1) / BWD_PPL, items = t.S * QN;
             for (int base = 0; base < items; base += blockDim.x) {
                 const int item = base + threadIdx.x;
                 const bool active = item < items;
                 const int s = active ? item / QN : 0x7fffffff;
                 CtrlSrc src{};
                 if (active) src = make_ctrl_src(a, t, s, sm.tab, ms, aff);
-                const LaneAcc acc = warp_points<false, 1, STRIDE, ORIGIN>(active, src, sm.tab, s, a.neval,
+                const LaneAcc acc = warp_points<false, 1, STRIDE, ORIGIN, BWD_PPL>(active, src, sm.tab, s, a.neval,
                                                                           active ? item - s * QN : 0, lane, a.rc, A, 0.0f, 0);
                 any_out |= acc.any_out;
                 reduce_by_substroke(active, s, acc.sum, acc.cnt, ms->sub, lane);
@@ -615,16 +624,18 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) bpl_backward_kernel(const KArg
                     active = active && (__float_as_int(v.w) >= 2 && v.z < a.rc.ink_pp);
                     CtrlSrc src{};
                     if (active) src = make_ctrl_src(a, t, s, sm.tab, ms, aff);
-                    warp_points<true, 1, STRIDE, ORIGIN>(active, src, sm.tab, s, a.neval, item < items ? item - s * QN : 0,
+                    warp_points<true, 1, STRIDE, ORIGIN, BWD_PPL>(active, src, sm.tab, s, a.neval, item < items ? item - s * QN : 0,
                                                          lane, a.rc, A, v.z, __float_as_int(v.w));
                 }
                 __syncthreads();
             }
         }
 
+        BPL_PT(1);      // forward splat (+fix)
         // ---- forward: broaden; A keeps I2 (pre-clamp); consumers apply min(.,1) on load ----
         broaden<BWD_R3, false>(A, B, a.rc);
 
+        BPL_PT(2);      // forward broaden
         const float bgv = eps > 0.0f ? eps : 0.0f;
         const float om = 1.0f - eps;
         const float mixd = eps > 0.0f ? (1.0f - 2.0f * eps) : 1.0f;     // d mix / d I6
@@ -712,9 +723,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) bpl_backward_kernel(const KArg
             }
             __syncthreads();
         }
+        BPL_PT(3);      // blur forward + tail + adjoint blur (9 sweeps)
         // adjoint broaden (symmetric kernel, zero padding): A -> A
         broaden<BWD_R3, false>(A, B, a.rc);
 
+        BPL_PT(4);      // adjoint broaden
         // ---- scalar outputs ----
         {
             double v[3] = {(double)acc_ll, (double)acc_eps, (double)acc_sig};
@@ -730,10 +743,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) bpl_backward_kernel(const KArg
             }
         }
 
+        BPL_PT(5);      // scalar reductions
         // ---- add_stroke backward: gather at the splat points ----
-        float *accs = B;       // [S][NACC] warp-reduced sums per sub-stroke (B is free; interior only)
-        for (int s = warp; s < t.S; s += nw) {
-            if (RAW) {
+        float *accs = B;       // [S][NACC] sums per sub-stroke (B is free; re-zeroed below)
+        if (RAW) {
+            for (int s = warp; s < t.S; s += nw) {
                 const int o = a.sub_pt_off[t.s0 + s], n = a.sub_pt_off[t.s0 + s + 1] - o;
                 const RawSrc src{reinterpret_cast<const float2 *>(a.pts) + o};
                 const Stats st = substroke_stats(src, n, lane, a.rc);
@@ -742,13 +756,60 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) bpl_backward_kernel(const KArg
                     atomicAdd(gp + 2 * j, gx);
                     atomicAdd(gp + 2 * j + 1, gy);
                 });
-            } else {
-                const CtrlSrc src = make_ctrl_src(a, t, s, sm.tab, ms, aff);
-                const Stats st = substroke_stats(src, a.neval, lane, a.rc);
+            }
+            __syncthreads();
+        } else {
+            const int QN = (a.neval + BWD_PPL - 1) / BWD_PPL, items = t.S * QN;
+            // zero the per-sub-stroke accumulators; does any sub-stroke sit in the rescale branch?
+            for (int i = threadIdx.x; i < t.S * NACC; i += blockDim.x) accs[ORIGIN + i] = 0.0f;
+            for (int i = threadIdx.x; i < t.S; i += blockDim.x) ms->dot[i] = 0.0f;
+            bool need_dot = false;
+            for (int s = 0; s < t.S; ++s) {
+                const float4 v = ms->sub[s];
+                need_dot |= (__float_as_int(v.w) >= 2 && v.z >= 2.22e-6f && v.z < a.rc.ink_pp);
+            }
+            __syncthreads();
+            auto noemit = [](int, float, float) {};
+            if (need_dot) {
+                for (int base = 0; base < items; base += blockDim.x) {
+                    const int item = base + threadIdx.x;
+                    bool active = item < items;
+                    const int s = active ? item / QN : 0x7fffffff;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (active) v = ms->sub[s];
+                    active = active && (__float_as_int(v.w) >= 2 && v.z >= 2.22e-6f && v.z < a.rc.ink_pp);
+                    CtrlSrc src{};
+                    if (active) src = make_ctrl_src(a, t, s, sm.tab, ms, aff);
+                    const float d = warp_points_bwd<true, STRIDE, ORIGIN, BWD_PPL>(active, src, sm.tab, s, a.neval,
+                                                                         item < items ? item - s * QN : 0, lane, a.rc, A, v.z,
+                                                                         __float_as_int(v.w), 0.0f, noemit);
+                    unsigned todo = __ballot_sync(0xffffffffu, active);
+                    while (todo) {
+                        const int leader = __ffs(todo) - 1;
+                        const int cur = __shfl_sync(0xffffffffu, s, leader);
+                        const bool mine = active && s == cur;
+                        const float tot = warp_sum(mine ? d : 0.0f);
+                        if (lane == leader) atomicAdd(&ms->dot[cur], tot);
+                        todo &= ~__ballot_sync(0xffffffffu, mine);
+                    }
+                }
+                __syncthreads();
+            }
+            for (int base = 0; base < items; base += blockDim.x) {
+                const int item = base + threadIdx.x;
+                bool active = item < items;
+                const int s = active ? item / QN : 0x7fffffff;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (active) v = ms->sub[s];
+                active = active && __float_as_int(v.w) >= 1;
+                CtrlSrc src{};
+                if (active) src = make_ctrl_src(a, t, s, sm.tab, ms, aff);
                 float wx[NCPT], wy[NCPT], sx = 0.0f, sy = 0.0f, ax = 0.0f, ay = 0.0f;
 #pragma unroll
                 for (int k = 0; k < NCPT; ++k) { wx[k] = 0.0f; wy[k] = 0.0f; }
-                substroke_backward(src, a.neval, lane, a.rc, st, A, [&](int j, float gx, float gy) {
+                warp_points_bwd<false, STRIDE, ORIGIN, BWD_PPL>(active, src, sm.tab, s, a.neval, item < items ? item - s * QN : 0, lane,
+                                                       a.rc, A, v.z, __float_as_int(v.w), active ? ms->dot[s] : 0.0f,
+                                                       [&](int j, float gx, float gy) {
                     const float *row = sm.tab + j * NCPT;
 #pragma unroll
                     for (int k = 0; k < NCPT; ++k) { wx[k] = fmaf(row[k], gx, wx[k]); wy[k] = fmaf(row[k], gy, wy[k]); }
@@ -759,25 +820,34 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) bpl_backward_kernel(const KArg
                         ax = fmaf(gx, px, ax); ay = fmaf(gy, py, ay);
                     }
                 });
-                float *o = accs + ORIGIN + s * NACC;      // inside B's interior rows? no: plain scratch, re-zeroed below
+                // combine the lanes of a warp that share a sub-stroke, then one set of atomics per (warp, sub-stroke)
+                unsigned todo = __ballot_sync(0xffffffffu, active);
+                while (todo) {
+                    const int leader = __ffs(todo) - 1;
+                    const int cur = __shfl_sync(0xffffffffu, s, leader);
+                    const bool mine = active && s == cur;
+                    float *o = accs + ORIGIN + cur * NACC;
 #pragma unroll
-                for (int k = 0; k < NCPT; ++k) {
-                    const float a0 = warp_sum(wx[k]), a1 = warp_sum(wy[k]);
-                    if (lane == 0) { o[2 * k] = a0; o[2 * k + 1] = a1; }
-                }
-                sx = warp_sum(sx); sy = warp_sum(sy);
-                if (lane == 0) { o[2 * NCPT] = sx; o[2 * NCPT + 1] = sy; }
-                if (aff) {
-                    ax = warp_sum(ax); ay = warp_sum(ay);
-                    if (lane == 0) {
-                        atomicAdd(&ms->aff_acc[0], (double)ax); atomicAdd(&ms->aff_acc[1], (double)ay);
-                        atomicAdd(&ms->aff_acc[2], (double)sx); atomicAdd(&ms->aff_acc[3], (double)sy);
+                    for (int k = 0; k < NCPT; ++k) {
+                        const float a0 = warp_sum(mine ? wx[k] : 0.0f), a1 = warp_sum(mine ? wy[k] : 0.0f);
+                        if (lane == leader) { atomicAdd(o + 2 * k, a0); atomicAdd(o + 2 * k + 1, a1); }
                     }
+                    const float tsx = warp_sum(mine ? sx : 0.0f), tsy = warp_sum(mine ? sy : 0.0f);
+                    if (lane == leader) { atomicAdd(o + 2 * NCPT, tsx); atomicAdd(o + 2 * NCPT + 1, tsy); }
+                    if (aff) {
+                        const float tax = warp_sum(mine ? ax : 0.0f), tay = warp_sum(mine ? ay : 0.0f);
+                        if (lane == leader) {
+                            atomicAdd(&ms->aff_acc[0], (double)tax); atomicAdd(&ms->aff_acc[1], (double)tay);
+                            atomicAdd(&ms->aff_acc[2], (double)tsx); atomicAdd(&ms->aff_acc[3], (double)tsy);
+                        }
+                    }
+                    todo &= ~__ballot_sync(0xffffffffu, mine);
                 }
             }
+            __syncthreads();
         }
-        __syncthreads();
 
+        BPL_PT(6);      // add_stroke backward (incl. rescale dot pre-pass)
         // ---- chain backward (part.py:316-326) and control-point gradients ----
         if (!RAW) {
             float gcx = 0.0f, gcy = 0.0f, b0 = 1.0f, b1 = 1.0f;
@@ -832,7 +902,12 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) bpl_backward_kernel(const KArg
             for (int i = threadIdx.x; i < t.S * NACC; i += blockDim.x) accs[ORIGIN + i] = 0.0f;
         }
         __syncthreads();
+        BPL_PT(7);      // chain backward + outputs
     }
+#ifdef BPL_PHASE_TIMING
+    if (threadIdx.x == 0 && a.pt_buf)
+        for (int i = 0; i < 8; ++i) a.pt_buf[blockIdx.x * 16 + i] = (float)pt_acc[i];
+#endif
 }
 
 
@@ -936,7 +1011,11 @@ static int launch(K kernel, int threads, size_t smem, int ctas_per_sm, const KAr
     if (work_items < 0) work_items = ka.n_tokens;
     if (grid > work_items) grid = work_items;
     if (grid <= 0) return 0;
-    kernel<<<grid, threads, smem, st>>>(ka);
+    KArgs kb = ka;
+#ifdef BPL_PHASE_TIMING
+    if (const char *pb = getenv("BPL_PT_BUF")) kb.pt_buf = reinterpret_cast<float *>(strtoull(pb, nullptr, 10));
+#endif
+    kernel<<<grid, threads, smem, st>>>(kb);
     count_launch(1);
     e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("kernel launch: %s", cudaGetErrorString(e)); return (int)e; }
@@ -996,9 +1075,6 @@ int bpl_score_tokens(const bpl_params *ps, const bpl_token_batch *b, const bpl_t
     if (r) return r;
     if ((r = fill_tokens(ka, b))) return r;
     static const bool force_single = getenv("BPL_FORCE_SINGLE") != nullptr;     // profiling aid: one token per CTA
-#ifdef BPL_PHASE_TIMING
-    if (const char *pb = getenv("BPL_PT_BUF")) ka.g_pts = reinterpret_cast<float *>(strtoull(pb, nullptr, 10));
-#endif
     if (ka.image_bits && !ka.pimg && !force_single)      // scoring hot path: two tokens per CTA, packed FP32 stencils
         return launch(bpl_forward2_kernel, F2_THREADS, sizeof(Fwd2Smem), F2_CTAS_PER_SM, ka, (cudaStream_t)stream,
                       (ka.n_tokens + 1) / 2);

@@ -40,3 +40,19 @@ tot = a[:, :8].sum()
 for n, v in zip(names, a.sum(0)):
     print(f"{n:26s} {100 * v / tot:5.1f} %   {v / 296 / (4096 / 2 / 296):9.0f} cycles per pair")
 print("total cycles per pair per CTA", tot / 296 / (4096 / 2 / 296))
+
+# ---- backward kernel (1024 parses, 1 CTA/SM) ----
+acc.zero_()
+wb = workload.permute(w, np.arange(1024))
+bb = workload.to_device(wb, dev, requires_grad=True)
+for _ in range(3):
+    acc.zero_()
+    llb, _ = ops.score_tokens(bb, imgs)
+torch.cuda.synchronize()
+a = acc.view(296, 16)[:148, :8].cpu().numpy()
+names = ["setup + chain offsets", "forward splat (+fix)", "forward broaden", "blur fwd + tail + adjoint blur", "adjoint broaden", "scalar reductions", "add_stroke backward", "chain backward + outputs"]
+tot = a.sum()
+print("backward kernel:")
+for n, v in zip(names, a.sum(0)):
+    print(f"{n:34s} {100 * v / tot:5.1f} %   {v / 148 / (1024 / 148):9.0f} cycles per token")
+print("total cycles per token per CTA", tot / 148 / (1024 / 148))
