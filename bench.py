@@ -29,6 +29,9 @@ METRIC = "rendered+scored 105x105 particles/sec (fwd)"
 UNIT = "particles/s"
 BATCH = 4096
 SEED = 1234
+# dram__bytes_read.sum + dram__bytes_write.sum of one bpl_forward2_kernel launch on this workload, from the
+# ncu --set full capture summarised in profiles/r01_forward2_final.raw.txt (1.330944 MB + 2.56 KB)
+NCU_DRAM_BYTES_PER_LAUNCH = 1333504
 
 
 def flops_fwd(S):      # algorithmic work per particle, separable minimal algorithm
@@ -119,7 +122,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE,
+                                          "-lms", "20", "-i", str(index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -313,7 +316,7 @@ def run_gpu(args):
     k_rate = BATCH / (k_ms * 1e-3)
     ach_tf = k_rate * flops_fwd(Sbar) / 1e12
     roofline = {"bound": "fp32", "achieved": ach_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach_tf / fp32_peak,
-                "traffic": None, "kernel": "bpl_forward_kernel<false>", "kernel_ms": k_ms,
+                "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "kernel": "bpl_forward2_kernel", "kernel_ms": k_ms,
                 "flop_per_particle": flops_fwd(Sbar), "mean_substrokes": Sbar,
                 "peak_source": "live FFMA probe (bpl_fp32_probe) in this run; MEASURED_PEAKS.json holds no CUDA-core FP32 "
                                "figure, and SURVEY.md 8(d) shows the path is FP32-issue/shared-memory bound, not HBM",
