@@ -163,22 +163,37 @@ __global__ void __launch_bounds__(F2_THREADS, F2_CTAS_PER_SM) bpl_forward2_kerne
     long long pt_t0 = clock64();
 #endif
     const int npairs = (a.n_tokens + 1) >> 1;
-    for (int q = blockIdx.x; q < npairs; q += gridDim.x) {
+    // The geometry (two dependent global loads), eps and sigma of the NEXT pair are fetched while the current
+    // pair is processed, so their latency is off the critical path of the prologue.
+    struct PairIn { TokGeom t[2]; float eps[2], sigma[2]; int pt[2]; bool have1; };
+    auto fetch = [&](int q) {
+        PairIn in;
         const int p0 = 2 * q;
-        const bool have1 = p0 + 1 < a.n_tokens;
-        const int pt[2] = {p0, have1 ? p0 + 1 : p0};
-        TokGeom t[2];
-        t[0] = token_geom<false>(a, pt[0]);
-        t[1] = token_geom<false>(a, pt[1]);
-        if (!have1) { t[1].S = 0; t[1].K = 0; }
+        in.have1 = p0 + 1 < a.n_tokens;
+        in.pt[0] = p0; in.pt[1] = in.have1 ? p0 + 1 : p0;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            in.t[k] = token_geom<false>(a, in.pt[k]);
+            in.eps[k] = a.eps[in.pt[k]];
+            in.sigma[k] = a.sigma[in.pt[k]];
+        }
+        if (!in.have1) { in.t[1].S = 0; in.t[1].K = 0; }
+        return in;
+    };
+    PairIn nxt{};
+    if ((int)blockIdx.x < npairs) nxt = fetch(blockIdx.x);
+    for (int q = blockIdx.x; q < npairs; q += gridDim.x) {
+        const PairIn cur = nxt;
+        if (q + (int)gridDim.x < npairs) nxt = fetch(q + gridDim.x);
+        const bool have1 = cur.have1;
+        const int pt[2] = {cur.pt[0], cur.pt[1]};
+        TokGeom t[2] = {cur.t[0], cur.t[1]};
         bool bad[2];
-        float eps[2], sigma[2];
+        float eps[2] = {cur.eps[0], cur.eps[1]}, sigma[2] = {cur.sigma[0], cur.sigma[1]};
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             bad[k] = t[k].S > MAXS || t[k].K > MAXK;      // beyond the per-CTA tables: flagged below, rendered empty
             if (bad[k]) { t[k].S = 0; t[k].K = 0; }
-            eps[k] = a.eps[pt[k]];
-            sigma[k] = a.sigma[pt[k]];
         }
 #pragma unroll
         for (int k = 0; k < 2; ++k) {

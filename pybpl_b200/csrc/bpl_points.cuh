@@ -87,6 +87,7 @@ template <bool FIX, int PIXSTRIDE, int ROWSTRIDE = IMG, int ORG = 0, int PPL = P
 __device__ __forceinline__ LaneAcc warp_points(bool active, const CtrlSrc &src, const float *tab, int sid, int n, int q,
                                                int lane, const RenderConsts &rc, float *img, float fix_sum, int fix_cnt) {
     LaneAcc acc{};
+    if (!__any_sync(0xffffffffu, active)) return acc;      // e.g. the fix pass: most warps have nothing to patch
     const int j0 = q * PPL;
 #ifdef BPL_PHASE_TIMING
     long long tt0 = clock64();
@@ -245,6 +246,7 @@ template <bool DOT, int ROWSTRIDE, int ORG, int PPL, class Emit>
 __device__ __forceinline__ float warp_points_bwd(bool active, const CtrlSrc &src, const float *tab, int sid, int n, int q,
                                                  int lane, const RenderConsts &rc, const float *G, float sum, int cnt,
                                                  float dot_in, Emit emit) {
+    if (!__any_sync(0xffffffffu, active)) return 0.0f;
     const int j0 = q * PPL;
     // ---- A: own points ----
     unsigned inbm = 0u;

@@ -134,3 +134,40 @@ def test_bench_reference_arm_runs():
     import json
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+
+
+def test_dropin_rebinds_reference_call_sites():
+    """dropin.install() must rebind every hot-path name of the reference and uninstall() restore it.
+    Needs the reference checkout (build container only); no compute is run."""
+    ref = os.environ.get("PYBPL_REFERENCE", "/root/reference")
+    if not os.path.isdir(os.path.join(ref, "pybpl")):
+        pytest.skip("reference checkout not present")
+    code = r'''
+import sys, types
+sys.dont_write_bytecode = True
+for name in ("matplotlib", "matplotlib.pyplot"):
+    sys.modules.setdefault(name, types.ModuleType(name))
+sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import pybpl.rendering as R, pybpl.splines as S, pybpl.objects.part as P, pybpl.objects.relation as REL
+import pybpl.model.image_dist as ID
+from pybpl_b200 import dropin, rendering, splines, objects, model
+orig = (R.render_image, ID.render_image, S.get_stk_from_bspline, REL.get_stk_from_bspline, P.vanilla_to_motor,
+        ID.CharacterImageDist.get_pimg, ID.CharacterImageDist.score_image, ID.CharacterImageDist.sample_image)
+dropin.install()
+assert R.render_image is rendering.render_image and ID.render_image is rendering.render_image
+assert S.get_stk_from_bspline is splines.get_stk_from_bspline and REL.get_stk_from_bspline is splines.get_stk_from_bspline
+assert S.bspline_eval is splines.bspline_eval
+assert P.vanilla_to_motor is objects.vanilla_to_motor
+assert ID.CharacterImageDist.get_pimg is model.CharacterImageDist.get_pimg
+assert ID.CharacterImageDist.score_image is model.CharacterImageDist.score_image
+assert ID.CharacterImageDist.sample_image is model.CharacterImageDist.sample_image
+dropin.uninstall()
+now = (R.render_image, ID.render_image, S.get_stk_from_bspline, REL.get_stk_from_bspline, P.vanilla_to_motor,
+       ID.CharacterImageDist.get_pimg, ID.CharacterImageDist.score_image, ID.CharacterImageDist.sample_image)
+assert all(a is b for a, b in zip(orig, now)) and not hasattr(S, "bspline_eval")
+print("dropin ok")
+''' % (ref, ROOT)
+    r = subprocess.run([sys.executable, "-W", "ignore", "-c", code], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                       timeout=240)
+    assert r.returncode == 0 and "dropin ok" in r.stdout, r.stderr[-2000:]

@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Per-phase cycle breakdown of bpl_forward2_kernel.  Builds a -DBPL_PHASE_TIMING copy of the library into /tmp,
-runs the bench workload once and prints the share of each phase (thread 0's clock64 between barriers)."""
+runs the bench workload once and prints the share of each phase (thread 0's clock64 between barriers).
+Caveat: warp 0 has the lowest issue priority, so right after a barrier it resumes late and a few thousand cycles of
+the following phase are booked on the preceding mark; use the split for proportions, not for exact boundaries."""
 import ctypes, os, subprocess, sys
 import numpy as np
 import torch
