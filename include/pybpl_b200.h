@@ -118,6 +118,12 @@ int bpl_spline_eval_bwd(const float *C, int neval, int nland, int nspl, const fl
  * clamp(ceil(dist/grain), min_neval, max_neval); C200 is the [max_neval][nland] table. */
 int bpl_spline_adaptive_neval(const float *C200, int max_neval, int nland, int nspl, const float *Y, float grain,
                               int min_neval, int *neval, float *dist, void *stream);
+/* fit_bspline_to_traj (splines.py:141-171; torch.linalg.lstsq gels = Householder QR): the least-squares operator
+ * P [nland][neval] of a coefficient matrix C [neval][nland] (host, double precision inside); then on the device
+ * Y[b] = P @ X[b] is bpl_spline_eval(P, nland, neval, nspl, X, Y) and the squared residuals are: */
+int bpl_lstsq_operator_host(int neval, int nland, const float *C, float *P);
+int bpl_spline_residual(const float *C, int neval, int nland, int nspl, const float *X, const float *Y, float *resid,
+                        void *stream);
 /* vanilla_to_motor (pybpl/objects/part.py:290-328) for a batch of strokes:
  * stroke_sub_off [K+1]; motor [S][neval][2]; motor_spline [S][ncpt][2] (or NULL). */
 int bpl_vanilla_to_motor(const float *C, int neval, int ncpt, int n_strokes, const int *stroke_sub_off,

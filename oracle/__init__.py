@@ -109,6 +109,14 @@ class Oracle:
         self._f("bplo_adaptive_neval")(_p(C200), C200.shape[1], n, _p(Y), _p(nev), _p(dist))
         return nev, dist
 
+    def lstsq(self, C, X):
+        """fit_bspline_to_traj for a batch: C [m,n], X [b,m,2] -> Y [b,n,2], residuals [b,2]."""
+        C = self._a(C); X = self._a(X)
+        b, m, n = X.shape[0], C.shape[0], C.shape[1]
+        Y = np.empty((b, n, 2), self.dt); res = np.empty((b, 2), self.dt)
+        self._f("bplo_lstsq")(_p(C), m, n, b, _p(X), _p(Y), _p(res))
+        return Y, res
+
     def vanilla_to_motor(self, C, ctrl, invscale, pos):
         C = self._a(C); ctrl = self._a(ctrl); invscale = self._a(invscale); pos = self._a(pos)
         nsub, ncpt = ctrl.shape[0], ctrl.shape[1]

@@ -74,6 +74,10 @@ void bplo_default_params(bplo_params *ps) {
         for (int b = 0; b < nspl; ++b)                                                                             \
             neval[b] = adaptive_neval##SUF(C200, nland, Y + (size_t)b * 2 * nland, dist ? dist + b : NULL);        \
     }                                                                                                              \
+    void bplo_lstsq##SUF(const REAL *C, int m, int n, int nprob, const REAL *X, REAL *Y, REAL *resid) {            \
+        for (int b = 0; b < nprob; ++b)                                                                            \
+            lstsq##SUF(C, m, n, X + (size_t)b * m * 2, Y + (size_t)b * n * 2, resid + 2 * b);                      \
+    }                                                                                                              \
     void bplo_vanilla_to_motor##SUF(const REAL *C, int neval, int ncpt, int nsub, const REAL *ctrl,                \
                                     const REAL *invscale, const REAL *pos, REAL *motor, REAL *mspline) {           \
         vanilla_to_motor##SUF(C, neval, ncpt, nsub, ctrl, invscale, pos, motor, mspline);                          \

@@ -105,6 +105,61 @@ static int FN(adaptive_neval)(const REAL *C200, int nland, const REAL *Y, REAL *
 }
 
 /* ---------------------------------------------------------------------------
+ * fit_bspline_to_traj, pybpl/splines.py:141-171: Y = argmin |C Y - X|, residuals.
+ * The arithmetic lives in torch.linalg.lstsq(driver='gels') = LAPACK ?gels
+ * (un-vendored; torch 2.11 links MKL 2024.2): Householder QR of C (geqrf), Q^T
+ * applied to X (ormqr), back-substitution with R (trtrs), residual = squared norm
+ * of the rows of Q^T X below n.  Restated here unblocked.
+ *   C [m][n] row-major, X [m][2], Y [n][2], resid[2] (0 when m <= n).
+ * ------------------------------------------------------------------------- */
+static void FN(lstsq)(const REAL *C, int m, int n, const REAL *X, REAL *Y, REAL *resid) {
+    REAL *A = (REAL *)malloc(sizeof(REAL) * (size_t)m * n);
+    REAL *B = (REAL *)malloc(sizeof(REAL) * (size_t)m * 2);
+    memcpy(A, C, sizeof(REAL) * (size_t)m * n);
+    memcpy(B, X, sizeof(REAL) * (size_t)m * 2);
+    for (int k = 0; k < n && k < m; ++k) {
+        /* Householder vector for column k, rows k..m-1 */
+        REAL norm = 0;
+        for (int i = k; i < m; ++i) norm += A[(size_t)i * n + k] * A[(size_t)i * n + k];
+        norm = R_SQRT(norm);
+        if (norm == 0) continue;
+        REAL alpha = A[(size_t)k * n + k] > 0 ? -norm : norm;
+        REAL v0 = A[(size_t)k * n + k] - alpha;
+        /* v = (v0, A[k+1..m-1][k]); beta = 2 / (v^T v) */
+        REAL vtv = v0 * v0;
+        for (int i = k + 1; i < m; ++i) vtv += A[(size_t)i * n + k] * A[(size_t)i * n + k];
+        if (vtv == 0) continue;
+        REAL beta = (REAL)2 / vtv;
+        for (int j = k + 1; j < n; ++j) {
+            REAL dot = v0 * A[(size_t)k * n + j];
+            for (int i = k + 1; i < m; ++i) dot += A[(size_t)i * n + k] * A[(size_t)i * n + j];
+            dot *= beta;
+            A[(size_t)k * n + j] -= dot * v0;
+            for (int i = k + 1; i < m; ++i) A[(size_t)i * n + j] -= dot * A[(size_t)i * n + k];
+        }
+        for (int c = 0; c < 2; ++c) {
+            REAL dot = v0 * B[2 * k + c];
+            for (int i = k + 1; i < m; ++i) dot += A[(size_t)i * n + k] * B[2 * i + c];
+            dot *= beta;
+            B[2 * k + c] -= dot * v0;
+            for (int i = k + 1; i < m; ++i) B[2 * i + c] -= dot * A[(size_t)i * n + k];
+        }
+        A[(size_t)k * n + k] = alpha;
+    }
+    for (int c = 0; c < 2; ++c) {
+        for (int k = n - 1; k >= 0; --k) {
+            REAL acc = B[2 * k + c];
+            for (int j = k + 1; j < n; ++j) acc -= A[(size_t)k * n + j] * Y[2 * j + c];
+            Y[2 * k + c] = acc / A[(size_t)k * n + k];
+        }
+        REAL r = 0;
+        for (int i = n; i < m; ++i) r += B[2 * i + c] * B[2 * i + c];
+        resid[c] = r;
+    }
+    free(A); free(B);
+}
+
+/* ---------------------------------------------------------------------------
  * vanilla_to_motor, pybpl/objects/part.py:305-328: scale, evaluate, chain.
  *   ctrl     [nsub][ncpt][2]  (the reference's shapes[:, :, i] per sub-stroke)
  *   motor    [nsub][neval][2]

@@ -62,6 +62,8 @@ EXPORTS = {
     "bpl_spline_eval_bwd": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp]),
     "bpl_spline_adaptive_neval": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, ctypes.c_float,
                                                  ctypes.c_int, vp, vp, vp]),
+    "bpl_lstsq_operator_host": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, vp, vp]),
+    "bpl_spline_residual": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp]),
     "bpl_vanilla_to_motor": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp]),
     "bpl_pack_images_u8": (ctypes.c_int, [vp, ctypes.c_int, vp, vp, vp]),
     "bpl_pack_images_f32": (ctypes.c_int, [vp, ctypes.c_int, vp, vp, vp]),

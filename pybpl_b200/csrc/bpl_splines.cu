@@ -50,6 +50,60 @@ static void gen_s(int nland, int neval, float *s) {
         s[j] = (j < neval / 2) ? lo + step * (float)j : hi - step * (float)(neval - 1 - j);
 }
 
+// ---- host: least-squares operator for fit_bspline_to_traj (pybpl/splines.py:141-171) --------------------
+// torch.linalg.lstsq(C, X, driver='gels') solves min |C Y - X| by Householder QR.  C depends only on
+// (nland, neval, s), never on the data, so the operator P = R^-1 Q^T (n x m) is formed once here in double
+// (same Householder sequence, applied to the identity) and the per-trajectory work -- Y = P X and the
+// residual -- runs on the GPU.
+static int lstsq_operator(int m, int n, const float *C, float *P) {
+    if (n > m) return -1;
+    double *A = (double *)malloc(sizeof(double) * (size_t)m * n);
+    double *Qt = (double *)calloc((size_t)m * m, sizeof(double));      // accumulates Q^T
+    if (!A || !Qt) { free(A); free(Qt); return -2; }
+    for (size_t i = 0; i < (size_t)m * n; ++i) A[i] = C[i];
+    for (int i = 0; i < m; ++i) Qt[(size_t)i * m + i] = 1.0;
+    int rc = 0;
+    for (int k = 0; k < n; ++k) {
+        double norm = 0.0;
+        for (int i = k; i < m; ++i) norm += A[(size_t)i * n + k] * A[(size_t)i * n + k];
+        norm = sqrt(norm);
+        if (norm == 0.0) { rc = -3; break; }          // rank deficient
+        const double alpha = A[(size_t)k * n + k] > 0 ? -norm : norm;
+        const double v0 = A[(size_t)k * n + k] - alpha;
+        double vtv = v0 * v0;
+        for (int i = k + 1; i < m; ++i) vtv += A[(size_t)i * n + k] * A[(size_t)i * n + k];
+        if (vtv == 0.0) { A[(size_t)k * n + k] = alpha; continue; }
+        const double beta = 2.0 / vtv;
+        for (int j = k + 1; j < n; ++j) {
+            double dot = v0 * A[(size_t)k * n + j];
+            for (int i = k + 1; i < m; ++i) dot += A[(size_t)i * n + k] * A[(size_t)i * n + j];
+            dot *= beta;
+            A[(size_t)k * n + j] -= dot * v0;
+            for (int i = k + 1; i < m; ++i) A[(size_t)i * n + j] -= dot * A[(size_t)i * n + k];
+        }
+        for (int j = 0; j < m; ++j) {                 // same reflection on the columns of Q^T
+            double dot = v0 * Qt[(size_t)k * m + j];
+            for (int i = k + 1; i < m; ++i) dot += A[(size_t)i * n + k] * Qt[(size_t)i * m + j];
+            dot *= beta;
+            Qt[(size_t)k * m + j] -= dot * v0;
+            for (int i = k + 1; i < m; ++i) Qt[(size_t)i * m + j] -= dot * A[(size_t)i * n + k];
+        }
+        A[(size_t)k * n + k] = alpha;
+    }
+    if (rc == 0) {
+        for (int j = 0; j < m; ++j)                   // back-substitute every column of Q^T[:n]
+            for (int k = n - 1; k >= 0; --k) {
+                double acc = Qt[(size_t)k * m + j];
+                for (int q = k + 1; q < n; ++q) acc -= A[(size_t)k * n + q] * Qt[(size_t)q * m + j];
+                acc /= A[(size_t)k * n + k];
+                Qt[(size_t)k * m + j] = acc;
+                P[(size_t)k * m + j] = (float)acc;
+            }
+    }
+    free(A); free(Qt);
+    return rc;
+}
+
 // ---- device kernels ------------------------------------------------------------------------------
 
 // X[b][j][:] = sum_k C[j][k] Y[b][k][:], sequential fma chain from 0 (== torch.matmul, App. B.1)
@@ -124,6 +178,30 @@ __global__ void adaptive_neval_kernel(const float *__restrict__ C, int max_neval
             if (dist) dist[b] = tot;
         }
         __syncwarp();
+    }
+}
+
+// resid[b][c] = sum_j (X[b][j][c] - sum_k C[j][k] Y[b][k][c])^2 : one warp per trajectory
+__global__ void spline_residual_kernel(const float *__restrict__ C, int neval, int nland, int nspl,
+                                       const float *__restrict__ X, const float *__restrict__ Y,
+                                       float *__restrict__ resid) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int b = blockIdx.x * wpb + (threadIdx.x >> 5); b < nspl; b += gridDim.x * wpb) {
+        const float2 *x = reinterpret_cast<const float2 *>(X) + (size_t)b * neval;
+        const float2 *y = reinterpret_cast<const float2 *>(Y) + (size_t)b * nland;
+        float rx = 0.0f, ry = 0.0f;
+        for (int j = lane; j < neval; j += 32) {
+            float ax = 0.0f, ay = 0.0f;
+            for (int k = 0; k < nland; ++k) {
+                const float c = C[(size_t)j * nland + k];
+                const float2 v = y[k];
+                ax = fmaf(c, v.x, ax); ay = fmaf(c, v.y, ay);
+            }
+            const float2 t = x[j];
+            rx = fmaf(t.x - ax, t.x - ax, rx); ry = fmaf(t.y - ay, t.y - ay, ry);
+        }
+        rx = warp_sum(rx); ry = warp_sum(ry);
+        if (lane == 0) reinterpret_cast<float2 *>(resid)[b] = make_float2(rx, ry);
     }
 }
 
@@ -306,6 +384,23 @@ int bpl_spline_adaptive_neval(const float *C200, int max_neval, int nland, int n
     adaptive_neval_kernel<<<grid_for(nspl, wpb), wpb * 32, sizeof(float) * wpb * max_neval, (cudaStream_t)stream>>>(
         C200, max_neval, nland, nspl, Y, grain, min_neval, neval, dist);
     return check_launch("adaptive_neval");
+}
+
+int bpl_lstsq_operator_host(int neval, int nland, const float *C, float *P) {
+    if (neval < 1 || nland < 1 || !C || !P) { set_error("%s", "bad lstsq_operator arguments"); return BPL_EINVAL; }
+    const int r = lstsq_operator(neval, nland, C, P);
+    if (r == -1) { set_error("%s", "fit_bspline_to_traj needs neval >= nland"); return BPL_EINVAL; }
+    if (r == -2) { set_error("%s", "out of host memory"); return BPL_EINVAL; }
+    if (r == -3) { set_error("%s", "coefficient matrix is rank deficient"); return BPL_EINVAL; }
+    return 0;
+}
+
+int bpl_spline_residual(const float *C, int neval, int nland, int nspl, const float *X, const float *Y, float *resid,
+                        void *stream) {
+    if (!C || !X || !Y || !resid || neval < 1 || nland < 1 || nspl < 0) { set_error("%s", "bad spline_residual arguments"); return BPL_EINVAL; }
+    if (nspl == 0) return 0;
+    spline_residual_kernel<<<grid_for(nspl, 4), 128, 0, (cudaStream_t)stream>>>(C, neval, nland, nspl, X, Y, resid);
+    return check_launch("spline_residual");
 }
 
 int bpl_vanilla_to_motor(const float *C, int neval, int ncpt, int n_strokes, const int *stroke_sub_off,

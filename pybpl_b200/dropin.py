@@ -8,6 +8,7 @@ Patched names (each bound by-name in the reference, so both the defining module 
   pybpl.rendering.render_image, pybpl.model.image_dist.render_image          (rendering.py:185)
   pybpl.splines.get_stk_from_bspline (+ new alias pybpl.splines.bspline_eval),
   pybpl.objects.relation.get_stk_from_bspline                                 (splines.py:108, relation.py:9)
+  pybpl.splines.fit_bspline_to_traj                                           (splines.py:141)
   pybpl.objects.part.vanilla_to_motor                                         (part.py:290)
   CharacterImageDist.get_pimg / sample_image / score_image                    (image_dist.py:32-80)
 """
@@ -37,6 +38,7 @@ def install(pybpl_module=None):
     _patch(ID, "render_image", rendering.render_image)
     _patch(S, "get_stk_from_bspline", splines.get_stk_from_bspline)
     _patch(S, "bspline_eval", splines.bspline_eval)
+    _patch(S, "fit_bspline_to_traj", splines.fit_bspline_to_traj)
     _patch(REL, "get_stk_from_bspline", splines.get_stk_from_bspline)
     _patch(P, "vanilla_to_motor", objects.vanilla_to_motor)
     mirror = model.CharacterImageDist

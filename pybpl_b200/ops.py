@@ -479,6 +479,30 @@ def spline_eval(C, Y):
     return _SplineEval.apply(C, Y)
 
 
+def lstsq_operator(C):
+    """P = R^-1 Q^T of a coefficient matrix C [neval, nland] (host, double inside); returned on C's device."""
+    Ch = C.detach().to("cpu", torch.float32).contiguous().numpy()
+    m, n = Ch.shape
+    P = np.empty((n, m), np.float32)
+    check(lib().bpl_lstsq_operator_host(m, n, Ch.ctypes.data_as(ctypes.c_void_p), P.ctypes.data_as(ctypes.c_void_p)))
+    return torch.from_numpy(P).to(C.device)
+
+
+def spline_fit(C, X, P=None):
+    """Least-squares control points of trajectories X [nspl, neval, 2] for the coefficient matrix C [neval, nland]
+    (fit_bspline_to_traj, pybpl/splines.py:141-171): returns (Y [nspl, nland, 2], residuals [nspl, 2]).
+    Differentiable w.r.t. X."""
+    _need_cuda(X, "X")
+    if P is None:
+        P = lstsq_operator(C)
+    Y = _SplineEval.apply(P, X)
+    Xc, Yc, Cc = _c32(X), _c32(Y), _c32(C)
+    res = torch.empty((Xc.shape[0], 2), dtype=torch.float32, device=X.device)
+    check(lib().bpl_spline_residual(_ptr(Cc), Cc.shape[0], Cc.shape[1], Xc.shape[0], _ptr(Xc), _ptr(Yc), _ptr(res),
+                                    _stream(X.device)))
+    return Y, res
+
+
 def adaptive_neval(Y, grain=1.5, min_neval=10, max_neval=200):
     """Integer neval per spline (pybpl/splines.py:129-133) and the trajectory lengths."""
     _need_cuda(Y, "Y")

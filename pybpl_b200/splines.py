@@ -6,7 +6,7 @@ import torch
 from . import ops
 from .parameters import Parameters
 
-__all__ = ['bspline_gen_s', 'coefficient_mat', 'get_stk_from_bspline', 'bspline_eval']
+__all__ = ['bspline_gen_s', 'coefficient_mat', 'get_stk_from_bspline', 'bspline_eval', 'fit_bspline_to_traj']
 
 PM = Parameters()
 
@@ -67,6 +67,25 @@ def get_stk_from_bspline(Y, neval=None, s=None):
         C = ops.basis_table(nland, int(neval), dev)
     X = ops.spline_eval(C, Yd.unsqueeze(0))[0]
     return X.to(Y.device)
+
+
+def fit_bspline_to_traj(X, nland, s=None, include_resid=False):
+    """Least-squares B-spline of a trajectory: X [neval,2] -> Y [nland,2] (pybpl/splines.py:141-171).
+    The residuals are the squared 2-norms of C Y - X per coordinate ([2]); like torch.linalg.lstsq they are
+    empty when neval <= nland."""
+    _check_input(X)
+    neval = X.size(0)
+    dev = _compute_device(X)
+    if s is not None:
+        sv = s.view(1) if s.dim() == 0 else s
+        C = ops.basis_rows(nland, sv).to(dev)
+    else:
+        C = ops.basis_table(nland, neval, dev)
+    Y, res = ops.spline_fit(C, X.to(dev).unsqueeze(0))
+    Y = Y[0].to(X.device)
+    if include_resid:
+        return Y, (res[0].to(X.device) if neval > nland else torch.empty(0, device=X.device))
+    return Y
 
 
 def bspline_eval(sval, cpts):

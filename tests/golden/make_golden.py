@@ -414,6 +414,52 @@ def make_tokens(n_prior=96, n_full=24):
           "off_page frac", np.mean(off_all), "ll range", min(ll_all), max(ll_all))
 
 
+# --------------------------------------------------------------------------
+# fit.npz : fit_bspline_to_traj (pybpl/splines.py:141-171, torch.linalg.lstsq gels)
+# --------------------------------------------------------------------------
+def make_fit():
+    out = {}
+    g = torch.Generator().manual_seed(31)
+    cases = [(5, 200), (5, 57), (8, 200), (3, 40), (12, 100), (20, 150), (1, 30), (30, 31)]
+    out["cases"] = np.array(cases, np.int32)
+    for ci, (nland, neval) in enumerate(cases):
+        S.coefficient_mat.cache_clear()
+        # smooth-ish trajectories: a random spline of 6 control points evaluated at neval points + noise
+        Yt = torch.randn(8, 6, 2, generator=g) * 25
+        X = torch.stack([S.get_stk_from_bspline(y, neval=neval) for y in Yt]) + 0.3 * torch.randn(8, neval, 2, generator=g)
+        Ys, Rs = [], []
+        for x in X:
+            Yf, res = S.fit_bspline_to_traj(x, nland, include_resid=True)
+            Ys.append(Yf.numpy().copy())
+            Rs.append(res.numpy().copy() if res.numel() else np.zeros(2, f32))
+        out[f"X_{ci}"] = X.numpy().copy()
+        out[f"Y_{ci}"] = np.stack(Ys)
+        out[f"res_{ci}"] = np.stack(Rs)
+        S.coefficient_mat.cache_clear()
+        out[f"C_{ci}"] = S.coefficient_mat(nland, neval).numpy().copy()
+    # explicit time points
+    S.coefficient_mat.cache_clear()
+    sv = torch.sort(2 + 4 * torch.rand(90, generator=g))[0]
+    Xs = torch.randn(4, 90, 2, generator=g).cumsum(1)
+    out["s_explicit"] = sv.numpy().copy()
+    out["X_s"] = Xs.numpy().copy()
+    ys, rs = [], []
+    for x in Xs:
+        S.coefficient_mat.cache_clear()
+        Yf, res = S.fit_bspline_to_traj(x, 5, s=sv, include_resid=True)
+        ys.append(Yf.numpy().copy()); rs.append(res.numpy().copy())
+    out["Y_s"] = np.stack(ys); out["res_s"] = np.stack(rs)
+    # gradient of the fit w.r.t. the trajectory
+    S.coefficient_mat.cache_clear()
+    xg = X[0].clone().requires_grad_(True)
+    ct = torch.randn(cases[-1][0], 2, generator=g)
+    Yg = S.fit_bspline_to_traj(xg, cases[-1][0])
+    (Yg * ct).sum().backward()
+    out["ct_fit"] = ct.numpy().copy(); out["gX_fit"] = xg.grad.numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "fit.npz"), **out)
+    print("fit.npz:", len(cases), "cases")
+
+
 def make_assets():
     """pybpl_b200/data/basis_5_200.npy: coefficient_mat(5, 200) exactly as the reference's torch builds it
     (splines.py:72-93).  torch assembles it with Sleef powf and an MKL dot, which portable C cannot
@@ -439,13 +485,15 @@ def make_assets():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["splines", "render", "tokens", "assets"]
+    which = sys.argv[1:] or ["splines", "render", "tokens", "fit", "assets"]
     if "splines" in which:
         make_splines()
     if "render" in which:
         make_render()
     if "tokens" in which:
         make_tokens()
+    if "fit" in which:
+        make_fit()
     if "assets" in which:
         make_assets()
     for f in sorted(os.listdir(OUT)):

@@ -410,3 +410,30 @@ def test_library_fails_loudly_without_cuda_tensors(ops):
     with pytest.raises(_lib.BplError):
         ops.TokenBatch([0, 0], [0], torch.zeros((0, 5, 2)), torch.zeros(0), torch.zeros((0, 2)), torch.zeros(1),
                        torch.zeros(1))
+
+
+def test_fit_bspline_to_traj(ops):
+    """fit_bspline_to_traj (pybpl/splines.py:141-171) against the reference's lstsq outputs and its autograd."""
+    from pybpl_b200 import splines
+    d = load("fit")
+    for ci, (nl, ne) in enumerate(d["cases"]):
+        C = T(d[f"C_{ci}"])
+        Y, res = ops.spline_fit(C, T(d[f"X_{ci}"]))
+        assert relinf(Y.cpu().numpy(), d[f"Y_{ci}"]) < 2e-5, (nl, ne)
+        if ne > nl + 1:
+            assert relinf(res.cpu().numpy(), d[f"res_{ci}"]) < 2e-4, (nl, ne)
+    # drop-in signature: CPU tensor in, CPU tensors out, explicit time points, residuals
+    X = torch.from_numpy(d["X_s"][0])
+    Y, res = splines.fit_bspline_to_traj(X, 5, s=torch.from_numpy(d["s_explicit"]), include_resid=True)
+    assert Y.shape == (5, 2) and res.shape == (2,) and Y.device.type == "cpu"
+    assert relinf(Y.numpy(), d["Y_s"][0]) < 5e-5 and relinf(res.numpy(), d["res_s"][0]) < 5e-4
+    Y0 = splines.fit_bspline_to_traj(torch.from_numpy(d["X_0"][0]), 5)
+    assert relinf(Y0.numpy(), d["Y_0"][0]) < 2e-5
+    _, r_empty = splines.fit_bspline_to_traj(torch.randn(5, 2), 5, include_resid=True)
+    assert r_empty.numel() == 0                      # torch.linalg.lstsq returns no residuals when m <= n
+    # gradient w.r.t. the trajectory
+    last = len(d["cases"]) - 1
+    xg = torch.from_numpy(d[f"X_{last}"][0]).requires_grad_(True)
+    Yg = splines.fit_bspline_to_traj(xg, int(d["cases"][last][0]))
+    (Yg * torch.from_numpy(d["ct_fit"])).sum().backward()
+    assert relinf(xg.grad.numpy(), d["gX_fit"]) < 1e-4

@@ -130,3 +130,14 @@ def test_fp64_noise_floor():
         r = o64.token(C64, t["nsub"], t["ctrl"], t["invscale"], t["position"], t["eps"], t["sigma"], image=t["image"])
         errs.append(abs(r["ll"] - t["ll"]) / abs(t["ll"]))
     assert max(errs) < 2e-4  # reference fp32 ll is itself only ~5e-5 from fp64
+
+
+def test_fit_bspline_to_traj():
+    # splines.py:141-171 (torch.linalg.lstsq gels): control points and residuals
+    d = load("fit")
+    for dt, tol in ((np.float32, 5e-6), (np.float64, 2e-6)):
+        o = Oracle(dt)
+        for ci, (nl, ne) in enumerate(d["cases"]):
+            Y, res = o.lstsq(d[f"C_{ci}"], d[f"X_{ci}"])
+            assert relinf(Y, d[f"Y_{ci}"]) < tol
+            assert relinf(res, d[f"res_{ci}"]) < 1e-4
