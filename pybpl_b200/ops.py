@@ -203,6 +203,54 @@ class TokenBatch:
         return b
 
 
+class HostStagedBatch:
+    """A token batch (+ one target image) staged in ONE pinned host buffer, so that a step needs a single
+    host->device copy: [tok_stroke_off | stroke_sub_off | ctrl | invscale | position | eps | sigma | image u8],
+    every section 16-byte aligned.  `upload()` copies it to a device buffer of the same layout on the current stream
+    (asynchronously) and returns (TokenBatch, image tensor) whose tensors are views of that buffer."""
+
+    _ORDER = (("tok_stroke_off", torch.int32), ("stroke_sub_off", torch.int32), ("ctrl", torch.float32),
+              ("invscale", torch.float32), ("position", torch.float32), ("eps", torch.float32), ("sigma", torch.float32))
+
+    def __init__(self, w, image_u8, device):
+        self.device = torch.device(device)
+        self.neval = int(w.get("neval", 200))
+        self.layout = []
+        off = 0
+        arrs = []
+        for name, dt in self._ORDER:
+            a = torch.from_numpy(np.ascontiguousarray(w[name])).to(dt).contiguous()
+            arrs.append(a)
+            nbytes = a.numel() * a.element_size()
+            self.layout.append((name, dt, tuple(a.shape), off, nbytes))
+            off = (off + nbytes + 15) // 16 * 16
+        img = torch.as_tensor(image_u8, dtype=torch.uint8).reshape(-1).contiguous()
+        self.img_off, self.img_bytes = off, img.numel()
+        self.nbytes = (off + self.img_bytes + 15) // 16 * 16
+        self.host = torch.empty(self.nbytes, dtype=torch.uint8).pin_memory()
+        for a, (_, _, _, o, nb) in zip(arrs, self.layout):
+            self.host[o:o + nb] = a.view(torch.uint8).reshape(-1)
+        self.host[self.img_off:self.img_off + self.img_bytes] = img
+        self.devs = [torch.empty(self.nbytes, dtype=torch.uint8, device=self.device) for _ in range(2)]
+
+    def upload(self, slot=0):
+        """Asynchronous H2D into device buffer `slot` (two slots allow the next step's copy to overlap this step's
+        kernels when issued on a second stream)."""
+        dev = self.devs[slot]
+        dev.copy_(self.host, non_blocking=True)
+        return self.views(slot)
+
+    def views(self, slot=0):
+        dev = self.devs[slot]
+        v = {}
+        for name, dt, shape, o, nb in self.layout:
+            v[name] = dev[o:o + nb].view(dt).view(shape)
+        batch = TokenBatch(v["tok_stroke_off"], v["stroke_sub_off"], v["ctrl"], v["invscale"], v["position"], v["eps"],
+                           v["sigma"], neval=self.neval, check_limits=False)
+        image = dev[self.img_off:self.img_off + self.img_bytes].view(IMSIZE, IMSIZE)
+        return batch, image
+
+
 def _targets(images, img_idx):
     t = _lib.Targets()
     if images is not None:
