@@ -84,6 +84,7 @@ __device__ __forceinline__ void gauss_inplace2(float2 *buf, const float2 (&g)[PA
 
 // ---- packed in-place broaden (see broaden_inplace) -------------------------------------------------------
 __device__ __forceinline__ void broaden_inplace2(float2 *A, float2 *side, const RenderConsts &rc) {
+    static_assert(F2_THREADS == 2 * (IMG / BR) * 32, "one warp per (band, half)");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int band = warp >> 1, half = warp & 1;
     const int i2 = half * 32 + lane;
@@ -198,7 +199,6 @@ __global__ void __launch_bounds__(F2_THREADS, F2_CTAS_PER_SM) bpl_forward2_kerne
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             load_image_bits(a, pt[k], &sm.ms[k]);
-            token_consts(eps[k], sigma[k], false, &sm.ms[k], k);
             if (threadIdx.x == 0) sm.ms[k].off_page = 0;
         }
         BPL_PT(0);      // geometry loads, zeroing, constants (no barrier yet)
@@ -241,6 +241,9 @@ __global__ void __launch_bounds__(F2_THREADS, F2_CTAS_PER_SM) bpl_forward2_kerne
             affine_setup(a, t[0], pt[0], sm.tab, &sm.ms[0]);
             affine_setup(a, t[1], pt[1], sm.tab, &sm.ms[1]);
         }
+        // double-precision constants by the last two warps, hidden behind the point phase of the others
+        token_consts(eps[0], sigma[0], false, &sm.ms[0], 0);
+        token_consts(eps[1], sigma[1], false, &sm.ms[1], 1);
         if (threadIdx.x < 2 && a.image_bits) sm.ms[threadIdx.x].cur_img = a.img_idx ? a.img_idx[pt[threadIdx.x]] : 0;
 
         BPL_PT(1);      // chain offsets

@@ -566,7 +566,6 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) bpl_backward_kernel(const KArg
         const bool aff = !RAW && a.affine != nullptr;
         zero_floats(A, BUFP);
         load_image_bits(a, p, ms);
-        token_consts(eps, sigma, true, ms);
         if (threadIdx.x == 0) {
             ms->off_page = 0;
             ms->aff_acc[0] = ms->aff_acc[1] = ms->aff_acc[2] = ms->aff_acc[3] = 0.0;
@@ -577,6 +576,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) bpl_backward_kernel(const KArg
         } else {
             __syncthreads();
         }
+        token_consts(eps, sigma, true, ms);      // double-precision constants by one warp, hidden behind the splat
         if (threadIdx.x == 0 && a.image_bits) ms->cur_img = a.img_idx ? a.img_idx[p] : 0;
 
         BPL_PT(0);      // setup + chain offsets
@@ -869,33 +869,43 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) bpl_backward_kernel(const KArg
                 ga[0] = ga[1] = ga[2] = ga[3] = 0.0f;
             }
             const float *rfirst = sm.tab, *rlast = sm.tab + (a.neval - 1) * NCPT;
+            // (i) one thread per stroke: suffix sums of the sub-strokes' summed gradients, on shared memory only;
+            //     the carry entering each sub-stroke and its total overwrite the two Gsum slots
             for (int k = threadIdx.x; k < t.K; k += blockDim.x) {
                 const int b = a.stroke_sub_off[t.k0 + k] - t.s0, e = a.stroke_sub_off[t.k0 + k + 1] - t.s0;
                 float cx = 0.0f, cy = 0.0f;       // gradient w.r.t. previous_pos of the following sub-stroke
                 for (int s = e - 1; s >= b; --s) {
-                    const float *o = accs + ORIGIN + s * NACC;
+                    float *o = accs + ORIGIN + s * NACC;
                     const float sx = fmaf(b0, o[2 * NCPT], (float)a.neval * gcx);
                     const float sy = fmaf(b1, o[2 * NCPT + 1], (float)a.neval * gcy);
-                    const float tx = sx + cx, ty = sy + cy;
-                    const float inv = a.invscale[t.s0 + s];
-                    const float *cp = a.ctrl + (size_t)(t.s0 + s) * NCPT * 2;
-                    float *gc = a.g_ctrl + (size_t)(t.s0 + s) * NCPT * 2;
-                    float gi = 0.0f;
-#pragma unroll
-                    for (int q = 0; q < NCPT; ++q) {
-                        const float wx = fmaf(b0, o[2 * q], gcx * ms->colsum[q]);
-                        const float wy = fmaf(b1, o[2 * q + 1], gcy * ms->colsum[q]);
-                        const float gyx = wx + rlast[q] * cx - rfirst[q] * tx;
-                        const float gyy = wy + rlast[q] * cy - rfirst[q] * ty;
-                        gc[2 * q] = inv * gyx;
-                        gc[2 * q + 1] = inv * gyy;
-                        gi = fmaf(cp[2 * q], gyx, fmaf(cp[2 * q + 1], gyy, gi));
-                    }
-                    a.g_invscale[t.s0 + s] = gi;
-                    cx = tx; cy = ty;
+                    ms->sub[s].z = cx; ms->sub[s].w = cy;            // carry (the forward's totals are no longer needed)
+                    cx += sx; cy += sy;
+                    o[2 * NCPT] = cx; o[2 * NCPT + 1] = cy;          // total
                 }
                 a.g_position[2 * (t.k0 + k)] = cx;
                 a.g_position[2 * (t.k0 + k) + 1] = cy;
+            }
+            __syncthreads();
+            // (ii) one thread per sub-stroke: control-point and scale gradients (global loads in parallel)
+            for (int s = threadIdx.x; s < t.S; s += blockDim.x) {
+                const float *o = accs + ORIGIN + s * NACC;
+                const float cx = ms->sub[s].z, cy = ms->sub[s].w;
+                const float tx = o[2 * NCPT], ty = o[2 * NCPT + 1];
+                const float inv = a.invscale[t.s0 + s];
+                const float *cp = a.ctrl + (size_t)(t.s0 + s) * NCPT * 2;
+                float *gc = a.g_ctrl + (size_t)(t.s0 + s) * NCPT * 2;
+                float gi = 0.0f;
+#pragma unroll
+                for (int q = 0; q < NCPT; ++q) {
+                    const float wx = fmaf(b0, o[2 * q], gcx * ms->colsum[q]);
+                    const float wy = fmaf(b1, o[2 * q + 1], gcy * ms->colsum[q]);
+                    const float gyx = wx + rlast[q] * cx - rfirst[q] * tx;
+                    const float gyy = wy + rlast[q] * cy - rfirst[q] * ty;
+                    gc[2 * q] = inv * gyx;
+                    gc[2 * q + 1] = inv * gyy;
+                    gi = fmaf(cp[2 * q], gyx, fmaf(cp[2 * q + 1], gyy, gi));
+                }
+                a.g_invscale[t.s0 + s] = gi;
             }
             __syncthreads();
             // B's interior was used as scratch: restore zeros (its border was never touched)
