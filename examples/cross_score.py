@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""BASELINE.json configs[4]: cross-scoring.  T types x K tokens are scored against M target images (all pairs);
-(token, image) pairs are one flat batch with an image index per pair."""
+"""BASELINE.json configs[4]: cross-scoring.  T types x K tokens are scored against M target images (all pairs):
+each token is rendered once and its per-pixel score differences are gathered at every image's set bits."""
 import os
 import sys
 import time
@@ -20,16 +20,14 @@ def cross_score(n_tokens=400, n_images=20, seed=5, device="cuda:0"):
         g = torch.Generator().manual_seed(seed)
         images = (torch.rand(pimg.shape, generator=g).to(dev) < pimg).to(torch.uint8)
     imgs = ops.pack_images(images)
-    # all pairs: token t repeated for every image
-    rep = np.repeat(np.arange(n_tokens), n_images)
-    batch = workload.to_device(workload.permute(w, rep), dev)
-    idx = torch.arange(n_images, dtype=torch.int32, device=dev).repeat(n_tokens)
+    batch = workload.to_device(w, dev)
+    ops.score_tokens_all_images(batch, imgs)            # warm-up
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    ll, _ = ops.score_tokens(batch, imgs, idx)
+    ll, _ = ops.score_tokens_all_images(batch, imgs)    # every token rendered once, scored against all images
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    return ll.view(n_tokens, n_images), dt, w, images
+    return ll, dt, w, images
 
 
 if __name__ == "__main__":

@@ -77,11 +77,12 @@ typedef struct {
     const uint32_t *image_bits; /* dev [T][345] from bpl_pack_images_*; NULL => no scoring */
     const int *img_idx;         /* dev [P] image per token, or NULL => image 0 */
     int n_images;               /* T */
+    int all_pairs;              /* 1: score every token against all T images (img_idx ignored); ll is [P][T] */
 } bpl_targets;
 
 /* Outputs of the forward (any may be NULL). */
 typedef struct {
-    float *ll;                  /* dev [P]  sum Bernoulli(pimg).log_prob(image) (image_dist.py:75-78) */
+    float *ll;                  /* dev [P] (or [P][T] with all_pairs)  sum Bernoulli(pimg).log_prob(image) (image_dist.py:75-78) */
     uint8_t *off_page;          /* dev [P]  ink_off_page (rendering.py:85-88,219-220) */
     float *pimg;                /* dev [P][105][105] probability maps (render_image / get_pimg) */
 } bpl_fwd_out;

@@ -39,7 +39,7 @@ class StrokeBatchC(ctypes.Structure):
 
 
 class Targets(ctypes.Structure):
-    _fields_ = [("image_bits", vp), ("img_idx", vp), ("n_images", ctypes.c_int)]
+    _fields_ = [("image_bits", vp), ("img_idx", vp), ("n_images", ctypes.c_int), ("all_pairs", ctypes.c_int)]
 
 
 class FwdOut(ctypes.Structure):

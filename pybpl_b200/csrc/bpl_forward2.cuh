@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(F2_THREADS, F2_CTAS_PER_SM) bpl_forward2_kerne
         }
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-            load_image_bits(a, pt[k], &sm.ms[k]);
+            if (!a.all_pairs) load_image_bits(a, pt[k], &sm.ms[k]);
             if (threadIdx.x == 0) sm.ms[k].off_page = 0;
         }
         BPL_PT(0);      // geometry loads, zeroing, constants (no barrier yet)
@@ -348,28 +348,67 @@ __global__ void __launch_bounds__(F2_THREADS, F2_CTAS_PER_SM) bpl_forward2_kerne
             const float l00 = sm.ms[0].lp_bg[0], l01 = sm.ms[0].lp_bg[1];
             const float l10 = sm.ms[1].lp_bg[0], l11 = sm.ms[1].lp_bg[1];
             const float2 zz = make_float2(0.0f, 0.0f);
-            for (int i = threadIdx.x; i < NPIX; i += blockDim.x) {
-                const float2 v = A[i];
-                A[i] = zz;                                               // leaves the buffer zeroed for the next pair
-                const bool x0 = (sm.ms[0].bits[i >> 5] >> (i & 31)) & 1u;
-                const bool x1 = (sm.ms[1].bits[i >> 5] >> (i & 31)) & 1u;
-                float u0 = fminf(fmaxf(v.x, 0.0f), 1.0f), u1 = fminf(fmaxf(v.y, 0.0f), 1.0f);      // clamp_(0,1) (:180)
-                if (eps[0] > 0.0f) u0 = __fadd_rn(__fmul_rn(om0, u0), __fmul_rn(eps[0], __fsub_rn(1.0f, u0)));
-                if (eps[1] > 0.0f) u1 = __fadd_rn(__fmul_rn(om1, u1), __fmul_rn(eps[1], __fsub_rn(1.0f, u1)));
-                float lp0 = x0 ? l01 : l00, lp1 = x1 ? l11 : l10;
-                if (u0 != bg0) lp0 = pixel_lp_fwd(u0, x0);
-                if (u1 != bg1) lp1 = pixel_lp_fwd(u1, x1);
-                acc[0] += lp0; acc[1] += lp1;
+            if (!a.all_pairs) {
+                for (int i = threadIdx.x; i < NPIX; i += blockDim.x) {
+                    const float2 v = A[i];
+                    A[i] = zz;                                               // leaves the buffer zeroed for the next pair
+                    const bool x0 = (sm.ms[0].bits[i >> 5] >> (i & 31)) & 1u;
+                    const bool x1 = (sm.ms[1].bits[i >> 5] >> (i & 31)) & 1u;
+                    float u0 = fminf(fmaxf(v.x, 0.0f), 1.0f), u1 = fminf(fmaxf(v.y, 0.0f), 1.0f);      // clamp_(0,1) (:180)
+                    if (eps[0] > 0.0f) u0 = __fadd_rn(__fmul_rn(om0, u0), __fmul_rn(eps[0], __fsub_rn(1.0f, u0)));
+                    if (eps[1] > 0.0f) u1 = __fadd_rn(__fmul_rn(om1, u1), __fmul_rn(eps[1], __fsub_rn(1.0f, u1)));
+                    float lp0 = x0 ? l01 : l00, lp1 = x1 ? l11 : l10;
+                    if (u0 != bg0) lp0 = pixel_lp_fwd(u0, x0);
+                    if (u1 != bg1) lp1 = pixel_lp_fwd(u1, x1);
+                    acc[0] += lp0; acc[1] += lp1;
+                }
+            } else {
+                // every token against every image: the per-pixel scores for x = 0 are summed once (base), the
+                // difference delta = lp(x=1) - lp(x=0) replaces the pixel, and each image then only visits its set bits
+                for (int i = threadIdx.x; i < NPIX; i += blockDim.x) {
+                    const float2 v = A[i];
+                    float u0 = fminf(fmaxf(v.x, 0.0f), 1.0f), u1 = fminf(fmaxf(v.y, 0.0f), 1.0f);
+                    if (eps[0] > 0.0f) u0 = __fadd_rn(__fmul_rn(om0, u0), __fmul_rn(eps[0], __fsub_rn(1.0f, u0)));
+                    if (eps[1] > 0.0f) u1 = __fadd_rn(__fmul_rn(om1, u1), __fmul_rn(eps[1], __fsub_rn(1.0f, u1)));
+                    float a0 = l00, b0 = l01, a1 = l10, b1 = l11;
+                    if (u0 != bg0) { a0 = pixel_lp_fwd(u0, false); b0 = pixel_lp_fwd(u0, true); }
+                    if (u1 != bg1) { a1 = pixel_lp_fwd(u1, false); b1 = pixel_lp_fwd(u1, true); }
+                    acc[0] += a0; acc[1] += a1;
+                    A[i] = make_float2(b0 - a0, b1 - a1);
+                }
             }
         }
         double v[2] = {(double)acc[0], (double)acc[1]};
         block_sum<2>(v, sm.ms[0].red);
-        if (threadIdx.x < 2) {
-            const int k = threadIdx.x;
-            if (k == 0 || have1) {
-                if (a.ll) a.ll[pt[k]] = bad[k] ? nanf("") : (float)v[k];
-                if (a.off_page) a.off_page[pt[k]] = bad[k] ? (uint8_t)255 : (uint8_t)(sm.ms[k].off_page != 0);
+        if (!a.all_pairs) {
+            if (threadIdx.x < 2) {
+                const int k = threadIdx.x;
+                if (k == 0 || have1) {
+                    if (a.ll) a.ll[pt[k]] = bad[k] ? nanf("") : (float)v[k];
+                    if (a.off_page) a.off_page[pt[k]] = bad[k] ? (uint8_t)255 : (uint8_t)(sm.ms[k].off_page != 0);
+                }
             }
+        } else {
+            // block_sum's barriers have made the deltas visible; one warp per image walks the image's set bits
+            for (int m = warp; m < a.n_images; m += nw) {
+                const uint32_t *bw = a.image_bits + (size_t)m * IMG_WORDS;
+                float s0 = 0.0f, s1 = 0.0f;
+                for (int wi = lane; wi < IMG_WORDS; wi += 32) {
+                    for (unsigned bits = bw[wi]; bits; bits &= bits - 1u) {
+                        const int i = wi * 32 + __ffs(bits) - 1;
+                        if (i < NPIX) { const float2 d = A[i]; s0 += d.x; s1 += d.y; }
+                    }
+                }
+                s0 = warp_sum(s0); s1 = warp_sum(s1);
+                if (lane == 0 && a.ll) {
+                    a.ll[(size_t)pt[0] * a.n_images + m] = bad[0] ? nanf("") : (float)(v[0] + (double)s0);
+                    if (have1) a.ll[(size_t)pt[1] * a.n_images + m] = bad[1] ? nanf("") : (float)(v[1] + (double)s1);
+                }
+            }
+            if (threadIdx.x < 2 && a.off_page && (threadIdx.x == 0 || have1))
+                a.off_page[pt[threadIdx.x]] = bad[threadIdx.x] ? (uint8_t)255 : (uint8_t)(sm.ms[threadIdx.x].off_page != 0);
+            __syncthreads();
+            zero_floats(reinterpret_cast<float *>(A), 2 * NPIX);      // the deltas must not leak into the next pair
         }
         __syncthreads();
         BPL_PT(5);      // tail + reduction

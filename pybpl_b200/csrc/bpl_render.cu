@@ -39,6 +39,7 @@ struct KArgs {
     const uint32_t *image_bits;
     const int *img_idx;
     int n_images;
+    int all_pairs;           // score every token against all images (forward scoring kernel only)
     float *ll;
     uint8_t *off_page;
     float *pimg;
@@ -1036,7 +1037,7 @@ static int fill_common(KArgs &ka, const bpl_params *ps, const bpl_targets *t, co
                        const bpl_grads *g) {
     int rcode = make_consts(ps, &ka.rc);
     if (rcode) return rcode;
-    if (t) { ka.image_bits = t->image_bits; ka.img_idx = t->img_idx; ka.n_images = t->n_images; }
+    if (t) { ka.image_bits = t->image_bits; ka.img_idx = t->img_idx; ka.n_images = t->n_images; ka.all_pairs = t->all_pairs; }
     if (out) { ka.ll = out->ll; ka.off_page = out->off_page; ka.pimg = out->pimg; }
     if (g) {
         ka.g_ll = g->g_ll; ka.g_pimg = g->g_pimg; ka.g_ctrl = g->g_ctrl; ka.g_invscale = g->g_invscale;
@@ -1084,8 +1085,11 @@ int bpl_score_tokens(const bpl_params *ps, const bpl_token_batch *b, const bpl_t
     int r = fill_common(ka, ps, t, out, nullptr);
     if (r) return r;
     if ((r = fill_tokens(ka, b))) return r;
+    if (ka.all_pairs && (!ka.image_bits || ka.pimg || ka.n_images < 1)) {
+        set_error("%s", "all_pairs scoring needs target images and no pimg output"); return BPL_EINVAL;
+    }
     static const bool force_single = getenv("BPL_FORCE_SINGLE") != nullptr;     // profiling aid: one token per CTA
-    if (ka.image_bits && !ka.pimg && !force_single)      // scoring hot path: two tokens per CTA, packed FP32 stencils
+    if (ka.image_bits && !ka.pimg && (!force_single || ka.all_pairs))      // scoring hot path: two tokens per CTA, packed FP32 stencils
         return launch(bpl_forward2_kernel, F2_THREADS, sizeof(Fwd2Smem), F2_CTAS_PER_SM, ka, (cudaStream_t)stream,
                       (ka.n_tokens + 1) / 2);
     return launch(bpl_forward_kernel<false>, FWD_THREADS, sizeof(FwdSmem), FWD_CTAS_PER_SM, ka, (cudaStream_t)stream);
@@ -1109,6 +1113,7 @@ int bpl_score_tokens_grad(const bpl_params *ps, const bpl_token_batch *b, const 
     if (r) return r;
     if ((r = fill_tokens(ka, b))) return r;
     if (!g || !g->g_ctrl || !g->g_invscale || !g->g_position) { set_error("%s", "g_ctrl/g_invscale/g_position required"); return BPL_EINVAL; }
+    if (ka.all_pairs) { set_error("%s", "all_pairs scoring is forward only"); return BPL_EINVAL; }
     if (!ka.image_bits && !ka.g_pimg) { set_error("%s", "need target images or a pimg cotangent"); return BPL_EINVAL; }
     return launch(bpl_backward_kernel<false>, BWD_THREADS, sizeof(BwdSmem), 1, ka, (cudaStream_t)stream);
 }

@@ -369,6 +369,24 @@ def score_tokens(batch, images, img_idx=None, ps=None):
     return ll, off.bool()
 
 
+def score_tokens_all_images(batch, images, ps=None):
+    """Every token of the batch against every image of `images` (PackedImages): ll [P, T], ink_off_page [P].
+    Each token is rendered once; forward only (no autograd)."""
+    if not isinstance(ps, _lib.Params):
+        ps = make_params(ps)
+    dev = batch.device
+    P, Tn = batch.P, images.n
+    ll = torch.empty((P, Tn), dtype=torch.float32, device=dev)
+    off = torch.empty(P, dtype=torch.uint8, device=dev)
+    tens = [_c32(batch.ctrl), _c32(batch.invscale), _c32(batch.position),
+            None if batch.affine is None else _c32(batch.affine), _c32(batch.eps), _c32(batch.sigma)]
+    b = batch.c_struct(*tens)
+    t = _lib.Targets(images.bits.data_ptr(), None, Tn, 1)
+    out = _lib.FwdOut(ll.data_ptr(), off.data_ptr(), None)
+    check(lib().bpl_score_tokens(ctypes.byref(ps), ctypes.byref(b), ctypes.byref(t), ctypes.byref(out), _stream(dev)))
+    return ll, off.bool()
+
+
 def render_tokens(batch, ps=None):
     """Probability maps of a TokenBatch: (pimg [P,105,105], ink_off_page [P] bool)."""
     if not isinstance(ps, _lib.Params):

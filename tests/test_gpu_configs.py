@@ -64,3 +64,22 @@ def test_config5_cross_scoring_against_oracle():
     own = np.arange(0, 40, 8)                  # tokens scored against their own image: well conditioned
     rel_own = np.abs(ll[own, np.arange(5)] - ref32.reshape(40, 5)[own, np.arange(5)]) / np.abs(ref32.reshape(40, 5)[own, np.arange(5)])
     assert rel_own.max() < 1e-5, rel_own.max()
+
+
+def test_all_images_scoring_equals_pairwise():
+    from pybpl_b200 import ops, workload
+    dev = torch.device("cuda:0")
+    w = workload.synth_tokens(37, seed=9, max_strokes=10, kappa="prior", sigma_mode="uniform")     # odd count: last pair is half empty
+    batch = workload.to_device(w, dev)
+    g = torch.Generator().manual_seed(3)
+    images = (torch.rand((7, 105, 105), generator=g) < 0.05).to(torch.uint8).to(dev)
+    packed = ops.pack_images(images)
+    ll_all, off_all = ops.score_tokens_all_images(batch, packed)
+    assert ll_all.shape == (37, 7)
+    for m in range(7):
+        ll_m, off_m = ops.score_tokens(batch, ops.pack_images(images[m]))
+        assert torch.equal(off_m, off_all)
+        assert ((ll_all[:, m] - ll_m).abs() <= 2e-5 * ll_m.abs()).all()
+    # a second call right after (buffer re-zeroing between pairs and launches)
+    ll2, _ = ops.score_tokens_all_images(batch, packed)
+    assert ((ll2 - ll_all).abs() <= 2e-5 * ll_all.abs()).all()
