@@ -40,6 +40,7 @@ struct RenderConsts {
     int ink_ncon;
     float ink_pp, ink_max_dist;
     float ink_f;     // ink_pp / ink_max_dist (d ink / d dist)
+    float inv_max_dist;   // 1 / ink_max_dist when that is exact (a power of two), else 0: x / 2 == x * 0.5 bit for bit
     float c1, c2;    // H_broaden = c1 * (1,2,1)x(1,2,1) + c2 * delta
 };
 

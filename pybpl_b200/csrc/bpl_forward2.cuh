@@ -13,6 +13,8 @@
 // two CTAs (= four tokens) per SM, 96 registers per thread.
 #pragma once
 
+#include <type_traits>
+
 namespace bpl {
 
 constexpr int F2_THREADS = 320;
@@ -126,7 +128,7 @@ __device__ __forceinline__ void broaden_inplace2(float2 *A, float2 *side, const 
         };
         float2 xc0, xc1, hc0, hc1;
         hrow(a0, xc0, xc1, hc0, hc1);
-#pragma unroll 21
+#pragma unroll
         for (int o = 0; o < BR; ++o) {
             float2 xn0 = z, xn1 = z, hn0 = ht0, hn1 = ht1;
             if (o + 1 < BR) hrow(a0 + o + 1, xn0, xn1, hn0, hn1);
@@ -348,6 +350,7 @@ __global__ void __launch_bounds__(F2_THREADS, F2_CTAS_PER_SM) bpl_forward2_kerne
             const float l00 = sm.ms[0].lp_bg[0], l01 = sm.ms[0].lp_bg[1];
             const float l10 = sm.ms[1].lp_bg[0], l11 = sm.ms[1].lp_bg[1];
             const float2 zz = make_float2(0.0f, 0.0f);
+            const bool same_img = sm.ms[0].cur_img == sm.ms[1].cur_img;      // the usual case: one target for all tokens
             if (!a.all_pairs) {
                 for (int i = threadIdx.x; i < NPIX; i += blockDim.x) {
                     const float2 v = A[i];

@@ -35,7 +35,8 @@ __device__ __forceinline__ PEval eval_pt(const CtrlSrc &src, int j, bool valid) 
 __device__ __forceinline__ float ink_from(float r, float c, float qr, float qc, const RenderConsts &rc) {
     const float dr = __fsub_rn(r, qr), dc = __fsub_rn(c, qc);
     const float dist = __fsqrt_rn(__fadd_rn(__fmul_rn(dr, dr), __fmul_rn(dc, dc)));
-    return __fdiv_rn(__fmul_rn(rc.ink_pp, fminf(dist, rc.ink_max_dist)), rc.ink_max_dist);
+    const float num = __fmul_rn(rc.ink_pp, fminf(dist, rc.ink_max_dist));
+    return rc.inv_max_dist != 0.0f ? __fmul_rn(num, rc.inv_max_dist) : __fdiv_rn(num, rc.ink_max_dist);
 }
 
 template <int PIXSTRIDE>

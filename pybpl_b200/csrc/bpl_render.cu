@@ -991,6 +991,11 @@ static int make_consts(const bpl_params *ps, RenderConsts *rc) {
     rc->ink_pp = ps->ink_pp;
     rc->ink_max_dist = ps->ink_max_dist;
     rc->ink_f = ps->ink_pp / ps->ink_max_dist;
+    {
+        int ex = 0;
+        const float mant = frexpf(ps->ink_max_dist, &ex);
+        rc->inv_max_dist = (mant == 0.5f && ex > -100 && ex < 100) ? 1.0f / ps->ink_max_dist : 0.0f;
+    }
     rc->c1 = (float)(hs * a / 12.0);
     rc->c2 = (float)(hs * (1.0 - 4.0 * a / 3.0));
     return 0;
