@@ -183,8 +183,14 @@ def run_gpu(args):
     tso = w["tok_stroke_off"].astype(np.int64)
     Sbar = float(np.diff(w["stroke_sub_off"].astype(np.int64)[tso]).mean())
     Kbar = float(np.diff(tso).mean())
+    # the target: a Bernoulli sample of token 0's probability map, rendered by the CUDA path itself (the oracle is
+    # only used by the cpu_baseline leg below); the uniform noise comes from a seeded numpy generator as in
+    # workload.target_image_for, so the CPU arm sees the same image up to pixels within 1e-6 of the noise
     if rank == 0:
-        img_np, C = cpu_target_image(w0)       # oracle renders the target once (input generation, untimed)
+        with torch.no_grad():
+            p0, _ = ops.render_tokens(workload.to_device(workload.permute(w0, np.array([0])), dev))
+        u = np.random.default_rng(99).random((105, 105))
+        img_np = (u < p0[0].cpu().numpy()).astype(np.uint8)
     else:
         img_np = np.zeros((105, 105), np.uint8)
     img_t = torch.from_numpy(img_np).to(dev)
@@ -356,6 +362,7 @@ def run_gpu(args):
     cores = os.cpu_count() or 1
     cpu = None
     if world == 1:
+        C = np.load(os.path.join(ROOT, "pybpl_b200", "data", "basis_5_200.npy"))
         cv, cn, cdt = cpu_baseline(w0, img_np, C, 4096, repeats=2)
         cpu = {"value": cv, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"all {cn} tokens of the step (best of 2), C oracle port, OpenMP over tokens, {cdt:.2f} s wall on {cores} cores"}
