@@ -26,7 +26,7 @@ extern "C" {
 #define BPL_MAX_SUBSTROKES 128  /* sub-strokes per token handled by one CTA */
 #define BPL_MAX_STROKES 32      /* strokes per token */
 #define BPL_NCPT 5              /* control points per sub-stroke on the fused path (lib_data shape/mu: 1212x10) */
-#define BPL_MAX_NEVAL 800       /* basis table rows held in shared memory on the fused path */
+#define BPL_MAX_NEVAL 204       /* fused path: neval * BPL_NCPT <= 1024 basis entries held in shared memory */
 
 #define BPL_EINVAL (-1)
 #define BPL_ELIMIT (-2)

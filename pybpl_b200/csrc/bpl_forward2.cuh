@@ -9,7 +9,7 @@
 // banks: sixteen lanes of a 64-bit access hit sixteen distinct even banks, so both orientations of the
 // separable passes remain conflict free.
 //
-// Shared memory: 88 KB image pairs + 1.7 KB side columns + 4 KB basis + 2 x 4.6 KB bookkeeping = 103 KB,
+// Shared memory: 88 KB image pairs + 1.7 KB side columns + 4 KB basis + 4 KB sub-stroke records + 2 x 5.1 KB bookkeeping = 108 KB,
 // two CTAs (= four tokens) per SM, 96 registers per thread.
 #pragma once
 
@@ -28,7 +28,6 @@ struct Fwd2Smem {
     Misc ms[2];
 };
 
-__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
 __device__ __forceinline__ float2 shfl_up2(float2 v) {
     return make_float2(__shfl_up_sync(0xffffffffu, v.x, 1), __shfl_up_sync(0xffffffffu, v.y, 1));
 }
@@ -94,7 +93,7 @@ __device__ __forceinline__ void broaden_inplace2(float2 *A, float2 *side, const 
     const bool ok0 = c0 < IMG, ok1 = c1 < IMG;
     const int a0 = band * BR;
     const float2 *side63 = side, *side64 = side + IMG;
-    const float2 z = make_float2(0.0f, 0.0f), two = make_float2(2.0f, 2.0f), one = make_float2(1.0f, 1.0f);
+    const float2 z = make_float2(0.0f, 0.0f), two = make_float2(2.0f, 2.0f);
     const float2 c1w = make_float2(rc.c1, rc.c1), c2w = make_float2(rc.c2, rc.c2);
     for (int it = 0; it < rc.ink_ncon; ++it) {
         for (int i = threadIdx.x; i < 2 * IMG; i += blockDim.x) {
@@ -145,7 +144,6 @@ __device__ __forceinline__ void broaden_inplace2(float2 *A, float2 *side, const 
         }
         __syncthreads();
     }
-    (void)one;
 }
 
 __global__ void __launch_bounds__(F2_THREADS, F2_CTAS_PER_SM) bpl_forward2_kernel(const KArgs a) {
