@@ -167,13 +167,20 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) bpl_forward_kern
     if (threadIdx.x == 0) ms->cur_img = -1;
     __syncthreads();
 
-    for (int p = blockIdx.x; p < a.n_tokens; p += gridDim.x) {
+    int p = blockIdx.x;
+    while (p < a.n_tokens) {
+        int p_next = 0;
+        if (threadIdx.x == 0) p_next = sched_claim(a, p);      // consumed at the end of the iteration
         const TokGeom t = token_geom<RAW>(a, p);
         if (!RAW && (t.S > MAXS || t.K > MAXK)) {      // beyond the per-CTA tables: flag, do not guess
             if (threadIdx.x == 0) {
                 if (a.ll) a.ll[p] = nanf("");
                 if (a.off_page) a.off_page[p] = 255;
+                ms->next_item = p_next;
             }
+            __syncthreads();
+            p = ms->next_item;
+            __syncthreads();
             continue;
         }
         const float eps = a.eps[p], sigma = a.sigma[p];
@@ -305,8 +312,11 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) bpl_forward_kern
             float *dst = a.pimg + (size_t)p * NPIX;
             for (int i = threadIdx.x; i < NPIX; i += blockDim.x) dst[i] = A[i];
         }
+        if (threadIdx.x == 0) ms->next_item = p_next;
         __syncthreads();
+        p = ms->next_item;      // rewritten only at the end of the next iteration, many barriers from here
     }
+    if (threadIdx.x == 0) sched_finish(a);
 }
 
 }  // namespace bpl

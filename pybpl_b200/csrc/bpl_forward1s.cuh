@@ -1,0 +1,335 @@
+// bpl_forward1s.cuh -- scoring kernel, one token per CTA, work confined to the token's ink bounding box.
+//
+// A token's ink touches about a third of the 105x105 canvas (34 % including the 12-pixel reach of two
+// broaden and two blur passes, measured on the bench workload); everything outside is exactly zero
+// before the epsilon mix and exactly epsilon after it.  The point phase records the bounding box of the
+// splatted pixels; every later phase maps its threads onto the lines and bands that can be non-zero:
+//   broaden    a warp skips its 21-row band when the band cannot hold ink yet
+//   Gaussian   items = (band, line) only for lines inside the box and bands that reach it (threads are
+//              re-packed, so whole warps drop out instead of lanes idling)
+//   Gaussian   ... with the shortest bands (15, 21 or 35 rows) whose items still fit one thread each
+//   tail       ll = [score of an all-background render: lp_bg[1] * ones(target) + lp_bg[0] * zeros(target)]
+//              + sum over the box's pixels of (lp - background lp); one warp per row of the box
+// The box grows by 1 per broaden pass and by 5 along the filtered axis per Gaussian pass.
+// Scalar FP32 (one token cannot use the packed float2 trick), 64 registers, 56 KB shared memory,
+// three CTAs per SM.
+#pragma once
+
+#ifndef BPL_S_THREADS
+#define BPL_S_THREADS 320
+#endif
+#ifndef BPL_S_CTAS
+#define BPL_S_CTAS 3
+#endif
+
+namespace bpl {
+
+constexpr int S_THREADS = BPL_S_THREADS;
+constexpr int S_CTAS_PER_SM = BPL_S_CTAS;
+
+struct BBox {
+    int r0, r1, c0, c1;     // inclusive; empty when r0 > r1
+    __device__ __forceinline__ bool empty() const { return r0 > r1; }
+    __device__ __forceinline__ void grow_rows(int d) { if (!empty()) { r0 = max(0, r0 - d); r1 = min(IMG - 1, r1 + d); } }
+    __device__ __forceinline__ void grow_cols(int d) { if (!empty()) { c0 = max(0, c0 - d); c1 = min(IMG - 1, c1 + d); } }
+};
+
+// in-place 11-tap pass over lines [l0, l0+nl) and bands [b0, b0+nb); see gauss_inplace for the scheme
+struct G6 { float v[PAD + 1]; };      // the half kernel by value: the pass is a real (non-inlined) function so that
+                                       // its six instantiations do not add to the register pressure of the kernel body
+template <bool VERT, int GR, int GU>
+__device__ __noinline__ void gauss_inplace_s(float *buf, const G6 gg, int l0, int nl, int b0, int nb) {
+    static_assert(IMG % GR == 0 && GR % GU == 0 && GU >= PAD, "band structure");
+    const float (&g)[PAD + 1] = gg.v;
+    constexpr int GNB = IMG / GR;
+    constexpr int SA = VERT ? IMG : 1;
+    constexpr int SL = VERT ? 1 : IMG;
+    const int item = threadIdx.x;
+    const bool active = item < nl * nb;
+    const int bi = item / nl;
+    const int band = b0 + bi;
+    const int line = l0 + (item - bi * nl);
+    float *p = buf + band * GR * SA + line * SL;
+    float W[GU + 2 * PAD];
+    float trail[PAD];
+    if (active) {
+#pragma unroll
+        for (int i = 0; i < PAD; ++i) {
+            W[i] = (band > 0) ? p[(i - PAD) * SA] : 0.0f;
+            trail[i] = (band < GNB - 1) ? p[(GR + i) * SA] : 0.0f;
+        }
+    }
+    __syncthreads();
+    if (!active) return;
+#pragma unroll
+    for (int i = 0; i < PAD; ++i) W[PAD + i] = p[i * SA];
+    auto block = [&](float *q) {
+#pragma unroll
+        for (int u = 0; u < GU; ++u) {
+            float acc = g[0] * W[u + PAD];
+#pragma unroll
+            for (int d = 1; d <= PAD; ++d) acc = fmaf(g[d], W[u + PAD - d] + W[u + PAD + d], acc);
+            q[u * SA] = acc;
+        }
+    };
+#pragma unroll 1
+    for (int ob = 0; ob < GR - GU; ob += GU) {
+        float *q = p + ob * SA;
+#pragma unroll
+        for (int u = 0; u < GU; ++u) W[2 * PAD + u] = q[(u + PAD) * SA];
+        block(q);
+#pragma unroll
+        for (int k = 0; k < 2 * PAD; ++k) W[k] = W[k + GU];
+    }
+    float *q = p + (GR - GU) * SA;
+#pragma unroll
+    for (int u = 0; u < GU; ++u) W[2 * PAD + u] = (u + PAD < GU) ? q[(u + PAD) * SA] : trail[u + PAD - GU];
+    block(q);
+}
+
+// Band size: the shortest runs whose items still fit one thread each.  Short runs spread a small box over more
+// threads (a 58 x 70 box is 133 items with 35-row bands but 290 with 15-row bands), at the price of more halo loads.
+#ifndef BPL_GAUSS_BANDS
+#define BPL_GAUSS_BANDS 3
+#endif
+template <bool VERT>
+__device__ __forceinline__ void gauss_box(float *buf, const G6 &g, int l0, int l1, int a0, int a1) {
+    const int nl = l1 - l0 + 1;
+    if (BPL_GAUSS_BANDS >= 3 && nl * (a1 / 15 - a0 / 15 + 1) <= (int)blockDim.x)
+        gauss_inplace_s<VERT, 15, 5>(buf, g, l0, nl, a0 / 15, a1 / 15 - a0 / 15 + 1);
+    else if (BPL_GAUSS_BANDS >= 2 && nl * (a1 / 21 - a0 / 21 + 1) <= (int)blockDim.x)
+        gauss_inplace_s<VERT, 21, 7>(buf, g, l0, nl, a0 / 21, a1 / 21 - a0 / 21 + 1);
+    else if (nl * (a1 / 35 - a0 / 35 + 1) <= (int)blockDim.x)
+        gauss_inplace_s<VERT, 35, 7>(buf, g, l0, nl, a0 / 35, a1 / 35 - a0 / 35 + 1);
+    else
+        gauss_inplace_s<VERT, 105, 7>(buf, g, l0, nl, 0, 1);      // whole lines: always fits (nl <= 105 <= threads)
+}
+
+// In-place 3x3 broaden confined to the box.  The lanes of a warp hold column pairs of the box, the warps split
+// the box's rows evenly: a box up to 64 columns wide takes one warp per row band (the columns left and right
+// of the warp's span are zero), a wider one two (the columns either side of the boundary between them are
+// served from `side`, a copy taken before anything is overwritten).  Halo rows are summed before the
+// barrier; horizontal neighbours travel by shuffle, so nothing is read after a neighbour may have written it.
+// bb is the box of non-zero INPUT pixels; the caller grows it by ink_ncon afterwards.
+__device__ __noinline__ void broaden_box(float *A, float *side, const RenderConsts rc, BBox bb) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const float c1w = rc.c1, c2w = rc.c2;
+    float *sideL = side, *sideR = side + IMG;      // columns cb-1 and cb, cb = first column of the second half
+    for (int it = 0; it < rc.ink_ncon; ++it) {
+        bb.grow_rows(1); bb.grow_cols(1);                  // now the OUTPUT box of this pass
+        const int cs = bb.c0 & ~1;
+        const int npair = (bb.c1 - cs) / 2 + 1;
+        const int nhalf = npair > 32 ? 2 : 1;
+        const int nbands = nw / nhalf;
+        const int nrows = bb.r1 - bb.r0 + 1;
+        const int h = (nrows + nbands - 1) / nbands;
+        const int band = warp / nhalf, half = warp - band * nhalf;
+        const int a0 = bb.r0 + band * h, a1 = min(a0 + h - 1, bb.r1);
+        const bool live = band < nbands && a0 <= a1;
+        const int cb = cs + 64;
+        const int pi = half * 32 + lane;
+        const int c0 = cs + 2 * pi, c1 = c0 + 1;
+        const bool ok0 = pi < npair && c0 < IMG, ok1 = pi < npair && c1 < IMG;
+        const bool last = (it == rc.ink_ncon - 1);
+        if (nhalf == 2)
+            for (int i = threadIdx.x; i < 2 * nrows; i += blockDim.x) {
+                const int sidx = i >= nrows, r = bb.r0 + i - sidx * nrows;
+                side[sidx * IMG + r] = (cb - 1 + sidx < IMG) ? A[r * IMG + cb - 1 + sidx] : 0.0f;
+            }
+        // horizontal (1,2,1) sums of a row.  DIRECT: before the barrier the boundary neighbours are still intact in A
+        auto hrow = [&](int r, bool direct, float &x0, float &x1, float &h0, float &h1) {
+            const float *row = A + r * IMG;
+            x0 = ok0 ? row[c0] : 0.0f;
+            x1 = ok1 ? row[c1] : 0.0f;
+            float xl = __shfl_up_sync(0xffffffffu, x1, 1);
+            float xr = __shfl_down_sync(0xffffffffu, x0, 1);
+            if (lane == 0) xl = (half == 0) ? 0.0f : (direct ? row[cb - 1] : sideL[r]);
+            if (lane == 31) xr = (nhalf == 1 || half == 1) ? 0.0f : (cb < IMG ? (direct ? row[cb] : sideR[r]) : 0.0f);
+            h0 = xl + 2.0f * x0 + x1;
+            h1 = x0 + 2.0f * x1 + xr;
+        };
+        float hp0 = 0.0f, hp1 = 0.0f, ht0 = 0.0f, ht1 = 0.0f, d0, d1;
+        if (live) {
+            if (a0 > 0) hrow(a0 - 1, true, d0, d1, hp0, hp1);
+            if (a1 < IMG - 1) hrow(a1 + 1, true, d0, d1, ht0, ht1);
+        }
+        __syncthreads();
+        if (live) {
+            float xc0, xc1, hc0, hc1;
+            hrow(a0, false, xc0, xc1, hc0, hc1);
+#pragma unroll 2
+            for (int r = a0; r <= a1; ++r) {
+                float xn0 = 0.0f, xn1 = 0.0f, hn0 = ht0, hn1 = ht1;
+                if (r < a1) hrow(r + 1, false, xn0, xn1, hn0, hn1);
+                float v0 = fmaf(c1w, hp0 + 2.0f * hc0 + hn0, c2w * xc0);
+                float v1 = fmaf(c1w, hp1 + 2.0f * hc1 + hn1, c2w * xc1);
+                if (last) { v0 = fminf(v0, 1.0f); v1 = fminf(v1, 1.0f); }      // clamp_(max=1)  (:171)
+                float *row = A + r * IMG;
+                if (ok0) row[c0] = v0;
+                if (ok1) row[c1] = v1;
+                hp0 = hc0; hp1 = hc1; hc0 = hn0; hc1 = hn1; xc0 = xn0; xc1 = xn1;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+struct Fwd1sSmem {
+    float A[FBUF];
+    float side[2 * IMG + 2];
+    float tab[MAX_TABLE];
+    int bbox[4];
+    Misc ms;
+};
+
+__global__ void __launch_bounds__(S_THREADS, S_CTAS_PER_SM) bpl_forward1s_kernel(const KArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Fwd1sSmem &sm = *reinterpret_cast<Fwd1sSmem *>(smem_raw);
+    float *A = sm.A;
+    Misc *ms = &sm.ms;
+    const int lane = threadIdx.x & 31;
+    const bool aff = a.affine != nullptr;
+
+    for (int i = threadIdx.x; i < a.neval * NCPT; i += blockDim.x) sm.tab[i] = a.basis[i];
+    if (threadIdx.x == 0) { ms->cur_img = -1; ms->n_ones = 0; ms->ones_acc = 0; }
+    zero_floats(A, FBUF);              // afterwards the tail re-zeroes exactly the rows it touched
+    __syncthreads();
+#ifdef BPL_PHASE_TIMING
+    long long pt_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long pt_t0 = clock64();
+#endif
+
+    int p = blockIdx.x;
+    while (p < a.n_tokens) {
+        int p_next = 0;
+        if (threadIdx.x == 0) p_next = sched_claim(a, p);      // consumed at the end of the iteration
+        TokGeom t = token_geom<false>(a, p);
+        const bool bad = t.S > MAXS || t.K > MAXK;
+        if (bad) { t.S = 0; t.K = 0; }
+        const float eps = a.eps[p], sigma = a.sigma[p];
+        load_image_bits(a, p, ms);
+        if (threadIdx.x == 0) { ms->off_page = 0; sm.bbox[0] = IMG; sm.bbox[1] = -1; sm.bbox[2] = IMG; sm.bbox[3] = -1; }
+        BPL_PT(0);
+        chain_offsets(a, t, sm.tab, ms);
+        if (aff) affine_setup(a, t, p, sm.tab, ms);
+        token_consts(eps, sigma, false, ms);
+        if (threadIdx.x == 0) {
+            const int img = a.img_idx ? a.img_idx[p] : 0;
+            if (img != ms->cur_img) { ms->n_ones = ms->ones_acc; ms->cur_img = img; }      // a new image was loaded above
+        }
+
+        BPL_PT(1);
+        // ---- add_stroke ----
+        const int QN = (a.neval + PPL - 1) / PPL, items = t.S * QN;
+        bool any_out = false;
+        for (int base = 0; base < items; base += blockDim.x) {
+            const int item = base + threadIdx.x;
+            const bool active = item < items;
+            const int s = active ? item / QN : 0x7fffffff;
+            CtrlSrc src{};
+            if (active) src = make_ctrl_src(a, t, s, sm.tab, ms, aff);
+            const LaneAcc acc = warp_points<false, 1>(active, src, sm.tab, s, a.neval, active ? item - s * QN : 0, lane,
+                                                      a.rc, A, 0.0f, 0, sm.bbox);
+            any_out |= acc.any_out;
+            reduce_by_substroke(active, s, acc.sum, acc.cnt, ms->sub, lane);
+        }
+        BPL_PT(6);
+        any_out = __any_sync(0xffffffffu, any_out);
+        if (any_out && lane == 0) atomicOr(&ms->off_page, 1);
+        __syncthreads();
+        BPL_PT(7);
+        bool need_fix = false;
+        for (int s = 0; s < t.S; ++s) {
+            const float4 v = ms->sub[s];
+            need_fix |= (__float_as_int(v.w) >= 2 && v.z < a.rc.ink_pp);
+        }
+        if (need_fix) {
+            for (int base = 0; base < items; base += blockDim.x) {
+                const int item = base + threadIdx.x;
+                bool active = item < items;
+                const int s = active ? item / QN : 0x7fffffff;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (active) v = ms->sub[s];
+                active = active && (__float_as_int(v.w) >= 2 && v.z < a.rc.ink_pp);
+                CtrlSrc src{};
+                if (active) src = make_ctrl_src(a, t, s, sm.tab, ms, aff);
+                warp_points<true, 1>(active, src, sm.tab, s, a.neval, item < items ? item - s * QN : 0, lane, a.rc, A, v.z,
+                                     __float_as_int(v.w));
+            }
+            __syncthreads();
+        }
+        BBox bb{sm.bbox[0], sm.bbox[1], sm.bbox[2], sm.bbox[3]};
+        BPL_PT(2);
+
+        // ---- broaden + clamp, blur: only where the image can be non-zero ----
+        if (!bb.empty()) {
+            broaden_box(A, sm.side, a.rc, bb);
+            bb.grow_rows(a.rc.ink_ncon); bb.grow_cols(a.rc.ink_ncon);
+            if (a.rc.ink_ncon == 0) {
+                for (int i = threadIdx.x; i < NPIX; i += blockDim.x) A[i] = fminf(A[i], 1.0f);
+                __syncthreads();
+            }
+            BPL_PT(3);
+            if (sigma > 0.0f) {
+                G6 g;
+#pragma unroll
+                for (int d = 0; d <= PAD; ++d) g.v[d] = ms->g[d];
+#pragma unroll 1
+                for (int rep = 0; rep < 2; ++rep) {
+                    // vertical: lines = the box's columns, bands = those holding output rows [r0-5, r1+5]
+                    bb.grow_rows(PAD);
+                    gauss_box<true>(A, g, bb.c0, bb.c1, bb.r0, bb.r1);
+                    __syncthreads();
+                    bb.grow_cols(PAD);
+                    gauss_box<false>(A, g, bb.r0, bb.r1, bb.c0, bb.c1);
+                    __syncthreads();
+                }
+            }
+        }
+
+        BPL_PT(4);
+        // ---- clamp, mix, likelihood ----
+        // ll = [score of an all-background render] + sum over the box of (lp - background lp): the first term is
+        // lp_bg[1] * (ones of the target) + lp_bg[0] * (zeros), the ones counted once per image; background pixels
+        // inside the box contribute exactly 0 to the second.
+        const float bgv = eps > 0.0f ? eps : 0.0f;
+        const float om = 1.0f - eps;
+        const float l0 = ms->lp_bg[0], l1 = ms->lp_bg[1];
+        float acc_ll = 0.0f;
+        if (!bb.empty()) {
+            const int wbox = bb.c1 - bb.c0 + 1;
+            const int nw_ = blockDim.x >> 5, warp_ = threadIdx.x >> 5;
+            for (int r = bb.r0 + warp_; r <= bb.r1; r += nw_) {            // one warp per row of the box
+                for (int cc = lane; cc < wbox; cc += 32) {
+                    const int i = r * IMG + bb.c0 + cc;
+                    float v = fminf(fmaxf(A[i], 0.0f), 1.0f);                                          // clamp_(0,1) (:180)
+                    A[i] = 0.0f;                                            // the buffer is all zero again afterwards
+                    if (eps > 0.0f) v = __fadd_rn(__fmul_rn(om, v), __fmul_rn(eps, __fsub_rn(1.0f, v)));   // (:227)
+                    if (v != bgv) {
+                        const bool x = (ms->bits[i >> 5] >> (i & 31)) & 1u;
+                        acc_ll += pixel_lp_fwd(v, x) - (x ? l1 : l0);
+                    }
+                }
+            }
+        }
+        double v[1] = {(double)acc_ll};
+        if (threadIdx.x == 0) v[0] += (double)ms->n_ones * (double)l1 + (double)(NPIX - ms->n_ones) * (double)l0;
+        block_sum<1>(v, ms->red);
+        if (threadIdx.x == 0) {
+            if (a.ll) a.ll[p] = bad ? nanf("") : (float)v[0];
+            if (a.off_page) a.off_page[p] = bad ? (uint8_t)255 : (uint8_t)(ms->off_page != 0);
+            ms->ones_acc = 0;
+            ms->next_item = p_next;
+        }
+        __syncthreads();
+        p = ms->next_item;      // rewritten only at the end of the next iteration, many barriers from here
+        BPL_PT(5);
+    }
+    if (threadIdx.x == 0) sched_finish(a);
+#ifdef BPL_PHASE_TIMING
+    if (threadIdx.x == 0 && a.pt_buf)
+        for (int i = 0; i < 8; ++i) a.pt_buf[blockIdx.x * 16 + i] = (float)pt_acc[i];
+#endif
+}
+
+}  // namespace bpl

@@ -155,8 +155,11 @@ __global__ void __launch_bounds__(F2_THREADS, F2_CTAS_PER_SM) bpl_forward2_kerne
 
     for (int i = threadIdx.x; i < a.neval * NCPT; i += blockDim.x) sm.tab[i] = a.basis[i];
     if (threadIdx.x < 2) sm.ms[threadIdx.x].cur_img = -1;
+    int q = blockIdx.x;                 // the pair being processed: the first one is fixed, later ones come from the queue
+    if (threadIdx.x == 0) sm.ms[0].next_item = sched_claim(a, q);
     zero_floats(reinterpret_cast<float *>(A), 2 * NPIX);      // afterwards the tail of every pair re-zeroes what it reads
     __syncthreads();
+    int q1 = sm.ms[0].next_item;        // the pair after it (claimed one ahead so that its geometry can be prefetched)
 
 #ifdef BPL_PHASE_TIMING
     long long pt_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -182,10 +185,12 @@ __global__ void __launch_bounds__(F2_THREADS, F2_CTAS_PER_SM) bpl_forward2_kerne
         return in;
     };
     PairIn nxt{};
-    if ((int)blockIdx.x < npairs) nxt = fetch(blockIdx.x);
-    for (int q = blockIdx.x; q < npairs; q += gridDim.x) {
+    if (q < npairs) nxt = fetch(q);
+    while (q < npairs) {
         const PairIn cur = nxt;
-        if (q + (int)gridDim.x < npairs) nxt = fetch(q + gridDim.x);
+        int q2 = 0;
+        if (threadIdx.x == 0) q2 = sched_claim(a, q1);      // consumed at the end of the iteration
+        if (q1 < npairs) nxt = fetch(q1);
         const bool have1 = cur.have1;
         const int pt[2] = {cur.pt[0], cur.pt[1]};
         TokGeom t[2] = {cur.t[0], cur.t[1]};
@@ -411,9 +416,13 @@ __global__ void __launch_bounds__(F2_THREADS, F2_CTAS_PER_SM) bpl_forward2_kerne
             __syncthreads();
             zero_floats(reinterpret_cast<float *>(A), 2 * NPIX);      // the deltas must not leak into the next pair
         }
+        if (threadIdx.x == 0) sm.ms[0].next_item = q2;
         __syncthreads();
+        q = q1;
+        q1 = sm.ms[0].next_item;      // rewritten only at the end of the next iteration, many barriers from here
         BPL_PT(5);      // tail + reduction
     }
+    if (threadIdx.x == 0) sched_finish(a);
 #ifdef BPL_PHASE_TIMING
     if (threadIdx.x == 0 && a.pt_buf)
         for (int i = 0; i < 8; ++i) a.pt_buf[blockIdx.x * 16 + i] = (float)pt_acc[i];

@@ -86,7 +86,8 @@ __device__ __forceinline__ CtrlSrc shfl_src(const CtrlSrc &s, int from, const fl
 // difference to the common-branch ink is splatted.
 template <bool FIX, int PIXSTRIDE, int ROWSTRIDE = IMG, int ORG = 0, int PPL = PPL_DEFAULT>
 __device__ __forceinline__ LaneAcc warp_points(bool active, const CtrlSrc &src, const float *tab, int sid, int n, int q,
-                                               int lane, const RenderConsts &rc, float *img, float fix_sum, int fix_cnt) {
+                                               int lane, const RenderConsts &rc, float *img, float fix_sum, int fix_cnt,
+                                               int *bbox = nullptr) {
     LaneAcc acc{};
     if (!__any_sync(0xffffffffu, active)) return acc;      // e.g. the fix pass: most warps have nothing to patch
     const int j0 = q * PPL;
@@ -156,6 +157,7 @@ __device__ __forceinline__ LaneAcc warp_points(bool active, const CtrlSrc &src, 
     // Consecutive points of a run mostly fall into the same pixel cell: their four corner contributions are
     // summed in registers and flushed with one set of atomics when the cell changes (2-4x fewer atomics).
     int cell = -1;
+    int brmin = IMG, brmax = -1, bcmin = IMG, bcmax = -1;      // pixels this lane touches (for the sparse kernel)
     float a00 = 0.0f, a10 = 0.0f, a01 = 0.0f, a11 = 0.0f;
     auto flush = [&]() {
         if (cell >= 0) {
@@ -177,6 +179,8 @@ __device__ __forceinline__ LaneAcc warp_points(bool active, const CtrlSrc &src, 
         if (key != cell) {
             flush();
             cell = key; a00 = a10 = a01 = a11 = 0.0f;
+            brmin = min(brmin, (int)rf); brmax = max(brmax, (int)rce);
+            bcmin = min(bcmin, (int)cf); bcmax = max(bcmax, (int)cce);
         }
         a00 += __fmul_rn(__fmul_rn(ink, gr), gc);
         a10 += __fmul_rn(__fmul_rn(ink, fr_), gc);
@@ -212,6 +216,14 @@ __device__ __forceinline__ LaneAcc warp_points(bool active, const CtrlSrc &src, 
     }
     if (have_first) emit(fr, fc, first_ink);
     flush();
+    if (bbox) {         // warp-uniform pointer: one set of shared-memory atomics per warp
+        brmin = __reduce_min_sync(0xffffffffu, brmin); brmax = __reduce_max_sync(0xffffffffu, brmax);
+        bcmin = __reduce_min_sync(0xffffffffu, bcmin); bcmax = __reduce_max_sync(0xffffffffu, bcmax);
+        if (lane == 0 && brmax >= 0) {
+            atomicMin(bbox + 0, brmin); atomicMax(bbox + 1, brmax);
+            atomicMin(bbox + 2, bcmin); atomicMax(bbox + 3, bcmax);
+        }
+    }
 #ifdef BPL_PHASE_TIMING
     { const long long t1 = clock64(); acc.tC = t1 - tt0; tt0 = t1; }
 #endif

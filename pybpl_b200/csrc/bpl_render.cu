@@ -24,6 +24,14 @@ namespace bpl {
 // ------------------------------------------------------------------------------------------
 // kernel arguments
 // ------------------------------------------------------------------------------------------
+// Work queue of one launch of a persistent kernel.  Tokens differ in cost by 3x (1-15 sub-strokes) and a launch of
+// the bench batch gives an SM only ~28 of them, so a fixed token -> CTA assignment leaves the slowest SM ~15 %
+// behind the mean.  CTAs take their first item by blockIdx.x and every later one from `next`; the CTA that
+// finishes last resets the slot, so a slot is all-zero again when its launch completes.
+struct Sched { unsigned next, done; };
+constexpr int SCHED_RING = 4096;      // launches in flight at once never come near this
+__device__ Sched g_sched[SCHED_RING];
+
 struct KArgs {
     RenderConsts rc;
     int n_tokens;
@@ -47,7 +55,19 @@ struct KArgs {
     const float *g_ll, *g_pimg;
     float *g_ctrl, *g_invscale, *g_position, *g_affine, *g_pts, *g_eps, *g_sigma;
     float *pt_buf;           // phase-timing counters (only read by -DBPL_PHASE_TIMING builds)
+    Sched *sched;            // work queue of this launch; NULL = fixed stride (BPL_STATIC_SCHED=1, A/B only)
 };
+
+// thread 0 only: the item after `cur`
+__device__ __forceinline__ int sched_claim(const KArgs &a, int cur) {
+    return a.sched ? (int)(atomicAdd(&a.sched->next, 1u) + gridDim.x) : cur + (int)gridDim.x;
+}
+// thread 0 only, once per CTA, after its last claim
+__device__ __forceinline__ void sched_finish(const KArgs &a) {
+    if (!a.sched) return;
+    __threadfence();
+    if (atomicAdd(&a.sched->done, 1u) == gridDim.x - 1u) { a.sched->next = 0u; a.sched->done = 0u; }
+}
 
 // Per-CTA bookkeeping in shared memory.
 struct Misc {
@@ -61,6 +81,9 @@ struct Misc {
     double aff_acc[4];       // sum gx*prex, sum gy*prey, sum gx, sum gy
     int off_page;
     int cur_img;
+    int next_item;           // work queue hand-over (thread 0 -> block)
+    int n_ones;              // set bits of the current target image (maintained by the sparse scoring kernel)
+    int ones_acc;            // accumulator for n_ones while a new image is loaded
     uint32_t bits[IMG_WORDS + 1];
 };
 
@@ -389,8 +412,14 @@ __device__ __forceinline__ void load_image_bits(const KArgs &a, int p, Misc *ms)
     if (!a.image_bits) return;
     const int t = a.img_idx ? a.img_idx[p] : 0;
     if (t == ms->cur_img) return;      // cur_img is only written after the barrier below, read before it
-    for (int i = threadIdx.x; i < IMG_WORDS; i += blockDim.x)
-        ms->bits[i] = a.image_bits[(size_t)t * IMG_WORDS + i];
+    int ones = 0;
+    for (int i = threadIdx.x; i < IMG_WORDS; i += blockDim.x) {
+        const uint32_t wv = a.image_bits[(size_t)t * IMG_WORDS + i];
+        ms->bits[i] = wv;
+        ones += __popc(wv);
+    }
+    ones = __reduce_add_sync(0xffffffffu, ones);      // every thread of the block is here (cur_img is block-uniform)
+    if ((threadIdx.x & 31) == 0 && ones) atomicAdd(&ms->ones_acc, ones);
 }
 
 __device__ __forceinline__ void zero_floats(float *p, int n) {
@@ -429,6 +458,7 @@ __device__ __forceinline__ void broaden(float *A, float *T, const RenderConsts &
 
 #include "bpl_forward.cuh"
 #include "bpl_forward2.cuh"
+#include "bpl_forward1s.cuh"
 
 namespace bpl {
 
@@ -554,14 +584,21 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) bpl_backward_kernel(const KArg
     long long pt_acc[12] = {0};
     long long pt_t0 = clock64();
 #endif
-    for (int p = blockIdx.x; p < a.n_tokens; p += gridDim.x) {
+    int p = blockIdx.x;
+    while (p < a.n_tokens) {
+        int p_next = 0;
+        if (threadIdx.x == 0) p_next = sched_claim(a, p);      // consumed at the end of the iteration
         const TokGeom t = token_geom<RAW>(a, p);
         const float eps = a.eps[p], sigma = a.sigma[p];
         if (!RAW && (t.S > MAXS || t.K > MAXK)) {      // beyond the per-CTA tables: flag, do not guess
             if (threadIdx.x == 0) {
                 if (a.ll) a.ll[p] = nanf("");
                 if (a.off_page) a.off_page[p] = 255;
+                ms->next_item = p_next;
             }
+            __syncthreads();
+            p = ms->next_item;
+            __syncthreads();
             continue;
         }
         const bool aff = !RAW && a.affine != nullptr;
@@ -912,9 +949,12 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) bpl_backward_kernel(const KArg
             // B's interior was used as scratch: restore zeros (its border was never touched)
             for (int i = threadIdx.x; i < t.S * NACC; i += blockDim.x) accs[ORIGIN + i] = 0.0f;
         }
+        if (threadIdx.x == 0) ms->next_item = p_next;
         __syncthreads();
+        p = ms->next_item;      // rewritten only at the end of the next iteration, many barriers from here
         BPL_PT(7);      // chain backward + outputs
     }
+    if (threadIdx.x == 0) sched_finish(a);
 #ifdef BPL_PHASE_TIMING
     if (threadIdx.x == 0 && a.pt_buf)
         for (int i = 0; i < 8; ++i) a.pt_buf[blockIdx.x * 16 + i] = (float)pt_acc[i];
@@ -1028,6 +1068,14 @@ static int launch(K kernel, int threads, size_t smem, int ctas_per_sm, const KAr
     if (grid > work_items) grid = work_items;
     if (grid <= 0) return 0;
     KArgs kb = ka;
+    static const bool static_sched = getenv("BPL_STATIC_SCHED") != nullptr;
+    if (!static_sched) {
+        static std::atomic<unsigned> slot{0};
+        Sched *base = nullptr;
+        cudaError_t es = cudaGetSymbolAddress(reinterpret_cast<void **>(&base), g_sched);      // per current device
+        if (es != cudaSuccess) { set_error("cudaGetSymbolAddress: %s", cudaGetErrorString(es)); return (int)es; }
+        kb.sched = base + (slot.fetch_add(1u) % SCHED_RING);
+    }
 #ifdef BPL_PHASE_TIMING
     if (const char *pb = getenv("BPL_PT_BUF")) kb.pt_buf = reinterpret_cast<float *>(strtoull(pb, nullptr, 10));
 #endif
@@ -1093,7 +1141,12 @@ int bpl_score_tokens(const bpl_params *ps, const bpl_token_batch *b, const bpl_t
     if (ka.all_pairs && (!ka.image_bits || ka.pimg || ka.n_images < 1)) {
         set_error("%s", "all_pairs scoring needs target images and no pimg output"); return BPL_EINVAL;
     }
-    static const bool force_single = getenv("BPL_FORCE_SINGLE") != nullptr;     // profiling aid: one token per CTA
+    // Scoring one target per token: the box-confined kernel (one token per CTA).  BPL_FWD_PAIRED=1 / BPL_FORCE_SINGLE=1
+    // select the dense paired / dense single kernels instead (A/B and profiling aids).
+    static const bool force_single = getenv("BPL_FORCE_SINGLE") != nullptr;
+    static const bool force_paired = getenv("BPL_FWD_PAIRED") != nullptr;
+    if (!force_single && !force_paired && ka.image_bits && !ka.pimg && !ka.all_pairs)
+        return launch(bpl_forward1s_kernel, S_THREADS, sizeof(Fwd1sSmem), S_CTAS_PER_SM, ka, (cudaStream_t)stream);
     if (ka.image_bits && !ka.pimg && (!force_single || ka.all_pairs))      // scoring hot path: two tokens per CTA, packed FP32 stencils
         return launch(bpl_forward2_kernel, F2_THREADS, sizeof(Fwd2Smem), F2_CTAS_PER_SM, ka, (cudaStream_t)stream,
                       (ka.n_tokens + 1) / 2);
