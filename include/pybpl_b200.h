@@ -59,6 +59,9 @@ typedef struct {
     const float *eps;           /* dev [P]  CharacterToken.epsilon */
     const float *sigma;         /* dev [P]  CharacterToken.blur_sigma */
     const float *basis;         /* dev [neval][ncpt]  coefficient_mat(ncpt, neval) (pybpl/splines.py:72-93) */
+    const int *order;           /* dev [P] or NULL: a permutation of 0..P-1, the order in which the persistent kernels
+                                 * take the tokens (results do not depend on it; bpl_order_tokens gives the order that
+                                 * ends a small launch on its cheapest tokens) */
 } bpl_token_batch;
 
 /* A ragged batch of characters given as raw motor-space trajectories = the `strokes`
@@ -144,6 +147,9 @@ int bpl_pack_images_f32(const float *img, int T, uint32_t *bits, int *bad, void 
  * Bernoulli log_prob.  One CTA per token; the image never leaves shared memory. */
 int bpl_score_tokens(const bpl_params *ps, const bpl_token_batch *b, const bpl_targets *t, const bpl_fwd_out *out,
                      void *stream);
+/* order[P] <- the tokens by decreasing sub-stroke count (only the CSR offsets of b are read).  No reference
+ * counterpart: the reference renders one token per Python call. */
+int bpl_order_tokens(const bpl_token_batch *b, int *order, void *stream);
 /* Same, plus the fused backward (autograd-equivalent gradients). */
 int bpl_score_tokens_grad(const bpl_params *ps, const bpl_token_batch *b, const bpl_targets *t,
                           const bpl_fwd_out *out, const bpl_grads *g, void *stream);

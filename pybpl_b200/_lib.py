@@ -30,7 +30,7 @@ class Params(ctypes.Structure):
 class TokenBatchC(ctypes.Structure):
     _fields_ = [("n_tokens", ctypes.c_int), ("ncpt", ctypes.c_int), ("neval", ctypes.c_int),
                 ("tok_stroke_off", vp), ("stroke_sub_off", vp), ("ctrl", vp), ("invscale", vp), ("position", vp),
-                ("affine", vp), ("eps", vp), ("sigma", vp), ("basis", vp)]
+                ("affine", vp), ("eps", vp), ("sigma", vp), ("basis", vp), ("order", vp)]
 
 
 class StrokeBatchC(ctypes.Structure):
@@ -69,6 +69,7 @@ EXPORTS = {
     "bpl_pack_images_f32": (ctypes.c_int, [vp, ctypes.c_int, vp, vp, vp]),
     "bpl_score_tokens": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.POINTER(TokenBatchC), ctypes.POINTER(Targets),
                                         ctypes.POINTER(FwdOut), vp]),
+    "bpl_order_tokens": (ctypes.c_int, [ctypes.POINTER(TokenBatchC), vp, vp]),
     "bpl_score_tokens_grad": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.POINTER(TokenBatchC),
                                              ctypes.POINTER(Targets), ctypes.POINTER(FwdOut), ctypes.POINTER(Grads), vp]),
     "bpl_render_strokes": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.POINTER(StrokeBatchC),

@@ -164,13 +164,14 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) bpl_forward_kern
 
     if (!RAW)
         for (int i = threadIdx.x; i < a.neval * NCPT; i += blockDim.x) sm.tab[i] = a.basis[i];
-    if (threadIdx.x == 0) ms->cur_img = -1;
+    if (threadIdx.x == 0) { ms->cur_img = -1; ms->c_eps = ms->c_sigma = nanf(""); }
     __syncthreads();
 
-    int p = blockIdx.x;
+    int item = blockIdx.x;                                      // position in the work queue (advanced by thread 0 only)
+    int p = (!RAW && a.order) ? a.order[item] : item;           // the token it stands for
     while (p < a.n_tokens) {
         int p_next = 0;
-        if (threadIdx.x == 0) p_next = sched_claim(a, p);      // consumed at the end of the iteration
+        if (threadIdx.x == 0) p_next = sched_next_token(a, item);      // consumed at the end of the iteration
         const TokGeom t = token_geom<RAW>(a, p);
         if (!RAW && (t.S > MAXS || t.K > MAXK)) {      // beyond the per-CTA tables: flag, do not guess
             if (threadIdx.x == 0) {

@@ -90,18 +90,20 @@ __device__ __noinline__ void gauss_inplace_s(float *buf, const G6 gg, int l0, in
 // Band size: the shortest runs whose items still fit one thread each.  Short runs spread a small box over more
 // threads (a 58 x 70 box is 133 items with 35-row bands but 290 with 15-row bands), at the price of more halo loads.
 #ifndef BPL_GAUSS_BANDS
-#define BPL_GAUSS_BANDS 3
+#define BPL_GAUSS_BANDS 1
 #endif
 template <bool VERT>
 __device__ __forceinline__ void gauss_box(float *buf, const G6 &g, int l0, int l1, int a0, int a1) {
     const int nl = l1 - l0 + 1;
     if (BPL_GAUSS_BANDS >= 3 && nl * (a1 / 15 - a0 / 15 + 1) <= (int)blockDim.x)
         gauss_inplace_s<VERT, 15, 5>(buf, g, l0, nl, a0 / 15, a1 / 15 - a0 / 15 + 1);
-    else if (BPL_GAUSS_BANDS >= 2 && nl * (a1 / 21 - a0 / 21 + 1) <= (int)blockDim.x)
+#if BPL_GAUSS_BANDS == 2 || BPL_GAUSS_BANDS == 4
+    else if (nl * (a1 / 21 - a0 / 21 + 1) <= (int)blockDim.x)
         gauss_inplace_s<VERT, 21, 7>(buf, g, l0, nl, a0 / 21, a1 / 21 - a0 / 21 + 1);
-    else if (nl * (a1 / 35 - a0 / 35 + 1) <= (int)blockDim.x)
+#endif
+    else if (S_THREADS >= 3 * IMG || nl * (a1 / 35 - a0 / 35 + 1) <= (int)blockDim.x)
         gauss_inplace_s<VERT, 35, 7>(buf, g, l0, nl, a0 / 35, a1 / 35 - a0 / 35 + 1);
-    else
+    else if (S_THREADS < 3 * IMG)
         gauss_inplace_s<VERT, 105, 7>(buf, g, l0, nl, 0, 1);      // whole lines: always fits (nl <= 105 <= threads)
 }
 
@@ -191,7 +193,7 @@ __global__ void __launch_bounds__(S_THREADS, S_CTAS_PER_SM) bpl_forward1s_kernel
     const bool aff = a.affine != nullptr;
 
     for (int i = threadIdx.x; i < a.neval * NCPT; i += blockDim.x) sm.tab[i] = a.basis[i];
-    if (threadIdx.x == 0) { ms->cur_img = -1; ms->n_ones = 0; ms->ones_acc = 0; }
+    if (threadIdx.x == 0) { ms->cur_img = -1; ms->c_eps = ms->c_sigma = nanf(""); ms->n_ones = 0; ms->ones_acc = 0; }
     zero_floats(A, FBUF);              // afterwards the tail re-zeroes exactly the rows it touched
     __syncthreads();
 #ifdef BPL_PHASE_TIMING
@@ -199,10 +201,11 @@ __global__ void __launch_bounds__(S_THREADS, S_CTAS_PER_SM) bpl_forward1s_kernel
     long long pt_t0 = clock64();
 #endif
 
-    int p = blockIdx.x;
+    int item = blockIdx.x;                                      // position in the work queue (advanced by thread 0 only)
+    int p = a.order ? a.order[item] : item;                     // the token it stands for
     while (p < a.n_tokens) {
         int p_next = 0;
-        if (threadIdx.x == 0) p_next = sched_claim(a, p);      // consumed at the end of the iteration
+        if (threadIdx.x == 0) p_next = sched_next_token(a, item);      // consumed at the end of the iteration
         TokGeom t = token_geom<false>(a, p);
         const bool bad = t.S > MAXS || t.K > MAXK;
         if (bad) { t.S = 0; t.K = 0; }

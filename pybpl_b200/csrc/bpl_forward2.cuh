@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(F2_THREADS, F2_CTAS_PER_SM) bpl_forward2_kerne
     const bool aff = a.affine != nullptr;
 
     for (int i = threadIdx.x; i < a.neval * NCPT; i += blockDim.x) sm.tab[i] = a.basis[i];
-    if (threadIdx.x < 2) sm.ms[threadIdx.x].cur_img = -1;
+    if (threadIdx.x < 2) { sm.ms[threadIdx.x].cur_img = -1; sm.ms[threadIdx.x].c_eps = sm.ms[threadIdx.x].c_sigma = nanf(""); }
     int q = blockIdx.x;                 // the pair being processed: the first one is fixed, later ones come from the queue
     if (threadIdx.x == 0) sm.ms[0].next_item = sched_claim(a, q);
     zero_floats(reinterpret_cast<float *>(A), 2 * NPIX);      // afterwards the tail of every pair re-zeroes what it reads

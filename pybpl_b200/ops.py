@@ -173,6 +173,24 @@ class TokenBatch:
         self.device = dev
         self._sub_token = None
         self._stroke_token = None
+        self._order = None
+
+    # Processing order for the persistent kernels: expensive tokens first, so that a launch of a few thousand tokens
+    # (a few dozen per SM) does not end with one SM still busy on a large one.  It depends only on the CSR offsets,
+    # so it is computed once per batch (one small kernel); large batches keep index order.
+    ORDER_MAX_TOKENS = 16384
+
+    def order_ptr(self):
+        if self.P > self.ORDER_MAX_TOKENS or self.P < 2 or os.environ.get("BPL_NO_ORDER"):      # (env: A/B aid)
+            return None
+        if self._order is None:
+            order = torch.empty(self.P, dtype=torch.int32, device=self.device)
+            b = _lib.TokenBatchC()
+            b.n_tokens = self.P
+            b.tok_stroke_off = self.tok_stroke_off.data_ptr(); b.stroke_sub_off = self.stroke_sub_off.data_ptr()
+            check(lib().bpl_order_tokens(ctypes.byref(b), order.data_ptr(), _stream(self.device)))
+            self._order = order
+        return self._order.data_ptr()
 
     # token index of every sub-stroke / stroke (for scaling gradients by the per-token cotangent)
     @property
@@ -200,6 +218,7 @@ class TokenBatch:
         b.affine = None if affine is None else affine.data_ptr()
         b.eps = eps.data_ptr(); b.sigma = sigma.data_ptr()
         b.basis = basis_table(NCPT, self.neval, self.device).data_ptr()
+        b.order = self.order_ptr()
         return b
 
 

@@ -10,7 +10,7 @@ cur_file = "?"
 data = []
 hdr = None
 for r in rows:
-    if len(r) >= 2 and r[0] == "File Name":
+    if len(r) >= 2 and r[0] in ("File Name", "File Path"):
         cur_file = r[1].split("/")[-1]
         continue
     if len(r) > 8 and r[0] == "Line No":
