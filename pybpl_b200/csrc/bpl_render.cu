@@ -87,9 +87,11 @@ struct Misc {
     float affB[4], com[2];
     float colsum[8];         // column sums of the basis table (affine backward)
     double aff_acc[4];       // sum gx*prex, sum gy*prey, sum gx, sum gy
+    double dlp_bg_d[2];      // d lp / d p of a background pixel, analytic in double (for the closed-form d/d epsilon)
     int off_page;
     int cur_img;
     int next_item;           // work queue hand-over (thread 0 -> block)
+    int bbox[4];             // rows / columns touched by the splat (min r, max r, min c, max c)
     int n_ones;              // set bits of the current target image (maintained by the sparse scoring kernel)
     int ones_acc;            // accumulator for n_ones while a new image is loaded
     uint32_t bits[IMG_WORDS + 1];
@@ -408,6 +410,7 @@ __device__ __noinline__ void token_consts_eps(float eps, bool x, Misc *ms) {
     pixel_lp_exact(bg, x, lp, dlp);
     ms->lp_bg[x] = lp;
     ms->dlp_bg[x] = dlp;
+    ms->dlp_bg_d[x] = (bg < TORCH_EPS || bg > 1.0f - TORCH_EPS) ? 0.0 : (x ? 1.0 / (double)bg : -1.0 / (1.0 - (double)bg));
 }
 
 __device__ __noinline__ void token_consts_sigma(float sigma, int lane, Misc *ms) {
@@ -452,25 +455,18 @@ __device__ __forceinline__ void zero_floats(float *p, int n) {
 
 // broaden (rendering.py:160-171): ncon x [ c1 * S_h S_v + c2 ], then min(.,1) if CLAMP.
 // A holds the image and receives the result; T is scratch.
-template <int R3, bool CLAMP>
-__device__ __forceinline__ void broaden(float *A, float *T, const RenderConsts &rc) {
+template <int R3>
+__device__ __forceinline__ void broaden(float *A, float *T, const RenderConsts &rc, const Box &bx) {
     const float w3[1][2] = {{2.0f, 1.0f}};
     for (int it = 0; it < rc.ink_ncon; ++it) {
-        sweep<3, R3, true, 1>(A, w3, LoadId(), [&](int r, int c, const float (&acc)[1]) {
+        sweep_box<3, R3, true, 1>(A, w3, LoadId(), [&](int r, int c, const float (&acc)[1]) {
             T[ORIGIN + r * STRIDE + c] = acc[0];
-        });
+        }, bx);
         __syncthreads();
-        const bool last = CLAMP && (it == rc.ink_ncon - 1);
-        sweep<3, R3, false, 1>(T, w3, LoadId(), [&](int r, int c, const float (&acc)[1]) {
+        sweep_box<3, R3, false, 1>(T, w3, LoadId(), [&](int r, int c, const float (&acc)[1]) {
             float *q = A + ORIGIN + r * STRIDE + c;
-            float v = fmaf(rc.c1, acc[0], rc.c2 * (*q));
-            if (last) v = fminf(v, 1.0f);
-            *q = v;
-        });
-        __syncthreads();
-    }
-    if (CLAMP && rc.ink_ncon == 0) {
-        for (int i = threadIdx.x; i < BUFN; i += blockDim.x) A[i] = fminf(A[i], 1.0f);
+            *q = fmaf(rc.c1, acc[0], rc.c2 * (*q));
+        }, bx);
         __syncthreads();
     }
 }
@@ -581,11 +577,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) bpl_backward_kernel(const KArg
     Misc *ms = &sm.ms;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
 
-    zero_floats(B, 3 * BUFP);    // B, C, D are contiguous
+    zero_floats(A, 4 * BUFP);    // A, B, C, D are contiguous; every token leaves them all-zero again (see the end of the loop)
     if (!RAW) {
         for (int i = threadIdx.x; i < a.neval * NCPT; i += blockDim.x) sm.tab[i] = a.basis[i];
     }
-    if (threadIdx.x == 0) { ms->cur_img = -1; ms->c_eps = ms->c_sigma = nanf(""); }
+    if (threadIdx.x == 0) { ms->cur_img = -1; ms->c_eps = ms->c_sigma = nanf(""); ms->n_ones = 0; ms->ones_acc = 0; }
     __syncthreads();
     if (!RAW && warp == 0) {     // column sums of the table (d com / d control points)
         float cs[NCPT];
@@ -624,11 +620,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) bpl_backward_kernel(const KArg
             continue;
         }
         const bool aff = !RAW && a.affine != nullptr;
-        zero_floats(A, BUFP);
         load_image_bits(a, p, ms);
         if (threadIdx.x == 0) {
             ms->off_page = 0;
             ms->aff_acc[0] = ms->aff_acc[1] = ms->aff_acc[2] = ms->aff_acc[3] = 0.0;
+            ms->bbox[0] = IMG; ms->bbox[1] = -1; ms->bbox[2] = IMG; ms->bbox[3] = -1;
         }
         if (!RAW) {
             chain_offsets(a, t, sm.tab, ms);
@@ -637,7 +633,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) bpl_backward_kernel(const KArg
             __syncthreads();
         }
         token_consts(eps, sigma, true, ms);      // double-precision constants by one warp, hidden behind the splat
-        if (threadIdx.x == 0 && a.image_bits) ms->cur_img = a.img_idx ? a.img_idx[p] : 0;
+        if (threadIdx.x == 0 && a.image_bits) {
+            const int img = a.img_idx ? a.img_idx[p] : 0;
+            if (img != ms->cur_img) { ms->n_ones = ms->ones_acc; ms->cur_img = img; }      // a new image was loaded above
+        }
 
         BPL_PT(0);      // setup + chain offsets
         // ---- forward: splat ----
@@ -652,6 +651,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) bpl_backward_kernel(const KArg
             }
             any_out = __any_sync(0xffffffffu, any_out);
             if (any_out && lane == 0) atomicOr(&ms->off_page, 1);
+            if (threadIdx.x == 0) { ms->bbox[0] = 0; ms->bbox[1] = IMG - 1; ms->bbox[2] = 0; ms->bbox[3] = IMG - 1; }      // raw mode: whole canvas
             __syncthreads();
         } else {
             const int QN = (a.neval + BWD_PPL - 1) / BWD_PPL, items = t.S * QN;
@@ -662,7 +662,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) bpl_backward_kernel(const KArg
                 CtrlSrc src{};
                 if (active) src = make_ctrl_src(a, t, s, sm.tab, ms, aff);
                 const LaneAcc acc = warp_points<false, 1, STRIDE, ORIGIN, BWD_PPL>(active, src, sm.tab, s, a.neval,
-                                                                          active ? item - s * QN : 0, lane, a.rc, A, 0.0f, 0);
+                                                                          active ? item - s * QN : 0, lane, a.rc, A, 0.0f, 0,
+                                                                          ms->bbox);
                 any_out |= acc.any_out;
                 reduce_by_substroke(active, s, acc.sum, acc.cnt, ms->sub, lane);
             }
@@ -692,8 +693,25 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) bpl_backward_kernel(const KArg
         }
 
         BPL_PT(1);      // forward splat (+fix)
+        // Everything from here to the gather stage works on one box of the canvas: the pixels the splat touched
+        // grown by the reach of all stencil passes (ink_ncon + 2 * 5).  Forward values are exactly zero outside it.
+        // The cotangent d L / d pimg is NOT zero outside it, but the gather stage only reads the adjoint at the
+        // splat's own pixels, and those are exact when the cotangent is known on the grown box (each adjoint pass
+        // gives up its reach at the box's rim: 5 + 5 + 5 + 5 + ncon + ncon along each axis in total).  The scalar
+        // outputs (ll, d/d epsilon) get the closed-form contribution of an all-background image and sum
+        // differences to it inside the box; d/d sigma has no contribution outside it.
+        Box bx{ms->bbox[0], ms->bbox[1], ms->bbox[2], ms->bbox[3]};
+        if (bx.r0 <= bx.r1) {
+            const int reach = a.rc.ink_ncon + 2 * PAD;
+            bx.r0 = max(0, bx.r0 - reach); bx.r1 = min(IMG - 1, bx.r1 + reach);
+            bx.c0 = max(0, bx.c0 - reach); bx.c1 = min(IMG - 1, bx.c1 + reach);
+            // rounded out to whole bands of the sweeps (105 = 7 * 15, so this stays on the canvas)
+            static_assert(BWD_R == BWD_R3, "one band size for all passes");
+            bx.r0 = bx.r0 / BWD_R * BWD_R; bx.r1 = bx.r1 / BWD_R * BWD_R + BWD_R - 1;
+            bx.c0 = bx.c0 / BWD_R * BWD_R; bx.c1 = bx.c1 / BWD_R * BWD_R + BWD_R - 1;
+        }
         // ---- forward: broaden; A keeps I2 (pre-clamp); consumers apply min(.,1) on load ----
-        broaden<BWD_R3, false>(A, B, a.rc);
+        broaden<BWD_R3>(A, B, a.rc, bx);
 
         BPL_PT(2);      // forward broaden
         const float bgv = eps > 0.0f ? eps : 0.0f;
@@ -704,7 +722,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) bpl_backward_kernel(const KArg
         const bool score = a.image_bits != nullptr;
         const float *gP_ext = a.g_pimg ? a.g_pimg + (size_t)p * NPIX : nullptr;
         const float gscale = (!gP_ext && a.g_ll) ? a.g_ll[p] : 1.0f;
-        float acc_ll = 0.0f, acc_eps = 0.0f, acc_sig = 0.0f;
+        const double dlp_bgd0 = ms->dlp_bg_d[0], dlp_bgd1 = ms->dlp_bg_d[1];
+        float acc_ll = 0.0f, acc_sig = 0.0f;
+        double acc_eps = 0.0;      // terms of +-1e4 that cancel to a few tens: summed in double
 
         // pointwise tail of the forward + head of the backward for pixel (r,c) with blurred value v:
         // returns d L / d I5 (cotangent entering the second blur pass).
@@ -716,15 +736,22 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) bpl_backward_kernel(const KArg
             float gp;
             if (gP_ext) {
                 gp = gP_ext[r * IMG + c];
+                if (eps > 0.0f) acc_eps += (double)(-2.0f * gp * i6);        // d/d eps of (1-eps) p + eps (1-p) is 1 - 2 p;
+                                                                            // the sum of gp over the canvas is added below
             } else {
                 const bool x = score && ((ms->bits[(r * IMG + c) >> 5] >> ((r * IMG + c) & 31)) & 1u);
-                float lp, d;
-                if (pm == bgv) { lp = x ? lp_bg1 : lp_bg0; d = x ? dlp_bg1 : dlp_bg0; }
-                else pixel_lp(pm, x, true, lp, d);
-                acc_ll += lp;
+                const float lb = x ? lp_bg1 : lp_bg0, db = x ? dlp_bg1 : dlp_bg0;
+                float lp = lb, d = db;
+                if (pm != bgv) {                                             // a background pixel adds nothing to the sum
+                    pixel_lp(pm, x, true, lp, d);
+                    acc_ll += lp - lb;
+                }
+                // A pixel without ink has the analytic background value (closed form below); pm == bgv alone does not
+                // mean "no ink" (eps = 0.5 maps every v to 0.5).
+                if (eps > 0.0f && (pm != bgv || i6 != 0.0f))
+                    acc_eps += ((double)(d * (1.0f - 2.0f * i6)) - (x ? dlp_bgd1 : dlp_bgd0)) * (double)gscale;
                 gp = d * gscale;
             }
-            if (eps > 0.0f) acc_eps += gp * (1.0f - 2.0f * i6);              // d/d eps of (1-eps) p + eps (1-p)
             return pass5 ? gp * mixd : 0.0f;
         };
 
@@ -733,49 +760,50 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) bpl_backward_kernel(const KArg
 #pragma unroll
             for (int d = 0; d <= PAD; ++d) { wg[0][d] = ms->g[d]; wgh[0][d] = ms->g[d]; wgh[1][d] = ms->ht[d]; }
             // blur A forward: I3 = min(A,1) -V-> B -H-> C = I4
-            sweep<BPL_FSIZE, BWD_R, true, 1>(A, wg, LoadMin1(), [&](int r, int c, const float (&acc)[1]) {
-                B[ORIGIN + r * STRIDE + c] = acc[0]; });
+            sweep_box<BPL_FSIZE, BWD_R, true, 1>(A, wg, LoadMin1(), [&](int r, int c, const float (&acc)[1]) {
+                B[ORIGIN + r * STRIDE + c] = acc[0]; }, bx);
             __syncthreads();
-            sweep<BPL_FSIZE, BWD_R, false, 1>(B, wg, LoadId(), [&](int r, int c, const float (&acc)[1]) {
-                C[ORIGIN + r * STRIDE + c] = acc[0]; });
+            sweep_box<BPL_FSIZE, BWD_R, false, 1>(B, wg, LoadId(), [&](int r, int c, const float (&acc)[1]) {
+                C[ORIGIN + r * STRIDE + c] = acc[0]; }, bx);
             __syncthreads();
             // blur B forward, first axis with both filters: U = g_v * I4 -> B, W = h~_v * I4 -> D
-            sweep<BPL_FSIZE, BWD_R, true, 2>(C, wgh, LoadId(), [&](int r, int c, const float (&acc)[2]) {
+            sweep_box<BPL_FSIZE, BWD_R, true, 2>(C, wgh, LoadId(), [&](int r, int c, const float (&acc)[2]) {
                 B[ORIGIN + r * STRIDE + c] = acc[0];
-                D[ORIGIN + r * STRIDE + c] = acc[1]; });
+                D[ORIGIN + r * STRIDE + c] = acc[1]; }, bx);
             __syncthreads();
             // second axis: I5 = g_h * U; pointwise tail; G_B -> C
-            sweep<BPL_FSIZE, BWD_R, false, 1>(B, wg, LoadId(), [&](int r, int c, const float (&acc)[1]) {
-                C[ORIGIN + r * STRIDE + c] = tail(r, c, acc[0]); });
+            sweep_box<BPL_FSIZE, BWD_R, false, 1>(B, wg, LoadId(), [&](int r, int c, const float (&acc)[1]) {
+                C[ORIGIN + r * STRIDE + c] = tail(r, c, acc[0]); }, bx);
             __syncthreads();
             // adjoint of blur B along h, reduced against U, W for d/d sigma; t_g -> D (in place of W)
-            sweep<BPL_FSIZE, BWD_R, false, 2>(C, wgh, LoadId(), [&](int r, int c, const float (&acc)[2]) {
+            sweep_box<BPL_FSIZE, BWD_R, false, 2>(C, wgh, LoadId(), [&](int r, int c, const float (&acc)[2]) {
                 const int q = ORIGIN + r * STRIDE + c;
                 acc_sig = fmaf(acc[0], D[q], fmaf(acc[1], B[q], acc_sig));
-                D[q] = acc[0]; });
+                D[q] = acc[0]; }, bx);
             __syncthreads();
             // adjoint along v: G_A = d L / d I4 -> C
-            sweep<BPL_FSIZE, BWD_R, true, 1>(D, wg, LoadId(), [&](int r, int c, const float (&acc)[1]) {
-                C[ORIGIN + r * STRIDE + c] = acc[0]; });
+            sweep_box<BPL_FSIZE, BWD_R, true, 1>(D, wg, LoadId(), [&](int r, int c, const float (&acc)[1]) {
+                C[ORIGIN + r * STRIDE + c] = acc[0]; }, bx);
             __syncthreads();
             // recompute U_A, W_A from I3 = min(A,1)
-            sweep<BPL_FSIZE, BWD_R, true, 2>(A, wgh, LoadMin1(), [&](int r, int c, const float (&acc)[2]) {
+            sweep_box<BPL_FSIZE, BWD_R, true, 2>(A, wgh, LoadMin1(), [&](int r, int c, const float (&acc)[2]) {
                 B[ORIGIN + r * STRIDE + c] = acc[0];
-                D[ORIGIN + r * STRIDE + c] = acc[1]; });
+                D[ORIGIN + r * STRIDE + c] = acc[1]; }, bx);
             __syncthreads();
-            sweep<BPL_FSIZE, BWD_R, false, 2>(C, wgh, LoadId(), [&](int r, int c, const float (&acc)[2]) {
+            sweep_box<BPL_FSIZE, BWD_R, false, 2>(C, wgh, LoadId(), [&](int r, int c, const float (&acc)[2]) {
                 const int q = ORIGIN + r * STRIDE + c;
                 acc_sig = fmaf(acc[0], D[q], fmaf(acc[1], B[q], acc_sig));
-                D[q] = acc[0]; });
+                D[q] = acc[0]; }, bx);
             __syncthreads();
             // G_3 = d L / d I3, masked by clamp_(max=1) (:171) -> A (pointwise in place over I2)
-            sweep<BPL_FSIZE, BWD_R, true, 1>(D, wg, LoadId(), [&](int r, int c, const float (&acc)[1]) {
+            sweep_box<BPL_FSIZE, BWD_R, true, 1>(D, wg, LoadId(), [&](int r, int c, const float (&acc)[1]) {
                 float *q = A + ORIGIN + r * STRIDE + c;
-                *q = (*q <= 1.0f) ? acc[0] : 0.0f; });
+                *q = (*q <= 1.0f) ? acc[0] : 0.0f; }, bx);
             __syncthreads();
         } else {
-            for (int i = threadIdx.x; i < NPIX; i += blockDim.x) {
-                const int r = i / IMG, c = i - r * IMG;
+            const int bw = bx.c1 - bx.c0 + 1, bn = bx.empty() ? 0 : bw * (bx.r1 - bx.r0 + 1);
+            for (int i = threadIdx.x; i < bn; i += blockDim.x) {
+                const int r = bx.r0 + i / bw, c = bx.c0 + i % bw;
                 float *q = A + ORIGIN + r * STRIDE + c;
                 const float i2 = *q;
                 const float g = tail(r, c, fminf(i2, 1.0f));
@@ -785,14 +813,22 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) bpl_backward_kernel(const KArg
         }
         BPL_PT(3);      // blur forward + tail + adjoint blur (9 sweeps)
         // adjoint broaden (symmetric kernel, zero padding): A -> A
-        broaden<BWD_R3, false>(A, B, a.rc);
+        broaden<BWD_R3>(A, B, a.rc, bx);
 
         BPL_PT(4);      // adjoint broaden
         // ---- scalar outputs ----
         {
-            double v[3] = {(double)acc_ll, (double)acc_eps, (double)acc_sig};
+            if (gP_ext && eps > 0.0f)
+                for (int i = threadIdx.x; i < NPIX; i += blockDim.x) acc_eps += (double)gP_ext[i];
+            double v[3] = {(double)acc_ll, acc_eps, (double)acc_sig};
             block_sum<3>(v, ms->red);
             if (threadIdx.x == 0) {
+                // the all-background image: lp_bg / dlp_bg at every pixel
+                const double n1 = (double)ms->n_ones, n0 = (double)(NPIX - ms->n_ones);
+                if (score && !gP_ext) {
+                    v[0] += n1 * (double)lp_bg1 + n0 * (double)lp_bg0;
+                    if (eps > 0.0f) v[1] += (double)gscale * (n1 * dlp_bgd1 + n0 * dlp_bgd0);
+                }
                 if (a.ll) a.ll[p] = (score && !gP_ext) ? (float)v[0] : 0.0f;
                 if (a.off_page) a.off_page[p] = (uint8_t)(ms->off_page != 0);
                 if (a.g_eps) a.g_eps[p] = (float)v[1];
@@ -971,7 +1007,15 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) bpl_backward_kernel(const KArg
             // B's interior was used as scratch: restore zeros (its border was never touched)
             for (int i = threadIdx.x; i < t.S * NACC; i += blockDim.x) accs[ORIGIN + i] = 0.0f;
         }
-        if (threadIdx.x == 0) ms->next_item = p_next;
+        // leave all four buffers zero: every pass wrote inside the box only
+        if (!bx.empty()) {
+            const int nc = bx.c1 - bx.c0 + 1, nn = nc * (bx.r1 - bx.r0 + 1);
+            for (int i = threadIdx.x; i < nn; i += blockDim.x) {
+                const int r = i / nc, q = ORIGIN + (bx.r0 + r) * STRIDE + bx.c0 + (i - r * nc);
+                A[q] = 0.0f; B[q] = 0.0f; C[q] = 0.0f; D[q] = 0.0f;
+            }
+        }
+        if (threadIdx.x == 0) { ms->next_item = p_next; ms->ones_acc = 0; }
         __syncthreads();
         p = ms->next_item;      // rewritten only at the end of the next iteration, many barriers from here
         BPL_PT(7);      // chain backward + outputs
