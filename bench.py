@@ -29,9 +29,9 @@ METRIC = "rendered+scored 105x105 particles/sec (fwd)"
 UNIT = "particles/s"
 BATCH = 4096
 SEED = 1234
-# dram__bytes_read.sum + dram__bytes_write.sum of one bpl_forward2_kernel launch on this workload, from the
-# ncu --set full capture summarised in profiles/r01_forward2_final.raw.txt (1.330944 MB + 2.56 KB)
-NCU_DRAM_BYTES_PER_LAUNCH = 1333504
+# dram__bytes_read.sum + dram__bytes_write.sum of one bpl_forward1s_kernel launch on this workload, from the
+# ncu --set full capture summarised in profiles/r01_fwd1s_v1.raw.txt (2.435840 MB + 965.12 KB)
+NCU_DRAM_BYTES_PER_LAUNCH = 3400960
 
 
 def flops_fwd(S):      # algorithmic work per particle, separable minimal algorithm
@@ -79,6 +79,17 @@ def cpu_baseline(w, img, C, n_sample, repeats=1):
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     return sub["P"] / best, sub["P"], best
+
+
+def cpu_baseline_bounded(w, img, C, budget_s=12.0):
+    """The whole step repeated for about `budget_s` seconds of wall time on all host cores; mean rate over the passes
+    after the first (which warms the OpenMP pool and the caches)."""
+    cpu_baseline(w, img, C, w["P"])
+    t_tot, n_tot, passes = 0.0, 0, 0
+    while t_tot < budget_s and passes < 64:
+        _, n, dt = cpu_baseline(w, img, C, w["P"])
+        t_tot += dt; n_tot += n; passes += 1
+    return n_tot / t_tot, n_tot, t_tot, passes
 
 
 def run_reference(args):
@@ -352,7 +363,7 @@ def run_gpu(args):
     k_rate = BATCH / (k_ms * 1e-3)
     ach_tf = k_rate * flops_fwd(Sbar) / 1e12
     roofline = {"bound": "fp32", "achieved": ach_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach_tf / fp32_peak,
-                "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "kernel": "bpl_forward2_kernel", "kernel_ms": k_ms,
+                "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "kernel": "bpl_forward1s_kernel", "kernel_ms": k_ms,
                 "flop_per_particle": flops_fwd(Sbar), "mean_substrokes": Sbar,
                 "peak_source": "live FFMA probe (bpl_fp32_probe) in this run; MEASURED_PEAKS.json holds no CUDA-core FP32 "
                                "figure, and SURVEY.md 8(d) shows the path is FP32-issue/shared-memory bound, not HBM",
@@ -363,9 +374,10 @@ def run_gpu(args):
     cpu = None
     if world == 1:
         C = np.load(os.path.join(ROOT, "pybpl_b200", "data", "basis_5_200.npy"))
-        cv, cn, cdt = cpu_baseline(w0, img_np, C, 4096, repeats=2)
+        cv, cn, cdt, cpasses = cpu_baseline_bounded(w0, img_np, C)
         cpu = {"value": cv, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"all {cn} tokens of the step (best of 2), C oracle port, OpenMP over tokens, {cdt:.2f} s wall on {cores} cores"}
+               "sample": f"the step's {BATCH} tokens x {cpasses} passes = {cn} particles, C oracle port (fp32), OpenMP over tokens, "
+                         f"{cdt:.1f} s wall on {cores} cores"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

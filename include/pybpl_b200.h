@@ -134,6 +134,54 @@ int bpl_vanilla_to_motor(const float *C, int neval, int ncpt, int n_strokes, con
                          const float *ctrl, const float *invscale, const float *position, float *motor,
                          float *motor_spline, void *stream);
 
+/* ---- token prior: log P(token | type) -------------------------------------------------
+ * CharacterTokenDist.score_token (pybpl/model/token_dist.py:264-287): per stroke the shapes and
+ * invscales of StrokeTokenDist.score_part_token (:410-430), RelationTokenDist.score_relation_token
+ * (:488-517) and score_location (:131-153) with RelationToken.get_attach_point
+ * (pybpl/objects/relation.py:34-67), plus score_image_blur (:203-224).  SURVEY.md 8(f)1. */
+#define BPL_REL_UNIHIST 0   /* relation categories (pybpl/objects/relation.py:11) */
+#define BPL_REL_START 1
+#define BPL_REL_END 2
+#define BPL_REL_MID 3
+
+/* Library constants the token distribution reads (token_dist.py:90-107,320-325,437-441). */
+typedef struct {
+    float sigma_shape;      /* lib.tokenvar['sigma_shape'] */
+    float sigma_invscale;   /* lib.tokenvar['sigma_invscale'] */
+    float sigma_attach;     /* lib.tokenvar['sigma_attach'] */
+    float sigma_x, sigma_y; /* lib.rel['sigma_x'], lib.rel['sigma_y'] */
+    float min_blur_sigma, max_blur_sigma;   /* Parameters (parameters.py:56-57) */
+} bpl_token_prior_params;
+
+/* Type-level parameters and relation tokens of the batch's tokens, aligned with the token batch's
+ * sub-strokes ([S]) and strokes ([K]) (CharacterType: objects/concept.py:66-107, objects/part.py:100-160,
+ * objects/relation.py:238-420). */
+typedef struct {
+    const float *ctrl_type;      /* dev [S][5][2]  StrokeType.shapes[:, :, i] */
+    const float *invscale_type;  /* dev [S]        StrokeType.invscales */
+    const int *rel_cat;          /* dev [K]  BPL_REL_* */
+    const int *attach_ix;        /* dev [K]  stroke (within its token) attached to; ignored for unihist */
+    const int *attach_subix;     /* dev [K]  sub-stroke of that stroke ('mid' only) */
+    const float *gpos;           /* dev [K][2]  RelationIndependent.gpos ('unihist' only) */
+    const float *eval_spot_type; /* dev [K]  RelationAttachAlong.eval_spot ('mid' only) */
+    const float *eval_spot;      /* dev [K]  RelationToken.eval_spot_token ('mid' only) */
+} bpl_token_type;
+
+/* d ll / d (every leaf of CharacterToken.parameters() and CharacterType.parameters()); the first three are
+ * required, the others may be NULL.  All are fully written by the call. */
+typedef struct {
+    float *g_ctrl, *g_invscale, *g_position;              /* dev [S][5][2], [S], [K][2] */
+    float *g_eval_spot;                                   /* dev [K] */
+    float *g_ctrl_type, *g_invscale_type;                 /* dev [S][5][2], [S] */
+    float *g_gpos, *g_eval_spot_type;                     /* dev [K][2], [K] */
+} bpl_token_prior_grads;
+
+/* ll[P] <- log P(token | type); -inf for a non-positive invscale, an eval_spot outside [2, ncpt+1] or a blur
+ * outside [min, max) (the reference raises on the last).  Reads b's CSR offsets, ctrl, invscale, position,
+ * sigma and basis (rows 0 and neval-1).  g == NULL: forward only. */
+int bpl_score_token_prior(const bpl_token_prior_params *c, const bpl_token_batch *b, const bpl_token_type *ty,
+                          float *ll, const bpl_token_prior_grads *g, void *stream);
+
 /* ---- images ------------------------------------------------------------------------ */
 /* Pack T 105x105 images into bit rows.  `bad` (dev int, zero-filled by the caller) is set
  * to 1 if any pixel is not exactly 0 or 1 (torch's Bernoulli.log_prob support check). */

@@ -51,6 +51,22 @@ class Grads(ctypes.Structure):
                 ("g_affine", vp), ("g_pts", vp), ("g_eps", vp), ("g_sigma", vp)]
 
 
+class TokenPriorParams(ctypes.Structure):
+    _fields_ = [("sigma_shape", ctypes.c_float), ("sigma_invscale", ctypes.c_float), ("sigma_attach", ctypes.c_float),
+                ("sigma_x", ctypes.c_float), ("sigma_y", ctypes.c_float), ("min_blur_sigma", ctypes.c_float),
+                ("max_blur_sigma", ctypes.c_float)]
+
+
+class TokenTypeC(ctypes.Structure):
+    _fields_ = [("ctrl_type", vp), ("invscale_type", vp), ("rel_cat", vp), ("attach_ix", vp), ("attach_subix", vp),
+                ("gpos", vp), ("eval_spot_type", vp), ("eval_spot", vp)]
+
+
+class TokenPriorGrads(ctypes.Structure):
+    _fields_ = [("g_ctrl", vp), ("g_invscale", vp), ("g_position", vp), ("g_eval_spot", vp), ("g_ctrl_type", vp),
+                ("g_invscale_type", vp), ("g_gpos", vp), ("g_eval_spot_type", vp)]
+
+
 EXPORTS = {
     "bpl_version": (ctypes.c_int, []),
     "bpl_last_error": (ctypes.c_char_p, []),
@@ -77,6 +93,8 @@ EXPORTS = {
     "bpl_render_strokes_grad": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.POINTER(StrokeBatchC),
                                                ctypes.POINTER(Targets), ctypes.POINTER(FwdOut), ctypes.POINTER(Grads), vp]),
     "bpl_token_points": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.POINTER(TokenBatchC), vp, vp, vp, vp, vp, vp]),
+    "bpl_score_token_prior": (ctypes.c_int, [ctypes.POINTER(TokenPriorParams), ctypes.POINTER(TokenBatchC),
+                                             ctypes.POINTER(TokenTypeC), vp, ctypes.POINTER(TokenPriorGrads), vp]),
     "bpl_logsumexp_partial": (ctypes.c_int, [vp, ctypes.c_int, vp, vp]),
     "bpl_fp32_probe": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, vp]),
     "bpl_launch_count": (ctypes.c_longlong, []),

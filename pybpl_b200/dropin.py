@@ -11,6 +11,7 @@ Patched names (each bound by-name in the reference, so both the defining module 
   pybpl.splines.fit_bspline_to_traj                                           (splines.py:141)
   pybpl.objects.part.vanilla_to_motor                                         (part.py:290)
   CharacterImageDist.get_pimg / sample_image / score_image                    (image_dist.py:32-80)
+  CharacterTokenDist.score_token                                              (token_dist.py:264-287)
 """
 import importlib
 
@@ -44,6 +45,26 @@ def install(pybpl_module=None):
     mirror = model.CharacterImageDist
     for meth in ("get_pimg", "sample_image", "score_image"):
         _patch(ID.CharacterImageDist, meth, getattr(mirror, meth))
+    TD = importlib.import_module("pybpl.model.token_dist")
+    scorer = {}
+
+    def score_token(self, ctype, ctoken):      # the reference's instance keeps its own lib constants
+        key = id(self)
+        if key not in scorer:
+            scorer[key] = model.CharacterTokenDist(_LibView(self))
+        return scorer[key].score_token(ctype, ctoken)
+    _patch(TD.CharacterTokenDist, "score_token", score_token)
+
+
+class _LibView:
+    """The constants a reference CharacterTokenDist instance holds (token_dist.py:90-98, 320-325, 437-441), presented
+    as the .tokenvar / .rel mappings ops.token_prior_params reads."""
+
+    def __init__(self, td):
+        self.tokenvar = {"sigma_shape": td.pdist.sigma_shape, "sigma_invscale": td.pdist.sigma_invscale,
+                         "sigma_attach": td.rdist.sigma_attach}
+        scale = td.loc_dist.base_dist.scale
+        self.rel = {"sigma_x": scale[0], "sigma_y": scale[1]}
 
 
 def uninstall():

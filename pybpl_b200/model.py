@@ -68,14 +68,61 @@ class CharacterImageDist:
         return ll[0].to(src)
 
 
+def token_types_from(ctypes_, ctokens, device):
+    """Pack the type-level parameters and the relation tokens of (type, token) pairs into one ops.TokenTypes, aligned
+    with token_batch_from(ctokens).  Duck-typed on the reference's objects: ctype.part_types[i].{shapes, invscales}
+    (pybpl/objects/part.py:100-160), ctype.relation_types[i].{category, gpos | attach_ix [, attach_subix, eval_spot]}
+    (objects/relation.py:238-420), ctoken.relation_tokens[i].eval_spot_token (relation.py:14-32)."""
+    ctrl, inv, cat, aix, asub, gpos, es_ty, es = [], [], [], [], [], [], [], []
+    z1 = torch.zeros(1)
+    for ct, tk in zip(ctypes_, ctokens):
+        for pt, rt, rtk in zip(ct.part_types, ct.relation_types, tk.relation_tokens):
+            ctrl.append(pt.shapes.permute(2, 0, 1))
+            inv.append(pt.invscales.reshape(-1))
+            c = ops.REL_CODES[rt.category]
+            cat.append(c)
+            aix.append(int(rt.attach_ix) if c != 0 else 0)
+            asub.append(int(rt.attach_subix) if c == 3 else 0)
+            gpos.append(rt.gpos.reshape(1, 2) if c == 0 else torch.zeros(1, 2))
+            es_ty.append(torch.as_tensor(rt.eval_spot, dtype=torch.float32).reshape(1) if c == 3 else z1)
+            es.append(torch.as_tensor(rtk.eval_spot_token, dtype=torch.float32).reshape(1) if c == 3 else z1)
+    to = lambda xs: torch.cat([x.to(device, torch.float32) for x in xs])
+    return ops.TokenTypes(to(ctrl).contiguous(), to(inv), cat, aix, asub, to(gpos), to(es_ty), to(es))
+
+
+class CharacterTokenDist:
+    """The scoring half of P(Token | Type) (pybpl/model/token_dist.py:85-287): score_token on the GPU.
+    Sampling (sample_token, :226-262) stays with the reference's prior objects."""
+
+    def __init__(self, lib=None):
+        self.lib = lib
+        self.ps = Parameters()
+        self._c = ops.token_prior_params(lib, self.ps)
+
+    def score_tokens(self, ctypes_, ctokens):
+        """[P] scores for paired lists of types and tokens (one launch)."""
+        batch = token_batch_from(ctokens)
+        types = token_types_from(ctypes_, ctokens, batch.device)
+        return ops.score_token_prior(batch, types, c=self._c)
+
+    def score_token(self, ctype, ctoken):
+        """log P(Token = ctoken | Type = ctype) (token_dist.py:264-287): 0-d float32 tensor on the token's device."""
+        src = ctoken.part_tokens[0].shapes.device
+        return self.score_tokens([ctype], [ctoken])[0].to(src)
+
+
 class CharacterModel:
-    """The hot-path third of pybpl/model/model.py:8-39.  Type and token priors are out of scope
-    (SURVEY.md 8): pass `type_dist`/`token_dist` objects (e.g. the reference's) to get the full façade."""
+    """The hot-path part of pybpl/model/model.py:8-39: image methods and score_token run on the GPU.  The type prior and
+    token sampling are out of scope: pass `type_dist`/`token_dist` objects (e.g. the reference's) for them."""
 
     def __init__(self, lib=None, type_dist=None, token_dist=None):
         self.type_dist = type_dist
-        self.token_dist = token_dist
+        self.token_dist = token_dist          # sample_token (and score_token unless overridden below)
+        self.token_score = CharacterTokenDist(lib)
         self.image_dist = CharacterImageDist(lib)
+
+    def score_token(self, ctype, ctoken):
+        return self.token_score.score_token(ctype, ctoken)
 
     def sample_image(self, ctoken):
         return self.image_dist.sample_image(ctoken)

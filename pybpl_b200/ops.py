@@ -659,6 +659,92 @@ def vanilla_to_motor_batch(ctrl, invscale, position, stroke_sub_off, neval=200):
 # ---------------------------------------------------------------------------------------------
 # particle-sweep reduction
 # ---------------------------------------------------------------------------------------------
+
+# ---------------------------------------------------------------------------------------------
+# token prior: log P(token | type)  (CharacterTokenDist.score_token, pybpl/model/token_dist.py:264-287)
+# ---------------------------------------------------------------------------------------------
+REL_CODES = {"unihist": 0, "start": 1, "end": 2, "mid": 3}      # pybpl/objects/relation.py:11
+
+
+def token_prior_params(lib=None, ps=None):
+    """The constants CharacterTokenDist reads from a Library and Parameters (token_dist.py:90-107, 320-325, 437-441).
+    `lib` is anything with .tokenvar / .rel mappings (the reference's Library); None gives the shipped values."""
+    c = _lib.TokenPriorParams()
+    if lib is None:
+        c.sigma_shape, c.sigma_invscale, c.sigma_attach = 3.3593, 0.0277, 0.1499
+        c.sigma_x, c.sigma_y = 1.3536, 1.2056
+    else:
+        c.sigma_shape = float(lib.tokenvar["sigma_shape"]); c.sigma_invscale = float(lib.tokenvar["sigma_invscale"])
+        c.sigma_attach = float(lib.tokenvar["sigma_attach"])
+        c.sigma_x = float(lib.rel["sigma_x"]); c.sigma_y = float(lib.rel["sigma_y"])
+    c.min_blur_sigma = float(getattr(ps, "min_blur_sigma", 0.5))
+    c.max_blur_sigma = float(getattr(ps, "max_blur_sigma", 16.0))
+    return c
+
+
+class TokenTypes:
+    """Type-level parameters and relation tokens aligned with a TokenBatch's sub-strokes [S] and strokes [K]:
+    ctrl_type [S,5,2], invscale_type [S], rel_cat [K] (REL_CODES), attach_ix [K], attach_subix [K], gpos [K,2],
+    eval_spot_type [K], eval_spot [K] (the relation TOKEN's spot).  Entries a category does not use are ignored."""
+
+    def __init__(self, ctrl_type, invscale_type, rel_cat, attach_ix, attach_subix, gpos, eval_spot_type, eval_spot):
+        dev = ctrl_type.device
+        _need_cuda(ctrl_type, "ctrl_type")
+        self.ctrl_type, self.invscale_type = ctrl_type, invscale_type
+        self.rel_cat, self.attach_ix, self.attach_subix = _i32(rel_cat, dev), _i32(attach_ix, dev), _i32(attach_subix, dev)
+        self.gpos, self.eval_spot_type, self.eval_spot = gpos, eval_spot_type, eval_spot
+        self.device = dev
+
+
+class _ScoreTokenPrior(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ctrl, invscale, position, eval_spot, ctrl_type, invscale_type, gpos, eval_spot_type, batch, types, c):
+        dev = batch.device
+        args = [_c32(t) for t in (ctrl, invscale, position, eval_spot, ctrl_type, invscale_type, gpos, eval_spot_type)]
+        ctrl_c, inv_c, pos_c, es_c, ctrl_ty, inv_ty, gpos_c, es_ty = args
+        b = _lib.TokenBatchC()
+        b.n_tokens = batch.P; b.ncpt = NCPT; b.neval = batch.neval
+        b.tok_stroke_off = batch.tok_stroke_off.data_ptr(); b.stroke_sub_off = batch.stroke_sub_off.data_ptr()
+        b.ctrl = ctrl_c.data_ptr(); b.invscale = inv_c.data_ptr(); b.position = pos_c.data_ptr()
+        sig = _c32(batch.sigma)
+        b.sigma = sig.data_ptr(); b.eps = _c32(batch.eps).data_ptr()
+        b.basis = basis_table(NCPT, batch.neval, dev).data_ptr()
+        ty = _lib.TokenTypeC(ctrl_ty.data_ptr(), inv_ty.data_ptr(), types.rel_cat.data_ptr(), types.attach_ix.data_ptr(),
+                             types.attach_subix.data_ptr(), gpos_c.data_ptr(), es_ty.data_ptr(), es_c.data_ptr())
+        ll = torch.empty(batch.P, dtype=torch.float32, device=dev)
+        need = any(ctx.needs_input_grad[:8])
+        if need:
+            gs = [torch.empty_like(t) for t in args]
+            g = _lib.TokenPriorGrads(*[t.data_ptr() for t in gs])
+            check(lib().bpl_score_token_prior(ctypes.byref(c), ctypes.byref(b), ctypes.byref(ty), ll.data_ptr(),
+                                              ctypes.byref(g), _stream(dev)))
+            ctx.batch = batch
+            ctx.save_for_backward(*gs)
+        else:
+            check(lib().bpl_score_token_prior(ctypes.byref(c), ctypes.byref(b), ctypes.byref(ty), ll.data_ptr(), None,
+                                              _stream(dev)))
+        return ll
+
+    @staticmethod
+    def backward(ctx, g_ll):
+        g_ctrl, g_inv, g_pos, g_es, g_ctrl_ty, g_inv_ty, g_gpos, g_es_ty = ctx.saved_tensors
+        b = ctx.batch
+        gs = g_ll.to(torch.float32)
+        st, kt = gs[b.sub_token], gs[b.stroke_token]
+        return (g_ctrl * st.view(-1, 1, 1), g_inv * st, g_pos * kt.view(-1, 1), g_es * kt, g_ctrl_ty * st.view(-1, 1, 1),
+                g_inv_ty * st, g_gpos * kt.view(-1, 1), g_es_ty * kt, None, None, None)
+
+
+def score_token_prior(batch, types, lib=None, ps=None, c=None):
+    """ll[p] = log P(token p | its type) = CharacterTokenDist.score_token (pybpl/model/token_dist.py:264-287), batched,
+    differentiable in the token's ctrl / invscale / position / eval_spot and the type's ctrl_type / invscale_type /
+    gpos / eval_spot_type.  A token whose score is -inf gets gradients of the finite terms only."""
+    if c is None:
+        c = token_prior_params(lib, ps)
+    return _ScoreTokenPrior.apply(batch.ctrl, batch.invscale, batch.position, types.eval_spot, types.ctrl_type,
+                                  types.invscale_type, types.gpos, types.eval_spot_type, batch, types, c)
+
+
 def logsumexp_partial(ll):
     """(max, sum exp(ll - max)) of a CUDA float32 vector as a 2-element tensor (one kernel)."""
     _need_cuda(ll, "ll")

@@ -460,6 +460,91 @@ def make_fit():
     print("fit.npz:", len(cases), "cases")
 
 
+# --------------------------------------------------------------------------
+# token_prior.npz : CharacterModel.score_token = log P(token | type)
+# (pybpl/model/token_dist.py:57-80,131-153,203-224,264-287,334-408,488-517,547-572;
+#  attach points objects/relation.py:34-67) with autograd gradients w.r.t. every
+#  token- and type-level parameter (objects/concept.py:93-107,243-258)
+# --------------------------------------------------------------------------
+REL_CODE = {"unihist": 0, "start": 1, "end": 2, "mid": 3}
+
+
+def make_token_prior(n=160):
+    torch.manual_seed(11)
+    lib = Library(use_hist=True)
+    model = CharacterModel(lib)
+    g = torch.Generator().manual_seed(5)
+    K, nsub_all = [], []
+    ctrl_ty, inv_ty, ctrl_tk, inv_tk, pos = [], [], [], [], []
+    cat, aix, asub, gpos, es_ty, es_tk = [], [], [], [], [], []
+    sig, ll_all = [], []
+    g_ctrl_ty, g_inv_ty, g_ctrl_tk, g_inv_tk, g_pos, g_gpos, g_es_ty, g_es_tk = ([] for _ in range(8))
+    ncat = np.zeros(4, int)
+    for i in range(n):
+        ctype = model.sample_type()
+        ctoken = model.sample_token(ctype)
+        if i % 3 == 1:
+            ctoken.blur_sigma = (0.5 + 15.0 * torch.rand((), generator=g))
+        ctoken.blur_sigma = torch.as_tensor(ctoken.blur_sigma, dtype=torch.float32).clone()
+        if i % 17 == 5:      # a non-positive scale: -inf (token_dist.py:404-406); gradients are not taken
+            with torch.no_grad():
+                ctoken.part_tokens[0].invscales[0] = -0.01
+        if i % 19 == 7:      # an evaluation spot outside [2, ncpt+1]: -inf (token_dist.py:563-564)
+            for rt in ctoken.relation_tokens:
+                if rt.rtype.category == "mid":
+                    rt.eval_spot_token = torch.tensor(6.25)
+        ctype.train(); ctoken.train()
+        # coefficient_mat is lru_cached on the IDENTITY of the tensor s (splines.py:72): sample_token has already
+        # evaluated the attach point with this eval_spot_token before it required grad, and a cache hit would hand
+        # score_location that graph-less matrix, silently dropping d ll / d eval_spot_token through the attach
+        # point.  Cleared, autograd differentiates the function the reference computes.
+        S.coefficient_mat.cache_clear()
+        ll = model.score_token(ctype, ctoken)
+        finite = bool(torch.isfinite(ll))
+        if finite:
+            ll.backward()
+        K.append(int(ctype.k))
+        sig.append(float(ctoken.blur_sigma)); ll_all.append(float(ll))
+        for pt, rt, ptk, rtk in zip(ctype.part_types, ctype.relation_types, ctoken.part_tokens, ctoken.relation_tokens):
+            ns = pt.shapes.shape[2]
+            nsub_all.append(ns)
+            z = lambda t: torch.zeros_like(t) if (t.grad is None or not finite) else t.grad
+            ctrl_ty.append(pt.shapes.detach().permute(2, 0, 1)); g_ctrl_ty.append(z(pt.shapes).permute(2, 0, 1))
+            inv_ty.append(pt.invscales.detach()); g_inv_ty.append(z(pt.invscales))
+            ctrl_tk.append(ptk.shapes.detach().permute(2, 0, 1)); g_ctrl_tk.append(z(ptk.shapes).permute(2, 0, 1))
+            inv_tk.append(ptk.invscales.detach()); g_inv_tk.append(z(ptk.invscales))
+            pos.append(ptk.position.detach()); g_pos.append(z(ptk.position))
+            c = REL_CODE[rt.category]
+            cat.append(c); ncat[c] += 1
+            if c == 0:
+                gpos.append(rt.gpos.detach()); g_gpos.append(z(rt.gpos))
+                aix.append(-1); asub.append(-1)
+            else:
+                gpos.append(torch.zeros(2)); g_gpos.append(torch.zeros(2))
+                aix.append(int(rt.attach_ix)); asub.append(int(rt.attach_subix) if c == 3 else -1)
+            if c == 3:
+                es_ty.append(float(rt.eval_spot.detach())); g_es_ty.append(float(z(rt.eval_spot)))
+                es_tk.append(float(rtk.eval_spot_token.detach())); g_es_tk.append(float(z(rtk.eval_spot_token)))
+            else:
+                es_ty.append(0.0); g_es_ty.append(0.0); es_tk.append(0.0); g_es_tk.append(0.0)
+    cat3 = lambda L: torch.cat(L).numpy().astype(f32)
+    st2 = lambda L: torch.stack(L).numpy().astype(f32)
+    out = dict(
+        K=np.array(K, np.int32), nsub=np.array(nsub_all, np.int32),
+        ctrl_type=cat3(ctrl_ty), invscale_type=cat3(inv_ty), ctrl=cat3(ctrl_tk), invscale=cat3(inv_tk), position=st2(pos),
+        rel_cat=np.array(cat, np.int32), attach_ix=np.array(aix, np.int32), attach_subix=np.array(asub, np.int32),
+        gpos=st2(gpos), eval_spot_type=np.array(es_ty, f32), eval_spot=np.array(es_tk, f32),
+        sigma=np.array(sig, f32), ll=np.array(ll_all, f32),
+        g_ctrl_type=cat3(g_ctrl_ty), g_invscale_type=cat3(g_inv_ty), g_ctrl=cat3(g_ctrl_tk), g_invscale=cat3(g_inv_tk),
+        g_position=st2(g_pos), g_gpos=st2(g_gpos), g_eval_spot_type=np.array(g_es_ty, f32), g_eval_spot=np.array(g_es_tk, f32),
+        consts=np.array([float(lib.tokenvar['sigma_shape']), float(lib.tokenvar['sigma_invscale']),
+                         float(lib.tokenvar['sigma_attach']), float(lib.rel['sigma_x']), float(lib.rel['sigma_y']),
+                         float(model.token_dist.ps.min_blur_sigma), float(model.token_dist.ps.max_blur_sigma)], f32))
+    np.savez_compressed(os.path.join(OUT, "token_prior.npz"), **out)
+    print("token_prior.npz:", n, "tokens; relation counts (unihist,start,end,mid)", ncat, "; -inf scores",
+          int(np.sum(~np.isfinite(out["ll"]))), "; ll range", np.nanmin(out["ll"][np.isfinite(out["ll"])]), out["ll"].max())
+
+
 def make_assets():
     """pybpl_b200/data/basis_5_200.npy: coefficient_mat(5, 200) exactly as the reference's torch builds it
     (splines.py:72-93).  torch assembles it with Sleef powf and an MKL dot, which portable C cannot
@@ -485,7 +570,7 @@ def make_assets():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["splines", "render", "tokens", "fit", "assets"]
+    which = sys.argv[1:] or ["splines", "render", "tokens", "fit", "token_prior", "assets"]
     if "splines" in which:
         make_splines()
     if "render" in which:
@@ -494,6 +579,8 @@ if __name__ == "__main__":
         make_tokens()
     if "fit" in which:
         make_fit()
+    if "token_prior" in which:
+        make_token_prior()
     if "assets" in which:
         make_assets()
     for f in sorted(os.listdir(OUT)):

@@ -141,3 +141,59 @@ def test_fit_bspline_to_traj():
             Y, res = o.lstsq(d[f"C_{ci}"], d[f"X_{ci}"])
             assert relinf(Y, d[f"Y_{ci}"]) < tol
             assert relinf(res, d[f"res_{ci}"]) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------
+# token prior, log P(token | type): oracle/token_prior.py against the live reference's outputs
+# ---------------------------------------------------------------------------------------------
+def _token_prior_golden():
+    d = dict(load("token_prior"))
+    C = load("tokens")["basis_5_200"]
+    K, nsub = d["K"], d["nsub"]
+    tok_of_stroke = np.repeat(np.arange(len(K)), K)
+    return d, C, tok_of_stroke, np.repeat(tok_of_stroke, nsub)
+
+
+def test_token_prior_oracle_matches_reference():
+    """score_token and its autograd gradients w.r.t. all token- and type-level leaves (160 prior-sampled pairs)."""
+    from oracle import token_prior as tp
+    d, C, tk, ts = _token_prior_golden()
+    ref = d["ll"]; fin = np.isfinite(ref)
+    assert (~fin).sum() >= 8 and fin.sum() >= 100            # the fixture holds -inf cases (invscale <= 0, spot out of range)
+    assert set(np.unique(d["rel_cat"])) == {0, 1, 2, 3}      # ... and every relation category
+    for dt, tol in ((np.float64, 1e-6), (np.float32, 1e-5)):
+        ll = tp.score(d, dt, C0=C[0], C1=C[-1])
+        assert np.array_equal(np.isfinite(ll), fin)
+        assert np.all(ll[~fin] == -np.inf)
+        assert np.max(np.abs(ll[fin] - ref[fin]) / np.abs(ref[fin])) < tol
+    _, g = tp.score(d, np.float64, grad=True, C0=C[0], C1=C[-1])
+    for name, idx in (("ctrl", ts), ("ctrl_type", ts), ("invscale", ts), ("invscale_type", ts), ("position", tk),
+                      ("gpos", tk), ("eval_spot", tk), ("eval_spot_type", tk)):
+        m = fin[idx]
+        a, b = g[name][m], d["g_" + name][m]
+        assert np.abs(a - b).max() <= 2e-5 * max(1.0, np.abs(b).max()), name
+
+
+def test_token_prior_oracle_gradient_is_the_derivative():
+    """Central differences of the float64 forward, for the leaves the attach point couples (the reference's own
+    autograd drops d/d eval_spot_token through a stale lru_cache unless the cache is cleared)."""
+    from oracle import token_prior as tp
+    d, C, tk, ts = _token_prior_golden()
+    C = C.astype(np.float64)
+    fin = np.isfinite(d["ll"])
+    _, g = tp.score(d, np.float64, grad=True, C0=C[0], C1=C[-1])
+    rng = np.random.default_rng(0)
+    mids = [k for k in range(len(tk)) if d["rel_cat"][k] == 3 and fin[tk[k]]]
+    checks = [("eval_spot", k, tk[k]) for k in mids[:10]]
+    for k in mids[:6]:                  # the stroke attached to: its position and first sub-stroke feed the attach point
+        j = int(np.flatnonzero(tk == tk[k])[0] + d["attach_ix"][k])
+        s = int(np.concatenate([[0], np.cumsum(d["nsub"])])[j])
+        checks += [("position", (j, 0), tk[k]), ("invscale", s, tk[k]), ("ctrl", (s, int(rng.integers(5)), 1), tk[k])]
+    h = 1e-6
+    for name, idx, p in checks:
+        hi = {k: (v.astype(np.float64) if v.dtype == np.float32 else v) for k, v in d.items()}
+        lo = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in hi.items()}
+        hi = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in hi.items()}
+        hi[name][idx] += h; lo[name][idx] -= h
+        fd = (tp.score(hi, np.float64, C0=C[0], C1=C[-1])[p] - tp.score(lo, np.float64, C0=C[0], C1=C[-1])[p]) / (2 * h)
+        assert abs(fd - g[name][idx]) <= 1e-5 * max(1.0, abs(fd)), (name, idx, fd, g[name][idx])
