@@ -46,7 +46,9 @@ __device__ __noinline__ void gauss_inplace_s(float *buf, const G6 gg, int l0, in
     constexpr int SL = VERT ? 1 : IMG;
     const int item = threadIdx.x;
     const bool active = item < nl * nb;
-    const int bi = item / nl;
+    int bi = 0;                          // item / nl without a division: a line has at most IMG / GR bands
+#pragma unroll
+    for (int k = 1; k < GNB; ++k) bi += (item >= k * nl);
     const int band = b0 + bi;
     const int line = l0 + (item - bi * nl);
     float *p = buf + band * GR * SA + line * SL;
@@ -95,6 +97,18 @@ __device__ __noinline__ void gauss_inplace_s(float *buf, const G6 gg, int l0, in
 template <bool VERT>
 __device__ __forceinline__ void gauss_box(float *buf, const G6 &g, int l0, int l1, int a0, int a1) {
     const int nl = l1 - l0 + 1;
+#if BPL_GAUSS_BANDS >= 5
+    // One band size (15 or 21 rows) for every box: lines are independent, so a box with more (line, band) items than
+    // threads is taken in groups of whole lines, one after the other (each group with its own halo-load barrier).
+    constexpr int GB = (BPL_GAUSS_BANDS == 5) ? 15 : 21, GBU = (BPL_GAUSS_BANDS == 5) ? 5 : 7;
+    const int b0 = a0 / GB, nb = a1 / GB - b0 + 1;
+    const int per = (int)blockDim.x / nb;               // lines per group
+    for (int l = l0; l <= l1; l += per) {
+        gauss_inplace_s<VERT, GB, GBU>(buf, g, l, min(per, l1 - l + 1), b0, nb);
+        if (l + per <= l1) __syncthreads();
+    }
+    return;
+#endif
     if (BPL_GAUSS_BANDS >= 3 && nl * (a1 / 15 - a0 / 15 + 1) <= (int)blockDim.x)
         gauss_inplace_s<VERT, 15, 5>(buf, g, l0, nl, a0 / 15, a1 / 15 - a0 / 15 + 1);
 #if BPL_GAUSS_BANDS == 2 || BPL_GAUSS_BANDS == 4
@@ -114,7 +128,8 @@ __device__ __forceinline__ void gauss_box(float *buf, const G6 &g, int l0, int l
 // barrier; horizontal neighbours travel by shuffle, so nothing is read after a neighbour may have written it.
 // bb is the box of non-zero INPUT pixels; the caller grows it by ink_ncon afterwards.
 __device__ __noinline__ void broaden_box(float *A, float *side, const RenderConsts rc, BBox bb) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int nw = S_THREADS / 32;             // (compile time: the divisions below become multiplications)
     const float c1w = rc.c1, c2w = rc.c2;
     float *sideL = side, *sideR = side + IMG;      // columns cb-1 and cb, cb = first column of the second half
     for (int it = 0; it < rc.ink_ncon; ++it) {
@@ -122,10 +137,10 @@ __device__ __noinline__ void broaden_box(float *A, float *side, const RenderCons
         const int cs = bb.c0 & ~1;
         const int npair = (bb.c1 - cs) / 2 + 1;
         const int nhalf = npair > 32 ? 2 : 1;
-        const int nbands = nw / nhalf;
         const int nrows = bb.r1 - bb.r0 + 1;
-        const int h = (nrows + nbands - 1) / nbands;
-        const int band = warp / nhalf, half = warp - band * nhalf;
+        const int nbands = nhalf == 2 ? nw / 2 : nw;
+        const int h = nhalf == 2 ? (nrows + nw / 2 - 1) / (nw / 2) : (nrows + nw - 1) / nw;
+        const int band = nhalf == 2 ? warp >> 1 : warp, half = nhalf == 2 ? (warp & 1) : 0;
         const int a0 = bb.r0 + band * h, a1 = min(a0 + h - 1, bb.r1);
         const bool live = band < nbands && a0 <= a1;
         const int cb = cs + 64;
@@ -145,8 +160,13 @@ __device__ __noinline__ void broaden_box(float *A, float *side, const RenderCons
             x1 = ok1 ? row[c1] : 0.0f;
             float xl = __shfl_up_sync(0xffffffffu, x1, 1);
             float xr = __shfl_down_sync(0xffffffffu, x0, 1);
-            if (lane == 0) xl = (half == 0) ? 0.0f : (direct ? row[cb - 1] : sideL[r]);
-            if (lane == 31) xr = (nhalf == 1 || half == 1) ? 0.0f : (cb < IMG ? (direct ? row[cb] : sideR[r]) : 0.0f);
+            if (nhalf == 1) {                    // the usual case: nothing lies left or right of the warp's span
+                if (lane == 0) xl = 0.0f;
+                if (lane == 31) xr = 0.0f;
+            } else {
+                if (lane == 0) xl = (half == 0) ? 0.0f : (direct ? row[cb - 1] : sideL[r]);
+                if (lane == 31) xr = (half == 1) ? 0.0f : (cb < IMG ? (direct ? row[cb] : sideR[r]) : 0.0f);
+            }
             h0 = xl + 2.0f * x0 + x1;
             h1 = x0 + 2.0f * x1 + xr;
         };

@@ -16,7 +16,10 @@
 
 namespace bpl {
 
-constexpr int PPL_DEFAULT = 7;      // points per lane (forward kernels)
+#ifndef BPL_PPL
+#define BPL_PPL 4
+#endif
+constexpr int PPL_DEFAULT = BPL_PPL;      // points per lane (forward kernels)
 constexpr int PPL = PPL_DEFAULT;
 
 struct PEval { float r, c; bool inb; };
