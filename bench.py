@@ -30,8 +30,8 @@ UNIT = "particles/s"
 BATCH = 4096
 SEED = 1234
 # dram__bytes_read.sum + dram__bytes_write.sum of one bpl_forward1s_kernel launch on this workload, from the
-# ncu --set full capture summarised in profiles/r01_fwd1s_v1.raw.txt (2.435840 MB + 965.12 KB)
-NCU_DRAM_BYTES_PER_LAUNCH = 3400960
+# ncu --set full capture of this command summarised in profiles/r01_fwd1s_final.raw.txt (1.832192 MB + 3.84 KB)
+NCU_DRAM_BYTES_PER_LAUNCH = 1836032
 
 
 def flops_fwd(S):      # algorithmic work per particle, separable minimal algorithm
@@ -99,7 +99,8 @@ def run_reference(args):
     from pybpl_b200 import workload
     w = workload.synth_tokens(BATCH, seed=SEED, sigma_mode="uniform")
     img, C = cpu_target_image(w)
-    cores = os.cpu_count() or 1
+    import oracle
+    cores = oracle.set_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1 to its workers
     n_sample = 1024
     for _ in range(max(args.warmup, 1)):
         cpu_baseline(w, img, C, 64)
@@ -373,6 +374,8 @@ def run_gpu(args):
     cores = os.cpu_count() or 1
     cpu = None
     if world == 1:
+        import oracle
+        cores = oracle.set_threads(cores)
         C = np.load(os.path.join(ROOT, "pybpl_b200", "data", "basis_5_200.npy"))
         cv, cn, cdt, cpasses = cpu_baseline_bounded(w0, img_np, C)
         cpu = {"value": cv, "unit": UNIT, "cores": cores, "kind": "port",

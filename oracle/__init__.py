@@ -50,6 +50,11 @@ def lib():
     return _lib
 
 
+def set_threads(n):
+    """OpenMP threads for the batch entry points (torchrun exports OMP_NUM_THREADS=1); returns the count in effect."""
+    return int(lib().bplo_set_threads(int(n)))
+
+
 def default_params(hinton=False):
     ps = Params()
     lib().bplo_default_params(ctypes.byref(ps))

@@ -164,3 +164,12 @@ void bplo_default_params(bplo_params *ps) {
 
 EXPORTS(float, _f32)
 EXPORTS(double, _f64)
+
+/* Number of OpenMP threads the batch entry points use (torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU
+ * arm of the bench sets the host's core count back explicitly).  Returns the count in effect. */
+#ifdef _OPENMP
+#include <omp.h>
+int bplo_set_threads(int n) { if (n > 0) omp_set_num_threads(n); return omp_get_max_threads(); }
+#else
+int bplo_set_threads(int n) { (void)n; return 1; }
+#endif

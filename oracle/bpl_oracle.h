@@ -15,5 +15,6 @@ typedef struct {
 
 int bplo_version(void);
 void bplo_default_params(bplo_params *ps);
+int bplo_set_threads(int n);
 
 #endif

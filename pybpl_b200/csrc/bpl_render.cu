@@ -1041,14 +1041,35 @@ __global__ void __launch_bounds__(1024) order_tokens_kernel(const int *__restric
         const int S = stroke_sub_off[tok_stroke_off[p + 1]] - stroke_sub_off[tok_stroke_off[p]];
         return MAXS - min(max(S, 0), MAXS);          // 0 = most expensive
     };
-    for (int p = threadIdx.x; p < n; p += blockDim.x) atomicAdd(&hist[key(p)], 1);
+    constexpr int KEEP = 16;                         // keys of a thread's first 16 tokens stay in registers
+    int keys[KEEP];
+#pragma unroll
+    for (int i = 0; i < KEEP; ++i) {
+        const int p = threadIdx.x + i * (int)blockDim.x;
+        keys[i] = p < n ? key(p) : 0;
+        if (p < n) atomicAdd(&hist[keys[i]], 1);
+    }
+    for (int p = threadIdx.x + KEEP * blockDim.x; p < n; p += blockDim.x) atomicAdd(&hist[key(p)], 1);
     __syncthreads();
-    if (threadIdx.x == 0) {
-        int acc = 0;
-        for (int i = 0; i <= MAXS; ++i) { start[i] = acc; acc += hist[i]; }
+    if (threadIdx.x < 32) {                          // exclusive scan of the 129 bins by one warp
+        int carry = 0;
+        for (int base = 0; base <= MAXS; base += 32) {
+            const int i = base + (int)threadIdx.x;
+            const int v = i <= MAXS ? hist[i] : 0;
+            int inc = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, inc, d); if ((int)threadIdx.x >= d) inc += o; }
+            if (i <= MAXS) start[i] = carry + inc - v;
+            carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
     }
     __syncthreads();
-    for (int p = threadIdx.x; p < n; p += blockDim.x) order[atomicAdd(&start[key(p)], 1)] = p;
+#pragma unroll
+    for (int i = 0; i < KEEP; ++i) {
+        const int p = threadIdx.x + i * (int)blockDim.x;
+        if (p < n) order[atomicAdd(&start[keys[i]], 1)] = p;
+    }
+    for (int p = threadIdx.x + KEEP * blockDim.x; p < n; p += blockDim.x) order[atomicAdd(&start[key(p)], 1)] = p;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -437,3 +437,27 @@ def test_fit_bspline_to_traj(ops):
     Yg = splines.fit_bspline_to_traj(xg, int(d["cases"][last][0]))
     (Yg * torch.from_numpy(d["ct_fit"])).sum().backward()
     assert relinf(xg.grad.numpy(), d["gX_fit"]) < 1e-4
+
+
+def test_token_order_is_a_permutation_by_decreasing_cost(ops):
+    """bpl_order_tokens: the processing order handed to the persistent kernels (results do not depend on it)."""
+    from pybpl_b200 import workload
+    for P in (1, 2, 777, 4096, 16384):
+        w = workload.synth_tokens(P, seed=5, sigma_mode="uniform")
+        b = workload.to_device(w, DEV)
+        if b.order_ptr() is None:
+            assert P < 2
+            continue
+        order = b._order.cpu().numpy()
+        assert np.array_equal(np.sort(order), np.arange(P))
+        S = np.diff(w["stroke_sub_off"][w["tok_stroke_off"]])
+        assert np.all(np.diff(S[order]) <= 0)
+    # scores with and without the order agree (to the summation order of the splat's shared-memory atomics)
+    w = workload.synth_tokens(512, seed=6, sigma_mode="uniform")
+    b = workload.to_device(w, DEV)
+    pimg, _ = ops.render_tokens(workload.to_device(workload.permute(w, np.arange(1)), DEV))
+    imgs = ops.pack_images((pimg[0] > 0.5).to(torch.uint8))
+    ll1, _ = ops.score_tokens(b, imgs)
+    b._order = torch.arange(512, dtype=torch.int32, device=DEV)
+    ll2, _ = ops.score_tokens(b, imgs)
+    assert torch.allclose(ll1, ll2, rtol=2e-6, atol=0)
