@@ -195,9 +195,15 @@ __device__ __forceinline__ LaneAcc warp_points(bool active, const CtrlSrc &src, 
     bool pend = false;          // the sub-stroke's first survivor waits for its successor (dist[:1], :98)
     bool have_first = false;    // ... and is splatted last, with that successor's ink
     float fr = 0.0f, fc = 0.0f, first_ink = 0.0f;
+#ifdef BPL_WALK_UNROLL
+#pragma unroll
+    for (int k = 0; k < PPL; ++k) {
+        if (!((inbm >> k) & 1u)) continue;
+#else
 #pragma unroll 1
     for (unsigned rest = inbm; rest; rest &= rest - 1u) {
         const int k = __ffs(rest) - 1;
+#endif
         const PEval e = eval_pt(src, j0 + k, true);
         ++acc.cnt;
         if (has_prev) {

@@ -93,6 +93,39 @@ def synth_tokens(P, seed=1234, max_strokes=5, kappa="uniform", sigma_mode="unifo
                 neval=neval)
 
 
+def synth_types(w, seed=4321):
+    """Type-level parameters and relations for the tokens of `w` (numpy arrays in the layout of ops.TokenTypes /
+    include/pybpl_b200.h:bpl_token_type), for the token-prior kernel: each token is read as a noisy copy of its type
+    (shapes +- sigma_shape, scales +- sigma_invscale), a token's first stroke is independent ('unihist', gpos near its
+    position), later strokes attach to the start, the end or a point along a random earlier stroke."""
+    L = _lib()
+    rng = np.random.default_rng(seed)
+    tso, sso = w["tok_stroke_off"].astype(np.int64), w["stroke_sub_off"].astype(np.int64)
+    K = np.diff(tso); Ktot, Stot = int(tso[-1]), int(sso[-1])
+    nsub = np.diff(sso)
+    ctrl_type = (w["ctrl"] + float(L["sigma_shape"]) * rng.standard_normal(w["ctrl"].shape)).astype(np.float32)
+    inv_type = np.abs(w["invscale"] + float(L["sigma_invscale"]) * rng.standard_normal(Stot)).astype(np.float32) + 1e-3
+    rank = np.arange(Ktot) - np.repeat(tso[:-1], K)
+    cat = np.where(rank == 0, 0, rng.integers(1, 4, size=Ktot)).astype(np.int32)
+    attach_ix = np.where(rank == 0, 0, (rng.random(Ktot) * np.maximum(rank, 1)).astype(np.int64)).astype(np.int32)
+    att_stroke = np.repeat(tso[:-1], K) + attach_ix
+    attach_subix = (rng.random(Ktot) * nsub[att_stroke]).astype(np.int32)
+    gpos = (w["position"] + L["rel_sigma"] * rng.standard_normal((Ktot, 2))).astype(np.float32)
+    es_type = rng.uniform(2.5, 5.5, size=Ktot).astype(np.float32)
+    es = np.clip(es_type + 0.1499 * rng.standard_normal(Ktot), 2.05, 5.95).astype(np.float32)
+    return dict(ctrl_type=ctrl_type, invscale_type=inv_type, rel_cat=cat, attach_ix=attach_ix, attach_subix=attach_subix,
+                gpos=gpos, eval_spot_type=es_type, eval_spot=es)
+
+
+def types_to_device(ty, device, requires_grad=False):
+    import torch
+    from . import ops
+    dev = torch.device(device)
+    f = lambda k, g: torch.from_numpy(ty[k]).to(dev).requires_grad_(g)
+    return ops.TokenTypes(f("ctrl_type", False), f("invscale_type", False), ty["rel_cat"], ty["attach_ix"], ty["attach_subix"],
+                          f("gpos", False), f("eval_spot_type", False), f("eval_spot", requires_grad))
+
+
 def permute(w, perm):
     """The same batch with tokens reordered / subset by `perm` (token indices)."""
     tso, sso = w["tok_stroke_off"].astype(np.int64), w["stroke_sub_off"].astype(np.int64)

@@ -19,6 +19,28 @@ def test_config3_fit_improves_and_matches_oracle_gradients():
     assert r["final_mean_ll"] > -r["losses"][0] / 64
 
 
+def test_config3_fit_with_token_prior_term():
+    """The fit objective with log P(token | type) added (model.py:59-62): finite, decreasing, and the prior term's
+    value on the synthetic types agrees with the numpy oracle."""
+    import fit_parses
+    from oracle import token_prior as tp
+    from pybpl_b200 import ops, workload
+    r = fit_parses.fit(P=64, steps=30, log_every=1, token_prior=True)
+    assert np.isfinite(r["losses"]).all() and r["losses"][-1] < r["losses"][0]
+    w = workload.synth_tokens(200, seed=9, sigma_mode="uniform")
+    ty = workload.synth_types(w, 10)
+    dev = torch.device("cuda:0")
+    got = ops.score_token_prior(workload.to_device(w, dev), workload.types_to_device(ty, dev)).cpu().numpy()
+    c = ops.token_prior_params()
+    d = dict(K=np.diff(w["tok_stroke_off"]), nsub=np.diff(w["stroke_sub_off"]), ctrl=w["ctrl"], invscale=w["invscale"],
+             position=w["position"], sigma=w["sigma"], consts=np.array([c.sigma_shape, c.sigma_invscale, c.sigma_attach,
+                                                                        c.sigma_x, c.sigma_y, c.min_blur_sigma, c.max_blur_sigma]), **ty)
+    C = np.load(os.path.join(ROOT, "pybpl_b200", "data", "basis_5_200.npy"))
+    ref = tp.score(d, np.float64, C0=C[0], C1=C[-1])
+    assert np.all(np.isfinite(ref))
+    assert (np.abs(got - ref) / np.abs(ref)).max() < 1e-5
+
+
 def test_config4_sweep_logsumexp_matches_torch():
     from pybpl_b200 import ops, sweep, workload
     dev = torch.device("cuda:0")
