@@ -171,3 +171,39 @@ print("dropin ok")
     r = subprocess.run([sys.executable, "-W", "ignore", "-c", code], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
                        timeout=240)
     assert r.returncode == 0 and "dropin ok" in r.stdout, r.stderr[-2000:]
+
+
+def test_parse_file_roundtrip_and_layout(tmp_path):
+    """pybpl_b200/packed.py: byte-exact round trip, the header layout include/pybpl_parsefile.h states,
+    bit packing of images, rejection of corrupt files."""
+    import struct
+    import numpy as np
+    from pybpl_b200 import packed, workload
+    w = workload.synth_tokens(300, seed=3, sigma_mode="uniform")
+    ty = workload.synth_types(w, 4)
+    rng = np.random.default_rng(0)
+    imgs = (rng.random((7, 105, 105)) < 0.1).astype(np.uint8)
+    path = str(tmp_path / "parses.bpl")
+    n = packed.save(path, w, ty, imgs)
+    assert n == os.path.getsize(path) and n % 16 == 0
+    raw = open(path, "rb").read()
+    magic, hb, nsec, P, K, S, T, ncpt, neval = struct.unpack_from("<8sII6i", raw, 0)
+    assert magic == b"BPLPARS1" and hb % 16 == 0 and (P, T, ncpt, neval) == (300, 7, 5, 200)
+    assert nsec == 7 + 8 + 1 and K == len(w["stroke_sub_off"]) - 1 and S == w["ctrl"].shape[0]
+    pf = packed.ParseFile.load(path, pin=False)
+    a = pf.arrays()
+    for k in packed.TOKEN_KEYS:
+        assert np.array_equal(a[k], w[k]) and a[k].dtype == w[k].dtype
+    for k in packed.TYPE_KEYS:
+        assert np.array_equal(a[k], ty[k])
+    assert np.array_equal(packed.unpack_bits(a["image_bits"]), imgs)
+    i = 105 * 17 + 33                                    # pixel (17, 33) of image 2 = bit i&31 of word i>>5
+    assert ((int(a["image_bits"][2, i >> 5]) >> (i & 31)) & 1) == imgs[2, 17, 33]
+    assert packed.to_bytes(a | {"neval": 200}, {k: a[k] for k in packed.TYPE_KEYS}, image_bits=a["image_bits"]) == raw
+    with pytest.raises(ValueError):
+        packed.ParseFile(b"NOTAFILE" + raw[8:], pin=False)
+    bad = bytearray(raw); struct.pack_into("<i", bad, hb + 4, 10 ** 6)       # tok_stroke_off[1] out of range
+    with pytest.raises(ValueError):
+        packed.ParseFile(bytes(bad), pin=False)
+    with pytest.raises(ValueError):
+        packed.pack_bits(np.full((1, 105, 105), 0.5))

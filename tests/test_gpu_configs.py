@@ -105,3 +105,36 @@ def test_all_images_scoring_equals_pairwise():
     # a second call right after (buffer re-zeroing between pairs and launches)
     ll2, _ = ops.score_tokens_all_images(batch, packed)
     assert ((ll2 - ll_all).abs() <= 2e-5 * ll_all.abs()).all()
+
+
+def test_parse_file_upload_scores_like_the_original(tmp_path):
+    """a batch + types + image set written to a parse file, loaded with ONE host->device copy, gives the
+    scores of the original tensors; the host bit packing equals bpl_pack_images_u8."""
+    import time
+    from pybpl_b200 import ops, packed, workload
+    dev = torch.device("cuda:0")
+    w = workload.synth_tokens(2000, seed=21, sigma_mode="uniform")
+    ty = workload.synth_types(w, 22)
+    rng = np.random.default_rng(1)
+    imgs = (rng.random((5, 105, 105)) < 0.08).astype(np.uint8)
+    idx = rng.integers(0, 5, size=2000).astype(np.int32)
+    path = str(tmp_path / "p.bpl")
+    nbytes = packed.save(path, w, ty, imgs)
+    pf = packed.ParseFile.load(path)
+    t0 = time.perf_counter()
+    batch, types, images = pf.upload(dev)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    print(f"parse file: {nbytes / 1e6:.2f} MB, upload {dt * 1e3:.2f} ms")
+    ref_imgs = ops.pack_images(torch.from_numpy(imgs).to(dev))
+    assert torch.equal(images.bits, ref_imgs.bits)
+    ti = torch.from_numpy(idx).to(dev)
+    ll_a, off_a = ops.score_tokens(batch, images, ti)
+    ll_b, off_b = ops.score_tokens(workload.to_device(w, dev), ref_imgs, ti)
+    assert torch.allclose(ll_a, ll_b, rtol=2e-6, atol=0) and torch.equal(off_a, off_b)
+    pr_a = ops.score_token_prior(batch, types)
+    pr_b = ops.score_token_prior(workload.to_device(w, dev), workload.types_to_device(ty, dev))
+    assert torch.equal(pr_a, pr_b)
+    allp = ops.score_tokens_all_images(batch, images)
+    assert allp.shape == (2000, 5)
+    assert torch.allclose(allp[torch.arange(2000, device=dev), ti.long()], ll_a, rtol=2e-5, atol=0)
