@@ -136,9 +136,9 @@ int bpl_vanilla_to_motor(const float *C, int neval, int ncpt, int n_strokes, con
 
 /* ---- token prior: log P(token | type) -------------------------------------------------
  * CharacterTokenDist.score_token (pybpl/model/token_dist.py:264-287): per stroke the shapes and
- * invscales of StrokeTokenDist.score_part_token (:410-430), RelationTokenDist.score_relation_token
- * (:488-517) and score_location (:131-153) with RelationToken.get_attach_point
- * (pybpl/objects/relation.py:34-67), plus score_image_blur (:203-224).  SURVEY.md 8(f)1. */
+ * invscales of StrokeTokenDist.score_part_token (:432-455), RelationTokenDist.score_relation_token
+ * (:489-515) and score_location (:131-153) with RelationToken.get_attach_point
+ * (pybpl/objects/relation.py:34-67), plus score_image_blur (:205-224).  SURVEY.md 8(f)1. */
 #define BPL_REL_UNIHIST 0   /* relation categories (pybpl/objects/relation.py:11) */
 #define BPL_REL_START 1
 #define BPL_REL_END 2
@@ -181,6 +181,15 @@ typedef struct {
  * sigma and basis (rows 0 and neval-1).  g == NULL: forward only. */
 int bpl_score_token_prior(const bpl_token_prior_params *c, const bpl_token_batch *b, const bpl_token_type *ty,
                           float *ll, const bpl_token_prior_grads *g, void *stream);
+
+/* Sample tokens from P(token | type): CharacterTokenDist.sample_token (pybpl/model/token_dist.py:226-262; strokes in
+ * order: sample_part_token :410-430, sample_relation_token :465-487, sample_location :109-129).  Reads b's CSR
+ * offsets, neval and basis, and ty's type-level arrays (ty->eval_spot is ignored); writes ctrl [S][5][2],
+ * invscale [S], position [K][2] and, unless NULL, eval_spot [K].  Token p draws from the Philox-4x32-10 stream
+ * (seed, subsequence first_token + p), so a particle set can be produced in shards.  SURVEY.md 8(f)3 (token half). */
+int bpl_sample_tokens(const bpl_token_prior_params *c, const bpl_token_batch *b, const bpl_token_type *ty,
+                      unsigned long long seed, unsigned long long first_token, float *ctrl, float *invscale,
+                      float *position, float *eval_spot, void *stream);
 
 /* ---- images ------------------------------------------------------------------------ */
 /* Pack T 105x105 images into bit rows.  `bad` (dev int, zero-filled by the caller) is set

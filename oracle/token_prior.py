@@ -4,12 +4,12 @@ A numpy restatement (pure-Python loops over strokes: small cases only) of the re
 CharacterTokenDist.score_token (pybpl/model/token_dist.py:264-287):
 
     sum over strokes i of
-        StrokeTokenDist.score_part_token        token_dist.py:410-430  (shapes :334-354, invscales :378-408)
-      + RelationTokenDist.score_relation_token  token_dist.py:488-517  (score_eval_spot_token :547-572)
+        StrokeTokenDist.score_part_token        token_dist.py:432-455  (shapes :334-354, invscales :379-408)
+      + RelationTokenDist.score_relation_token  token_dist.py:489-515  (score_eval_spot_token :542-572)
       + CharacterTokenDist.score_location       token_dist.py:131-153  (attach point objects/relation.py:34-67,
                                                                         trajectories objects/part.py:290-328,
                                                                         spline row splines.py:19-54,72-93,108-138)
-    + score_affine (0, :169-170) + score_image_noise (0, :186-187) + score_image_blur (:203-224)
+    + score_affine (0, :169-170) + score_image_noise (0, :186-187) + score_image_blur (:205-224)
 
 and of its gradient with respect to every token- and type-level parameter (what autograd returns for the
 leaves listed by objects/concept.py:93-107 and :243-258), written out analytically.  The CUDA kernel
@@ -93,11 +93,11 @@ def score(d, dtype=np.float64, grad=False, C0=None, C1=None):
         tot = f(0)
         for i in range(K[p]):
             ki = k0 + i
-            # ---- score_part_token (token_dist.py:410-430) ----
+            # ---- score_part_token (token_dist.py:432-455) ----
             for s in range(stroke_sub[ki], stroke_sub[ki + 1]):
                 diff = ctrl[s] - ctrl_ty[s]                                                    # Normal(shapes_type, sigma_shape) :334-354
                 tot += np.sum(-(diff * diff) / (2 * sig_s * sig_s) - f(math.log(sig_s)) - f(LOG_SQRT_2PI))
-                di = inv[s] - inv_ty[s]                                                        # :378-408
+                di = inv[s] - inv_ty[s]                                                        # :379-408
                 l = -(di * di) / (2 * sig_i * sig_i) - f(math.log(sig_i)) - f(LOG_SQRT_2PI)
                 p_above = 1 - f(_Phi((0 - inv_ty[s]) / sig_i))                                 # :399-401
                 l = l - f(math.log(p_above)) if p_above > 0 else f(np.inf)
@@ -109,7 +109,7 @@ def score(d, dtype=np.float64, grad=False, C0=None, C1=None):
                     g["invscale"][s] += -di / (sig_i * sig_i)
                     z = inv_ty[s] / sig_i
                     g["invscale_type"][s] += di / (sig_i * sig_i) - f(_phi(z)) / (sig_i * f(_Phi(z)))
-            # ---- score_relation_token (token_dist.py:488-517, 547-572) ----
+            # ---- score_relation_token (token_dist.py:489-515, 542-572) ----
             cat = int(d["rel_cat"][ki])
             if cat == REL_MID:
                 u = es[ki]
@@ -173,7 +173,7 @@ def score(d, dtype=np.float64, grad=False, C0=None, C1=None):
                         g["ctrl"][sub] += inv[sub] * gY
                         g["invscale"][sub] += np.sum(ctrl[sub] * gY)
                         g["eval_spot"][ki] += np.dot(dc @ (Y - off), gb)
-        # ---- image blur (token_dist.py:203-224): Uniform(lb, ub).log_prob; affine and noise score 0 ----
+        # ---- image blur (token_dist.py:205-224): Uniform(lb, ub).log_prob; affine and noise score 0 ----
         sg_b = f(d["sigma"][p])
         tot += -f(math.log(blur_hi - blur_lo)) if (blur_lo <= sg_b < blur_hi) else f(-np.inf)
         ll[p] = tot

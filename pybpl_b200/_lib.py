@@ -95,6 +95,8 @@ EXPORTS = {
     "bpl_token_points": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.POINTER(TokenBatchC), vp, vp, vp, vp, vp, vp]),
     "bpl_score_token_prior": (ctypes.c_int, [ctypes.POINTER(TokenPriorParams), ctypes.POINTER(TokenBatchC),
                                              ctypes.POINTER(TokenTypeC), vp, ctypes.POINTER(TokenPriorGrads), vp]),
+    "bpl_sample_tokens": (ctypes.c_int, [ctypes.POINTER(TokenPriorParams), ctypes.POINTER(TokenBatchC),
+                                         ctypes.POINTER(TokenTypeC), ctypes.c_ulonglong, ctypes.c_ulonglong, vp, vp, vp, vp, vp]),
     "bpl_logsumexp_partial": (ctypes.c_int, [vp, ctypes.c_int, vp, vp]),
     "bpl_fp32_probe": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, vp]),
     "bpl_launch_count": (ctypes.c_longlong, []),

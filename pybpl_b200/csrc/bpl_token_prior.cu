@@ -1,11 +1,11 @@
 // bpl_token_prior.cu -- log P(token | type) for a ragged batch of character tokens, with its gradient.
 //
 // Replaces CharacterTokenDist.score_token (pybpl/model/token_dist.py:264-287), i.e. per stroke
-//   StrokeTokenDist.score_part_token        token_dist.py:410-430  (shapes :334-354, invscales :378-408)
-//   RelationTokenDist.score_relation_token  token_dist.py:488-517  (score_eval_spot_token :547-572)
+//   StrokeTokenDist.score_part_token        token_dist.py:432-455  (shapes :334-354, invscales :379-408)
+//   RelationTokenDist.score_relation_token  token_dist.py:489-515  (score_eval_spot_token :542-572)
 //   CharacterTokenDist.score_location       token_dist.py:131-153  (get_attach_point, objects/relation.py:34-67;
 //                                                                   trajectories objects/part.py:290-328)
-// plus score_image_blur (:203-224); score_affine and score_image_noise are 0 in the reference (:169-170,186-187).
+// plus score_image_blur (:205-224); score_affine and score_image_noise are 0 in the reference (:169-170,186-187).
 // It is the other per-particle term of the fit_image objective (model/model.py:59-62), SURVEY.md 8(f)1.
 //
 // One warp per token: lanes over the control-point coordinates (coalesced), then over the sub-strokes, then
@@ -17,6 +17,7 @@
 #include <math.h>
 
 #include "bpl_common.cuh"
+#include "bpl_token_common.cuh"
 
 namespace bpl {
 void set_error(const char *fmt, const char *detail);
@@ -48,29 +49,6 @@ __device__ __forceinline__ float normal_cdf(float x, float mu, float sigma) {
 }
 __device__ __forceinline__ float std_pdf(float z) { return INV_SQRT_2PI * expf(-0.5f * z * z); }
 
-// One normalised row of the cubic B-spline basis at time u, and its derivative (splines.py:19-54, 72-93).
-__device__ __forceinline__ void basis_row_dev(float u, float (&c)[NCPT], float (&dc)[NCPT], float &csum) {
-    float tot = 0.0f, dtot = 0.0f;
-#pragma unroll
-    for (int k = 0; k < NCPT; ++k) {
-        const float d = u - (float)k;
-        float b = 0.0f, db = 0.0f;
-        if (d >= 0.0f && d < 1.0f) { b = d * d * d; db = 3.0f * d * d; }
-        else if (d >= 1.0f && d < 2.0f) { const float e = d - 1.0f; b = ((-3.0f * e * e * e + 3.0f * e * e) + 3.0f * e) + 1.0f; db = (-9.0f * e * e + 6.0f * e) + 3.0f; }
-        else if (d >= 2.0f && d < 3.0f) { const float e = d - 2.0f; b = (3.0f * e * e * e - 6.0f * e * e) + 4.0f; db = 9.0f * e * e - 12.0f * e; }
-        else if (d >= 3.0f && d < 4.0f) { const float e = 1.0f - (d - 3.0f); b = e * e * e; db = -3.0f * e * e; }
-        c[k] = b / 6.0f; dc[k] = db / 6.0f;
-        tot += c[k]; dtot += dc[k];
-    }
-    csum = 0.0f;
-#pragma unroll
-    for (int k = 0; k < NCPT; ++k) {
-        c[k] = c[k] / tot;
-        dc[k] = (dc[k] - c[k] * dtot) / tot;
-        csum += c[k];
-    }
-}
-
 __global__ void __launch_bounds__(256) token_prior_kernel(const TPArgs a) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -95,7 +73,7 @@ __global__ void __launch_bounds__(256) token_prior_kernel(const TPArgs a) {
                 if (wg) { a.g.g_ctrl[e] = -diff * inv2; if (a.g.g_ctrl_type) a.g.g_ctrl_type[e] = diff * inv2; }
             }
         }
-        // ---- invscales: Normal restricted to positive values (token_dist.py:378-408) ----
+        // ---- invscales: Normal restricted to positive values (token_dist.py:379-408) ----
         for (int s = s0 + lane; s < s1; s += 32) {
             const float tk = a.invscale[s], tyv = a.ty.invscale_type[s];
             const float diff = tk - tyv;
@@ -123,7 +101,7 @@ __global__ void __launch_bounds__(256) token_prior_kernel(const TPArgs a) {
             __threadfence_block();
         }
         __syncwarp();
-        // ---- per stroke: relation token + location (token_dist.py:488-517, 131-153) ----
+        // ---- per stroke: relation token + location (token_dist.py:489-515, 131-153) ----
         for (int k = k0 + lane; k < k1; k += 32) {
             const int cat = a.ty.rel_cat[k];
             float cu[NCPT], dcu[NCPT], csum = 1.0f;
@@ -242,7 +220,7 @@ __global__ void __launch_bounds__(256) token_prior_kernel(const TPArgs a) {
         }
         acc = warp_sum(acc);
         if (lane == 0) {
-            // score_image_blur: Uniform(lb, ub).log_prob (token_dist.py:203-224); outside the support the reference
+            // score_image_blur: Uniform(lb, ub).log_prob (token_dist.py:205-224); outside the support the reference
             // raises (validate_args), here the score is -inf.  score_affine and score_image_noise are 0.
             const float sg = a.sigma[p];
             const float blur = (sg >= a.c.min_blur_sigma && sg < a.c.max_blur_sigma) ? -logf(a.c.max_blur_sigma - a.c.min_blur_sigma)

@@ -12,6 +12,7 @@ import torch
 
 from . import _lib
 from ._lib import IMSIZE, IMG_WORDS, NCPT, check, lib
+lib_ = lib      # (sample_tokens has a parameter named lib)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -743,6 +744,38 @@ def score_token_prior(batch, types, lib=None, ps=None, c=None):
         c = token_prior_params(lib, ps)
     return _ScoreTokenPrior.apply(batch.ctrl, batch.invscale, batch.position, types.eval_spot, types.ctrl_type,
                                   types.invscale_type, types.gpos, types.eval_spot_type, batch, types, c)
+
+
+def sample_tokens(tok_stroke_off, stroke_sub_off, types, seed, first_token=0, eps=1e-4, sigma=0.5, lib=None, ps=None, c=None,
+                  neval=200):
+    """Draw one token per entry of the (expanded) type batch from P(token | type): the batched, on-device
+    CharacterTokenDist.sample_token (pybpl/model/token_dist.py:226-262).  `types` holds the type-level arrays aligned with
+    the CSR structure; its eval_spot is replaced by the sampled relation tokens' spots.  eps / sigma: the reference fixes
+    them to Parameters.min_epsilon / min_blur_sigma (token_dist.py:253-260); scalars or [P] tensors.  Token p uses the
+    Philox stream (seed, first_token + p).  Returns (TokenBatch, TokenTypes)."""
+    dev = types.device
+    if c is None:
+        c = token_prior_params(lib, ps)
+    tso, sso = _i32(tok_stroke_off, dev), _i32(stroke_sub_off, dev)
+    P, K, S = tso.numel() - 1, sso.numel() - 1, types.ctrl_type.shape[0]
+    ctrl = torch.empty((S, NCPT, 2), dtype=torch.float32, device=dev)
+    inv = torch.empty(S, dtype=torch.float32, device=dev)
+    pos = torch.empty((K, 2), dtype=torch.float32, device=dev)
+    es = torch.empty(K, dtype=torch.float32, device=dev)
+    b = _lib.TokenBatchC()
+    b.n_tokens = P; b.ncpt = NCPT; b.neval = int(neval)
+    b.tok_stroke_off = tso.data_ptr(); b.stroke_sub_off = sso.data_ptr()
+    b.basis = basis_table(NCPT, int(neval), dev).data_ptr()
+    ty = _lib.TokenTypeC(_c32(types.ctrl_type).data_ptr(), _c32(types.invscale_type).data_ptr(), types.rel_cat.data_ptr(),
+                         types.attach_ix.data_ptr(), types.attach_subix.data_ptr(), _c32(types.gpos).data_ptr(),
+                         _c32(types.eval_spot_type).data_ptr(), None)
+    check(lib_().bpl_sample_tokens(ctypes.byref(c), ctypes.byref(b), ctypes.byref(ty), int(seed), int(first_token),
+                                   ctrl.data_ptr(), inv.data_ptr(), pos.data_ptr(), es.data_ptr(), _stream(dev)))
+    full = lambda v: v.to(dev, torch.float32) if isinstance(v, torch.Tensor) else torch.full((P,), float(v), device=dev)
+    batch = TokenBatch(tso, sso, ctrl, inv, pos, full(eps), full(sigma), neval=neval, check_limits=False)
+    out_types = TokenTypes(types.ctrl_type, types.invscale_type, types.rel_cat, types.attach_ix, types.attach_subix,
+                           types.gpos, types.eval_spot_type, es)
+    return batch, out_types
 
 
 def logsumexp_partial(ll):

@@ -462,7 +462,7 @@ def make_fit():
 
 # --------------------------------------------------------------------------
 # token_prior.npz : CharacterModel.score_token = log P(token | type)
-# (pybpl/model/token_dist.py:57-80,131-153,203-224,264-287,334-408,488-517,547-572;
+# (pybpl/model/token_dist.py:57-80,131-153,205-224,264-287,334-455,489-515,542-572;
 #  attach points objects/relation.py:34-67) with autograd gradients w.r.t. every
 #  token- and type-level parameter (objects/concept.py:93-107,243-258)
 # --------------------------------------------------------------------------
@@ -545,6 +545,56 @@ def make_token_prior(n=160):
           int(np.sum(~np.isfinite(out["ll"]))), "; ll range", np.nanmin(out["ll"][np.isfinite(out["ll"])]), out["ll"].max())
 
 
+# --------------------------------------------------------------------------
+# token_samples.npz : CharacterModel.sample_token draws for a few fixed types
+# (pybpl/model/token_dist.py:226-262), the distributional fixture for the
+# on-device sampler (RNG streams cannot match; distributions must)
+# --------------------------------------------------------------------------
+def make_token_samples(n_types=4, n_draws=600):
+    torch.manual_seed(23)
+    lib = Library(use_hist=True)
+    model = CharacterModel(lib)
+    out = {}
+    chosen = []
+    want = {3: 2, 2: 1, 1: 1}           # strokes -> how many types (so that attach relations are exercised)
+    while sum(want.values()) > 0:
+        ct = model.sample_type()
+        k = int(ct.k)
+        cats = [r.category for r in ct.relation_types]
+        if want.get(k, 0) > 0 and (k == 1 or any(c != "unihist" for c in cats)):
+            want[k] -= 1; chosen.append(ct)
+    for ti, ct in enumerate(chosen):
+        K = int(ct.k)
+        nsub = np.array([p.shapes.shape[2] for p in ct.part_types], np.int32)
+        out[f"t{ti}_nsub"] = nsub
+        out[f"t{ti}_ctrl_type"] = torch.cat([p.shapes.permute(2, 0, 1) for p in ct.part_types]).numpy().astype(f32)
+        out[f"t{ti}_invscale_type"] = torch.cat([p.invscales for p in ct.part_types]).numpy().astype(f32)
+        cat = [REL_CODE[r.category] for r in ct.relation_types]
+        out[f"t{ti}_rel_cat"] = np.array(cat, np.int32)
+        out[f"t{ti}_attach_ix"] = np.array([int(r.attach_ix) if c else 0 for r, c in zip(ct.relation_types, cat)], np.int32)
+        out[f"t{ti}_attach_subix"] = np.array([int(r.attach_subix) if c == 3 else 0 for r, c in zip(ct.relation_types, cat)], np.int32)
+        out[f"t{ti}_gpos"] = np.stack([r.gpos.numpy() if c == 0 else np.zeros(2, f32) for r, c in zip(ct.relation_types, cat)]).astype(f32)
+        out[f"t{ti}_eval_spot_type"] = np.array([float(r.eval_spot) if c == 3 else 0.0 for r, c in zip(ct.relation_types, cat)], f32)
+        ctrl, inv, pos, es = [], [], [], []
+        for _ in range(n_draws):
+            tk = model.sample_token(ct)
+            ctrl.append(torch.cat([p.shapes.permute(2, 0, 1) for p in tk.part_tokens]).numpy())
+            inv.append(torch.cat([p.invscales for p in tk.part_tokens]).numpy())
+            pos.append(torch.stack([p.position for p in tk.part_tokens]).numpy())
+            es.append(np.array([float(r.eval_spot_token) if c == 3 else 0.0 for r, c in zip(tk.relation_tokens, cat)], f32))
+        out[f"t{ti}_ctrl"] = np.stack(ctrl).astype(f32)            # [draws, S, 5, 2]
+        out[f"t{ti}_invscale"] = np.stack(inv).astype(f32)
+        out[f"t{ti}_position"] = np.stack(pos).astype(f32)
+        out[f"t{ti}_eval_spot"] = np.stack(es).astype(f32)
+    out["n_types"] = np.int32(len(chosen))
+    out["consts"] = np.array([float(lib.tokenvar['sigma_shape']), float(lib.tokenvar['sigma_invscale']),
+                              float(lib.tokenvar['sigma_attach']), float(lib.rel['sigma_x']), float(lib.rel['sigma_y']),
+                              float(model.token_dist.ps.min_blur_sigma), float(model.token_dist.ps.max_blur_sigma)], f32)
+    np.savez_compressed(os.path.join(OUT, "token_samples.npz"), **out)
+    print("token_samples.npz:", len(chosen), "types x", n_draws, "draws; relations",
+          [list(out[f"t{i}_rel_cat"]) for i in range(len(chosen))])
+
+
 def make_assets():
     """pybpl_b200/data/basis_5_200.npy: coefficient_mat(5, 200) exactly as the reference's torch builds it
     (splines.py:72-93).  torch assembles it with Sleef powf and an MKL dot, which portable C cannot
@@ -570,7 +620,7 @@ def make_assets():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["splines", "render", "tokens", "fit", "token_prior", "assets"]
+    which = sys.argv[1:] or ["splines", "render", "tokens", "fit", "token_prior", "token_samples", "assets"]
     if "splines" in which:
         make_splines()
     if "render" in which:
@@ -581,6 +631,8 @@ if __name__ == "__main__":
         make_fit()
     if "token_prior" in which:
         make_token_prior()
+    if "token_samples" in which:
+        make_token_samples()
     if "assets" in which:
         make_assets()
     for f in sorted(os.listdir(OUT)):

@@ -135,6 +135,6 @@ def test_parse_file_upload_scores_like_the_original(tmp_path):
     pr_a = ops.score_token_prior(batch, types)
     pr_b = ops.score_token_prior(workload.to_device(w, dev), workload.types_to_device(ty, dev))
     assert torch.equal(pr_a, pr_b)
-    allp = ops.score_tokens_all_images(batch, images)
+    allp, _ = ops.score_tokens_all_images(batch, images)
     assert allp.shape == (2000, 5)
     assert torch.allclose(allp[torch.arange(2000, device=dev), ti.long()], ll_a, rtol=2e-5, atol=0)
