@@ -39,6 +39,24 @@ for grad in (False, True):
     nb = bytes_bwd if grad else bytes_fwd
     out["fwd+grad" if grad else "fwd"] = {"ms": best, "tokens_per_s": P / best * 1e3, "GBps": nb / best / 1e6,
                                           "hbm_frac": nb / best / 1e6 / peaks["hbm_gbs"]}
+# ---- the sampler on the same structure: writes 44 B per sub-stroke + 12 B per stroke, reads as much of type data ----
+batch, types, c, _ = make_inputs(ops, big)
+def draw():
+    return ops.sample_tokens(batch.tok_stroke_off, batch.stroke_sub_off, types, seed=1, c=c)
+for _ in range(3):
+    draw()
+torch.cuda.synchronize()
+best = 1e9
+for _ in range(5):
+    a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(5):
+        draw()
+    e.record(); torch.cuda.synchronize()
+    best = min(best, a.elapsed_time(e) / 5)
+nb = 2 * 44 * S + 44 * K + 8 * P
+out["sample"] = {"ms": best, "tokens_per_s": P / best * 1e3, "GBps": nb / best / 1e6, "hbm_frac": nb / best / 1e6 / peaks["hbm_gbs"],
+                 "note": "includes torch.empty of the outputs and the eps/sigma fills of ops.sample_tokens"}
 from oracle import token_prior as tp
 C = load("tokens")["basis_5_200"]
 t0 = time.perf_counter(); tp.score(d, np.float32, C0=C[0], C1=C[-1]); dt = time.perf_counter() - t0
