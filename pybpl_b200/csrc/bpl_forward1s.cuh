@@ -204,6 +204,8 @@ struct Fwd1sSmem {
     Misc ms;
 };
 
+// AP: all-pairs mode (bpl_targets.all_pairs): the token is rendered once and scored against every target image.
+template <bool AP>
 __global__ void __launch_bounds__(S_THREADS, S_CTAS_PER_SM) bpl_forward1s_kernel(const KArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Fwd1sSmem &sm = *reinterpret_cast<Fwd1sSmem *>(smem_raw);
@@ -230,7 +232,7 @@ __global__ void __launch_bounds__(S_THREADS, S_CTAS_PER_SM) bpl_forward1s_kernel
         const bool bad = t.S > MAXS || t.K > MAXK;
         if (bad) { t.S = 0; t.K = 0; }
         const float eps = a.eps[p], sigma = a.sigma[p];
-        load_image_bits(a, p, ms);
+        if (!AP) load_image_bits(a, p, ms);
         if (threadIdx.x == 0) { ms->off_page = 0; sm.bbox[0] = IMG; sm.bbox[1] = -1; sm.bbox[2] = IMG; sm.bbox[3] = -1; }
         BPL_PT(0);
         chain_offsets(a, t, sm.tab, ms);
@@ -319,30 +321,86 @@ __global__ void __launch_bounds__(S_THREADS, S_CTAS_PER_SM) bpl_forward1s_kernel
         const float om = 1.0f - eps;
         const float l0 = ms->lp_bg[0], l1 = ms->lp_bg[1];
         float acc_ll = 0.0f;
-        if (!bb.empty()) {
-            const int wbox = bb.c1 - bb.c0 + 1;
-            const int nw_ = blockDim.x >> 5, warp_ = threadIdx.x >> 5;
-            for (int r = bb.r0 + warp_; r <= bb.r1; r += nw_) {            // one warp per row of the box
-                for (int cc = lane; cc < wbox; cc += 32) {
-                    const int i = r * IMG + bb.c0 + cc;
-                    float v = fminf(fmaxf(A[i], 0.0f), 1.0f);                                          // clamp_(0,1) (:180)
-                    A[i] = 0.0f;                                            // the buffer is all zero again afterwards
-                    if (eps > 0.0f) v = __fadd_rn(__fmul_rn(om, v), __fmul_rn(eps, __fsub_rn(1.0f, v)));   // (:227)
-                    if (v != bgv) {
-                        const bool x = (ms->bits[i >> 5] >> (i & 31)) & 1u;
-                        acc_ll += pixel_lp_fwd(v, x) - (x ? l1 : l0);
+        if (!AP) {
+            if (!bb.empty()) {
+                const int wbox = bb.c1 - bb.c0 + 1;
+                const int nw_ = blockDim.x >> 5, warp_ = threadIdx.x >> 5;
+                for (int r = bb.r0 + warp_; r <= bb.r1; r += nw_) {            // one warp per row of the box
+                    for (int cc = lane; cc < wbox; cc += 32) {
+                        const int i = r * IMG + bb.c0 + cc;
+                        float v = fminf(fmaxf(A[i], 0.0f), 1.0f);                                          // clamp_(0,1) (:180)
+                        A[i] = 0.0f;                                            // the buffer is all zero again afterwards
+                        if (eps > 0.0f) v = __fadd_rn(__fmul_rn(om, v), __fmul_rn(eps, __fsub_rn(1.0f, v)));   // (:227)
+                        if (v != bgv) {
+                            const bool x = (ms->bits[i >> 5] >> (i & 31)) & 1u;
+                            acc_ll += pixel_lp_fwd(v, x) - (x ? l1 : l0);
+                        }
                     }
                 }
             }
-        }
-        double v[1] = {(double)acc_ll};
-        if (threadIdx.x == 0) v[0] += (double)ms->n_ones * (double)l1 + (double)(NPIX - ms->n_ones) * (double)l0;
-        block_sum<1>(v, ms->red);
-        if (threadIdx.x == 0) {
-            if (a.ll) a.ll[p] = bad ? nanf("") : (float)v[0];
-            if (a.off_page) a.off_page[p] = bad ? (uint8_t)255 : (uint8_t)(ms->off_page != 0);
-            ms->ones_acc = 0;
-            ms->next_item = p_next;
+            double v[1] = {(double)acc_ll};
+            if (threadIdx.x == 0) v[0] += (double)ms->n_ones * (double)l1 + (double)(NPIX - ms->n_ones) * (double)l0;
+            block_sum<1>(v, ms->red);
+            if (threadIdx.x == 0) {
+                if (a.ll) a.ll[p] = bad ? nanf("") : (float)v[0];
+                if (a.off_page) a.off_page[p] = bad ? (uint8_t)255 : (uint8_t)(ms->off_page != 0);
+                ms->ones_acc = 0;
+                ms->next_item = p_next;
+            }
+        } else {
+            // Every image m: ll_m = [all pixels scored as x = 0] + sum over the set bits of m of delta, delta = lp(x=1) - lp(x=0).
+            // With delta_bg the background's delta: ll_m = base + ones(m) * delta_bg + sum over set bits of (delta - delta_bg),
+            // and (delta - delta_bg) is zero outside the box and at background pixels, i.e. wherever the buffer holds zero.
+            const float dbg = l1 - l0;
+            if (!bb.empty()) {
+                const int wbox = bb.c1 - bb.c0 + 1;
+                const int nw_ = blockDim.x >> 5, warp_ = threadIdx.x >> 5;
+                for (int r = bb.r0 + warp_; r <= bb.r1; r += nw_) {
+                    for (int cc = lane; cc < wbox; cc += 32) {
+                        const int i = r * IMG + bb.c0 + cc;
+                        float v = fminf(fmaxf(A[i], 0.0f), 1.0f);
+                        if (eps > 0.0f) v = __fadd_rn(__fmul_rn(om, v), __fmul_rn(eps, __fsub_rn(1.0f, v)));
+                        float dl = 0.0f;
+                        if (v != bgv) {
+                            const float s0 = pixel_lp_fwd(v, false), s1 = pixel_lp_fwd(v, true);
+                            acc_ll += s0 - l0;
+                            dl = (s1 - s0) - dbg;
+                        }
+                        A[i] = dl;
+                    }
+                }
+            }
+            double v[1] = {(double)acc_ll};
+            block_sum<1>(v, ms->red);      // its barriers also publish the deltas
+            const double base = v[0] + (double)NPIX * (double)l0;
+            const int nw_ = blockDim.x >> 5, warp_ = threadIdx.x >> 5;
+            for (int m = warp_; m < a.n_images; m += nw_) {      // one warp per image walks the image's set bits
+                const uint32_t *bw = a.image_bits + (size_t)m * IMG_WORDS;
+                float s = 0.0f;
+                int ones = 0;
+                for (int wi = lane; wi < IMG_WORDS; wi += 32) {
+                    unsigned bits = bw[wi];
+                    if (wi == IMG_WORDS - 1) bits &= (1u << (NPIX - 32 * (IMG_WORDS - 1))) - 1u;      // 11025 = 344 * 32 + 17
+                    ones += __popc(bits);
+                    for (; bits; bits &= bits - 1u) s += A[wi * 32 + __ffs(bits) - 1];
+                }
+                s = warp_sum(s);
+                ones = __reduce_add_sync(0xffffffffu, ones);
+                if (lane == 0 && a.ll)
+                    a.ll[(size_t)p * a.n_images + m] = bad ? nanf("") : (float)(base + (double)ones * (double)dbg + (double)s);
+            }
+            if (threadIdx.x == 0) {
+                if (a.off_page) a.off_page[p] = bad ? (uint8_t)255 : (uint8_t)(ms->off_page != 0);
+                ms->next_item = p_next;
+            }
+            __syncthreads();
+            if (!bb.empty()) {                                      // the deltas must not leak into the next token
+                const int wbox = bb.c1 - bb.c0 + 1, nbox = wbox * (bb.r1 - bb.r0 + 1);
+                for (int i = threadIdx.x; i < nbox; i += blockDim.x) {
+                    const int r = i / wbox;
+                    A[(bb.r0 + r) * IMG + bb.c0 + (i - r * wbox)] = 0.0f;
+                }
+            }
         }
         __syncthreads();
         p = ms->next_item;      // rewritten only at the end of the next iteration, many barriers from here

@@ -1181,10 +1181,16 @@ static int launch(K kernel, int threads, size_t smem, int ctas_per_sm, const KAr
     static const bool static_sched = getenv("BPL_STATIC_SCHED") != nullptr;
     if (!static_sched) {
         static std::atomic<unsigned> slot{0};
-        Sched *base = nullptr;
-        cudaError_t es = cudaGetSymbolAddress(reinterpret_cast<void **>(&base), g_sched);      // per current device
-        if (es != cudaSuccess) { set_error("cudaGetSymbolAddress: %s", cudaGetErrorString(es)); return (int)es; }
-        kb.sched = base + (slot.fetch_add(1u) % SCHED_RING);
+        static thread_local int ring_dev = -1;
+        static thread_local Sched *ring = nullptr;      // g_sched has one instance per device
+        int dev = -1;
+        cudaGetDevice(&dev);
+        if (dev != ring_dev) {
+            cudaError_t es = cudaGetSymbolAddress(reinterpret_cast<void **>(&ring), g_sched);
+            if (es != cudaSuccess) { set_error("cudaGetSymbolAddress: %s", cudaGetErrorString(es)); return (int)es; }
+            ring_dev = dev;
+        }
+        kb.sched = ring + (slot.fetch_add(1u) % SCHED_RING);
     }
 #ifdef BPL_PHASE_TIMING
     if (const char *pb = getenv("BPL_PT_BUF")) kb.pt_buf = reinterpret_cast<float *>(strtoull(pb, nullptr, 10));
@@ -1266,8 +1272,13 @@ int bpl_score_tokens(const bpl_params *ps, const bpl_token_batch *b, const bpl_t
     // select the dense paired / dense single kernels instead (A/B and profiling aids).
     static const bool force_single = getenv("BPL_FORCE_SINGLE") != nullptr;
     static const bool force_paired = getenv("BPL_FWD_PAIRED") != nullptr;
-    if (!force_single && !force_paired && ka.image_bits && !ka.pimg && !ka.all_pairs)
-        return launch(bpl_forward1s_kernel, S_THREADS, sizeof(Fwd1sSmem), S_CTAS_PER_SM, ka, (cudaStream_t)stream);
+    if (!force_single && !force_paired && ka.image_bits && !ka.pimg) {
+        if (ka.all_pairs) {      // (tokens are few in this mode: no processing order)
+            ka.order = nullptr;
+            return launch(bpl_forward1s_kernel<true>, S_THREADS, sizeof(Fwd1sSmem), S_CTAS_PER_SM, ka, (cudaStream_t)stream);
+        }
+        return launch(bpl_forward1s_kernel<false>, S_THREADS, sizeof(Fwd1sSmem), S_CTAS_PER_SM, ka, (cudaStream_t)stream);
+    }
     if (ka.image_bits && !ka.pimg && (!force_single || ka.all_pairs))      // scoring hot path: two tokens per CTA, packed FP32 stencils
         return launch(bpl_forward2_kernel, F2_THREADS, sizeof(Fwd2Smem), F2_CTAS_PER_SM, ka, (cudaStream_t)stream,
                       (ka.n_tokens + 1) / 2);

@@ -12,7 +12,6 @@ import torch
 
 from . import _lib
 from ._lib import IMSIZE, IMG_WORDS, NCPT, check, lib
-lib_ = lib      # (sample_tokens has a parameter named lib)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -667,10 +666,11 @@ def vanilla_to_motor_batch(ctrl, invscale, position, stroke_sub_off, neval=200):
 REL_CODES = {"unihist": 0, "start": 1, "end": 2, "mid": 3}      # pybpl/objects/relation.py:11
 
 
-def token_prior_params(lib=None, ps=None):
+def token_prior_params(library=None, ps=None):
     """The constants CharacterTokenDist reads from a Library and Parameters (token_dist.py:90-107, 320-325, 437-441).
     `lib` is anything with .tokenvar / .rel mappings (the reference's Library); None gives the shipped values."""
     c = _lib.TokenPriorParams()
+    lib = library
     if lib is None:
         c.sigma_shape, c.sigma_invscale, c.sigma_attach = 3.3593, 0.0277, 0.1499
         c.sigma_x, c.sigma_y = 1.3536, 1.2056
@@ -736,18 +736,18 @@ class _ScoreTokenPrior(torch.autograd.Function):
                 g_inv_ty * st, g_gpos * kt.view(-1, 1), g_es_ty * kt, None, None, None)
 
 
-def score_token_prior(batch, types, lib=None, ps=None, c=None):
+def score_token_prior(batch, types, library=None, ps=None, c=None):
     """ll[p] = log P(token p | its type) = CharacterTokenDist.score_token (pybpl/model/token_dist.py:264-287), batched,
     differentiable in the token's ctrl / invscale / position / eval_spot and the type's ctrl_type / invscale_type /
     gpos / eval_spot_type.  A token whose score is -inf gets gradients of the finite terms only."""
     if c is None:
-        c = token_prior_params(lib, ps)
+        c = token_prior_params(library, ps)
     return _ScoreTokenPrior.apply(batch.ctrl, batch.invscale, batch.position, types.eval_spot, types.ctrl_type,
                                   types.invscale_type, types.gpos, types.eval_spot_type, batch, types, c)
 
 
-def sample_tokens(tok_stroke_off, stroke_sub_off, types, seed, first_token=0, eps=1e-4, sigma=0.5, lib=None, ps=None, c=None,
-                  neval=200):
+def sample_tokens(tok_stroke_off, stroke_sub_off, types, seed, first_token=0, eps=1e-4, sigma=0.5, library=None, ps=None,
+                  c=None, neval=200):
     """Draw one token per entry of the (expanded) type batch from P(token | type): the batched, on-device
     CharacterTokenDist.sample_token (pybpl/model/token_dist.py:226-262).  `types` holds the type-level arrays aligned with
     the CSR structure; its eval_spot is replaced by the sampled relation tokens' spots.  eps / sigma: the reference fixes
@@ -755,7 +755,7 @@ def sample_tokens(tok_stroke_off, stroke_sub_off, types, seed, first_token=0, ep
     Philox stream (seed, first_token + p).  Returns (TokenBatch, TokenTypes)."""
     dev = types.device
     if c is None:
-        c = token_prior_params(lib, ps)
+        c = token_prior_params(library, ps)
     tso, sso = _i32(tok_stroke_off, dev), _i32(stroke_sub_off, dev)
     P, K, S = tso.numel() - 1, sso.numel() - 1, types.ctrl_type.shape[0]
     ctrl = torch.empty((S, NCPT, 2), dtype=torch.float32, device=dev)
@@ -769,7 +769,7 @@ def sample_tokens(tok_stroke_off, stroke_sub_off, types, seed, first_token=0, ep
     ty = _lib.TokenTypeC(_c32(types.ctrl_type).data_ptr(), _c32(types.invscale_type).data_ptr(), types.rel_cat.data_ptr(),
                          types.attach_ix.data_ptr(), types.attach_subix.data_ptr(), _c32(types.gpos).data_ptr(),
                          _c32(types.eval_spot_type).data_ptr(), None)
-    check(lib_().bpl_sample_tokens(ctypes.byref(c), ctypes.byref(b), ctypes.byref(ty), int(seed), int(first_token),
+    check(lib().bpl_sample_tokens(ctypes.byref(c), ctypes.byref(b), ctypes.byref(ty), int(seed), int(first_token),
                                    ctrl.data_ptr(), inv.data_ptr(), pos.data_ptr(), es.data_ptr(), _stream(dev)))
     full = lambda v: v.to(dev, torch.float32) if isinstance(v, torch.Tensor) else torch.full((P,), float(v), device=dev)
     batch = TokenBatch(tso, sso, ctrl, inv, pos, full(eps), full(sigma), neval=neval, check_limits=False)
