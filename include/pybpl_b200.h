@@ -191,6 +191,46 @@ int bpl_sample_tokens(const bpl_token_prior_params *c, const bpl_token_batch *b,
                       unsigned long long seed, unsigned long long first_token, float *ctrl, float *invscale,
                       float *position, float *eval_spot, void *stream);
 
+/* Sample character types from the prior: CharacterTypeDist.sample_type (pybpl/model/type_dist.py:56-96,187-207; per
+ * stroke sample_part_type :480-505 and sample_relation_type :541-597).  SURVEY.md 8(f)3 (type half).
+ * The library tables are device arrays prepared from the reference's Library (pybpl/library/library.py:30-72;
+ * pybpl_b200/data/type_lib.npz): every categorical distribution as a cumulative sum whose last entry is 1. */
+typedef struct {
+    int n_prim;               /* primitives (1212) */
+    int kmax;                 /* entries of pkappa = largest stroke count (10) */
+    int nsub_max;             /* columns of pmat_nsub = largest sub-stroke count per stroke (10) */
+    int n_hist, hist_bins;    /* position histograms (3: stroke 0, 1, >= 2), bins per side (25) */
+    const float *pkappa;      /* dev [kmax]             cdf of the stroke count (lib.pkappa) */
+    const float *pmat_nsub;   /* dev [kmax][nsub_max]   cdf of the sub-stroke count given the stroke count */
+    const float *cdf_start;   /* dev [n_prim]           cdf of the first primitive (exp lib.logStart) */
+    const float *cdf_T;       /* dev [n_prim][n_prim]   cdf of the next primitive given the previous one (lib.pT) */
+    const float *shape_mu;    /* dev [n_prim][10]       lib.shape['mu'] */
+    const float *shape_L;     /* dev [n_prim][10][10]   lower Cholesky factor of lib.shape['Sigma'] */
+    const float *gamma_con;   /* dev [n_prim]           lib.scale['theta'][:, 0] */
+    const float *gamma_rate;  /* dev [n_prim]           1 / lib.scale['theta'][:, 1] */
+    const float *rel_mixprob; /* dev [4]                cdf of the relation category (lib.rel['mixprob']) */
+    const float *sp_cdf;      /* dev [n_hist][bins*bins] cdf over bins, linear index = x bin * bins + y bin */
+    const float *sp_xlab, *sp_ylab;   /* dev [bins+1]   bin edges */
+} bpl_type_lib;
+
+/* Outputs of the writing pass, at the offsets the caller scanned from the counting pass. */
+typedef struct {
+    int *stroke_nsub;         /* dev [K]   sub-strokes per stroke (scan it for stroke_sub_off) */
+    int *subid;               /* dev [S]   StrokeType.ids */
+    float *ctrl_type;         /* dev [S][5][2] */
+    float *invscale_type;     /* dev [S] */
+    int *rel_cat, *attach_ix, *attach_subix;   /* dev [K] */
+    float *gpos;              /* dev [K][2] */
+    float *eval_spot_type;    /* dev [K] */
+} bpl_type_out;
+
+/* Counting pass (tok_stroke_off == NULL): n_strokes[P], n_subs[P] <- strokes / sub-strokes of every type.
+ * Writing pass: tok_stroke_off[P+1], tok_sub_off[P+1] = exclusive scans of those; draws the same types again (type p
+ * uses the Philox stream (seed, first_type + p)) and fills *out. */
+int bpl_sample_types(const bpl_type_lib *lib, int n_types, unsigned long long seed, unsigned long long first_type,
+                     const int *tok_stroke_off, const int *tok_sub_off, int *n_strokes, int *n_subs,
+                     const bpl_type_out *out, void *stream);
+
 /* ---- images ------------------------------------------------------------------------ */
 /* Pack T 105x105 images into bit rows.  `bad` (dev int, zero-filled by the caller) is set
  * to 1 if any pixel is not exactly 0 or 1 (torch's Bernoulli.log_prob support check). */

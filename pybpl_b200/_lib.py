@@ -67,6 +67,18 @@ class TokenPriorGrads(ctypes.Structure):
                 ("g_invscale_type", vp), ("g_gpos", vp), ("g_eval_spot_type", vp)]
 
 
+class TypeLibC(ctypes.Structure):
+    _fields_ = [("n_prim", ctypes.c_int), ("kmax", ctypes.c_int), ("nsub_max", ctypes.c_int), ("n_hist", ctypes.c_int),
+                ("hist_bins", ctypes.c_int), ("pkappa", vp), ("pmat_nsub", vp), ("cdf_start", vp), ("cdf_T", vp),
+                ("shape_mu", vp), ("shape_L", vp), ("gamma_con", vp), ("gamma_rate", vp), ("rel_mixprob", vp), ("sp_cdf", vp),
+                ("sp_xlab", vp), ("sp_ylab", vp)]
+
+
+class TypeOutC(ctypes.Structure):
+    _fields_ = [("stroke_nsub", vp), ("subid", vp), ("ctrl_type", vp), ("invscale_type", vp), ("rel_cat", vp),
+                ("attach_ix", vp), ("attach_subix", vp), ("gpos", vp), ("eval_spot_type", vp)]
+
+
 EXPORTS = {
     "bpl_version": (ctypes.c_int, []),
     "bpl_last_error": (ctypes.c_char_p, []),
@@ -97,6 +109,8 @@ EXPORTS = {
                                              ctypes.POINTER(TokenTypeC), vp, ctypes.POINTER(TokenPriorGrads), vp]),
     "bpl_sample_tokens": (ctypes.c_int, [ctypes.POINTER(TokenPriorParams), ctypes.POINTER(TokenBatchC),
                                          ctypes.POINTER(TokenTypeC), ctypes.c_ulonglong, ctypes.c_ulonglong, vp, vp, vp, vp, vp]),
+    "bpl_sample_types": (ctypes.c_int, [ctypes.POINTER(TypeLibC), ctypes.c_int, ctypes.c_ulonglong, ctypes.c_ulonglong, vp, vp,
+                                        vp, vp, ctypes.POINTER(TypeOutC), vp]),
     "bpl_logsumexp_partial": (ctypes.c_int, [vp, ctypes.c_int, vp, vp]),
     "bpl_fp32_probe": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, vp]),
     "bpl_launch_count": (ctypes.c_longlong, []),

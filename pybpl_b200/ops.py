@@ -778,6 +778,53 @@ def sample_tokens(tok_stroke_off, stroke_sub_off, types, seed, first_token=0, ep
     return batch, out_types
 
 
+class TypeLibrary:
+    """The type prior's tables on one device, in the form bpl_sample_types reads them (include/pybpl_b200.h:bpl_type_lib).
+    Default: pybpl_b200/data/type_lib.npz, generated from the reference's Library(use_hist=True) by
+    tests/golden/make_golden.py:make_assets (pybpl/library/library.py:30-72)."""
+    _KEYS = ("pkappa", "pmat_nsub", "cdf_start", "cdf_T", "shape_mu", "shape_L", "gamma_con", "gamma_rate", "rel_mixprob",
+             "sp_cdf", "sp_xlab", "sp_ylab")
+
+    def __init__(self, device, path=None):
+        path = path or os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "type_lib.npz")
+        d = np.load(path)
+        self.device = torch.device(device)
+        self.t = {k: torch.from_numpy(np.ascontiguousarray(d[k], dtype=np.float32)).to(self.device) for k in self._KEYS}
+        c = _lib.TypeLibC()
+        c.n_prim = d["cdf_start"].shape[0]; c.kmax = d["pkappa"].shape[0]; c.nsub_max = d["pmat_nsub"].shape[1]
+        c.n_hist = d["sp_cdf"].shape[0]; c.hist_bins = d["sp_xlab"].shape[0] - 1
+        for k in self._KEYS:
+            setattr(c, k, self.t[k].data_ptr())
+        self.c = c
+
+
+def sample_types(library, n_types, seed, first_type=0):
+    """Draw n_types character types from the prior on the device: the batched CharacterTypeDist.sample_type
+    (pybpl/model/type_dist.py:56-96,187-207).  Two launches over the same counter-based streams (count, scan, write).
+    Returns (tok_stroke_off [P+1], stroke_sub_off [K+1], TokenTypes with eval_spot = 0, subid [S])."""
+    dev = library.device
+    P = int(n_types)
+    nk = torch.empty(P, dtype=torch.int32, device=dev)
+    ns = torch.empty(P, dtype=torch.int32, device=dev)
+    L = lib()
+    check(L.bpl_sample_types(ctypes.byref(library.c), P, int(seed), int(first_type), None, None, nk.data_ptr(), ns.data_ptr(),
+                             None, _stream(dev)))
+    tso = torch.zeros(P + 1, dtype=torch.int32, device=dev); tso[1:] = torch.cumsum(nk, 0)
+    tsub = torch.zeros(P + 1, dtype=torch.int32, device=dev); tsub[1:] = torch.cumsum(ns, 0)
+    K, S = int(tso[-1]), int(tsub[-1])               # (one synchronisation: the output sizes)
+    i32 = lambda n: torch.empty(n, dtype=torch.int32, device=dev)
+    f32 = lambda *n: torch.empty(n, dtype=torch.float32, device=dev)
+    stroke_nsub, subid, cat, aix, asub = i32(K), i32(S), i32(K), i32(K), i32(K)
+    ctrl, inv, gpos, es = f32(S, NCPT, 2), f32(S), f32(K, 2), f32(K)
+    out = _lib.TypeOutC(stroke_nsub.data_ptr(), subid.data_ptr(), ctrl.data_ptr(), inv.data_ptr(), cat.data_ptr(), aix.data_ptr(),
+                        asub.data_ptr(), gpos.data_ptr(), es.data_ptr())
+    check(L.bpl_sample_types(ctypes.byref(library.c), P, int(seed), int(first_type), tso.data_ptr(), tsub.data_ptr(), None, None,
+                             ctypes.byref(out), _stream(dev)))
+    sso = torch.zeros(K + 1, dtype=torch.int32, device=dev); sso[1:] = torch.cumsum(stroke_nsub, 0)
+    types = TokenTypes(ctrl, inv, cat, aix, asub, gpos, es, torch.zeros(K, dtype=torch.float32, device=dev))
+    return tso, sso, types, subid
+
+
 def logsumexp_partial(ll):
     """(max, sum exp(ll - max)) of a CUDA float32 vector as a 2-element tensor (one kernel)."""
     _need_cuda(ll, "ll")

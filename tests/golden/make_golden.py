@@ -595,6 +595,43 @@ def make_token_samples(n_types=4, n_draws=600):
           [list(out[f"t{i}_rel_cat"]) for i in range(len(chosen))])
 
 
+# --------------------------------------------------------------------------
+# type_samples.npz : CharacterModel.sample_type draws (pybpl/model/type_dist.py:56-96,
+# 148-161, 245-267, 296-326, 355-386, 425-448, 480-505, 541-597), flattened: the
+# distributional fixture for the on-device type sampler
+# --------------------------------------------------------------------------
+def make_type_samples(n_draws=4000):
+    torch.manual_seed(31)
+    lib = Library(use_hist=True)
+    model = CharacterModel(lib)
+    K, nsub, rank, kof = [], [], [], []
+    subid, inv, ctrl0, sub_first = [], [], [], []
+    cat, aix, asub, gpos, es = [], [], [], [], []
+    for _ in range(n_draws):
+        ct = model.sample_type()
+        k = int(ct.k)
+        K.append(k)
+        for i, (pt, rt) in enumerate(zip(ct.part_types, ct.relation_types)):
+            nsub.append(int(pt.nsub)); rank.append(i); kof.append(k)
+            subid.append(pt.ids.numpy().astype(np.int32))
+            inv.append(pt.invscales.numpy())
+            ctrl0.append(pt.shapes.permute(2, 0, 1).reshape(-1, 10).numpy())
+            sub_first.append(np.arange(int(pt.nsub)) == 0)
+            c = REL_CODE[rt.category]
+            cat.append(c)
+            aix.append(int(rt.attach_ix) if c else -1)
+            asub.append(int(rt.attach_subix) if c == 3 else -1)
+            gpos.append(rt.gpos.numpy() if c == 0 else np.full(2, np.nan, f32))
+            es.append(float(rt.eval_spot) if c == 3 else np.nan)
+    out = dict(K=np.array(K, np.int32), nsub=np.array(nsub, np.int32), rank=np.array(rank, np.int32), k_of_stroke=np.array(kof, np.int32),
+               subid=np.concatenate(subid), invscale=np.concatenate(inv).astype(f32), ctrl=np.concatenate(ctrl0).astype(f32),
+               sub_first=np.concatenate(sub_first), rel_cat=np.array(cat, np.int32), attach_ix=np.array(aix, np.int32),
+               attach_subix=np.array(asub, np.int32), gpos=np.stack(gpos).astype(f32), eval_spot=np.array(es, f32))
+    np.savez_compressed(os.path.join(OUT, "type_samples.npz"), **out)
+    print("type_samples.npz:", n_draws, "types;", len(nsub), "strokes;", len(out["subid"]), "sub-strokes; K hist",
+          np.bincount(out["K"])[1:], "; relation counts", np.bincount(out["rel_cat"]))
+
+
 def make_assets():
     """pybpl_b200/data/basis_5_200.npy: coefficient_mat(5, 200) exactly as the reference's torch builds it
     (splines.py:72-93).  torch assembles it with Sleef powf and an MKL dot, which portable C cannot
@@ -617,10 +654,38 @@ def make_assets():
                         sigma_shape=f32(lib.tokenvar['sigma_shape']), sigma_invscale=f32(lib.tokenvar['sigma_invscale']),
                         rel_sigma=np.array([float(lib.rel['sigma_x']), float(lib.rel['sigma_y'])], f32))
     print("asset workload_lib.npz")
+    # Tables of the type prior (pybpl/library/library.py:30-72, model/type_dist.py:137-146, 224-243, 535-539) in the
+    # form the on-device type sampler reads them: categorical distributions as cumulative sums, shape covariances
+    # as Cholesky factors, the position histograms in the linear bin order SpatialHist.sample draws from
+    # (library/spatial_OLD/spatial_hist.py:107-143).  Data, not code.
+    def cdf(p):
+        p = np.asarray(p, np.float64)
+        c = np.cumsum(p / p.sum(-1, keepdims=True), -1)
+        c[..., -1] = 1.0
+        return c.astype(f32)
+    logT = lib.logT.numpy().astype(np.float64)
+    SM = lib.Spatial
+    sp = []
+    for h in SM.list_SH:
+        sp.append(np.exp(h.logpYX.numpy().astype(np.float64)).T.reshape(-1))       # lin = xi * ny + yi
+    np.savez_compressed(os.path.join(dst, "type_lib.npz"),
+                        pkappa=cdf(lib.pkappa.numpy()), pmat_nsub=cdf(lib.pmat_nsub.numpy()),
+                        cdf_start=cdf(np.exp(lib.logStart.numpy().astype(np.float64))), cdf_T=cdf(np.exp(logT)),
+                        shape_mu=lib.shape['mu'].numpy().astype(f32),
+                        shape_L=np.linalg.cholesky(lib.shape['Sigma'].numpy().astype(np.float64)).astype(f32),
+                        gamma_con=lib.scale['theta'][:, 0].numpy().astype(f32),
+                        gamma_rate=(1.0 / lib.scale['theta'][:, 1].numpy().astype(np.float64)).astype(f32),
+                        rel_mixprob=cdf(lib.rel['mixprob'].numpy()), sp_cdf=cdf(np.stack(sp)),
+                        sp_xlab=SM.list_SH[0].xlab.numpy().astype(f32), sp_ylab=SM.list_SH[0].ylab.numpy().astype(f32),
+                        # the same distributions as plain probabilities, for tests and inspection
+                        p_kappa=(lib.pkappa / lib.pkappa.sum()).numpy().astype(f32),
+                        p_nsub=(lib.pmat_nsub / lib.pmat_nsub.sum(1, keepdim=True)).numpy().astype(f32),
+                        p_start=np.exp(lib.logStart.numpy().astype(np.float64)).astype(f32))
+    print("asset type_lib.npz", os.path.getsize(os.path.join(dst, "type_lib.npz")) // 1024, "KiB")
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["splines", "render", "tokens", "fit", "token_prior", "token_samples", "assets"]
+    which = sys.argv[1:] or ["splines", "render", "tokens", "fit", "token_prior", "token_samples", "type_samples", "assets"]
     if "splines" in which:
         make_splines()
     if "render" in which:
@@ -633,6 +698,8 @@ if __name__ == "__main__":
         make_token_prior()
     if "token_samples" in which:
         make_token_samples()
+    if "type_samples" in which:
+        make_type_samples()
     if "assets" in which:
         make_assets()
     for f in sorted(os.listdir(OUT)):

@@ -57,6 +57,20 @@ for _ in range(5):
 nb = 2 * 44 * S + 44 * K + 8 * P
 out["sample"] = {"ms": best, "tokens_per_s": P / best * 1e3, "GBps": nb / best / 1e6, "hbm_frac": nb / best / 1e6 / peaks["hbm_gbs"],
                  "note": "includes torch.empty of the outputs and the eps/sigma fills of ops.sample_tokens"}
+# ---- the type sampler: two launches (count, write) + two scans; the prior -> token -> score chain for 1 M particles ----
+tl = ops.TypeLibrary("cuda:0")
+def draw_types():
+    return ops.sample_types(tl, P, seed=3)
+for _ in range(2):
+    draw_types()
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(5):
+    tso, sso, ty, _ = draw_types()
+torch.cuda.synchronize()
+dt = (time.perf_counter() - t0) / 5
+out["sample_types"] = {"ms": dt * 1e3, "types_per_s": P / dt, "strokes": int(sso.numel() - 1), "substrokes": int(ty.ctrl_type.shape[0]),
+                       "note": "wall clock incl. the size read-back between the two passes"}
 from oracle import token_prior as tp
 C = load("tokens")["basis_5_200"]
 t0 = time.perf_counter(); tp.score(d, np.float32, C0=C[0], C1=C[-1]); dt = time.perf_counter() - t0
