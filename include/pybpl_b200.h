@@ -231,6 +231,26 @@ int bpl_sample_types(const bpl_type_lib *lib, int n_types, unsigned long long se
                      const int *tok_stroke_off, const int *tok_sub_off, int *n_strokes, int *n_subs,
                      const bpl_type_out *out, void *stream);
 
+/* Log-probability tables of the type prior, for the type score (device arrays; pybpl_b200/data/type_lib.npz). */
+typedef struct {
+    const float *logp_kappa;   /* dev [kmax]             log lib.pkappa (normalised) */
+    const float *logp_nsub;    /* dev [kmax][nsub_max]   log lib.pmat_nsub rows */
+    const float *logp_start;   /* dev [n_prim]           lib.logStart (normalised) */
+    const float *logp_T;       /* dev [n_prim][n_prim]   log lib.pT(prev)[next] */
+    const float *logp_mix;     /* dev [4]                log lib.rel['mixprob'] */
+    const float *sp_logp;      /* dev [n_hist][bins*bins] SpatialHist.logpYX, linear index = x bin * bins + y bin */
+    float sp_log_binarea;      /* log rg_bin[0] + log rg_bin[1] (spatial_hist.py:163-164) */
+} bpl_type_logtables;
+
+/* ll[P] <- log P(type): CharacterTypeDist.score_type (pybpl/model/type_dist.py:98-125; score_k :163-185,
+ * score_part_type :507-531, score_relation_type :599-650).  The types are given as for bpl_score_token_prior (CSR
+ * offsets + bpl_token_type; eval_spot and eval_spot_type only enter through a constant) plus the primitive id of
+ * every sub-stroke.  g_ctrl_type [S][5][2] / g_invscale_type [S]: gradients, or NULL.  -inf for a position outside
+ * the histogram's range or an impossible count. */
+int bpl_score_type_prior(const bpl_type_lib *lib, const bpl_type_logtables *tabs, int n_types,
+                         const int *tok_stroke_off, const int *stroke_sub_off, const int *subid,
+                         const bpl_token_type *ty, float *ll, float *g_ctrl_type, float *g_invscale_type, void *stream);
+
 /* ---- images ------------------------------------------------------------------------ */
 /* Pack T 105x105 images into bit rows.  `bad` (dev int, zero-filled by the caller) is set
  * to 1 if any pixel is not exactly 0 or 1 (torch's Bernoulli.log_prob support check). */

@@ -74,6 +74,11 @@ class TypeLibC(ctypes.Structure):
                 ("sp_xlab", vp), ("sp_ylab", vp)]
 
 
+class TypeLogTablesC(ctypes.Structure):
+    _fields_ = [("logp_kappa", vp), ("logp_nsub", vp), ("logp_start", vp), ("logp_T", vp), ("logp_mix", vp), ("sp_logp", vp),
+                ("sp_log_binarea", ctypes.c_float)]
+
+
 class TypeOutC(ctypes.Structure):
     _fields_ = [("stroke_nsub", vp), ("subid", vp), ("ctrl_type", vp), ("invscale_type", vp), ("rel_cat", vp),
                 ("attach_ix", vp), ("attach_subix", vp), ("gpos", vp), ("eval_spot_type", vp)]
@@ -111,6 +116,8 @@ EXPORTS = {
                                          ctypes.POINTER(TokenTypeC), ctypes.c_ulonglong, ctypes.c_ulonglong, vp, vp, vp, vp, vp]),
     "bpl_sample_types": (ctypes.c_int, [ctypes.POINTER(TypeLibC), ctypes.c_int, ctypes.c_ulonglong, ctypes.c_ulonglong, vp, vp,
                                         vp, vp, ctypes.POINTER(TypeOutC), vp]),
+    "bpl_score_type_prior": (ctypes.c_int, [ctypes.POINTER(TypeLibC), ctypes.POINTER(TypeLogTablesC), ctypes.c_int, vp, vp, vp,
+                                            ctypes.POINTER(TokenTypeC), vp, vp, vp, vp]),
     "bpl_logsumexp_partial": (ctypes.c_int, [vp, ctypes.c_int, vp, vp]),
     "bpl_fp32_probe": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, vp]),
     "bpl_launch_count": (ctypes.c_longlong, []),

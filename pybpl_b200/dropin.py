@@ -12,6 +12,9 @@ Patched names (each bound by-name in the reference, so both the defining module 
   pybpl.objects.part.vanilla_to_motor                                         (part.py:290)
   CharacterImageDist.get_pimg / sample_image / score_image                    (image_dist.py:32-80)
   CharacterTokenDist.score_token                                              (token_dist.py:264-287)
+  CharacterTypeDist.score_type                                                (type_dist.py:98-125; only when the
+                                                                               instance's library is the shipped one,
+                                                                               Library(use_hist=True))
 """
 import importlib
 
@@ -54,6 +57,17 @@ def install(pybpl_module=None):
             scorer[key] = model.CharacterTokenDist(_LibView(self))
         return scorer[key].score_token(ctype, ctoken)
     _patch(TD.CharacterTokenDist, "score_token", score_token)
+    YD = importlib.import_module("pybpl.model.type_dist")
+    ref_score_type = YD.CharacterTypeDist.score_type
+    type_scorer = model.CharacterTypeDist()
+
+    def score_type(self, ctype):
+        # the shipped tables are Library(use_hist=True)'s: any other library keeps the reference's own code
+        hist = type(self.rdist.Spatial).__module__.endswith("spatial_OLD.spatial_model")
+        if not hist or self.pdist.shapes_mu.shape[0] != 1212:
+            return ref_score_type(self, ctype)
+        return type_scorer.score_type(ctype)
+    _patch(YD.CharacterTypeDist, "score_type", score_type)
 
 
 class _LibView:

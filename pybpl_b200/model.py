@@ -111,6 +111,47 @@ class CharacterTokenDist:
         return self.score_tokens([ctype], [ctoken])[0].to(src)
 
 
+class CharacterTypeDist:
+    """The scoring half of P(Type) (pybpl/model/type_dist.py:98-125, 127-207): score_type on the GPU, differentiable in the
+    stroke types' shapes and scales (what examples/optimize_type.py optimises).  `library`: an ops.TypeLibrary."""
+
+    def __init__(self, library=None, device=None):
+        self.library = library
+        self._device = device
+
+    def _lib(self, dev):
+        if self.library is None:
+            self.library = ops.TypeLibrary(dev)
+        return self.library
+
+    def score_types(self, ctypes_):
+        """[P] scores for a list of types (one launch).  Duck-typed on ctype.part_types[i].{shapes, invscales, ids} and
+        ctype.relation_types[i] (pybpl/objects/part.py:100-160, relation.py:238-420)."""
+        dev = self._device or _compute_device(ctypes_[0].part_types[0].shapes)
+        lib = self._lib(dev)
+        ctrl, inv, ids, tso, sso, cat, aix, asub, gpos, es = [], [], [], [0], [0], [], [], [], [], []
+        z1 = torch.zeros(1)
+        for ct in ctypes_:
+            for pt, rt in zip(ct.part_types, ct.relation_types):
+                ctrl.append(pt.shapes.permute(2, 0, 1)); inv.append(pt.invscales.reshape(-1))
+                ids.append(torch.as_tensor(pt.ids).reshape(-1).to(torch.int32))
+                sso.append(sso[-1] + pt.shapes.shape[2])
+                c = ops.REL_CODES[rt.category]
+                cat.append(c); aix.append(int(rt.attach_ix) if c else 0); asub.append(int(rt.attach_subix) if c == 3 else 0)
+                gpos.append(rt.gpos.detach().reshape(1, 2) if c == 0 else torch.zeros(1, 2))
+                es.append(torch.as_tensor(rt.eval_spot, dtype=torch.float32).detach().reshape(1) if c == 3 else z1)
+            tso.append(tso[-1] + len(ct.part_types))
+        to = lambda xs: torch.cat([x.to(dev, torch.float32) for x in xs])
+        types = ops.TokenTypes(to(ctrl).contiguous(), to(inv), cat, aix, asub, to(gpos), to(es),
+                               torch.zeros(len(cat), dtype=torch.float32, device=dev))
+        return ops.score_type_prior(lib, tso, sso, types, torch.cat(ids).to(dev))
+
+    def score_type(self, ctype):
+        """log P(Type = ctype) (type_dist.py:98-125): 0-d float32 tensor on the type's device."""
+        src = ctype.part_types[0].shapes.device
+        return self.score_types([ctype])[0].to(src)
+
+
 class CharacterModel:
     """The hot-path part of pybpl/model/model.py:8-39: image methods and score_token run on the GPU.  The type prior and
     token sampling are out of scope: pass `type_dist`/`token_dist` objects (e.g. the reference's) for them."""
@@ -119,10 +160,14 @@ class CharacterModel:
         self.type_dist = type_dist
         self.token_dist = token_dist          # sample_token (and score_token unless overridden below)
         self.token_score = CharacterTokenDist(lib)
+        self.type_score = CharacterTypeDist()          # shipped prior tables (pybpl_b200/data/type_lib.npz)
         self.image_dist = CharacterImageDist(lib)
 
     def score_token(self, ctype, ctoken):
         return self.token_score.score_token(ctype, ctoken)
+
+    def score_type(self, ctype):
+        return self.type_score.score_type(ctype)
 
     def sample_image(self, ctoken):
         return self.image_dist.sample_image(ctoken)

@@ -796,6 +796,12 @@ class TypeLibrary:
         for k in self._KEYS:
             setattr(c, k, self.t[k].data_ptr())
         self.c = c
+        lt = _lib.TypeLogTablesC()
+        for k in ("logp_kappa", "logp_nsub", "logp_start", "logp_T", "logp_mix", "sp_logp"):
+            self.t[k] = torch.from_numpy(np.ascontiguousarray(d[k], dtype=np.float32)).to(self.device)
+            setattr(lt, k, self.t[k].data_ptr())
+        lt.sp_log_binarea = float(d["sp_log_binarea"])
+        self.logtables = lt
 
 
 def sample_types(library, n_types, seed, first_type=0):
@@ -823,6 +829,44 @@ def sample_types(library, n_types, seed, first_type=0):
     sso = torch.zeros(K + 1, dtype=torch.int32, device=dev); sso[1:] = torch.cumsum(stroke_nsub, 0)
     types = TokenTypes(ctrl, inv, cat, aix, asub, gpos, es, torch.zeros(K, dtype=torch.float32, device=dev))
     return tso, sso, types, subid
+
+
+class _ScoreTypePrior(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ctrl_type, invscale_type, library, tok_stroke_off, stroke_sub_off, subid, types):
+        dev = library.device
+        ct, it = _c32(ctrl_type), _c32(invscale_type)
+        P = tok_stroke_off.numel() - 1
+        ty = _lib.TokenTypeC(ct.data_ptr(), it.data_ptr(), types.rel_cat.data_ptr(), types.attach_ix.data_ptr(),
+                             types.attach_subix.data_ptr(), _c32(types.gpos).data_ptr(), _c32(types.eval_spot_type).data_ptr(), None)
+        ll = torch.empty(P, dtype=torch.float32, device=dev)
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        g_c = torch.empty_like(ct) if need else None
+        g_i = torch.empty_like(it) if need else None
+        check(lib().bpl_score_type_prior(ctypes.byref(library.c), ctypes.byref(library.logtables), P, tok_stroke_off.data_ptr(),
+                                         stroke_sub_off.data_ptr(), subid.data_ptr(), ctypes.byref(ty), ll.data_ptr(),
+                                         None if g_c is None else g_c.data_ptr(), None if g_i is None else g_i.data_ptr(),
+                                         _stream(dev)))
+        if need:
+            tso = tok_stroke_off.long()
+            sub_off = stroke_sub_off.long()[tso]
+            ctx.sub_token = torch.repeat_interleave(torch.arange(P, device=dev), sub_off[1:] - sub_off[:-1], output_size=ct.shape[0])
+            ctx.save_for_backward(g_c, g_i)
+        return ll
+
+    @staticmethod
+    def backward(ctx, g_ll):
+        g_c, g_i = ctx.saved_tensors
+        st = g_ll.to(torch.float32)[ctx.sub_token]
+        return g_c * st.view(-1, 1, 1), g_i * st, None, None, None, None, None
+
+
+def score_type_prior(library, tok_stroke_off, stroke_sub_off, types, subid):
+    """ll[p] = log P(type p) = CharacterTypeDist.score_type (pybpl/model/type_dist.py:98-125), batched; differentiable in
+    types.ctrl_type and types.invscale_type (the leaves the reference's autograd reaches).  `subid` [S]: primitive ids."""
+    dev = library.device
+    return _ScoreTypePrior.apply(types.ctrl_type, types.invscale_type, library, _i32(tok_stroke_off, dev),
+                                 _i32(stroke_sub_off, dev), _i32(subid, dev), types)
 
 
 def logsumexp_partial(ll):

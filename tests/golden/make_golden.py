@@ -632,6 +632,49 @@ def make_type_samples(n_draws=4000):
           np.bincount(out["K"])[1:], "; relation counts", np.bincount(out["rel_cat"]))
 
 
+# --------------------------------------------------------------------------
+# type_prior.npz : CharacterModel.score_type = log P(type)
+# (pybpl/model/type_dist.py:98-125, 163-185, 269-294, 328-353, 388-423, 450-478,
+#  507-531, 599-650; position histograms library/spatial_OLD/spatial_model.py:86-112,
+#  spatial_hist.py:145-167,235-256) with autograd gradients w.r.t. shapes and invscales
+#  (gpos is detached: the histogram score calls .numpy() on it and raises when it requires grad)
+# --------------------------------------------------------------------------
+def make_type_prior(n=300):
+    torch.manual_seed(41)
+    lib = Library(use_hist=True)
+    model = CharacterModel(lib)
+    K, nsub, subid, ctrl, inv, cat, aix, asub, gpos, es, ll_all, g_ctrl, g_inv = ([] for _ in range(13))
+    for i in range(n):
+        ct = model.sample_type()
+        if i % 23 == 7:          # a position outside the histogram's range: -inf (spatial_hist.py:252-253)
+            for r in ct.relation_types:
+                if r.category == "unihist":
+                    r.gpos = torch.tensor([120.0, -10.0])
+        for p in ct.part_types:
+            p.shapes.requires_grad_(True); p.invscales.requires_grad_(True)
+        ll = model.score_type(ct)
+        finite = bool(torch.isfinite(ll))
+        if finite:
+            ll.backward()
+        K.append(int(ct.k)); ll_all.append(float(ll))
+        for p, r in zip(ct.part_types, ct.relation_types):
+            nsub.append(int(p.nsub)); subid.append(p.ids.numpy().astype(np.int32))
+            ctrl.append(p.shapes.detach().permute(2, 0, 1)); inv.append(p.invscales.detach())
+            z = lambda t: torch.zeros_like(t) if (t.grad is None or not finite) else t.grad
+            g_ctrl.append(z(p.shapes).permute(2, 0, 1)); g_inv.append(z(p.invscales))
+            c = REL_CODE[r.category]; cat.append(c)
+            aix.append(int(r.attach_ix) if c else 0); asub.append(int(r.attach_subix) if c == 3 else 0)
+            gpos.append(r.gpos.detach() if c == 0 else torch.zeros(2)); es.append(float(r.eval_spot) if c == 3 else 0.0)
+    out = dict(K=np.array(K, np.int32), nsub=np.array(nsub, np.int32), subid=np.concatenate(subid),
+               ctrl_type=torch.cat(ctrl).numpy().astype(f32), invscale_type=torch.cat(inv).numpy().astype(f32),
+               rel_cat=np.array(cat, np.int32), attach_ix=np.array(aix, np.int32), attach_subix=np.array(asub, np.int32),
+               gpos=torch.stack(gpos).numpy().astype(f32), eval_spot_type=np.array(es, f32), ll=np.array(ll_all, f32),
+               g_ctrl_type=torch.cat(g_ctrl).numpy().astype(f32), g_invscale_type=torch.cat(g_inv).numpy().astype(f32))
+    np.savez_compressed(os.path.join(OUT, "type_prior.npz"), **out)
+    print("type_prior.npz:", n, "types; -inf scores", int(np.sum(~np.isfinite(out["ll"]))), "; ll range",
+          out["ll"][np.isfinite(out["ll"])].min(), out["ll"].max())
+
+
 def make_assets():
     """pybpl_b200/data/basis_5_200.npy: coefficient_mat(5, 200) exactly as the reference's torch builds it
     (splines.py:72-93).  torch assembles it with Sleef powf and an MKL dot, which portable C cannot
@@ -677,6 +720,14 @@ def make_assets():
                         gamma_rate=(1.0 / lib.scale['theta'][:, 1].numpy().astype(np.float64)).astype(f32),
                         rel_mixprob=cdf(lib.rel['mixprob'].numpy()), sp_cdf=cdf(np.stack(sp)),
                         sp_xlab=SM.list_SH[0].xlab.numpy().astype(f32), sp_ylab=SM.list_SH[0].ylab.numpy().astype(f32),
+                        # log-probability tables for the type score (type_dist.py:163-185, 269-294, 328-353, 599-650)
+                        logp_kappa=torch.distributions.Categorical(probs=lib.pkappa).logits.numpy().astype(f32),
+                        logp_nsub=torch.distributions.Categorical(probs=lib.pmat_nsub).logits.numpy().astype(f32),
+                        logp_start=torch.distributions.Categorical(probs=torch.exp(lib.logStart)).logits.numpy().astype(f32),
+                        logp_T=(logT - np.log(np.exp(logT).sum(1, keepdims=True))).astype(f32),
+                        logp_mix=torch.distributions.Categorical(probs=lib.rel['mixprob']).logits.numpy().astype(f32),
+                        sp_logp=np.stack([h.logpYX.numpy().T.reshape(-1) for h in SM.list_SH]).astype(f32),
+                        sp_log_binarea=f32(float(torch.log(SM.list_SH[0].rg_bin[0]) + torch.log(SM.list_SH[0].rg_bin[1]))),
                         # the same distributions as plain probabilities, for tests and inspection
                         p_kappa=(lib.pkappa / lib.pkappa.sum()).numpy().astype(f32),
                         p_nsub=(lib.pmat_nsub / lib.pmat_nsub.sum(1, keepdim=True)).numpy().astype(f32),
@@ -685,7 +736,7 @@ def make_assets():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["splines", "render", "tokens", "fit", "token_prior", "token_samples", "type_samples", "assets"]
+    which = sys.argv[1:] or ["splines", "render", "tokens", "fit", "token_prior", "token_samples", "type_samples", "type_prior", "assets"]
     if "splines" in which:
         make_splines()
     if "render" in which:
@@ -700,6 +751,8 @@ if __name__ == "__main__":
         make_token_samples()
     if "type_samples" in which:
         make_type_samples()
+    if "type_prior" in which:
+        make_type_prior()
     if "assets" in which:
         make_assets()
     for f in sorted(os.listdir(OUT)):

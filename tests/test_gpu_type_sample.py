@@ -145,3 +145,83 @@ def test_streams_shard_and_tokens_follow(draw):
     img = ops.pack_images(torch.zeros(105, 105, dtype=torch.uint8, device=DEV))
     ll, off = ops.score_tokens(batch, img)
     assert torch.isfinite(ll).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# the type score, log P(type)  (CharacterTypeDist.score_type, pybpl/model/type_dist.py:98-125)
+# ---------------------------------------------------------------------------------------------
+def _type_inputs(ops, d, grad=False):
+    T = lambda a, dt=torch.float32: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=DEV)
+    tso = np.concatenate([[0], np.cumsum(d["K"])]).astype(np.int32)
+    sso = np.concatenate([[0], np.cumsum(d["nsub"])]).astype(np.int32)
+    ctrl, inv = T(d["ctrl_type"]).requires_grad_(grad), T(d["invscale_type"]).requires_grad_(grad)
+    K = len(d["nsub"])
+    types = ops.TokenTypes(ctrl, inv, d["rel_cat"], d["attach_ix"], d["attach_subix"], T(d["gpos"]), T(d["eval_spot_type"]),
+                           T(np.zeros(K, np.float32)))
+    return tso, sso, types, T(d["subid"], torch.int32)
+
+
+def test_type_score_matches_reference():
+    from oracle import type_prior as tp
+    from pybpl_b200 import ops
+    d = dict(load("type_prior"))
+    lib = ops.TypeLibrary(DEV)
+    tso, sso, types, subid = _type_inputs(ops, d, grad=True)
+    ll = ops.score_type_prior(lib, tso, sso, types, subid)
+    ref = d["ll"]; fin = np.isfinite(ref)
+    got = ll.detach().cpu().numpy()
+    assert np.array_equal(np.isfinite(got), fin) and np.all(got[~fin] == -np.inf)
+    rel = np.abs(got[fin] - ref[fin]) / np.abs(ref[fin])
+    print("type score max rel vs reference", rel.max())
+    assert rel.max() < 1e-5
+    ll[torch.as_tensor(fin, device=DEV)].sum().backward()
+    ts = np.repeat(np.repeat(np.arange(len(d["K"])), d["K"]), d["nsub"]); m = fin[ts]
+    gc, gi = types.ctrl_type.grad.cpu().numpy(), types.invscale_type.grad.cpu().numpy()
+    assert np.abs(gc[m] - d["g_ctrl_type"][m]).max() <= 2e-5 * np.abs(d["g_ctrl_type"]).max()
+    assert np.abs(gi[m] - d["g_invscale_type"][m]).max() <= 2e-5 * np.abs(d["g_invscale_type"]).max()
+    # float64 oracle on the same inputs
+    tab = dict(np.load(os.path.join(ROOT, "pybpl_b200", "data", "type_lib.npz")))
+    o = tp.score(d, tab, np.float64)
+    assert np.max(np.abs(got[fin] - o[fin]) / np.abs(o[fin])) < 2e-6
+
+
+def test_type_score_of_sampled_types_is_the_negative_entropy_rate(draw):
+    """Consistency of sampler and scorer on 200 000 draws: every drawn type has a finite score, and the mean score of
+    types with exactly one stroke and one sub-stroke matches the mean score of the reference's own such draws."""
+    ops, lib, tab, g = draw
+    tso, sso, types, subid = ops.sample_types(lib, 50_000, seed=77)
+    ll = ops.score_type_prior(lib, tso, sso, types, subid).cpu().numpy()
+    assert np.isfinite(ll).all()
+    d = dict(load("type_prior"))
+    from oracle import type_prior as tp
+    sel = np.flatnonzero((d["K"] == 1) & np.isfinite(d["ll"]))
+    K = np.diff(tso.cpu().numpy())
+    mine = ll[K == 1]
+    ref = d["ll"][sel]
+    z = (mine.mean() - ref.mean()) / np.sqrt(mine.var() / len(mine) + ref.var() / len(ref))
+    print(f"one-stroke types: mean log P GPU draws {mine.mean():.2f} (n={len(mine)}), reference draws {ref.mean():.2f} (n={len(ref)}), z={z:.2f}")
+    assert abs(z) < 4.5
+
+
+def test_model_mirror_score_type():
+    """CharacterTypeDist.score_type on duck-typed type objects equals the golden reference scores."""
+    from types import SimpleNamespace as NS
+    from pybpl_b200 import ops
+    from pybpl_b200.model import CharacterModel
+    d = dict(load("type_prior"))
+    inv_codes = {v: n for n, v in ops.REL_CODES.items()}
+    model = CharacterModel()
+    k = s = 0
+    for p in range(12):
+        parts, rels = [], []
+        for i in range(d["K"][p]):
+            n = d["nsub"][k]; sl = slice(s, s + n)
+            parts.append(NS(shapes=torch.from_numpy(d["ctrl_type"][sl]).permute(1, 2, 0), invscales=torch.from_numpy(d["invscale_type"][sl]),
+                            ids=torch.from_numpy(d["subid"][sl])))
+            rels.append(NS(category=inv_codes[int(d["rel_cat"][k])], gpos=torch.from_numpy(d["gpos"][k]), attach_ix=int(d["attach_ix"][k]),
+                           attach_subix=int(d["attach_subix"][k]), eval_spot=torch.tensor(d["eval_spot_type"][k])))
+            k += 1; s += n
+        got = model.score_type(NS(part_types=parts, relation_types=rels))
+        ref = d["ll"][p]
+        assert got.dim() == 0 and got.device.type == "cpu"
+        assert (np.isinf(ref) and float(got) == ref) or abs(float(got) - ref) <= 1e-5 * abs(ref)

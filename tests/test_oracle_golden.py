@@ -7,6 +7,8 @@ fixtures are the pin.  Tolerances: integer work bit-exact; trajectories
 bit-exact given the reference's basis table; fp32 images/ll/grads to the
 reference's own fp32 noise.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -197,3 +199,21 @@ def test_token_prior_oracle_gradient_is_the_derivative():
         hi[name][idx] += h; lo[name][idx] -= h
         fd = (tp.score(hi, np.float64, C0=C[0], C1=C[-1])[p] - tp.score(lo, np.float64, C0=C[0], C1=C[-1])[p]) / (2 * h)
         assert abs(fd - g[name][idx]) <= 1e-5 * max(1.0, abs(fd)), (name, idx, fd, g[name][idx])
+
+
+def test_type_prior_oracle_matches_reference():
+    """oracle/type_prior.py against the live reference's score_type + autograd (300 prior-sampled types, 13 with a
+    position outside the histogram -> -inf)."""
+    from oracle import type_prior as tp
+    d = dict(load("type_prior"))
+    tab = dict(np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pybpl_b200", "data",
+                                    "type_lib.npz")))
+    ref = d["ll"]; fin = np.isfinite(ref)
+    assert (~fin).sum() >= 5 and set(np.unique(d["rel_cat"])) == {0, 1, 2, 3}
+    ll, g = tp.score(d, tab, np.float64, grad=True)
+    assert np.array_equal(np.isfinite(ll), fin) and np.all(ll[~fin] == -np.inf)
+    assert np.max(np.abs(ll[fin] - ref[fin]) / np.abs(ref[fin])) < 1e-5          # the reference is float32
+    ts = np.repeat(np.repeat(np.arange(len(d["K"])), d["K"]), d["nsub"])
+    m = fin[ts]
+    assert np.abs(g["ctrl_type"][m] - d["g_ctrl_type"][m]).max() <= 2e-5 * np.abs(d["g_ctrl_type"]).max()
+    assert np.abs(g["invscale_type"][m] - d["g_invscale_type"][m]).max() <= 2e-5 * np.abs(d["g_invscale_type"]).max()
