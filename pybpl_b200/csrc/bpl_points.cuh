@@ -112,6 +112,16 @@ __device__ __forceinline__ LaneAcc warp_points(bool active, const CtrlSrc &src, 
     { const long long t1 = clock64(); acc.tA = t1 - tt0; tt0 = t1; }
 #endif
     // ---- B ----
+    // Fast path: the predecessor of a run is simply point j0-1 when that point is on the page (nearly always);
+    // only a warp in which some run's predecessor is off the page takes the scan below.
+    bool has_prev = false;
+    float pr = 0.0f, pc = 0.0f;
+    bool need_scan = false;
+    if (active && hv && j0 > 0) {
+        const PEval e = eval_pt(src, j0 - 1, true);
+        if (e.inb) { has_prev = true; pr = e.r; pc = e.c; } else need_scan = true;
+    }
+    if (__any_sync(0xffffffffu, need_scan)) {
     bool iv = hv;
     float ir = lr, ic = lc;
 #pragma unroll
@@ -121,8 +131,8 @@ __device__ __forceinline__ LaneAcc warp_points(bool active, const CtrlSrc &src, 
         const int os = __shfl_up_sync(0xffffffffu, sid, d);
         if (lane >= d && os == sid && !iv && ov) { iv = true; ir = orr; ic = oc; }
     }
-    bool has_prev = __shfl_up_sync(0xffffffffu, (int)iv, 1) != 0;
-    float pr = __shfl_up_sync(0xffffffffu, ir, 1), pc = __shfl_up_sync(0xffffffffu, ic, 1);
+    has_prev = __shfl_up_sync(0xffffffffu, (int)iv, 1) != 0;
+    pr = __shfl_up_sync(0xffffffffu, ir, 1); pc = __shfl_up_sync(0xffffffffu, ic, 1);
     {
         const int ps = __shfl_up_sync(0xffffffffu, sid, 1);
         if (lane == 0 || ps != sid) has_prev = false;
@@ -147,6 +157,7 @@ __device__ __forceinline__ LaneAcc warp_points(bool active, const CtrlSrc &src, 
             }
         }
         if (found && sid == sid0 && !has_prev) { has_prev = true; pr = cr; pc = cc; }
+    }
     }
 #ifdef BPL_PHASE_TIMING
     { const long long t1 = clock64(); acc.tB = t1 - tt0; tt0 = t1; }
@@ -282,6 +293,16 @@ __device__ __forceinline__ float warp_points_bwd(bool active, const CtrlSrc &src
         if (e.inb) { inbm |= 1u << k; hv = true; lr = e.r; lc = e.c; lj = j; }
     }
     // ---- B: last survivor before the run (position and point index) ----
+    // Fast path as in warp_points: point j0-1 when it is on the page; the scan only when some run's is not.
+    bool has_prev = false;
+    float pr = 0.0f, pc = 0.0f;
+    int pj = 0;
+    bool need_scan = false;
+    if (active && hv && j0 > 0) {
+        const PEval e = eval_pt(src, j0 - 1, true);
+        if (e.inb) { has_prev = true; pr = e.r; pc = e.c; pj = j0 - 1; } else need_scan = true;
+    }
+    if (__any_sync(0xffffffffu, need_scan)) {
     bool iv = hv;
     float ir = lr, ic = lc;
     int ij = lj;
@@ -292,9 +313,9 @@ __device__ __forceinline__ float warp_points_bwd(bool active, const CtrlSrc &src
         const int oj = __shfl_up_sync(0xffffffffu, ij, d), os = __shfl_up_sync(0xffffffffu, sid, d);
         if (lane >= d && os == sid && !iv && ov) { iv = true; ir = orr; ic = oc; ij = oj; }
     }
-    bool has_prev = __shfl_up_sync(0xffffffffu, (int)iv, 1) != 0;
-    float pr = __shfl_up_sync(0xffffffffu, ir, 1), pc = __shfl_up_sync(0xffffffffu, ic, 1);
-    int pj = __shfl_up_sync(0xffffffffu, ij, 1);
+    has_prev = __shfl_up_sync(0xffffffffu, (int)iv, 1) != 0;
+    pr = __shfl_up_sync(0xffffffffu, ir, 1); pc = __shfl_up_sync(0xffffffffu, ic, 1);
+    pj = __shfl_up_sync(0xffffffffu, ij, 1);
     {
         const int ps = __shfl_up_sync(0xffffffffu, sid, 1);
         if (lane == 0 || ps != sid) has_prev = false;
@@ -320,6 +341,7 @@ __device__ __forceinline__ float warp_points_bwd(bool active, const CtrlSrc &src
             }
         }
         if (found && sid == sid0 && !has_prev) { has_prev = true; pr = cr; pc = cc; pj = cj; }
+    }
     }
     // ---- C: walk ----
     const bool fill = sum < 2.22e-6f;                               // (:104-105): constant ink, no distance gradient
