@@ -118,7 +118,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -392,12 +392,34 @@ def run_gpu(args):
             "fwd_bwd": {"value": world * 1024 * n_bwd / (ms_bwd * 1e-3), "unit": UNIT, "batch_per_gpu": 1024,
                         "ms_per_step": ms_bwd / n_bwd,
                         "achieved_tflops": (1024 * n_bwd / (ms_bwd * 1e-3)) * flops_fwd_bwd(Sb) / 1e12}}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """Everything any library writes to file descriptor 1 while the bench runs (NCCL prints its version line there) goes
+    to stderr instead; emit() writes the one JSON line to the real stdout."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
