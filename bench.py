@@ -213,13 +213,28 @@ def run_gpu(args):
     batch = workload.to_device(w, dev)
     imgs = ops.pack_images(img_t)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    gathered = torch.empty((world * 2,), dtype=torch.float32, device=dev) if world > 1 else None
+    # The per-step collective (2 floats per rank) is issued asynchronously on NCCL's stream and overlaps the NEXT step's
+    # kernel; a step waits (stream-side) for the previous step's gather, and finish_collectives() -- timed as part of the
+    # run -- waits for the last one, so every step's exchange completes inside the timed region.
+    gathered = [torch.empty((world * 2,), dtype=torch.float32, device=dev) for _ in range(2)] if world > 1 else None
+    coll = {"work": None, "i": 0}
+
+    def exchange(part):
+        if world > 1:
+            if coll["work"] is not None:
+                coll["work"].wait()
+            coll["work"] = dist.all_gather_into_tensor(gathered[coll["i"] & 1], part, async_op=True)
+            coll["i"] += 1
+
+    def finish_collectives():
+        if coll["work"] is not None:
+            coll["work"].wait()
+            coll["work"] = None
 
     def step_device():
         ll, off = ops.score_tokens(batch, imgs, ps=ps)
         part = ops.logsumexp_partial(ll)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, part)
+        exchange(part)
         return ll, part
 
     # host-resident inputs for the end-to-end arm: one pinned staging buffer per step's inputs (token arrays + the
@@ -262,8 +277,7 @@ def run_gpu(args):
         packed = ops.pack_images(im, validate=False)
         ll, _ = ops.score_tokens(b, packed, ps=ps)
         part = ops.logsumexp_partial(ll)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, part)
+        exchange(part)
         host_ll.copy_(ll, non_blocking=True)
         done[slot].record(cur)
         state["i"] = i + 1
@@ -279,6 +293,7 @@ def run_gpu(args):
             begin(warmup)
         for _ in range(warmup):
             fn()
+        finish_collectives()
         barrier()
         if begin:
             begin(steps)
@@ -293,6 +308,11 @@ def run_gpu(args):
             fn()
             b.record()
             evs.append((a, b))
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        finish_collectives()                 # the last step's exchange
+        b.record()
+        evs.append((a, b))
         barrier()
         wall = time.perf_counter() - t0
         ms = sum(a.elapsed_time(b) for a, b in evs)
