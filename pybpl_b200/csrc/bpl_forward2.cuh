@@ -353,7 +353,6 @@ __global__ void __launch_bounds__(F2_THREADS, F2_CTAS_PER_SM) bpl_forward2_kerne
             const float l00 = sm.ms[0].lp_bg[0], l01 = sm.ms[0].lp_bg[1];
             const float l10 = sm.ms[1].lp_bg[0], l11 = sm.ms[1].lp_bg[1];
             const float2 zz = make_float2(0.0f, 0.0f);
-            const bool same_img = sm.ms[0].cur_img == sm.ms[1].cur_img;      // the usual case: one target for all tokens
             if (!a.all_pairs) {
                 for (int i = threadIdx.x; i < NPIX; i += blockDim.x) {
                     const float2 v = A[i];

@@ -61,7 +61,7 @@ def get_stk_from_bspline(Y, neval=None, s=None):
         sv = s.view(1) if s.dim() == 0 else s
         C = ops.basis_rows(nland, sv).to(dev)
         if s.requires_grad:
-            # d C / d s: derivative of the normalised cubic basis, by differences of the same host routine
+            # d C / d s: analytic derivative of the normalised cubic basis
             C = _BasisRowsWithGrad.apply(sv.to(dev), nland, C)
     else:
         C = ops.basis_table(nland, int(neval), dev)
@@ -93,9 +93,28 @@ def bspline_eval(sval, cpts):
     return get_stk_from_bspline(cpts, s=sval)
 
 
+def _basis_rows_derivative(nland, s):
+    """d C / d s of coefficient_mat's rows (pybpl/splines.py:19-54, 72-93): the piecewise-cubic basis B_k(s) / 6,
+    row-normalised, differentiated analytically: c = B / sum B, c' = (B' - c sum B') / sum B.  s: [n] -> [n, nland]."""
+    s = s.detach().to(torch.float64).view(-1, 1)
+    d = s - torch.arange(nland, dtype=torch.float64, device=s.device).view(1, -1)
+    B = torch.zeros_like(d); dB = torch.zeros_like(d)
+    m = (d >= 0) & (d < 1); e = d
+    B = torch.where(m, e ** 3, B); dB = torch.where(m, 3 * e ** 2, dB)
+    m = (d >= 1) & (d < 2); e = d - 1
+    B = torch.where(m, -3 * e ** 3 + 3 * e ** 2 + 3 * e + 1, B); dB = torch.where(m, -9 * e ** 2 + 6 * e + 3, dB)
+    m = (d >= 2) & (d < 3); e = d - 2
+    B = torch.where(m, 3 * e ** 3 - 6 * e ** 2 + 4, B); dB = torch.where(m, 9 * e ** 2 - 12 * e, dB)
+    m = (d >= 3) & (d < 4); e = d - 3
+    B = torch.where(m, (1 - e) ** 3, B); dB = torch.where(m, -3 * (1 - e) ** 2, dB)
+    tot = B.sum(1, keepdim=True)
+    c = B / tot
+    return ((dB - c * dB.sum(1, keepdim=True)) / tot).to(torch.float32)
+
+
 class _BasisRowsWithGrad(torch.autograd.Function):
-    """Attaches d C / d s (central differences of the piecewise-cubic basis, exact to ~1e-4 relative) so that
-    eval_spot-style parameters receive a gradient, which the reference intends but loses to its cache."""
+    """Attaches d C / d s (analytic) so that eval_spot-style parameters receive a gradient, which the reference intends
+    but loses to its cache."""
 
     @staticmethod
     def forward(ctx, s, nland, C):
@@ -106,9 +125,5 @@ class _BasisRowsWithGrad(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gC):
         (s,) = ctx.saved_tensors
-        h = 1e-3
-        lo = torch.clamp(s.detach() - h, min=2.0)
-        hi = torch.clamp(s.detach() + h, max=float(ctx.nland + 1))
-        dC = (ops.basis_rows(ctx.nland, hi).to(gC.device) - ops.basis_rows(ctx.nland, lo).to(gC.device)) \
-            / (hi - lo).view(-1, 1)
+        dC = _basis_rows_derivative(ctx.nland, s).to(gC.device)
         return (gC * dC).sum(1), None, None

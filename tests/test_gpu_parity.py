@@ -95,6 +95,25 @@ def test_get_stk_from_bspline_dropin():
     assert np.array_equal(X200.numpy(), d["X_200"][0])
 
 
+def test_bspline_eval_gradient_in_s_and_Y():
+    """BSplineEval's autograd: d X / d s through the analytic derivative of the normalised basis and d X / d Y,
+    against central differences of the float64 oracle row (oracle/token_prior.py:basis_row)."""
+    from oracle.token_prior import basis_row
+    from pybpl_b200 import splines
+    rng = np.random.default_rng(0)
+    Y = rng.normal(0, 10, (5, 2))
+    w = rng.normal(0, 1, (3, 2))
+    sv = np.array([2.4, 3.77, 5.6])
+    st = torch.tensor(sv, dtype=torch.float32, requires_grad=True)
+    Yt = torch.tensor(Y, dtype=torch.float32, requires_grad=True)
+    X = splines.bspline_eval(st, Yt)
+    (X * torch.tensor(w, dtype=torch.float32)).sum().backward()
+    C = np.stack([basis_row(u, 5, np.float64)[0] for u in sv]); dC = np.stack([basis_row(u, 5, np.float64)[1] for u in sv])
+    assert np.abs(X.detach().numpy() - C @ Y).max() < 1e-4
+    assert np.abs(st.grad.numpy() - ((dC @ Y) * w).sum(1)).max() < 1e-4 * np.abs((dC @ Y) * w).max()
+    assert np.abs(Yt.grad.numpy() - C.T @ w).max() < 1e-5
+
+
 # ---------------------------------------------------------------------------------------------
 # vanilla_to_motor + integer work
 # ---------------------------------------------------------------------------------------------
