@@ -63,7 +63,8 @@ def cpu_target_image(w):
     from oracle import Oracle
     from pybpl_b200 import workload
     C = np.load(os.path.join(ROOT, "pybpl_b200", "data", "basis_5_200.npy"))
-    return workload.target_image_for(w, Oracle(np.float32), C), C
+    import oracle
+    return oracle.target_image_for(w, Oracle(np.float32), C), C
 
 
 def cpu_baseline(w, img, C, n_sample, repeats=1):
@@ -197,7 +198,7 @@ def run_gpu(args):
     Kbar = float(np.diff(tso).mean())
     # the target: a Bernoulli sample of token 0's probability map, rendered by the CUDA path itself (the oracle is
     # only used by the cpu_baseline leg below); the uniform noise comes from a seeded numpy generator as in
-    # workload.target_image_for, so the CPU arm sees the same image up to pixels within 1e-6 of the noise
+    # oracle.target_image_for, so the CPU arm sees the same image up to pixels within 1e-6 of the noise
     if rank == 0:
         with torch.no_grad():
             p0, _ = ops.render_tokens(workload.to_device(workload.permute(w0, np.array([0])), dev))

@@ -221,3 +221,15 @@ class Oracle:
         if want_pimg:
             res["pimg"] = pimg
         return res
+
+
+def target_image_for(w, oracle, C, token=0, seed=99):
+    """Binary target for a packed batch `w` (pybpl_b200.workload layout) = Bernoulli sample of one token's probability
+    map, rendered by this CPU oracle (tests, smoke() and the bench's CPU arm)."""
+    sub_k0, sub_k1 = int(w["tok_stroke_off"][token]), int(w["tok_stroke_off"][token + 1])
+    s0, s1 = int(w["stroke_sub_off"][sub_k0]), int(w["stroke_sub_off"][sub_k1])
+    nsub = np.diff(w["stroke_sub_off"][sub_k0:sub_k1 + 1])
+    r = oracle.token(C, nsub, w["ctrl"][s0:s1], w["invscale"][s0:s1], w["position"][sub_k0:sub_k1], float(w["eps"][token]),
+                     float(w["sigma"][token]))
+    rng = np.random.default_rng(seed)
+    return (rng.random((105, 105)) < r["pimg"]).astype(np.uint8)

@@ -162,13 +162,3 @@ def to_device(w, device, requires_grad=False, pin=False):
     return ops.TokenBatch(f(w["tok_stroke_off"]), f(w["stroke_sub_off"]), f(w["ctrl"]), f(w["invscale"]),
                           f(w["position"]), f(w["eps"]), f(w["sigma"]), neval=w["neval"], check_limits=False)
 
-
-def target_image_for(w, oracle, C, token=0, seed=99):
-    """Binary target = Bernoulli sample of one token's probability map, rendered by the CPU oracle
-    (tests only: the product never imports oracle/)."""
-    sub = permute(w, np.array([token]))
-    nsub = np.diff(sub["stroke_sub_off"])
-    r = oracle.token(C, nsub, sub["ctrl"], sub["invscale"], sub["position"], float(sub["eps"][0]),
-                     float(sub["sigma"][0]))
-    rng = np.random.default_rng(seed)
-    return (rng.random((105, 105)) < r["pimg"]).astype(np.uint8)

@@ -281,7 +281,8 @@ def test_score_matches_oracle_on_random_batch(ops):
     w = workload.synth_tokens(96, seed=1234, sigma_mode="uniform")
     o = Oracle(np.float32)
     C = load("tokens")["basis_5_200"]
-    img = workload.target_image_for(w, o, C)
+    import oracle as _oracle
+    img = _oracle.target_image_for(w, o, C)
     ref = o.token_batch(C, w["tok_stroke_off"], w["stroke_sub_off"], w["ctrl"], w["invscale"], w["position"],
                         w["eps"], w["sigma"], img[None], grad=True)
     ctrl, inv, pos = T(w["ctrl"]).requires_grad_(True), T(w["invscale"]).requires_grad_(True), T(w["position"]).requires_grad_(True)
