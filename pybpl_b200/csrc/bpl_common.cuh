@@ -149,7 +149,9 @@ __device__ __forceinline__ void sweep_box(const float *__restrict__ in, const fl
     const int s0 = VERT ? bx.r0 : bx.c0, nb = ((VERT ? bx.r1 : bx.c1) - s0 + 1) / R;
     if (nl <= 0 || nb <= 0) return;
     for (int item = threadIdx.x; item < nb * nl; item += blockDim.x) {
-        const int bi = item / nl;
+        int bi = 0;                          // item / nl without a division: a line has at most IMG / R bands
+#pragma unroll
+        for (int k = 1; k < IMG / R; ++k) bi += (item >= k * nl);
         const int line = l0 + item - bi * nl;
         const int a0 = s0 + bi * R;
         const float *p = in + ORIGIN + (a0 - HALF) * SA + line * SL;

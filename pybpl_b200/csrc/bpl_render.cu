@@ -743,7 +743,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) bpl_backward_kernel(const KArg
                 const float lb = x ? lp_bg1 : lp_bg0, db = x ? dlp_bg1 : dlp_bg0;
                 float lp = lb, d = db;
                 if (pm != bgv) {                                             // a background pixel adds nothing to the sum
-                    pixel_lp(pm, x, true, lp, d);
+                    lp = pixel_lp_fwd(pm, x);                                // the forward kernels' single bounded-error logarithm
+                    d = (pm < TORCH_EPS || pm > 1.0f - TORCH_EPS) ? 0.0f : (x ? __frcp_rn(pm) : -__frcp_rn(1.0f - pm));
                     acc_ll += lp - lb;
                 }
                 // A pixel without ink has the analytic background value (closed form below); pm == bgv alone does not
@@ -1009,10 +1010,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) bpl_backward_kernel(const KArg
         }
         // leave all four buffers zero: every pass wrote inside the box only
         if (!bx.empty()) {
-            const int nc = bx.c1 - bx.c0 + 1, nn = nc * (bx.r1 - bx.r0 + 1);
-            for (int i = threadIdx.x; i < nn; i += blockDim.x) {
-                const int r = i / nc, q = ORIGIN + (bx.r0 + r) * STRIDE + bx.c0 + (i - r * nc);
-                A[q] = 0.0f; B[q] = 0.0f; C[q] = 0.0f; D[q] = 0.0f;
+            for (int r = bx.r0 + warp; r <= bx.r1; r += nw) {      // a warp per row: no index divisions
+                const int q0 = ORIGIN + r * STRIDE;
+                for (int c = bx.c0 + lane; c <= bx.c1; c += 32) { A[q0 + c] = 0.0f; B[q0 + c] = 0.0f; C[q0 + c] = 0.0f; D[q0 + c] = 0.0f; }
             }
         }
         if (threadIdx.x == 0) { ms->next_item = p_next; ms->ones_acc = 0; }
