@@ -30,8 +30,8 @@ UNIT = "particles/s"
 BATCH = 4096
 SEED = 1234
 # dram__bytes_read.sum + dram__bytes_write.sum of one bpl_forward1s_kernel launch on this workload, from the
-# ncu --set full capture of this command summarised in profiles/r01_fwd1s_final.raw.txt (1.832192 MB + 3.84 KB)
-NCU_DRAM_BYTES_PER_LAUNCH = 1836032
+# ncu --set full capture of this command summarised in profiles/r01_fwd1s_final.raw.txt (1.831168 MB + 3.84 KB)
+NCU_DRAM_BYTES_PER_LAUNCH = 1835008
 
 
 def flops_fwd(S):      # algorithmic work per particle, separable minimal algorithm
@@ -385,7 +385,7 @@ def run_gpu(args):
     k_rate = BATCH / (k_ms * 1e-3)
     ach_tf = k_rate * flops_fwd(Sbar) / 1e12
     roofline = {"bound": "fp32", "achieved": ach_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach_tf / fp32_peak,
-                "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "kernel": "bpl_forward1s_kernel", "kernel_ms": k_ms,
+                "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "kernel": "bpl_forward1s_kernel<false>", "kernel_ms": k_ms,
                 "flop_per_particle": flops_fwd(Sbar), "mean_substrokes": Sbar,
                 "peak_source": "live FFMA probe (bpl_fp32_probe) in this run; MEASURED_PEAKS.json holds no CUDA-core FP32 "
                                "figure, and SURVEY.md 8(d) shows the path is FP32-issue/shared-memory bound, not HBM",
