@@ -229,7 +229,8 @@ class HostStagedBatch:
     (asynchronously) and returns (TokenBatch, image tensor) whose tensors are views of that buffer."""
 
     _ORDER = (("tok_stroke_off", torch.int32), ("stroke_sub_off", torch.int32), ("ctrl", torch.float32),
-              ("invscale", torch.float32), ("position", torch.float32), ("eps", torch.float32), ("sigma", torch.float32))
+              ("invscale", torch.float32), ("position", torch.float32), ("eps", torch.float32), ("sigma", torch.float32),
+              ("order", torch.int32))
 
     def __init__(self, w, image_u8, device):
         self.device = torch.device(device)
@@ -237,6 +238,11 @@ class HostStagedBatch:
         self.layout = []
         off = 0
         arrs = []
+        # the processing order (expensive tokens first, TokenBatch.order_ptr) depends only on the offsets: made here on
+        # the host once and shipped with the inputs, instead of one more kernel per step
+        tso = np.asarray(w["tok_stroke_off"], np.int64)
+        S_tok = np.diff(np.asarray(w["stroke_sub_off"], np.int64)[tso])
+        w = dict(w, order=np.argsort(-S_tok, kind="stable").astype(np.int32))
         for name, dt in self._ORDER:
             a = torch.from_numpy(np.ascontiguousarray(w[name])).to(dt).contiguous()
             arrs.append(a)
@@ -266,6 +272,8 @@ class HostStagedBatch:
             v[name] = dev[o:o + nb].view(dt).view(shape)
         batch = TokenBatch(v["tok_stroke_off"], v["stroke_sub_off"], v["ctrl"], v["invscale"], v["position"], v["eps"],
                            v["sigma"], neval=self.neval, check_limits=False)
+        if 2 <= batch.P <= TokenBatch.ORDER_MAX_TOKENS:
+            batch._order = v["order"]
         image = dev[self.img_off:self.img_off + self.img_bytes].view(IMSIZE, IMSIZE)
         return batch, image
 
