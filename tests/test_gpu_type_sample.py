@@ -225,3 +225,11 @@ def test_model_mirror_score_type():
         ref = d["ll"][p]
         assert got.dim() == 0 and got.device.type == "cpu"
         assert (np.isinf(ref) and float(got) == ref) or abs(float(got) - ref) <= 1e-5 * abs(ref)
+
+
+def test_optimize_types_example_raises_the_prior_score():
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "examples"))
+    import optimize_types
+    r = optimize_types.optimise(n_types=256, steps=40, lr=1e-2)
+    assert np.isfinite(r["scores"]).all() and r["scores"][-1] > r["scores"][0]
