@@ -49,7 +49,10 @@ __device__ __forceinline__ float normal_cdf(float x, float mu, float sigma) {
 }
 __device__ __forceinline__ float std_pdf(float z) { return INV_SQRT_2PI * expf(-0.5f * z * z); }
 
-__global__ void __launch_bounds__(256) token_prior_kernel(const TPArgs a) {
+#ifndef BPL_TP_BLOCKS
+#define BPL_TP_BLOCKS 8      // 32 registers, 64 warps per SM: the kernel is latency-bound (dependent offset -> data loads); measured 1 / 4 / 6 / 8 blocks: 412 / 616 / 656 / 768 M tokens/s
+#endif
+__global__ void __launch_bounds__(256, BPL_TP_BLOCKS) token_prior_kernel(const TPArgs a) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     const float ss = a.c.sigma_shape, si = a.c.sigma_invscale, sa = a.c.sigma_attach;
