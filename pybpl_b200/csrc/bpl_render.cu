@@ -1305,7 +1305,8 @@ int bpl_score_tokens_grad(const bpl_params *ps, const bpl_token_batch *b, const 
     if (!g || !g->g_ctrl || !g->g_invscale || !g->g_position) { set_error("%s", "g_ctrl/g_invscale/g_position required"); return BPL_EINVAL; }
     if (ka.all_pairs) { set_error("%s", "all_pairs scoring is forward only"); return BPL_EINVAL; }
     if (!ka.image_bits && !ka.g_pimg) { set_error("%s", "need target images or a pimg cotangent"); return BPL_EINVAL; }
-    ka.order = nullptr;      // measured: the fused backward (one CTA per SM, cost dominated by the fixed stencil work) is 2 % faster in index order
+    static const bool bwd_order = getenv("BPL_BWD_ORDER") != nullptr;      // A/B aid
+    if (!bwd_order) ka.order = nullptr;      // measured: the fused backward (one CTA per SM) is faster in index order
     return launch(bpl_backward_kernel<false>, BWD_THREADS, sizeof(BwdSmem), 1, ka, (cudaStream_t)stream);
 }
 
