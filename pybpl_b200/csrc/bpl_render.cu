@@ -485,7 +485,10 @@ namespace bpl {
 constexpr int BWD_THREADS = 768;   // 24 warps: 7 bands x 105 lines = 735 sweep items in one round
 constexpr int BWD_R = 15;
 constexpr int BWD_R3 = 15;
-constexpr int BWD_PPL = 3;         // points per lane in the backward kernel's point stages: the CTA has the SM to
+#ifndef BPL_BWD_PPL
+#define BPL_BWD_PPL 3
+#endif
+constexpr int BWD_PPL = BPL_BWD_PPL;         // points per lane in the backward kernel's point stages: the CTA has the SM to
                                    // itself, so shorter runs (more lanes busy) beat fewer atomic collisions
 constexpr int NACC = 2 * NCPT + 2; // per sub-stroke: W[k].x, W[k].y, Gsum.x, Gsum.y
 
