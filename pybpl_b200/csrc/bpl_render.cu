@@ -482,7 +482,10 @@ namespace bpl {
 // ------------------------------------------------------------------------------------------
 // fused forward + backward kernel (4 image buffers, one CTA per SM)
 // ------------------------------------------------------------------------------------------
-constexpr int BWD_THREADS = 768;   // 24 warps: 7 bands x 105 lines = 735 sweep items in one round
+#ifndef BPL_BWD_THREADS
+#define BPL_BWD_THREADS 640
+#endif
+constexpr int BWD_THREADS = BPL_BWD_THREADS;   // 20 warps (measured 384 / 512 / 640 / 768 threads: 3.57 / 3.70 / 3.81 / 3.65 M particles/s; a box rarely has more than 375 sweep items, a full canvas takes two rounds)
 constexpr int BWD_R = 15;
 constexpr int BWD_R3 = 15;
 #ifndef BPL_BWD_PPL
