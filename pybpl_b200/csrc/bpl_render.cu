@@ -486,8 +486,11 @@ namespace bpl {
 #define BPL_BWD_THREADS 640
 #endif
 constexpr int BWD_THREADS = BPL_BWD_THREADS;   // 20 warps (measured 384 / 512 / 640 / 768 threads: 3.57 / 3.70 / 3.81 / 3.65 M particles/s; a box rarely has more than 375 sweep items, a full canvas takes two rounds)
-constexpr int BWD_R = 15;
-constexpr int BWD_R3 = 15;
+#ifndef BPL_BWD_R
+#define BPL_BWD_R 15
+#endif
+constexpr int BWD_R = BPL_BWD_R;      // outputs per sweep item = granularity of the box (measured 15 / 21 / 35 below)
+constexpr int BWD_R3 = BPL_BWD_R;
 #ifndef BPL_BWD_PPL
 #define BPL_BWD_PPL 3
 #endif
