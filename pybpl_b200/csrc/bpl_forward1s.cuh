@@ -37,8 +37,13 @@ struct BBox {
 // in-place 11-tap pass over lines [l0, l0+nl) and bands [b0, b0+nb); see gauss_inplace for the scheme
 struct G6 { float v[PAD + 1]; };      // the half kernel by value: the pass is a real (non-inlined) function so that
                                        // its six instantiations do not add to the register pressure of the kernel body
+#ifdef BPL_GAUSS_INLINE
+#define BPL_GAUSS_ATTR __forceinline__
+#else
+#define BPL_GAUSS_ATTR __noinline__
+#endif
 template <bool VERT, int GR, int GU>
-__device__ __noinline__ void gauss_inplace_s(float *buf, const G6 gg, int l0, int nl, int b0, int nb) {
+__device__ BPL_GAUSS_ATTR void gauss_inplace_s(float *buf, const G6 gg, int l0, int nl, int b0, int nb) {
     static_assert(IMG % GR == 0 && GR % GU == 0 && GU >= PAD, "band structure");
     const float (&g)[PAD + 1] = gg.v;
     constexpr int GNB = IMG / GR;
@@ -127,7 +132,12 @@ __device__ __forceinline__ void gauss_box(float *buf, const G6 &g, int l0, int l
 // served from `side`, a copy taken before anything is overwritten).  Halo rows are summed before the
 // barrier; horizontal neighbours travel by shuffle, so nothing is read after a neighbour may have written it.
 // bb is the box of non-zero INPUT pixels; the caller grows it by ink_ncon afterwards.
-__device__ __noinline__ void broaden_box(float *A, float *side, const RenderConsts rc, BBox bb) {
+#ifdef BPL_BROADEN_INLINE
+#define BPL_BROADEN_ATTR __forceinline__
+#else
+#define BPL_BROADEN_ATTR __noinline__
+#endif
+__device__ BPL_BROADEN_ATTR void broaden_box(float *A, float *side, const RenderConsts rc, BBox bb) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int nw = S_THREADS / 32;             // (compile time: the divisions below become multiplications)
     const float c1w = rc.c1, c2w = rc.c2;
