@@ -3,17 +3,27 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-A "step" is one pass of the hot path (spline eval -> rasterise -> broaden/blur -> Bernoulli
-log-likelihood, one fused kernel) over one batch of 4,096 synthetic tokens scored against one 105x105
-binary image (BASELINE.json configs[1]); under torchrun each rank steps its own batch (weak scaling) and the
-ranks' (max, sum-exp) partials are combined with one NCCL all-gather per step (the log-sum-exp of the
-particle sweep).  One JSON line on stdout (rank 0).
+A "step" is one particle sweep, BASELINE.json configs[3]: 1,000,000 synthetic token particles scored against one
+105x105 binary image, the particles sharded over the N ranks of a torchrun job (STRONG scaling: 1M / N each), every rank
+running ONE fused launch of the hot path over its share (spline eval -> rasterise -> broaden/blur -> Bernoulli
+log-likelihood -> the rank's log-sum-exp partial), then one NCCL all-gather of 2 floats per rank and a one-warp combine
+into the global log-sum-exp.  K steps run back to back inside ONE timed region (CUDA events on the launching stream
+and wall clock; nothing is untimed between steps); the collective is on the critical path of every step.
 
-`--impl reference` times the CPU restatement of the reference (oracle/, C + OpenMP on all host cores;
-the reference itself is Python and does not travel to the GPU box) on a bounded sample of the same workload.
+`value`   : particles/s with the particles resident in HBM when the timed region starts
+`e2e`     : the same sweep from HOST numpy arrays through the public API: host-side ragged packing of every chunk into
+            pinned memory, H2D, fused kernel, D2H of the scores, wall clock
+`config1` : configs[1], the 4,096-token step on one GPU (kernel time, roofline)       \\
+`fwd_bwd` : configs[2] shape, 1,024 parses/step through the fused forward+backward     > secondary objects
+`config2` : configs[2], 1,024 parses x 100 Adam steps, total seconds                   /
+`cpu_baseline` (C oracle port, all cores) and `cpu_baseline_torch` (the reference's own torch code from
+baseline/_ref, one single-thread process per core) are timed on rank 0 at N=1 on a bounded sample of the same particles.
+
+`--impl reference` times the CPU arm alone (same config; rank 0 only under torchrun).
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -27,11 +37,15 @@ sys.path.insert(0, ROOT)
 
 METRIC = "rendered+scored 105x105 particles/sec (fwd)"
 UNIT = "particles/s"
-BATCH = 4096
-SEED = 1234
-# dram__bytes_read.sum + dram__bytes_write.sum of one bpl_forward1s_kernel launch on this workload, from the
-# ncu --set full capture of this command summarised in profiles/r01_fwd1s_final.raw.txt (1.831168 MB + 3.84 KB)
-NCU_DRAM_BYTES_PER_LAUNCH = 1835008
+L2_BYTES = 126 * 1024 * 1024
+E2E_CHUNK = 65536
+CFG1_BATCH = 4096
+CFG1_SEED = 1234
+BWD_BATCH = 1024
+CPU_SAMPLE = 8192            # particles per step of the CPU arm (first tokens of sweep block 0)
+# dram__bytes_read.sum + dram__bytes_write.sum of one scoring launch, from the ncu --set full capture summarised under
+# profiles/ (filled in from the round's capture; None until one exists for the current kernel)
+NCU_DRAM_BYTES_PER_PARTICLE = None
 
 
 def flops_fwd(S):      # algorithmic work per particle, separable minimal algorithm
@@ -46,77 +60,99 @@ def hbm_bytes(S, K):   # control points in, score out
     return 44.0 * S + 8.0 * K + 12.0 + 5.0
 
 
-def workload_config(n_gpus, extra=None):
-    cfg = {"workload": "configs[1]: 4096 synthetic tokens (1-5 strokes, ragged sub-strokes, blur_sigma~U(0.5,16), "
-                       "eps=1e-4) rendered+scored against one 105x105 binary image per GPU",
-           "batch_per_gpu": BATCH, "seed": SEED, "parallelism": f"particle-sharded x{n_gpus}",
-           "l2": "flushed between timed steps (256 MiB write)"}
-    if extra:
-        cfg.update(extra)
-    return cfg
+def mean_sk(w):
+    tso = w["tok_stroke_off"].astype(np.int64)
+    return float(np.diff(w["stroke_sub_off"].astype(np.int64)[tso]).mean()), float(np.diff(tso).mean())
+
+
+def sweep_config(n_gpus):
+    """The `config` object: identical for the GPU arm and `--impl reference`."""
+    from pybpl_b200 import workload
+    per_rank_mb = 277.0 / n_gpus
+    copies = max(1, math.ceil(2.0 * L2_BYTES / 1e6 / per_rank_mb))
+    return {"workload": "configs[3]: particle sweep, 1,000,000 synthetic token particles (1-5 strokes, ragged sub-strokes, "
+                        "blur_sigma~U(0.5,16), eps=1e-4) x one 105x105 binary target, sharded across the ranks; per step and "
+                        "rank one fused render+score+log-sum-exp launch, then one all-gather of 2 floats per rank",
+            "particles": workload.SWEEP_PARTICLES, "blocks": workload.SWEEP_BLOCKS, "seed": workload.SWEEP_SEED,
+            "parallelism": f"particle-sharded x{n_gpus} (strong scaling)",
+            "l2": f"inputs larger than L2: every rank cycles through {copies} resident cop{'y' if copies == 1 else 'ies'} of its "
+                  f"{per_rank_mb:.0f} MB of particles (> 2 x 126 MB in total), a different one each step"}
 
 
 # ---------------------------------------------------------------------------------------------
-# CPU arm: the oracle port on all host cores
+# CPU arms
 # ---------------------------------------------------------------------------------------------
-def cpu_target_image(w):
-    from oracle import Oracle
-    from pybpl_b200 import workload
-    C = np.load(os.path.join(ROOT, "pybpl_b200", "data", "basis_5_200.npy"))
-    import oracle
-    return oracle.target_image_for(w, Oracle(np.float32), C), C
+def basis():
+    return np.load(os.path.join(ROOT, "pybpl_b200", "data", "basis_5_200.npy"))
 
 
-def cpu_baseline(w, img, C, n_sample, repeats=1):
+def oracle_rate(w, img, C, grad=False, budget_s=12.0, max_passes=64):
+    """The C oracle port (OpenMP over tokens, all host cores) repeated over `w` for about budget_s seconds."""
     from oracle import Oracle
-    from pybpl_b200 import workload
     o = Oracle(np.float32)
-    sub = workload.permute(w, np.arange(min(n_sample, w["P"])))
-    best = None
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        o.token_batch(C, sub["tok_stroke_off"], sub["stroke_sub_off"], sub["ctrl"], sub["invscale"], sub["position"],
-                      sub["eps"], sub["sigma"], img[None])
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return sub["P"] / best, sub["P"], best
-
-
-def cpu_baseline_bounded(w, img, C, budget_s=12.0):
-    """The whole step repeated for about `budget_s` seconds of wall time on all host cores; mean rate over the passes
-    after the first (which warms the OpenMP pool and the caches)."""
-    cpu_baseline(w, img, C, w["P"])
+    args = (C, w["tok_stroke_off"], w["stroke_sub_off"], w["ctrl"], w["invscale"], w["position"], w["eps"], w["sigma"], img[None])
+    o.token_batch(*args, grad=grad)                     # warms the OpenMP pool and the caches
     t_tot, n_tot, passes = 0.0, 0, 0
-    while t_tot < budget_s and passes < 64:
-        _, n, dt = cpu_baseline(w, img, C, w["P"])
-        t_tot += dt; n_tot += n; passes += 1
+    while t_tot < budget_s and passes < max_passes:
+        t0 = time.perf_counter()
+        o.token_batch(*args, grad=grad)
+        t_tot += time.perf_counter() - t0; n_tot += w["P"]; passes += 1
     return n_tot / t_tot, n_tot, t_tot, passes
+
+
+def torch_reference_rate(w, img, grad=False, budget_s=10.0):
+    """The reference's own torch code (baseline/_ref), one single-thread process per core; None when it is not installed."""
+    from baseline import ref_loader, torch_ref
+    if not ref_loader.available():
+        return None
+    cores = os.cpu_count() or 1
+    try:
+        rate, n, procs, _ = torch_ref.score_rate(w, img, n_procs=cores, per_proc=max(8, w["P"] // cores), grad=grad,
+                                                 budget_s=budget_s)
+    except Exception as e:                               # a reported baseline must not take the bench down
+        return {"unavailable": str(e)[:200]}
+    return {"value": rate, "unit": UNIT, "cores": procs, "kind": "reference",
+            "sample": f"{n} particles of sweep block 0 scored by the unmodified pybpl CharacterImageDist.score_image"
+                      f"{' + .backward() (rendering.py:97 patched in memory)' if grad else ''} from baseline/_ref, "
+                      f"{procs} single-thread processes (torch.set_num_threads(1)) side by side, <= {budget_s:.0f} s each"}
+
+
+def cpu_sample():
+    from pybpl_b200 import workload
+    import oracle
+    from oracle import Oracle
+    w0 = workload.sweep_block(0)
+    C = basis()
+    img = oracle.target_image_for(w0, Oracle(np.float32), C)
+    return workload.permute(w0, np.arange(CPU_SAMPLE)), img, C
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from pybpl_b200 import workload
-    w = workload.synth_tokens(BATCH, seed=SEED, sigma_mode="uniform")
-    img, C = cpu_target_image(w)
     import oracle
     cores = oracle.set_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1 to its workers
-    n_sample = 1024
+    w, img, C = cpu_sample()
+    from oracle import Oracle
+    o = Oracle(np.float32)
+    call = lambda: o.token_batch(C, w["tok_stroke_off"], w["stroke_sub_off"], w["ctrl"], w["invscale"], w["position"],
+                                 w["eps"], w["sigma"], img[None])
     for _ in range(max(args.warmup, 1)):
-        cpu_baseline(w, img, C, 64)
-    t_tot = 0.0
-    n_tot = 0
+        call()
+    t0 = time.perf_counter()
     for _ in range(args.steps):
-        v, n, dt = cpu_baseline(w, img, C, n_sample)
-        t_tot += dt; n_tot += n
-    value = n_tot / t_tot
-    sample = f"{n_sample} of the 4096 tokens per step, C oracle port with OpenMP over tokens"
+        call()
+    t_tot = time.perf_counter() - t0
+    value = w["P"] * args.steps / t_tot
+    sample = (f"{CPU_SAMPLE} particles of sweep block 0 per step (of the 1,000,000), C oracle port (fp32) with OpenMP over "
+              f"tokens on {cores} cores")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.gpus),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": sweep_config(args.gpus),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline_torch": torch_reference_rate(w, img, budget_s=args.cpu_budget),
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -132,6 +168,7 @@ class ClockSampler:
 
     def __init__(self, index):
         self.rows = []
+        self.marks = []
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
@@ -144,7 +181,10 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.rows.append(ln.strip())
+            self.rows.append((time.perf_counter(), ln.strip()))
+
+    def mark(self):
+        self.marks.append(time.perf_counter())
 
     def stop(self):
         if not self.proc:
@@ -156,7 +196,10 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        lo, hi = (self.marks[0], self.marks[-1]) if len(self.marks) >= 2 else (-1e30, 1e30)
+        for ts, r in self.rows:
+            if not (lo <= ts <= hi + 0.05):
+                continue                                  # only samples taken during the timed regions
             f = [x.strip() for x in r.split(",")]
             if len(f) < 9:
                 continue
@@ -175,9 +218,10 @@ class ClockSampler:
 # GPU arm
 # ---------------------------------------------------------------------------------------------
 def run_gpu(args):
+    import ctypes
     import torch
     import torch.distributed as dist
-    from pybpl_b200 import _lib, ops, workload
+    from pybpl_b200 import _lib, ops, sweep, workload
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -189,185 +233,213 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()
-
-    # per-rank batch (weak scaling): same generator, rank-offset seed; one shared target image
-    w0 = workload.synth_tokens(BATCH, seed=SEED, sigma_mode="uniform")
-    w = w0 if rank == 0 else workload.synth_tokens(BATCH, seed=SEED + rank, sigma_mode="uniform")
-    tso = w["tok_stroke_off"].astype(np.int64)
-    Sbar = float(np.diff(w["stroke_sub_off"].astype(np.int64)[tso]).mean())
-    Kbar = float(np.diff(tso).mean())
-    # the target: a Bernoulli sample of token 0's probability map, rendered by the CUDA path itself (the oracle is
-    # only used by the cpu_baseline leg below); the uniform noise comes from a seeded numpy generator as in
-    # oracle.target_image_for, so the CPU arm sees the same image up to pixels within 1e-6 of the noise
-    if rank == 0:
-        with torch.no_grad():
-            p0, _ = ops.render_tokens(workload.to_device(workload.permute(w0, np.array([0])), dev))
-        u = np.random.default_rng(99).random((105, 105))
-        img_np = (u < p0[0].cpu().numpy()).astype(np.uint8)
-    else:
-        img_np = np.zeros((105, 105), np.uint8)
-    img_t = torch.from_numpy(img_np).to(dev)
-    if world > 1:
-        dist.broadcast(img_t, 0)
+    steps, warmup = args.steps, max(args.warmup, 3)
     ps = ops.make_params(None)
-
-    batch = workload.to_device(w, dev)
-    imgs = ops.pack_images(img_t)
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    # The per-step collective (2 floats per rank) is issued asynchronously on NCCL's stream and overlaps the NEXT step's
-    # kernel; a step waits (stream-side) for the previous step's gather, and finish_collectives() -- timed as part of the
-    # run -- waits for the last one, so every step's exchange completes inside the timed region.
-    gathered = [torch.empty((world * 2,), dtype=torch.float32, device=dev) for _ in range(2)] if world > 1 else None
-    coll = {"work": None, "i": 0}
-
-    def exchange(part):
-        if world > 1:
-            if coll["work"] is not None:
-                coll["work"].wait()
-            coll["work"] = dist.all_gather_into_tensor(gathered[coll["i"] & 1], part, async_op=True)
-            coll["i"] += 1
-
-    def finish_collectives():
-        if coll["work"] is not None:
-            coll["work"].wait()
-            coll["work"] = None
-
-    def step_device():
-        ll, off = ops.score_tokens(batch, imgs, ps=ps)
-        part = ops.logsumexp_partial(ll)
-        exchange(part)
-        return ll, part
-
-    # host-resident inputs for the end-to-end arm: one pinned staging buffer per step's inputs (token arrays + the
-    # target image), one H2D copy, pack + render+score + log-sum-exp partial, one D2H copy of the scores; all
-    # asynchronous on the current stream, the timed region ends with a synchronize
-    staged = ops.HostStagedBatch(w, img_np, dev)
-    host_ll = torch.empty(BATCH, dtype=torch.float32).pin_memory()
-    h2d = staged.nbytes
-    d2h = host_ll.numel() * 4
-
-    # two device slots: the H2D copy of step i+1 is issued on a copy stream before step i's kernels, so copies and
-    # kernels overlap; every step's copy still lies inside the timed region (the first step of a phase uploads its
-    # own input, the last one prefetches nothing)
-    copy_stream = torch.cuda.Stream(device=dev)
-    ready = [torch.cuda.Event(), torch.cuda.Event()]
-    done = [torch.cuda.Event(), torch.cuda.Event()]
-    state = {"i": 0, "n": 0}
-
-    def upload_async(slot):
-        copy_stream.wait_event(done[slot])              # the kernels that last read this slot have finished
-        with torch.cuda.stream(copy_stream):
-            staged.upload(slot)
-            ready[slot].record(copy_stream)
-
-    def begin_e2e(nsteps):
-        torch.cuda.synchronize()
-        state["i"], state["n"] = 0, nsteps
-        for ev in done:
-            ev.record()
-
-    def step_e2e():
-        i = state["i"]; slot = i & 1
-        if i == 0:
-            upload_async(0)                             # the first step of a phase copies its own input
-        if i + 1 < state["n"]:
-            upload_async(slot ^ 1)
-        cur = torch.cuda.current_stream()
-        cur.wait_event(ready[slot])
-        b, im = staged.views(slot)
-        packed = ops.pack_images(im, validate=False)
-        ll, _ = ops.score_tokens(b, packed, ps=ps)
-        part = ops.logsumexp_partial(ll)
-        exchange(part)
-        host_ll.copy_(ll, non_blocking=True)
-        done[slot].record(cur)
-        state["i"] = i + 1
-        return host_ll
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup, flush_l2=True, begin=None):
-        if begin:
-            begin(warmup)
-        for _ in range(warmup):
-            fn()
-        finish_collectives()
-        barrier()
-        if begin:
-            begin(steps)
-        evs = []
-        l0 = _lib.launch_count()
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            if flush_l2:
-                flush.fill_(1)
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            fn()
-            b.record()
-            evs.append((a, b))
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        finish_collectives()                 # the last step's exchange
-        b.record()
-        evs.append((a, b))
-        barrier()
-        wall = time.perf_counter() - t0
-        ms = sum(a.elapsed_time(b) for a, b in evs)
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), wall, _lib.launch_count() - l0
+        return float(t.item())
+
+    # ---- the rank's share of the 1M particles (host numpy; then resident on the device) ----
+    w = workload.sweep_shard(rank, world)
+    P_rank = int(w["P"])
+    P_total = workload.SWEEP_PARTICLES
+    Sbar, Kbar = mean_sk(w)
+    # target = Bernoulli sample of particle 0's probability map, rendered by the CUDA path (rank 0) and broadcast; the
+    # CPU arms render the same particle with the oracle and draw from the same seeded uniform field
+    if rank == 0:
+        with torch.no_grad():
+            p0, _ = ops.render_tokens(workload.to_device(workload.permute(w, np.array([0])), dev))
+        img_np = (np.random.default_rng(99).random((105, 105)) < p0[0].cpu().numpy()).astype(np.uint8)
+    else:
+        img_np = np.zeros((105, 105), np.uint8)
+    img_t = torch.from_numpy(img_np).to(dev)
+    if world > 1:
+        dist.broadcast(img_t, 0)
+        img_np = img_t.cpu().numpy()
+    imgs = ops.pack_images(img_t)
+    in_bytes = sum(v.nbytes for v in w.values() if isinstance(v, np.ndarray))
+    n_copies = max(1, math.ceil(2.0 * L2_BYTES / max(in_bytes, 1)))
+    copies = [workload.to_device(w, dev) for _ in range(n_copies)]
+    sw = sweep.Sweep(copies[0], imgs, want_ll=True, ps=ps)
+    counter = {"i": 0}
+
+    def step_device():
+        counter["i"] += 1
+        return sw.step(copies[counter["i"] % n_copies])
+
+    def timed(fn, nsteps, nwarm, finish=None):
+        """nwarm untimed steps, then nsteps back to back inside one region: CUDA events on the launching stream around the
+        whole loop (max over ranks) and wall clock around the same loop; a barrier + synchronize on both sides."""
+        for _ in range(nwarm):
+            fn()
+        if finish:
+            finish()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = _lib.launch_count()
+        if sampler:
+            sampler.mark()
+        t0 = time.perf_counter()
+        a.record()
+        for _ in range(nsteps):
+            fn()
+        if finish:
+            finish()
+        b.record()
+        torch.cuda.synchronize()
+        wall_local = time.perf_counter() - t0
+        barrier()
+        if sampler:
+            sampler.mark()
+        return max_over_ranks(a.elapsed_time(b)), max_over_ranks(wall_local * 1e3), _lib.launch_count() - l0
 
     sampler = ClockSampler(local) if rank == 0 else None
-    ms_total, wall, launches = timed(step_device, args.steps, max(args.warmup, 3))
-    ms_e2e, wall_e2e, _ = timed(step_e2e, args.steps, max(args.warmup, 3), begin=begin_e2e)
-    clocks = sampler.stop() if sampler else None
+    ms_dev, wall_dev_ms, launches = timed(step_device, steps, warmup)
+    lse_dev = float(sw.total.item())
 
-    # kernel-only duration of the dominant kernel (events directly around the C-ABI call on this stream)
-    ll_buf = torch.empty(BATCH, dtype=torch.float32, device=dev)
-    off_buf = torch.empty(BATCH, dtype=torch.uint8, device=dev)
+    # ---- end to end: the same sweep from host numpy arrays ----
+    stager = ops.HostSweepStager(w, dev, chunk=E2E_CHUNK)
+    nchunks = len(stager.chunks)
+    host_ll = torch.empty(P_rank, dtype=torch.float32).pin_memory()
+    host_total = torch.empty(1, dtype=torch.float32).pin_memory()
+    copy_stream = torch.cuda.Stream(device=dev)
+    copied = [torch.cuda.Event() for _ in range(2)]
+    done = [torch.cuda.Event() for _ in range(2)]
+    state = ops.LseState(dev)
+    gathered = torch.empty(2 * world, dtype=torch.float32, device=dev)
+    e2e_n = {"c": 0}
 
-    def kernel_only():
-        ll, _ = ops.score_tokens(batch, imgs, ps=ps)
-        return ll
+    def step_e2e():
+        cur = torch.cuda.current_stream()
+        for c in range(nchunks):
+            slot = e2e_n["c"] & 1
+            e2e_n["c"] += 1
+            copied[slot].synchronize()                   # the H2D copy that last read this pinned slot has completed
+            stager.pack(c, slot)                         # host-side ragged packing into pinned memory
+            copy_stream.wait_event(done[slot])           # ... and the kernel that last read the device slot
+            with torch.cuda.stream(copy_stream):
+                stager.upload(slot)
+                copied[slot].record(copy_stream)
+            cur.wait_event(copied[slot])
+            b = stager.batch(c, slot)
+            ll_c, _ = ops.score_tokens_lse(b, imgs, state, accumulate=c > 0, want_ll=True, ps=ps)
+            c0, c1 = stager.chunks[c][0], stager.chunks[c][1]
+            host_ll[c0:c1].copy_(ll_c, non_blocking=True)
+            done[slot].record(cur)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, state.partial)
+            total = ops.logsumexp_combine(gathered)
+        else:
+            total = ops.logsumexp_combine(state.partial)
+        host_total.copy_(total, non_blocking=True)
+
+    for ev in copied + done:
+        ev.record()
+    _, wall_e2e_ms, _ = timed(step_e2e, steps, warmup)
+    lse_e2e = float(host_total.item())
+    h2d = nchunks * stager.nbytes
+    d2h = 4 * P_rank + 4
+
+    # ---- kernel-only duration of the dominant kernel on this workload (events directly around the launch) ----
     kms = []
-    for i in range(13):
-        flush.fill_(1)
+    for i in range(6):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); kernel_only(); b.record()
+        bt = copies[i % n_copies]
+        a.record(); ops.score_tokens_lse(bt, imgs, sw.state, want_ll=True, ps=ps); b.record()
         torch.cuda.synchronize()
-        if i >= 3:
+        if i >= 2:
             kms.append(a.elapsed_time(b))
     k_ms = float(np.mean(kms))
 
-    # fwd+bwd (config 3 shape: 1024 parses, gradients to ctrl/invscale/position/eps/sigma)
-    wb = workload.permute(w, np.arange(1024))
+    # ---- fwd+bwd (configs[2] shape: 1024 parses per GPU and step; gradients to ctrl/invscale/position/eps/sigma) ----
+    wb = workload.synth_tokens(BWD_BATCH, seed=2024 + rank, sigma_mode=10.0)
+    Sb, _ = mean_sk(wb)
     bb = workload.to_device(wb, dev, requires_grad=True)
-    Sb = float(np.diff(wb["stroke_sub_off"].astype(np.int64)[wb["tok_stroke_off"].astype(np.int64)]).mean())
+    flush = torch.empty(2 * L2_BYTES, dtype=torch.uint8, device=dev)
 
     def step_bwd():
         ll, _ = ops.score_tokens(bb, imgs, ps=ps)
         return ll
-    ms_bwd, _, _ = timed(step_bwd, max(args.steps // 4, 5), 3)
-    n_bwd = max(args.steps // 4, 5)
+    n_bwd = max(steps * 5, 50)
+    ms_bwd, _, _ = timed(step_bwd, n_bwd, 5)
+    kb = []
+    for i in range(8):
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); step_bwd(); b.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            kb.append(a.elapsed_time(b))
+    kb_ms = float(np.mean(kb))
+    # end to end: host numpy -> pinned -> H2D -> fused kernel -> D2H of the scores and all gradients
+    hb = ops.HostSweepStager(wb, dev, chunk=BWD_BATCH, slots=1)
+    g_host = {k: torch.empty(v.shape, dtype=torch.float32).pin_memory() for k, v in
+              dict(ll=wb["eps"], ctrl=wb["ctrl"], invscale=wb["invscale"], position=wb["position"], eps=wb["eps"],
+                   sigma=wb["sigma"]).items()}
 
-    # live FP32 FMA peak (roofline denominator)
+    def step_bwd_e2e():
+        torch.cuda.current_stream().synchronize()          # the pinned slot and the gradient buffers are free again
+        hb.pack(0, 0)
+        hb.upload(0)
+        b = hb.batch(0, 0)
+        leaves = [b.ctrl, b.invscale, b.position, b.eps, b.sigma]
+        for t in leaves:
+            t.requires_grad_(True)
+        ll, _ = ops.score_tokens(b, imgs, ps=ps)
+        grads = torch.autograd.grad(ll.sum(), leaves)
+        g_host["ll"].copy_(ll.detach(), non_blocking=True)
+        for k, g in zip(("ctrl", "invscale", "position", "eps", "sigma"), grads):
+            g_host[k].copy_(g, non_blocking=True)
+    _, wall_bwd_e2e_ms, _ = timed(step_bwd_e2e, n_bwd, 5)
+    bwd_h2d = hb.nbytes
+    bwd_d2h = sum(t.numel() * 4 for t in g_host.values())
+
+    # ---- live FP32 FMA peak (roofline denominator) ----
     scratch = torch.zeros(1, device=dev)
-    import ctypes
     iters, blocks = 4096, 148 * 8
+    probe = lambda: _lib.check(_lib.lib().bpl_fp32_probe(ctypes.c_void_p(scratch.data_ptr()), iters, blocks,
+                                                         ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
     for _ in range(2):
-        _lib.check(_lib.lib().bpl_fp32_probe(ctypes.c_void_p(scratch.data_ptr()), iters, blocks,
-                                             ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        probe()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    _lib.check(_lib.lib().bpl_fp32_probe(ctypes.c_void_p(scratch.data_ptr()), iters, blocks,
-                                         ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
-    b.record(); torch.cuda.synchronize()
+    a.record(); probe(); b.record(); torch.cuda.synchronize()
     fp32_peak = (blocks * 1024.0 * iters * 8 * 2) / (a.elapsed_time(b) * 1e-3) / 1e12
+    clocks = sampler.stop() if sampler else None
+
+    # ---- secondary single-GPU objects (N=1 only) ----
+    config1 = config2 = None
+    if world == 1:
+        w1 = workload.synth_tokens(CFG1_BATCH, seed=CFG1_SEED, sigma_mode="uniform")
+        S1, _ = mean_sk(w1)
+        b1 = workload.to_device(w1, dev)
+        st1 = lambda: ops.score_tokens(b1, imgs, ps=ps)
+        ms1, _, _ = timed(st1, 200, 10)
+        k1 = []
+        for i in range(13):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); st1(); b.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                k1.append(a.elapsed_time(b))
+        k1_ms = float(np.mean(k1))
+        config1 = {"workload": "configs[1]: 4096 synthetic tokens (seed 1234) scored against one image on 1 GPU",
+                   "value": CFG1_BATCH * 200 / (ms1 * 1e-3), "unit": UNIT, "ms_per_step": ms1 / 200,
+                   "kernel_ms_l2_flushed": k1_ms,
+                   "roofline_frac": (CFG1_BATCH / (k1_ms * 1e-3)) * flops_fwd(S1) / 1e12 / fp32_peak}
+        sys.path.insert(0, os.path.join(ROOT, "examples"))
+        import fit_parses
+        r = fit_parses.fit(P=1024, steps=100, device=str(dev))
+        config2 = {"workload": "configs[2]: 1024 parses x 100 Adam steps (fused fwd+bwd, fused Adam, clamps; one CUDA graph per step)",
+                   "seconds": r["seconds"], "particles_per_s": r["particles_per_s"], "final_mean_ll": r["final_mean_ll"]}
 
     if rank != 0:
         if world > 1:
@@ -380,39 +452,52 @@ def run_gpu(args):
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    value = world * BATCH * args.steps / (ms_total * 1e-3)
-    e2e = world * BATCH * args.steps / (ms_e2e * 1e-3)
-    k_rate = BATCH / (k_ms * 1e-3)
+    value = P_total * steps / (ms_dev * 1e-3)
+    e2e = P_total * steps / (wall_e2e_ms * 1e-3)
+    k_rate = P_rank / (k_ms * 1e-3)
     ach_tf = k_rate * flops_fwd(Sbar) / 1e12
+    peak_note = ("live FFMA probe (bpl_fp32_probe) in this run; MEASURED_PEAKS.json holds no CUDA-core FP32 figure, and "
+                 "SURVEY.md 8(d) shows the path is FP32-issue/shared-memory bound, not HBM")
     roofline = {"bound": "fp32", "achieved": ach_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach_tf / fp32_peak,
-                "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "kernel": "bpl_forward1s_kernel<false>", "kernel_ms": k_ms,
-                "flop_per_particle": flops_fwd(Sbar), "mean_substrokes": Sbar,
-                "peak_source": "live FFMA probe (bpl_fp32_probe) in this run; MEASURED_PEAKS.json holds no CUDA-core FP32 "
-                               "figure, and SURVEY.md 8(d) shows the path is FP32-issue/shared-memory bound, not HBM",
+                "traffic": None if NCU_DRAM_BYTES_PER_PARTICLE is None else NCU_DRAM_BYTES_PER_PARTICLE * P_rank,
+                "kernel": "bpl_forward1s_kernel<false>", "kernel_ms": k_ms, "particles_per_launch": P_rank,
+                "flop_per_particle": flops_fwd(Sbar), "mean_substrokes": Sbar, "mean_strokes": Kbar, "peak_source": peak_note,
                 "hbm": {"achieved": k_rate * hbm_bytes(Sbar, Kbar) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": k_rate * hbm_bytes(Sbar, Kbar) / 1e9 / hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
+    bwd_rate = BWD_BATCH / (kb_ms * 1e-3)
+    fwd_bwd = {"value": world * BWD_BATCH * n_bwd / (ms_bwd * 1e-3), "unit": UNIT, "batch_per_gpu": BWD_BATCH, "steps": n_bwd,
+               "scaling": "weak", "ms_per_step": ms_bwd / n_bwd,
+               "roofline": {"bound": "fp32", "achieved": bwd_rate * flops_fwd_bwd(Sb) / 1e12, "peak": fp32_peak,
+                            "unit": "TFLOP/s", "frac": bwd_rate * flops_fwd_bwd(Sb) / 1e12 / fp32_peak, "traffic": None,
+                            "kernel": "bpl_backward_kernel<false>", "kernel_ms": kb_ms, "flop_per_particle": flops_fwd_bwd(Sb),
+                            "mean_substrokes": Sb},
+               "e2e": {"value": world * BWD_BATCH * n_bwd / (wall_bwd_e2e_ms * 1e-3), "unit": UNIT,
+                       "h2d_bytes_per_step": int(bwd_h2d), "d2h_bytes_per_step": int(bwd_d2h)}}
     cores = os.cpu_count() or 1
-    cpu = None
+    cpu = cpu_torch = None
     if world == 1:
         import oracle
         cores = oracle.set_threads(cores)
-        C = np.load(os.path.join(ROOT, "pybpl_b200", "data", "basis_5_200.npy"))
-        cv, cn, cdt, cpasses = cpu_baseline_bounded(w0, img_np, C)
+        ws, img_cpu, C = cpu_sample()
+        cv, cn, cdt, cpasses = oracle_rate(ws, img_cpu, C, budget_s=args.cpu_budget * 1.2)
         cpu = {"value": cv, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"the step's {BATCH} tokens x {cpasses} passes = {cn} particles, C oracle port (fp32), OpenMP over tokens, "
-                         f"{cdt:.1f} s wall on {cores} cores"}
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(world, {"mean_strokes": Kbar, "mean_substrokes": Sbar}),
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-            "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu,
-            "clocks": clocks, "wall_s": wall,
-            "fwd_bwd": {"value": world * 1024 * n_bwd / (ms_bwd * 1e-3), "unit": UNIT, "batch_per_gpu": 1024,
-                        "ms_per_step": ms_bwd / n_bwd,
-                        "achieved_tflops": (1024 * n_bwd / (ms_bwd * 1e-3)) * flops_fwd_bwd(Sb) / 1e12}}
+               "sample": f"{CPU_SAMPLE} particles of sweep block 0 x {cpasses} passes = {cn} particles, C oracle port (fp32), OpenMP "
+                         f"over tokens, {cdt:.1f} s wall on {cores} cores"}
+        cpu_torch = torch_reference_rate(ws, img_cpu, budget_s=args.cpu_budget)
+        wbs = workload.permute(wb, np.arange(256))
+        gv, gn, gdt, gp = oracle_rate(wbs, img_cpu, C, grad=True, budget_s=6.0)
+        fwd_bwd["cpu_baseline"] = {"value": gv, "unit": UNIT, "cores": cores, "kind": "port",
+                                   "sample": f"256 of the step's parses x {gp} passes, C oracle port fwd+bwd, {gdt:.1f} s wall"}
+        fwd_bwd["cpu_baseline_torch"] = torch_reference_rate(wbs, img_cpu, grad=True, budget_s=8.0)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_dev / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": sweep_config(world),
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "timing": "wall clock around all steps", "chunk": E2E_CHUNK},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "cpu_baseline_torch": cpu_torch,
+            "clocks": clocks, "wall_s": wall_dev_ms * 1e-3, "logsumexp": {"device": lse_dev, "e2e": lse_e2e},
+            "particles_per_rank": P_rank, "fwd_bwd": fwd_bwd, "config1": config1, "config2": config2}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -443,9 +528,10 @@ def main():
     _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-budget", type=float, default=10.0, help="seconds per CPU-baseline leg (tests shorten it)")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps > 20:

@@ -264,6 +264,16 @@ int bpl_pack_images_f32(const float *img, int T, uint32_t *bits, int *bad, void 
  * Bernoulli log_prob.  One CTA per token; the image never leaves shared memory. */
 int bpl_score_tokens(const bpl_params *ps, const bpl_token_batch *b, const bpl_targets *t, const bpl_fwd_out *out,
                      void *stream);
+/* Particle sweep (BASELINE.json configs[3]): bpl_score_tokens with one target per token, plus the log-sum-exp partial
+ * of the launch's scores produced by the same kernel (each CTA keeps a running (max, sum exp) of its tokens, the CTA
+ * that finishes last combines them): lse[0] = max_p ll[p], lse[1] = sum_p exp(ll[p] - max) (dev float[2]; NaN scores
+ * are skipped).  accumulate != 0 merges with the value already in lse, so a sweep scored in several launches still ends
+ * with one pair.  lse_scratch: dev float[2 * BPL_LSE_SCRATCH_CTAS], private to the call while it runs.  out->ll may be
+ * NULL when only the partial is wanted.  Semantics of the reduction: torch.logsumexp over
+ * CharacterImageDist.score_image values (pybpl/model/image_dist.py:60-80); the reference has no batched counterpart. */
+#define BPL_LSE_SCRATCH_CTAS 2048
+int bpl_score_tokens_lse(const bpl_params *ps, const bpl_token_batch *b, const bpl_targets *t, const bpl_fwd_out *out,
+                         float *lse, float *lse_scratch, int accumulate, void *stream);
 /* order[P] <- the tokens by decreasing sub-stroke count (only the CSR offsets of b are read).  No reference
  * counterpart: the reference renders one token per Python call. */
 int bpl_order_tokens(const bpl_token_batch *b, int *order, void *stream);
@@ -286,6 +296,9 @@ int bpl_token_points(const bpl_params *ps, const bpl_token_batch *b, float *moto
 /* ---- particle sweep reduction (per-GPU partial of the final log-sum-exp) ------------- */
 /* out[0] = max_p ll[p], out[1] = sum_p exp(ll[p] - max)   (dev float[2]); one launch. */
 int bpl_logsumexp_partial(const float *ll, int n, float *out2, void *stream);
+/* out[0] = log sum_i parts[2i+1] * exp(parts[2i]) over n (max, sum-exp) pairs (dev), e.g. the ranks' partials after
+ * the all-gather: the sweep's final log-sum-exp without leaving the device. */
+int bpl_logsumexp_combine(const float *parts, int n, float *out, void *stream);
 
 /* Roofline probe: `blocks` CTAs x 1024 threads x `iters` x 8 FFMA (2 flop each); scratch = 1 dev float. */
 int bpl_fp32_probe(float *scratch, int iters, int blocks, void *stream);

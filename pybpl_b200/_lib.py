@@ -102,6 +102,8 @@ EXPORTS = {
     "bpl_pack_images_f32": (ctypes.c_int, [vp, ctypes.c_int, vp, vp, vp]),
     "bpl_score_tokens": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.POINTER(TokenBatchC), ctypes.POINTER(Targets),
                                         ctypes.POINTER(FwdOut), vp]),
+    "bpl_score_tokens_lse": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.POINTER(TokenBatchC), ctypes.POINTER(Targets),
+                                            ctypes.POINTER(FwdOut), vp, vp, ctypes.c_int, vp]),
     "bpl_order_tokens": (ctypes.c_int, [ctypes.POINTER(TokenBatchC), vp, vp]),
     "bpl_score_tokens_grad": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.POINTER(TokenBatchC),
                                              ctypes.POINTER(Targets), ctypes.POINTER(FwdOut), ctypes.POINTER(Grads), vp]),
@@ -119,11 +121,15 @@ EXPORTS = {
     "bpl_score_type_prior": (ctypes.c_int, [ctypes.POINTER(TypeLibC), ctypes.POINTER(TypeLogTablesC), ctypes.c_int, vp, vp, vp,
                                             ctypes.POINTER(TokenTypeC), vp, vp, vp, vp]),
     "bpl_logsumexp_partial": (ctypes.c_int, [vp, ctypes.c_int, vp, vp]),
+    "bpl_logsumexp_combine": (ctypes.c_int, [vp, ctypes.c_int, vp, vp]),
     "bpl_fp32_probe": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, vp]),
     "bpl_launch_count": (ctypes.c_longlong, []),
 }
 
 _lib = None
+
+
+LSE_SCRATCH_CTAS = 2048      # BPL_LSE_SCRATCH_CTAS (include/pybpl_b200.h)
 
 
 class BplError(RuntimeError):

@@ -233,6 +233,7 @@ __global__ void __launch_bounds__(S_THREADS, S_CTAS_PER_SM) bpl_forward1s_kernel
     long long pt_t0 = clock64();
 #endif
 
+    float run_m = -INFINITY, run_s = 0.0f;                      // thread 0: log-sum-exp of this CTA's scores (a.lse)
     int item = blockIdx.x;                                      // position in the work queue (advanced by thread 0 only)
     int p = a.order ? a.order[item] : item;                     // the token it stands for
     while (p < a.n_tokens) {
@@ -354,6 +355,7 @@ __global__ void __launch_bounds__(S_THREADS, S_CTAS_PER_SM) bpl_forward1s_kernel
             if (threadIdx.x == 0) {
                 if (a.ll) a.ll[p] = bad ? nanf("") : (float)v[0];
                 if (a.off_page) a.off_page[p] = bad ? (uint8_t)255 : (uint8_t)(ms->off_page != 0);
+                if (a.lse && !bad) lse_push(run_m, run_s, (float)v[0]);
                 ms->ones_acc = 0;
                 ms->next_item = p_next;
             }
@@ -416,7 +418,8 @@ __global__ void __launch_bounds__(S_THREADS, S_CTAS_PER_SM) bpl_forward1s_kernel
         p = ms->next_item;      // rewritten only at the end of the next iteration, many barriers from here
         BPL_PT(5);
     }
-    if (threadIdx.x == 0) sched_finish(a);
+    if (!AP && a.lse) lse_finish(a, run_m, run_s, &ms->next_item);
+    else if (threadIdx.x == 0) sched_finish(a);
 #ifdef BPL_PHASE_TIMING
     if (threadIdx.x == 0 && a.pt_buf)
         for (int i = 0; i < 8; ++i) a.pt_buf[blockIdx.x * 16 + i] = (float)pt_acc[i];

@@ -57,6 +57,10 @@ struct KArgs {
     float *g_ctrl, *g_invscale, *g_position, *g_affine, *g_pts, *g_eps, *g_sigma;
     float *pt_buf;           // phase-timing counters (only read by -DBPL_PHASE_TIMING builds)
     Sched *sched;            // work queue of this launch; NULL = fixed stride (BPL_STATIC_SCHED=1, A/B only)
+    // particle sweep: log-sum-exp partial of this launch's scores, produced by the scoring kernel itself
+    float *lse;              // [2] (max, sum exp(ll - max)); NULL = not wanted
+    float *lse_scratch;      // [2 * gridDim.x] per-CTA partials
+    int lse_accumulate;      // merge with the value already in lse (a sweep scored in several launches)
 };
 
 // thread 0 only: the item after `cur`
@@ -74,6 +78,42 @@ __device__ __forceinline__ void sched_finish(const KArgs &a) {
     if (!a.sched) return;
     __threadfence();
     if (atomicAdd(&a.sched->done, 1u) == gridDim.x - 1u) { a.sched->next = 0u; a.sched->done = 0u; }
+}
+
+// Online log-sum-exp: (m, s) stands for m + log s.  -inf scores add nothing; NaN (a token beyond the per-CTA limits)
+// is skipped.
+__device__ __forceinline__ void lse_push(float &m, float &s, float x) {
+    if (!(x > -INFINITY)) return;                 // -inf or NaN
+    if (x > m) { s = fmaf(s, __expf(m - x), 1.0f); m = x; }
+    else s += __expf(x - m);
+}
+__device__ __forceinline__ void lse_merge(float &m, float &s, float m2, float s2) {
+    if (!(m2 > -INFINITY) || !(s2 > 0.0f)) return;
+    if (m2 > m) { s = fmaf(s, __expf(m - m2), s2); m = m2; }
+    else s = fmaf(s2, __expf(m2 - m), s);
+}
+// Whole CTA, once, after its last token (replaces sched_finish when a.lse is set): every CTA publishes its partial,
+// the CTA that finishes last combines them (one warp) and resets the queue slot.
+__device__ __forceinline__ void lse_finish(const KArgs &a, float m, float s, int *flag) {
+    if (threadIdx.x == 0) {
+        a.lse_scratch[2 * blockIdx.x] = m;
+        a.lse_scratch[2 * blockIdx.x + 1] = s;
+        __threadfence();
+        *flag = (atomicAdd(&a.sched->done, 1u) == gridDim.x - 1u);
+    }
+    __syncthreads();
+    if (!*flag || threadIdx.x >= 32) return;
+    __threadfence();
+    const int lane = threadIdx.x;
+    float M = -INFINITY, S = 0.0f;
+    for (int i = lane; i < (int)gridDim.x; i += 32) lse_merge(M, S, __ldcg(a.lse_scratch + 2 * i), __ldcg(a.lse_scratch + 2 * i + 1));
+    if (a.lse_accumulate && lane == 0) lse_merge(M, S, a.lse[0], a.lse[1]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float m2 = __shfl_xor_sync(0xffffffffu, M, o), s2 = __shfl_xor_sync(0xffffffffu, S, o);
+        lse_merge(M, S, m2, s2);
+    }
+    if (lane == 0) { a.lse[0] = M; a.lse[1] = S; a.sched->next = 0u; a.sched->done = 0u; }
 }
 
 // Per-CTA bookkeeping in shared memory.
@@ -1174,9 +1214,14 @@ static DevInfo dev_info() {
     return info;
 }
 
+int sm_count() {      // SMs of the current device (148 on B200); 0 when there is no device
+    const DevInfo di = dev_info();
+    return di.ok ? di.sm_count : 0;
+}
+
 template <class K>
 static int launch(K kernel, int threads, size_t smem, int ctas_per_sm, const KArgs &ka, cudaStream_t st,
-                  int work_items = -1) {
+                  int work_items = -1, bool need_queue = false) {
     const DevInfo di = dev_info();
     if (!di.ok) { set_error("%s", "no CUDA device"); return BPL_ENODEV; }
     if ((size_t)di.smem_optin < smem) { set_error("%s", "device lacks the shared memory this kernel needs (built for sm_100a)"); return BPL_ENODEV; }
@@ -1188,7 +1233,7 @@ static int launch(K kernel, int threads, size_t smem, int ctas_per_sm, const KAr
     if (grid <= 0) return 0;
     KArgs kb = ka;
     static const bool static_sched = getenv("BPL_STATIC_SCHED") != nullptr;
-    if (!static_sched) {
+    if (!static_sched || need_queue) {
         static std::atomic<unsigned> slot{0};
         static thread_local int ring_dev = -1;
         static thread_local Sched *ring = nullptr;      // g_sched has one instance per device
@@ -1294,6 +1339,27 @@ int bpl_score_tokens(const bpl_params *ps, const bpl_token_batch *b, const bpl_t
     return launch(bpl_forward_kernel<false>, FWD_THREADS, sizeof(FwdSmem), FWD_CTAS_PER_SM, ka, (cudaStream_t)stream);
 }
 
+int bpl_score_tokens_lse(const bpl_params *ps, const bpl_token_batch *b, const bpl_targets *t, const bpl_fwd_out *out,
+                         float *lse, float *lse_scratch, int accumulate, void *stream) {
+    if (!lse || !lse_scratch) { set_error("%s", "bpl_score_tokens_lse: lse and lse_scratch are required"); return BPL_EINVAL; }
+    if (!b) { set_error("%s", "batch is NULL"); return BPL_EINVAL; }
+    KArgs ka{};
+    int r = fill_common(ka, ps, t, out, nullptr);
+    if (r) return r;
+    if ((r = fill_tokens(ka, b))) return r;
+    if (!ka.image_bits || ka.pimg || ka.all_pairs) { set_error("%s", "bpl_score_tokens_lse scores one target per token (no pimg, no all_pairs)"); return BPL_EINVAL; }
+    if (b->n_tokens == 0) {      // an empty shard: (-inf, 0) unless accumulating
+        if (!accumulate) {
+            const float init[2] = {-INFINITY, 0.0f};
+            cudaError_t e = cudaMemcpyAsync(lse, init, sizeof(init), cudaMemcpyHostToDevice, (cudaStream_t)stream);
+            if (e != cudaSuccess) { set_error("cudaMemcpyAsync: %s", cudaGetErrorString(e)); return (int)e; }
+        }
+        return 0;
+    }
+    ka.lse = lse; ka.lse_scratch = lse_scratch; ka.lse_accumulate = accumulate;
+    return launch(bpl_forward1s_kernel<false>, S_THREADS, sizeof(Fwd1sSmem), S_CTAS_PER_SM, ka, (cudaStream_t)stream, -1, true);
+}
+
 int bpl_render_strokes(const bpl_params *ps, const bpl_stroke_batch *b, const bpl_targets *t, const bpl_fwd_out *out,
                        void *stream) {
     if (b && b->n_tokens == 0) return 0;
@@ -1327,7 +1393,8 @@ int bpl_token_points(const bpl_params *ps, const bpl_token_batch *b, float *moto
     if (r) return r;
     if ((r = fill_tokens(ka, b))) return r;
     if (ka.n_tokens <= 0) return 0;
-    int grid = ka.n_tokens < 148 * 8 ? ka.n_tokens : 148 * 8;
+    const int cap = sm_count() * 8;
+    int grid = ka.n_tokens < cap ? ka.n_tokens : cap;
     bpl_points_kernel<<<grid, 256, sizeof(PtsSmem), (cudaStream_t)stream>>>(ka, motor, mask_out, fl, ce, n_in);
     count_launch(1);
     cudaError_t e = cudaGetLastError();

@@ -2,6 +2,8 @@
 // image bit-packing and the per-GPU log-sum-exp partial.  Small kernels around the fused
 // render+score kernels in bpl_render.cu; all HBM-bound or latency-bound, no tensor cores.
 #include <cuda_runtime.h>
+
+#include <atomic>
 #include <math.h>
 #include <stdlib.h>
 
@@ -11,6 +13,7 @@ namespace bpl {
 void set_error(const char *fmt, const char *detail);
 const char *last_error();
 void count_launch(int n);
+int sm_count();
 long long launch_count();
 
 // ---- host: basis table (pybpl/splines.py:19-93) ----------------------------------------------
@@ -267,30 +270,63 @@ __global__ void pack_images_kernel(const T *__restrict__ img, int n_img, uint32_
     }
 }
 
-// out[0] = max ll, out[1] = sum exp(ll - max): one CTA, one pass held in registers where possible.
-__global__ void logsumexp_partial_kernel(const float *__restrict__ ll, int n, float *__restrict__ out2) {
-    __shared__ float red[32];
+// out[0] = max ll, out[1] = sum exp(ll - max).  Grid-stride online log-sum-exp per thread ((m, s) stands for
+// m + log s; -inf and NaN entries add nothing), combined per warp, per CTA and -- by the CTA that finishes last --
+// over the CTAs' partials parked in one slot of a small ring (a slot is all-zero again when its launch completes,
+// so launches on different streams never share state).
+constexpr int LSE_MAX_CTAS = 256, LSE_RING = 64, LSE_THREADS = 512;
+struct LseSlot { unsigned done; float part[2 * LSE_MAX_CTAS]; };
+__device__ LseSlot g_lse_ring[LSE_RING];
+
+__device__ __forceinline__ void lse_merge2(float &m, float &s, float m2, float s2) {
+    if (!(m2 > -INFINITY) || !(s2 > 0.0f)) return;
+    if (m2 > m) { s = fmaf(s, __expf(m - m2), s2); m = m2; }
+    else s = fmaf(s2, __expf(m2 - m), s);
+}
+__device__ __forceinline__ void lse_warp(float &m, float &s) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+        lse_merge2(m, s, m2, s2);
+    }
+}
+
+__global__ void __launch_bounds__(LSE_THREADS) logsumexp_partial_kernel(const float *__restrict__ ll, int n,
+                                                                        float *__restrict__ out2, LseSlot *slot) {
+    __shared__ float rm[32], rs[32];
+    __shared__ int last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    float m = -INFINITY;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, ll[i]);
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (lane == 0) red[warp] = m;
-    __syncthreads();
-    m = (lane < nw) ? red[lane] : -INFINITY;
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    __syncthreads();
-    double s = 0.0;
-    if (m > -INFINITY)
-        for (int i = threadIdx.x; i < n; i += blockDim.x) s += (double)expf(ll[i] - m);
-    s = warp_sum(s);
-    __shared__ double reds[32];
-    if (lane == 0) reds[warp] = s;
+    float m = -INFINITY, s = 0.0f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        lse_merge2(m, s, ll[i], 1.0f);
+    lse_warp(m, s);
+    if (lane == 0) { rm[warp] = m; rs[warp] = s; }
     __syncthreads();
     if (warp == 0) {
-        s = (lane < nw) ? reds[lane] : 0.0;
-        s = warp_sum(s);
-        if (lane == 0) { out2[0] = m; out2[1] = (float)s; }
+        m = lane < nw ? rm[lane] : -INFINITY; s = lane < nw ? rs[lane] : 0.0f;
+        lse_warp(m, s);
+        if (lane == 0) {
+            slot->part[2 * blockIdx.x] = m; slot->part[2 * blockIdx.x + 1] = s;
+            __threadfence();
+            last = (atomicAdd(&slot->done, 1u) == gridDim.x - 1u);
+        }
     }
+    __syncthreads();
+    if (!last || warp != 0) return;
+    __threadfence();
+    m = -INFINITY; s = 0.0f;
+    for (int i = lane; i < (int)gridDim.x; i += 32) lse_merge2(m, s, __ldcg(slot->part + 2 * i), __ldcg(slot->part + 2 * i + 1));
+    lse_warp(m, s);
+    if (lane == 0) { out2[0] = m; out2[1] = s; slot->done = 0u; }
+}
+
+// out[0] = log sum_i s_i exp(m_i) over n (max, sum-exp) pairs, e.g. the ranks' partials after the all-gather
+__global__ void logsumexp_combine_kernel(const float *__restrict__ parts, int n, float *__restrict__ out) {
+    const int lane = threadIdx.x;
+    float m = -INFINITY, s = 0.0f;
+    for (int i = lane; i < n; i += 32) lse_merge2(m, s, parts[2 * i], parts[2 * i + 1]);
+    lse_warp(m, s);
+    if (lane == 0) out[0] = (m > -INFINITY && s > 0.0f) ? (float)((double)m + log((double)s)) : -INFINITY;
 }
 
 // Live FP32 peak probe for the roofline denominator (MEASURED_PEAKS.json has HBM and bf16-tensor
@@ -316,7 +352,8 @@ static int check_launch(const char *what) {
 static int grid_for(long long work_items, int per_block) {
     long long g = (work_items + per_block - 1) / per_block;
     if (g < 1) g = 1;
-    if (g > 148 * 16) g = 148 * 16;
+    const long long cap = (long long)sm_count() * 16;
+    if (cap > 0 && g > cap) g = cap;
     return (int)g;
 }
 
@@ -437,8 +474,28 @@ int bpl_fp32_probe(float *scratch, int iters, int blocks, void *stream) {
 
 int bpl_logsumexp_partial(const float *ll, int n, float *out2, void *stream) {
     if (!ll || !out2 || n < 0) { set_error("%s", "bad logsumexp arguments"); return BPL_EINVAL; }
-    logsumexp_partial_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(ll, n, out2);
+    static std::atomic<unsigned> next_slot{0};
+    static thread_local int ring_dev = -1;
+    static thread_local LseSlot *ring = nullptr;      // one instance of g_lse_ring per device
+    int dev = -1;
+    cudaGetDevice(&dev);
+    if (dev != ring_dev) {
+        const cudaError_t es = cudaGetSymbolAddress(reinterpret_cast<void **>(&ring), g_lse_ring);
+        if (es != cudaSuccess) { set_error("cudaGetSymbolAddress: %s", cudaGetErrorString(es)); return (int)es; }
+        ring_dev = dev;
+    }
+    int grid = (n + LSE_THREADS * 8 - 1) / (LSE_THREADS * 8);
+    const int cap = sm_count() * 1 < LSE_MAX_CTAS ? sm_count() : LSE_MAX_CTAS;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    logsumexp_partial_kernel<<<grid, LSE_THREADS, 0, (cudaStream_t)stream>>>(ll, n, out2, ring + (next_slot.fetch_add(1u) % LSE_RING));
     return check_launch("logsumexp_partial");
+}
+
+int bpl_logsumexp_combine(const float *parts, int n, float *out, void *stream) {
+    if (!parts || !out || n < 0) { set_error("%s", "bad logsumexp_combine arguments"); return BPL_EINVAL; }
+    logsumexp_combine_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(parts, n, out);
+    return check_launch("logsumexp_combine");
 }
 
 }  // extern "C"

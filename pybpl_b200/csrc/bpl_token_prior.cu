@@ -22,6 +22,7 @@
 namespace bpl {
 void set_error(const char *fmt, const char *detail);
 void count_launch(int n);
+int sm_count();
 
 namespace {
 
@@ -259,7 +260,8 @@ extern "C" int bpl_score_token_prior(const bpl_token_prior_params *c, const bpl_
     if (g) a.g = *g;
     const int wpb = 8;
     long long blocks = ((long long)b->n_tokens + wpb - 1) / wpb;
-    if (blocks > 148 * 32) blocks = 148 * 32;
+    const int cap = sm_count() * 32;
+    if (cap > 0 && blocks > cap) blocks = cap;
     token_prior_kernel<<<(int)blocks, wpb * 32, 0, (cudaStream_t)stream>>>(a);
     count_launch(1);
     const cudaError_t e = cudaGetLastError();

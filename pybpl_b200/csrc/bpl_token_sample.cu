@@ -27,6 +27,7 @@
 namespace bpl {
 void set_error(const char *fmt, const char *detail);
 void count_launch(int n);
+int sm_count();
 
 namespace {
 
@@ -117,7 +118,8 @@ extern "C" int bpl_sample_tokens(const bpl_token_prior_params *c, const bpl_toke
     a.ty = *ty; a.c = *c; a.seed = seed; a.first_token = first_token;
     a.ctrl = ctrl; a.invscale = invscale; a.position = position; a.eval_spot = eval_spot;
     long long blocks = ((long long)b->n_tokens + 127) / 128;
-    if (blocks > 148 * 64) blocks = 148 * 64;
+    const int cap = sm_count() * 64;
+    if (cap > 0 && blocks > cap) blocks = cap;
     token_sample_kernel<<<(int)blocks, 128, 0, (cudaStream_t)stream>>>(a);
     count_launch(1);
     const cudaError_t e = cudaGetLastError();

@@ -19,6 +19,7 @@
 namespace bpl {
 void set_error(const char *fmt, const char *detail);
 void count_launch(int n);
+int sm_count();
 
 namespace {
 
@@ -132,7 +133,8 @@ extern "C" int bpl_score_type_prior(const bpl_type_lib *lib, const bpl_type_logt
     a.ty = *ty; a.ll = ll; a.g_ctrl_type = g_ctrl_type; a.g_invscale_type = g_invscale_type;
     const int wpb = 8;
     long long blocks = ((long long)n_types + wpb - 1) / wpb;
-    if (blocks > 148 * 32) blocks = 148 * 32;
+    const int cap = sm_count() * 32;
+    if (cap > 0 && blocks > cap) blocks = cap;
     type_prior_kernel<<<(int)blocks, wpb * 32, 0, (cudaStream_t)stream>>>(a);
     count_launch(1);
     const cudaError_t e = cudaGetLastError();

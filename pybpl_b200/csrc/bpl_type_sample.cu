@@ -32,6 +32,7 @@
 namespace bpl {
 void set_error(const char *fmt, const char *detail);
 void count_launch(int n);
+int sm_count();
 
 namespace {
 
@@ -183,7 +184,8 @@ extern "C" int bpl_sample_types(const bpl_type_lib *lib, int n_types, unsigned l
     a.tok_stroke_off = tok_stroke_off; a.tok_sub_off = tok_sub_off; a.n_strokes = n_strokes; a.n_subs = n_subs;
     if (out) a.o = *out;
     long long blocks = ((long long)n_types + 127) / 128;
-    if (blocks > 148 * 64) blocks = 148 * 64;
+    const int cap = sm_count() * 64;
+    if (cap > 0 && blocks > cap) blocks = cap;
     type_sample_kernel<<<(int)blocks, 128, 0, (cudaStream_t)stream>>>(a);
     count_launch(1);
     const cudaError_t e = cudaGetLastError();

@@ -147,7 +147,7 @@ class TokenBatch:
     """
 
     def __init__(self, tok_stroke_off, stroke_sub_off, ctrl, invscale, position, eps, sigma, affine=None, neval=200,
-                 check_limits=True):
+                 check_limits=True, use_order=True):
         dev = ctrl.device
         _need_cuda(ctrl, "ctrl")
         if check_limits:
@@ -174,6 +174,7 @@ class TokenBatch:
         self._sub_token = None
         self._stroke_token = None
         self._order = None
+        self.use_order = use_order      # False: index order (streamed chunks: the order kernel would cost more than it saves)
 
     # Processing order for the persistent kernels: expensive tokens first, so that a launch of a few thousand tokens
     # (a few dozen per SM) does not end with one SM still busy on a large one.  It depends only on the CSR offsets,
@@ -181,7 +182,7 @@ class TokenBatch:
     ORDER_MAX_TOKENS = 65536      # measured gain: +6.7 % at 4 096 tokens, +2.5 % at 8 192, +1.2 % at 16 384
 
     def order_ptr(self):
-        if self.P > self.ORDER_MAX_TOKENS or self.P < 2 or os.environ.get("BPL_NO_ORDER"):      # (env: A/B aid)
+        if not self.use_order or self.P > self.ORDER_MAX_TOKENS or self.P < 2 or os.environ.get("BPL_NO_ORDER"):      # (env: A/B aid)
             return None
         if self._order is None:
             order = torch.empty(self.P, dtype=torch.int32, device=self.device)
@@ -278,6 +279,76 @@ class HostStagedBatch:
         return batch, image
 
 
+class HostSweepStager:
+    """Streams a HOST-resident numpy token batch (pybpl_b200.workload layout) to the GPU in chunks of `chunk` tokens.
+
+    pack(c, slot) is the host-side ragged packing of chunk c: the chunk's slices of the CSR offsets (rebased to the
+    chunk) and of ctrl / invscale / position / eps / sigma are copied into ONE pinned staging buffer (16-byte aligned
+    sections sized for the largest chunk); upload(slot) is one asynchronous H2D copy of that buffer; batch(c, slot)
+    views the device copy as a TokenBatch.  Two slots let the packing / copy of chunk c+1 overlap the kernels of c."""
+
+    _SECTIONS = (("tok_stroke_off", np.int32, 1), ("stroke_sub_off", np.int32, 1), ("ctrl", np.float32, 2 * NCPT),
+                 ("invscale", np.float32, 1), ("position", np.float32, 2), ("eps", np.float32, 1), ("sigma", np.float32, 1))
+
+    def __init__(self, w, device, chunk=65536, slots=2, pin=True):
+        self.device = torch.device(device)
+        self.w = w
+        self.neval = int(w.get("neval", 200))
+        P = int(w["P"])
+        tso, sso = w["tok_stroke_off"].astype(np.int64), w["stroke_sub_off"].astype(np.int64)
+        self.chunks = []
+        for c0 in range(0, P, chunk):
+            c1 = min(P, c0 + chunk)
+            k0, k1 = int(tso[c0]), int(tso[c1])
+            self.chunks.append((c0, c1, k0, k1, int(sso[k0]), int(sso[k1])))
+        n = max((c[1] - c[0] for c in self.chunks), default=0)
+        K = max((c[3] - c[2] for c in self.chunks), default=0)
+        S = max((c[5] - c[4] for c in self.chunks), default=0)
+        rows = dict(tok_stroke_off=n + 1, stroke_sub_off=K + 1, ctrl=S, invscale=S, position=K, eps=n, sigma=n)
+        self.layout, off = {}, 0
+        for name, dt, width in self._SECTIONS:
+            nb = rows[name] * width * 4
+            self.layout[name] = (off, dt, width)
+            off = (off + nb + 15) // 16 * 16
+        self.nbytes = max(off, 16)
+        self.host = [torch.empty(self.nbytes, dtype=torch.uint8) for _ in range(slots)]
+        if pin:
+            self.host = [h.pin_memory() for h in self.host]
+        self.host_np = [h.numpy() for h in self.host]
+        self.dev = [torch.empty(self.nbytes, dtype=torch.uint8, device=self.device) for _ in range(slots)]
+
+    def _host_view(self, slot, name, rows):
+        off, dt, width = self.layout[name]
+        v = self.host_np[slot][off:off + rows * width * 4].view(dt)
+        return v.reshape(rows, width) if width > 1 else v
+
+    def pack(self, c, slot):
+        c0, c1, k0, k1, s0, s1 = self.chunks[c]
+        w = self.w
+        np.subtract(w["tok_stroke_off"][c0:c1 + 1], k0, out=self._host_view(slot, "tok_stroke_off", c1 - c0 + 1))
+        np.subtract(w["stroke_sub_off"][k0:k1 + 1], s0, out=self._host_view(slot, "stroke_sub_off", k1 - k0 + 1))
+        np.copyto(self._host_view(slot, "ctrl", s1 - s0), w["ctrl"][s0:s1].reshape(s1 - s0, 2 * NCPT))
+        np.copyto(self._host_view(slot, "invscale", s1 - s0), w["invscale"][s0:s1])
+        np.copyto(self._host_view(slot, "position", k1 - k0), w["position"][k0:k1])
+        np.copyto(self._host_view(slot, "eps", c1 - c0), w["eps"][c0:c1])
+        np.copyto(self._host_view(slot, "sigma", c1 - c0), w["sigma"][c0:c1])
+
+    def upload(self, slot):
+        self.dev[slot].copy_(self.host[slot], non_blocking=True)
+
+    def batch(self, c, slot):
+        c0, c1, k0, k1, s0, s1 = self.chunks[c]
+        d = self.dev[slot]
+
+        def view(name, rows):
+            off, dt, width = self.layout[name]
+            t = d[off:off + rows * width * 4].view(torch.int32 if dt == np.int32 else torch.float32)
+            return t.view(rows, width) if width > 1 else t
+        return TokenBatch(view("tok_stroke_off", c1 - c0 + 1), view("stroke_sub_off", k1 - k0 + 1),
+                          view("ctrl", s1 - s0).view(s1 - s0, NCPT, 2), view("invscale", s1 - s0), view("position", k1 - k0),
+                          view("eps", c1 - c0), view("sigma", c1 - c0), neval=self.neval, check_limits=False, use_order=False)
+
+
 def _targets(images, img_idx):
     t = _lib.Targets()
     if images is not None:
@@ -309,7 +380,7 @@ class _ScoreTokens(torch.autograd.Function):
         out = _lib.FwdOut(ll.data_ptr(), off.data_ptr(), None)
         b = batch.c_struct(ctrl_c, inv_c, pos_c, aff_c, eps_c, sig_c)
         t = _targets(images, img_idx)
-        need = any(ctx.needs_input_grad[:6])
+        need = torch.is_grad_enabled() and any(ctx.needs_input_grad[:6])
         if need:
             g_ctrl = torch.empty_like(ctrl_c); g_inv = torch.empty_like(inv_c); g_pos = torch.empty_like(pos_c)
             g_aff = None if aff_c is None else torch.empty_like(aff_c)
@@ -391,9 +462,51 @@ def score_tokens(batch, images, img_idx=None, ps=None):
         ps = make_params(ps)
     if img_idx is not None:
         img_idx = _i32(img_idx, batch.device)
+        _check_img_idx(img_idx, images)
     ll, off = _ScoreTokens.apply(batch.ctrl, batch.invscale, batch.position, batch.affine, batch.eps, batch.sigma,
                                  batch, images, img_idx, ps)
     return ll, off.bool()
+
+
+def _check_img_idx(img_idx, images):
+    """An index outside [0, T) would read beyond the packed images: one synchronising reduction, once per index tensor."""
+    if not img_idx.numel() or images is None or getattr(img_idx, "_bpl_checked_n", None) == images.n:
+        return
+    if torch.cuda.is_current_stream_capturing():      # a graph capture must not synchronise; checked on the eager warm-up
+        return
+    lo, hi = int(img_idx.min()), int(img_idx.max())
+    if lo < 0 or hi >= images.n:
+        raise IndexError(f"img_idx must lie in [0, {images.n}); got [{lo}, {hi}]")
+    img_idx._bpl_checked_n = images.n                 # the same index tensor is not reduced again (fit loops)
+
+
+class LseState:
+    """Device state of a particle sweep's log-sum-exp partial on one GPU: `partial` = (max, sum exp(ll - max)) and
+    the scratch the fused kernel needs (bpl_score_tokens_lse)."""
+
+    def __init__(self, device):
+        self.partial = torch.tensor([-float("inf"), 0.0], dtype=torch.float32, device=device)
+        self.scratch = torch.empty(2 * _lib.LSE_SCRATCH_CTAS, dtype=torch.float32, device=device)
+
+
+def score_tokens_lse(batch, images, state, accumulate=False, want_ll=True, ps=None):
+    """score_tokens against image 0 plus the launch's log-sum-exp partial, in ONE kernel (forward only, no autograd):
+    returns (ll [P] or None, ink_off_page [P] uint8); state.partial holds (max, sum exp(ll - max)) afterwards, merged
+    with its previous value when `accumulate`."""
+    if not isinstance(ps, _lib.Params):
+        ps = make_params(ps)
+    dev = batch.device
+    P = batch.P
+    tens = [_c32(batch.ctrl), _c32(batch.invscale), _c32(batch.position),
+            None if batch.affine is None else _c32(batch.affine), _c32(batch.eps), _c32(batch.sigma)]
+    ll = torch.empty(P, dtype=torch.float32, device=dev) if want_ll else None
+    off = torch.empty(P, dtype=torch.uint8, device=dev)
+    b = batch.c_struct(*tens)
+    t = _targets(images, None)
+    out = _lib.FwdOut(None if ll is None else ll.data_ptr(), off.data_ptr(), None)
+    check(lib().bpl_score_tokens_lse(ctypes.byref(ps), ctypes.byref(b), ctypes.byref(t), ctypes.byref(out),
+                                     _ptr(state.partial), _ptr(state.scratch), int(bool(accumulate)), _stream(dev)))
+    return ll, off
 
 
 def score_tokens_all_images(batch, images, ps=None):
@@ -715,13 +828,13 @@ class _ScoreTokenPrior(torch.autograd.Function):
         b.n_tokens = batch.P; b.ncpt = NCPT; b.neval = batch.neval
         b.tok_stroke_off = batch.tok_stroke_off.data_ptr(); b.stroke_sub_off = batch.stroke_sub_off.data_ptr()
         b.ctrl = ctrl_c.data_ptr(); b.invscale = inv_c.data_ptr(); b.position = pos_c.data_ptr()
-        sig = _c32(batch.sigma)
-        b.sigma = sig.data_ptr(); b.eps = _c32(batch.eps).data_ptr()
+        sig, eps_c = _c32(batch.sigma), _c32(batch.eps)          # bound to locals: the pointers must outlive the launch
+        b.sigma = sig.data_ptr(); b.eps = eps_c.data_ptr()
         b.basis = basis_table(NCPT, batch.neval, dev).data_ptr()
         ty = _lib.TokenTypeC(ctrl_ty.data_ptr(), inv_ty.data_ptr(), types.rel_cat.data_ptr(), types.attach_ix.data_ptr(),
                              types.attach_subix.data_ptr(), gpos_c.data_ptr(), es_ty.data_ptr(), es_c.data_ptr())
         ll = torch.empty(batch.P, dtype=torch.float32, device=dev)
-        need = any(ctx.needs_input_grad[:8])
+        need = torch.is_grad_enabled() and any(ctx.needs_input_grad[:8])
         if need:
             gs = [torch.empty_like(t) for t in args]
             g = _lib.TokenPriorGrads(*[t.data_ptr() for t in gs])
@@ -774,9 +887,12 @@ def sample_tokens(tok_stroke_off, stroke_sub_off, types, seed, first_token=0, ep
     b.n_tokens = P; b.ncpt = NCPT; b.neval = int(neval)
     b.tok_stroke_off = tso.data_ptr(); b.stroke_sub_off = sso.data_ptr()
     b.basis = basis_table(NCPT, int(neval), dev).data_ptr()
-    ty = _lib.TokenTypeC(_c32(types.ctrl_type).data_ptr(), _c32(types.invscale_type).data_ptr(), types.rel_cat.data_ptr(),
-                         types.attach_ix.data_ptr(), types.attach_subix.data_ptr(), _c32(types.gpos).data_ptr(),
-                         _c32(types.eval_spot_type).data_ptr(), None)
+    # converted copies are bound to locals so that they outlive the launch (a temporary's block could be handed to the
+    # next allocation before the kernel reads it)
+    ct_c, it_c, gp_c, est_c = _c32(types.ctrl_type), _c32(types.invscale_type), _c32(types.gpos), _c32(types.eval_spot_type)
+    ty = _lib.TokenTypeC(ct_c.data_ptr(), it_c.data_ptr(), types.rel_cat.data_ptr(),
+                         types.attach_ix.data_ptr(), types.attach_subix.data_ptr(), gp_c.data_ptr(),
+                         est_c.data_ptr(), None)
     check(lib().bpl_sample_tokens(ctypes.byref(c), ctypes.byref(b), ctypes.byref(ty), int(seed), int(first_token),
                                    ctrl.data_ptr(), inv.data_ptr(), pos.data_ptr(), es.data_ptr(), _stream(dev)))
     full = lambda v: v.to(dev, torch.float32) if isinstance(v, torch.Tensor) else torch.full((P,), float(v), device=dev)
@@ -845,10 +961,11 @@ class _ScoreTypePrior(torch.autograd.Function):
         dev = library.device
         ct, it = _c32(ctrl_type), _c32(invscale_type)
         P = tok_stroke_off.numel() - 1
+        gp_c, est_c = _c32(types.gpos), _c32(types.eval_spot_type)      # locals: must outlive the launch
         ty = _lib.TokenTypeC(ct.data_ptr(), it.data_ptr(), types.rel_cat.data_ptr(), types.attach_ix.data_ptr(),
-                             types.attach_subix.data_ptr(), _c32(types.gpos).data_ptr(), _c32(types.eval_spot_type).data_ptr(), None)
+                             types.attach_subix.data_ptr(), gp_c.data_ptr(), est_c.data_ptr(), None)
         ll = torch.empty(P, dtype=torch.float32, device=dev)
-        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        need = torch.is_grad_enabled() and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
         g_c = torch.empty_like(ct) if need else None
         g_i = torch.empty_like(it) if need else None
         check(lib().bpl_score_type_prior(ctypes.byref(library.c), ctypes.byref(library.logtables), P, tok_stroke_off.data_ptr(),
@@ -883,4 +1000,13 @@ def logsumexp_partial(ll):
     llc = _c32(ll)
     out = torch.empty(2, dtype=torch.float32, device=ll.device)
     check(lib().bpl_logsumexp_partial(_ptr(llc), llc.numel(), _ptr(out), _stream(ll.device)))
+    return out
+
+
+def logsumexp_combine(parts):
+    """log sum_i s_i exp(m_i) of (max, sum-exp) pairs ([n,2] or flat [2n] CUDA float32) as a 1-element tensor (one kernel)."""
+    _need_cuda(parts, "parts")
+    pc = _c32(parts).reshape(-1)
+    out = torch.empty(1, dtype=torch.float32, device=parts.device)
+    check(lib().bpl_logsumexp_combine(_ptr(pc), pc.numel() // 2, _ptr(out), _stream(parts.device)))
     return out

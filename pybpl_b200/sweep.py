@@ -38,3 +38,34 @@ def logsumexp_from_partials(parts):
         return float("-inf")
     s = (p[:, 1] * (p[:, 0] - m).exp()).sum()
     return float(m + s.log())
+
+
+class Sweep:
+    """BASELINE.json configs[3] on one rank: the rank's share of the particles resident on its GPU, one target image.
+    step() = ONE fused launch (render + score + the rank's log-sum-exp partial, bpl_score_tokens_lse), one all-gather
+    of 2 floats per rank when a process group is up, one tiny combine kernel; nothing synchronises with the host.
+    The global log-sum-exp is left in `self.total` (1-element CUDA tensor), the scores in `self.ll`."""
+
+    def __init__(self, batch, images, group=None, want_ll=True, ps=None):
+        import torch.distributed as dist
+        from . import ops
+        self.batch, self.images, self.group, self.want_ll = batch, images, group, want_ll
+        self.ps = ops.make_params(ps)
+        self.state = ops.LseState(batch.device)
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.gathered = torch.empty(2 * self.world, dtype=torch.float32, device=batch.device)
+        self.total = None
+        self.ll = None
+
+    def step(self, batch=None):
+        import torch.distributed as dist
+        from . import ops
+        b = self.batch if batch is None else batch
+        self.ll, _ = ops.score_tokens_lse(b, self.images, self.state, accumulate=False, want_ll=self.want_ll, ps=self.ps)
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.gathered, self.state.partial, group=self.group)
+            parts = self.gathered
+        else:
+            parts = self.state.partial
+        self.total = ops.logsumexp_combine(parts)
+        return self.total

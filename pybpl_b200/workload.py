@@ -162,3 +162,43 @@ def to_device(w, device, requires_grad=False, pin=False):
     return ops.TokenBatch(f(w["tok_stroke_off"]), f(w["stroke_sub_off"]), f(w["ctrl"]), f(w["invscale"]),
                           f(w["position"]), f(w["eps"]), f(w["sigma"]), neval=w["neval"], check_limits=False)
 
+
+
+def concat(ws):
+    """Concatenate numpy batches (CSR offsets rebased)."""
+    ws = list(ws)
+    if len(ws) == 1:
+        return ws[0]
+    tso, sso = [np.zeros(1, np.int64)], [np.zeros(1, np.int64)]
+    k = s = 0
+    for w in ws:
+        tso.append(w["tok_stroke_off"][1:].astype(np.int64) + k)
+        sso.append(w["stroke_sub_off"][1:].astype(np.int64) + s)
+        k += int(w["tok_stroke_off"][-1]); s += int(w["stroke_sub_off"][-1])
+    cat = lambda key: np.concatenate([w[key] for w in ws])
+    return dict(P=sum(w["P"] for w in ws), tok_stroke_off=np.concatenate(tso).astype(np.int32),
+                stroke_sub_off=np.concatenate(sso).astype(np.int32), ctrl=cat("ctrl"), invscale=cat("invscale"),
+                position=cat("position"), eps=cat("eps"), sigma=cat("sigma"), neval=ws[0]["neval"])
+
+
+# BASELINE.json configs[3]: the particle sweep.  The particle set is defined block-wise (block b = synth_tokens with seed
+# SWEEP_SEED + b) so that every sharding over 1/2/4/8 ranks -- and the CPU arms, which take the first blocks -- sees the
+# very same particles without anyone generating more than its share.
+SWEEP_PARTICLES = 1_000_000
+SWEEP_BLOCKS = 64
+SWEEP_SEED = 7000
+
+
+def sweep_block(b, particles=SWEEP_PARTICLES, blocks=SWEEP_BLOCKS):
+    per = particles // blocks
+    n = per + (particles - per * blocks if b == blocks - 1 else 0)
+    return synth_tokens(n, seed=SWEEP_SEED + b, sigma_mode="uniform")
+
+
+def sweep_shard(rank, world, particles=SWEEP_PARTICLES, blocks=SWEEP_BLOCKS):
+    """Rank `rank`'s contiguous share of the sweep's blocks as one numpy batch (strong scaling: blocks / world each)."""
+    per = (blocks + world - 1) // world
+    lo, hi = min(blocks, rank * per), min(blocks, (rank + 1) * per)
+    if lo >= hi:
+        return permute(sweep_block(0, particles, blocks), np.zeros(0, np.int64))
+    return concat([sweep_block(b, particles, blocks) for b in range(lo, hi)])

@@ -481,3 +481,96 @@ def test_token_order_is_a_permutation_by_decreasing_cost(ops):
     b._order = torch.arange(512, dtype=torch.int32, device=DEV)
     ll2, _ = ops.score_tokens(b, imgs)
     assert torch.allclose(ll1, ll2, rtol=2e-6, atol=0)
+
+
+# ---------------------------------------------------------------------------------------------
+# the benchmarked kernel (bpl_forward1s_kernel<false>, forward only) on the bench workloads, against the oracle
+# ---------------------------------------------------------------------------------------------
+def _forward_vs_oracle(ops, w, img, sel=None, tag=""):
+    """Scores all of `w` WITHOUT gradients (the box-confined scoring kernel) and compares the tokens `sel` with the fp32
+    and fp64 oracles.  Bars: ink_off_page bit-exact; ll within 1e-5 relative of the fp32 oracle for every token scored
+    against an image it could have produced, and -- for all tokens, including those scored against somebody else's
+    image, where log(1 - p) at p ~ 0.9996 turns ulps of p into 1e-4 of ll -- no further from the fp64 oracle than the
+    reference's own fp32 arithmetic is (tests/test_gpu_configs.py::test_config5 explains the conditioning)."""
+    from oracle import Oracle
+    from pybpl_b200 import workload
+    batch = workload.to_device(w, DEV)
+    imgs = ops.pack_images(T(img, torch.uint8))
+    with torch.no_grad():
+        ll, off = ops.score_tokens(batch, imgs)
+    assert not ll.requires_grad
+    ll = ll.cpu().numpy(); off = off.cpu().numpy()
+    sub = w if sel is None else workload.permute(w, sel)
+    if sel is not None:
+        ll, off = ll[sel], off[sel]
+    C = load("tokens")["basis_5_200"]
+    args = (sub["tok_stroke_off"], sub["stroke_sub_off"], sub["ctrl"], sub["invscale"], sub["position"], sub["eps"], sub["sigma"], img[None])
+    r32 = Oracle(np.float32).token_batch(C, *args)
+    r64 = Oracle(np.float64).token_batch(C.astype(np.float64), *args)
+    assert np.array_equal(off, r32["off_page"])
+    l32, l64 = r32["ll"].astype(np.float64), r64["ll"]
+    e_gpu32 = np.abs(ll - l32) / np.abs(l32)
+    e_gpu64 = np.abs(ll - l64) / np.abs(l64)
+    e_ref64 = np.abs(l32 - l64) / np.abs(l64)
+    print(f"{tag}: {len(ll)} tokens; vs fp32 oracle max {e_gpu32.max():.2e} (within 1e-5: {(e_gpu32 <= 1e-5).mean():.4f}); "
+          f"vs fp64 max {e_gpu64.max():.2e} median {np.median(e_gpu64):.2e} | fp32 oracle vs fp64 max {e_ref64.max():.2e} "
+          f"median {np.median(e_ref64):.2e}")
+    assert e_gpu64.max() <= max(e_ref64.max(), 1e-5)
+    assert np.median(e_gpu64) <= max(np.median(e_ref64), 2e-6)
+    assert np.percentile(e_gpu64, 99) <= max(np.percentile(e_ref64, 99), 1e-5)
+    return ll, e_gpu32
+
+
+def test_forward_kernel_on_the_full_config1_batch(ops):
+    """configs[1] exactly as bench.py's config1 object runs it: synth_tokens(4096, 1234, 'uniform'), the target sampled
+    from token 0, forward only."""
+    from oracle import Oracle
+    import oracle as _oracle
+    from pybpl_b200 import workload
+    w = workload.synth_tokens(4096, seed=1234, sigma_mode="uniform")
+    C = load("tokens")["basis_5_200"]
+    img = _oracle.target_image_for(w, Oracle(np.float32), C)
+    ll, e32 = _forward_vs_oracle(ops, w, img, tag="config1 batch")
+    assert e32[0] <= 1e-5                         # token 0 against its own sample
+
+
+def test_forward_kernel_on_a_sweep_shard(ops):
+    """configs[3]: the 8-rank shard of the particle sweep (125,000 particles = sweep blocks 0..7) in one launch, 8,192
+    of them checked against the oracle; the fused log-sum-exp partial against torch.logsumexp of the scores."""
+    from oracle import Oracle
+    import oracle as _oracle
+    from pybpl_b200 import sweep, workload
+    w = workload.sweep_shard(0, 8)
+    assert w["P"] == 125000
+    C = load("tokens")["basis_5_200"]
+    img = _oracle.target_image_for(w, Oracle(np.float32), C)
+    sel = np.sort(np.random.default_rng(3).choice(w["P"], 8192, replace=False))
+    ll_sel, _ = _forward_vs_oracle(ops, w, img, sel=sel, tag="sweep shard")
+    sw = sweep.Sweep(workload.to_device(w, DEV), ops.pack_images(T(img, torch.uint8)))
+    total = sw.step()
+    assert ((sw.ll.cpu().numpy()[sel] - ll_sel) == 0).all() or np.allclose(sw.ll.cpu().numpy()[sel], ll_sel, rtol=2e-5)
+    want = torch.logsumexp(sw.ll.double(), 0).item()
+    assert abs(total.item() - want) <= 1e-4 * max(1.0, abs(want)), (total.item(), want)
+    # chunked accumulation gives the same partial; a second step (queue slot reuse) the same total
+    st = ops.LseState(DEV)
+    for c, lo in enumerate(range(0, w["P"], 40000)):
+        wc = workload.permute(w, np.arange(lo, min(w["P"], lo + 40000)))
+        ops.score_tokens_lse(workload.to_device(wc, DEV), sw.images, st, accumulate=c > 0, want_ll=False)
+    assert abs(ops.logsumexp_combine(st.partial).item() - want) <= 1e-4 * max(1.0, abs(want))
+    assert abs(sw.step().item() - want) <= 1e-4 * max(1.0, abs(want))
+
+
+def test_logsumexp_partial_and_combine(ops):
+    g = torch.Generator().manual_seed(5)
+    for n in (1, 31, 4097, 300001):
+        x = (torch.randn(n, generator=g) * 50 - 3000).to(DEV)
+        if n > 31:
+            x[7] = float("-inf"); x[11] = float("nan")
+        part = ops.logsumexp_partial(x)
+        ok = torch.isfinite(x)
+        want = torch.logsumexp(x[ok].double(), 0).item()
+        got = ops.logsumexp_combine(part).item()
+        assert abs(got - want) <= 1e-5 * abs(want), (n, got, want)
+        assert part[0].item() == x[ok].max().item()
+    empty = ops.logsumexp_combine(torch.tensor([float("-inf"), 0.0], device=DEV))
+    assert empty.item() == float("-inf")
