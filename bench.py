@@ -402,16 +402,19 @@ def run_gpu(args):
     bwd_h2d = hb.nbytes
     bwd_d2h = sum(t.numel() * 4 for t in g_host.values())
 
-    # ---- live FP32 FMA peak (roofline denominator) ----
+    # ---- live FP32 FMA peak (roofline denominator): best of 5 timed launches of the FFMA probe ----
     scratch = torch.zeros(1, device=dev)
-    iters, blocks = 4096, 148 * 8
+    iters, blocks = 16384, 148 * 8
     probe = lambda: _lib.check(_lib.lib().bpl_fp32_probe(ctypes.c_void_p(scratch.data_ptr()), iters, blocks,
                                                          ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
     for _ in range(2):
         probe()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record(); probe(); b.record(); torch.cuda.synchronize()
-    fp32_peak = (blocks * 1024.0 * iters * 8 * 2) / (a.elapsed_time(b) * 1e-3) / 1e12
+    torch.cuda.synchronize()
+    fp32_peak = 0.0
+    for _ in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); probe(); b.record(); torch.cuda.synchronize()
+        fp32_peak = max(fp32_peak, (blocks * 1024.0 * iters * 8 * 2) / (a.elapsed_time(b) * 1e-3) / 1e12)
     clocks = sampler.stop() if sampler else None
 
     # ---- secondary single-GPU objects (N=1 only) ----

@@ -42,6 +42,8 @@ def _i32(t, device):
 
 def make_params(ps=None):
     """bpl_params from None or a reference-style Parameters object (pybpl/parameters.py:19-41)."""
+    if isinstance(ps, _lib.Params):
+        return ps
     p = _lib.default_params()
     if ps is not None:
         imsize = tuple(int(v) for v in getattr(ps, "imsize", (IMSIZE, IMSIZE)))
@@ -369,7 +371,7 @@ class _ScoreTokens(torch.autograd.Function):
     d ll / d inputs; backward() only scales them by the incoming cotangent (one scalar per token)."""
 
     @staticmethod
-    def forward(ctx, ctrl, invscale, position, affine, eps, sigma, batch, images, img_idx, ps):
+    def forward(ctx, ctrl, invscale, position, affine, eps, sigma, batch, images, img_idx, ps, grad_on=True):
         dev = batch.device
         P = batch.P
         ctrl_c, inv_c, pos_c = _c32(ctrl), _c32(invscale), _c32(position)
@@ -380,7 +382,9 @@ class _ScoreTokens(torch.autograd.Function):
         out = _lib.FwdOut(ll.data_ptr(), off.data_ptr(), None)
         b = batch.c_struct(ctrl_c, inv_c, pos_c, aff_c, eps_c, sig_c)
         t = _targets(images, img_idx)
-        need = torch.is_grad_enabled() and any(ctx.needs_input_grad[:6])
+        # grad_on = torch.is_grad_enabled() of the CALLER (inside forward() it is always off): leaves evaluated under
+        # no_grad take the cheaper forward-only kernel
+        need = grad_on and any(ctx.needs_input_grad[:6])
         if need:
             g_ctrl = torch.empty_like(ctrl_c); g_inv = torch.empty_like(inv_c); g_pos = torch.empty_like(pos_c)
             g_aff = None if aff_c is None else torch.empty_like(aff_c)
@@ -407,7 +411,7 @@ class _ScoreTokens(torch.autograd.Function):
         gs = g_ll.to(torch.float32)
         st, kt = b.sub_token, b.stroke_token
         return (g_ctrl * gs[st].view(-1, 1, 1), g_inv * gs[st], g_pos * gs[kt].view(-1, 1),
-                None if g_aff is None else g_aff * gs.view(-1, 1), g_eps * gs, g_sig * gs, None, None, None, None)
+                None if g_aff is None else g_aff * gs.view(-1, 1), g_eps * gs, g_sig * gs, None, None, None, None, None)
 
 
 class _RenderTokens(torch.autograd.Function):
@@ -464,7 +468,7 @@ def score_tokens(batch, images, img_idx=None, ps=None):
         img_idx = _i32(img_idx, batch.device)
         _check_img_idx(img_idx, images)
     ll, off = _ScoreTokens.apply(batch.ctrl, batch.invscale, batch.position, batch.affine, batch.eps, batch.sigma,
-                                 batch, images, img_idx, ps)
+                                 batch, images, img_idx, ps, torch.is_grad_enabled())
     return ll, off.bool()
 
 
@@ -820,7 +824,8 @@ class TokenTypes:
 
 class _ScoreTokenPrior(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, ctrl, invscale, position, eval_spot, ctrl_type, invscale_type, gpos, eval_spot_type, batch, types, c):
+    def forward(ctx, ctrl, invscale, position, eval_spot, ctrl_type, invscale_type, gpos, eval_spot_type, batch, types, c,
+                grad_on=True):
         dev = batch.device
         args = [_c32(t) for t in (ctrl, invscale, position, eval_spot, ctrl_type, invscale_type, gpos, eval_spot_type)]
         ctrl_c, inv_c, pos_c, es_c, ctrl_ty, inv_ty, gpos_c, es_ty = args
@@ -834,7 +839,7 @@ class _ScoreTokenPrior(torch.autograd.Function):
         ty = _lib.TokenTypeC(ctrl_ty.data_ptr(), inv_ty.data_ptr(), types.rel_cat.data_ptr(), types.attach_ix.data_ptr(),
                              types.attach_subix.data_ptr(), gpos_c.data_ptr(), es_ty.data_ptr(), es_c.data_ptr())
         ll = torch.empty(batch.P, dtype=torch.float32, device=dev)
-        need = torch.is_grad_enabled() and any(ctx.needs_input_grad[:8])
+        need = grad_on and any(ctx.needs_input_grad[:8])      # grad_on: the caller's torch.is_grad_enabled()
         if need:
             gs = [torch.empty_like(t) for t in args]
             g = _lib.TokenPriorGrads(*[t.data_ptr() for t in gs])
@@ -854,7 +859,7 @@ class _ScoreTokenPrior(torch.autograd.Function):
         gs = g_ll.to(torch.float32)
         st, kt = gs[b.sub_token], gs[b.stroke_token]
         return (g_ctrl * st.view(-1, 1, 1), g_inv * st, g_pos * kt.view(-1, 1), g_es * kt, g_ctrl_ty * st.view(-1, 1, 1),
-                g_inv_ty * st, g_gpos * kt.view(-1, 1), g_es_ty * kt, None, None, None)
+                g_inv_ty * st, g_gpos * kt.view(-1, 1), g_es_ty * kt, None, None, None, None)
 
 
 def score_token_prior(batch, types, library=None, ps=None, c=None):
@@ -864,7 +869,7 @@ def score_token_prior(batch, types, library=None, ps=None, c=None):
     if c is None:
         c = token_prior_params(library, ps)
     return _ScoreTokenPrior.apply(batch.ctrl, batch.invscale, batch.position, types.eval_spot, types.ctrl_type,
-                                  types.invscale_type, types.gpos, types.eval_spot_type, batch, types, c)
+                                  types.invscale_type, types.gpos, types.eval_spot_type, batch, types, c, torch.is_grad_enabled())
 
 
 def sample_tokens(tok_stroke_off, stroke_sub_off, types, seed, first_token=0, eps=1e-4, sigma=0.5, library=None, ps=None,
@@ -957,7 +962,7 @@ def sample_types(library, n_types, seed, first_type=0):
 
 class _ScoreTypePrior(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, ctrl_type, invscale_type, library, tok_stroke_off, stroke_sub_off, subid, types):
+    def forward(ctx, ctrl_type, invscale_type, library, tok_stroke_off, stroke_sub_off, subid, types, grad_on=True):
         dev = library.device
         ct, it = _c32(ctrl_type), _c32(invscale_type)
         P = tok_stroke_off.numel() - 1
@@ -965,7 +970,7 @@ class _ScoreTypePrior(torch.autograd.Function):
         ty = _lib.TokenTypeC(ct.data_ptr(), it.data_ptr(), types.rel_cat.data_ptr(), types.attach_ix.data_ptr(),
                              types.attach_subix.data_ptr(), gp_c.data_ptr(), est_c.data_ptr(), None)
         ll = torch.empty(P, dtype=torch.float32, device=dev)
-        need = torch.is_grad_enabled() and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
+        need = grad_on and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1])      # grad_on: the caller's grad mode
         g_c = torch.empty_like(ct) if need else None
         g_i = torch.empty_like(it) if need else None
         check(lib().bpl_score_type_prior(ctypes.byref(library.c), ctypes.byref(library.logtables), P, tok_stroke_off.data_ptr(),
@@ -983,7 +988,7 @@ class _ScoreTypePrior(torch.autograd.Function):
     def backward(ctx, g_ll):
         g_c, g_i = ctx.saved_tensors
         st = g_ll.to(torch.float32)[ctx.sub_token]
-        return g_c * st.view(-1, 1, 1), g_i * st, None, None, None, None, None
+        return g_c * st.view(-1, 1, 1), g_i * st, None, None, None, None, None, None
 
 
 def score_type_prior(library, tok_stroke_off, stroke_sub_off, types, subid):
@@ -991,7 +996,7 @@ def score_type_prior(library, tok_stroke_off, stroke_sub_off, types, subid):
     types.ctrl_type and types.invscale_type (the leaves the reference's autograd reaches).  `subid` [S]: primitive ids."""
     dev = library.device
     return _ScoreTypePrior.apply(types.ctrl_type, types.invscale_type, library, _i32(tok_stroke_off, dev),
-                                 _i32(stroke_sub_off, dev), _i32(subid, dev), types)
+                                 _i32(stroke_sub_off, dev), _i32(subid, dev), types, torch.is_grad_enabled())
 
 
 def logsumexp_partial(ll):
