@@ -24,6 +24,15 @@ constexpr int PPL = PPL_DEFAULT;
 
 struct PEval { float r, c; bool inb; };
 
+// Where pixel (r, c) of the canvas lives in an image buffer: a compile-time layout (the full-canvas kernels) or a
+// run-time one (the team kernels' box-sized buffers: org = -(r0 * stride + c0) of the box).
+template <int PIXSTRIDE, int ROWSTRIDE, int ORG>
+struct LayS { __device__ __forceinline__ int operator()(int r, int c) const { return ORG + PIXSTRIDE * (r * ROWSTRIDE + c); } };
+struct LayD {
+    int stride, org;
+    __device__ __forceinline__ int operator()(int r, int c) const { return org + r * stride + c; }
+};
+
 // one trajectory point in image space: spline + chain offset (+ affine), flip (rendering.py:52-53), check_bounds (:27-31)
 __device__ __forceinline__ PEval eval_pt(const CtrlSrc &src, int j, bool valid) {
     PEval e;
@@ -87,10 +96,11 @@ __device__ __forceinline__ CtrlSrc shfl_src(const CtrlSrc &s, int from, const fl
 //  C. every lane walks its points: ink from the distance to the previous survivor, splat.
 // FIX: fix_sum / fix_cnt are the sub-stroke totals; ink becomes fill or scale*ink and only the
 // difference to the common-branch ink is splatted.
-template <bool FIX, int PIXSTRIDE, int ROWSTRIDE = IMG, int ORG = 0, int PPL = PPL_DEFAULT>
+template <bool FIX, int PIXSTRIDE, int ROWSTRIDE = IMG, int ORG = 0, int PPL = PPL_DEFAULT,
+          class Lay = LayS<PIXSTRIDE, ROWSTRIDE, ORG>>
 __device__ __forceinline__ LaneAcc warp_points(bool active, const CtrlSrc &src, const float *tab, int sid, int n, int q,
                                                int lane, const RenderConsts &rc, float *img, float fix_sum, int fix_cnt,
-                                               int *bbox = nullptr) {
+                                               int *bbox = nullptr, Lay lay = Lay()) {
     LaneAcc acc{};
     if (!__any_sync(0xffffffffu, active)) return acc;      // e.g. the fix pass: most warps have nothing to patch
     const int j0 = q * PPL;
@@ -176,10 +186,10 @@ __device__ __forceinline__ LaneAcc warp_points(bool active, const CtrlSrc &src, 
     auto flush = [&]() {
         if (cell >= 0) {
             const int r0 = cell & 127, c0 = (cell >> 7) & 127, r1 = r0 + ((cell >> 14) & 1), c1 = c0 + ((cell >> 15) & 1);
-            atomicAdd(img + ORG + PIXSTRIDE * (r0 * ROWSTRIDE + c0), a00);
-            atomicAdd(img + ORG + PIXSTRIDE * (r1 * ROWSTRIDE + c0), a10);
-            atomicAdd(img + ORG + PIXSTRIDE * (r0 * ROWSTRIDE + c1), a01);
-            atomicAdd(img + ORG + PIXSTRIDE * (r1 * ROWSTRIDE + c1), a11);
+            atomicAdd(img + lay(r0, c0), a00);
+            atomicAdd(img + lay(r1, c0), a10);
+            atomicAdd(img + lay(r0, c1), a01);
+            atomicAdd(img + lay(r1, c1), a11);
         }
     };
     auto emit = [&](float r, float c, float ink0) {
@@ -261,13 +271,13 @@ __device__ __forceinline__ LaneAcc warp_points(bool active, const CtrlSrc &src, 
 // ------------------------------------------------------------------------------------------------
 struct Corner2 { float gink, gr, gc; };
 
-template <int ROWSTRIDE, int ORG>
-__device__ __forceinline__ Corner2 gather_px(const float *G, float r, float c) {
+template <class Lay>
+__device__ __forceinline__ Corner2 gather_px(const float *G, float r, float c, const Lay &lay) {
     const float rf = floorf(r), cf = floorf(c), rce = ceilf(r), cce = ceilf(c);
     const float fr = r - rf, fc = c - cf, gr = 1.0f - fr, gc = 1.0f - fc;
     const int r0 = (int)rf, c0 = (int)cf, r1 = (int)rce, c1 = (int)cce;
-    const float G00 = G[ORG + r0 * ROWSTRIDE + c0], G10 = G[ORG + r1 * ROWSTRIDE + c0];
-    const float G01 = G[ORG + r0 * ROWSTRIDE + c1], G11 = G[ORG + r1 * ROWSTRIDE + c1];
+    const float G00 = G[lay(r0, c0)], G10 = G[lay(r1, c0)];
+    const float G01 = G[lay(r0, c1)], G11 = G[lay(r1, c1)];
     Corner2 k;
     k.gink = gr * gc * G00 + fr * gc * G10 + gr * fc * G01 + fr * fc * G11;
     k.gr = gc * (G10 - G00) + fc * (G11 - G01);
@@ -275,10 +285,10 @@ __device__ __forceinline__ Corner2 gather_px(const float *G, float r, float c) {
     return k;
 }
 
-template <bool DOT, int ROWSTRIDE, int ORG, int PPL, class Emit>
+template <bool DOT, int ROWSTRIDE, int ORG, int PPL, class Emit, class Lay = LayS<1, ROWSTRIDE, ORG>>
 __device__ __forceinline__ float warp_points_bwd(bool active, const CtrlSrc &src, const float *tab, int sid, int n, int q,
                                                  int lane, const RenderConsts &rc, const float *G, float sum, int cnt,
-                                                 float dot_in, Emit emit) {
+                                                 float dot_in, Emit emit, Lay lay = Lay()) {
     if (!__any_sync(0xffffffffu, active)) return 0.0f;
     const int j0 = q * PPL;
     // ---- A: own points ----
@@ -368,18 +378,18 @@ __device__ __forceinline__ float warp_points_bwd(bool active, const CtrlSrc &src
     for (unsigned rest = active ? inbm : 0u; rest; rest &= rest - 1u) {
         const int j = j0 + __ffs(rest) - 1;
         const PEval e = eval_pt(src, j, true);
-        const Corner2 K = gather_px<ROWSTRIDE, ORG>(G, e.r, e.c);
+        const Corner2 K = gather_px(G, e.r, e.c, lay);
         if (has_prev) {
             const float ink0 = ink_from(e.r, e.c, pr, pc, rc);
             if (DOT) {
                 dot = fmaf(K.gink, ink0, dot);
-                if (pend) dot = fmaf(gather_px<ROWSTRIDE, ORG>(G, fr, fc).gink, ink0, dot);
+                if (pend) dot = fmaf(gather_px(G, fr, fc, lay).gink, ink0, dot);
             } else {
                 const float ink = fill ? fillv : __fmul_rn(sc, ink0);
                 emit(j, ink * K.gc, -(ink * K.gr));
                 segment(pr, pc, pj, e.r, e.c, j, fmaf(K.gink, sc, gsum));
                 if (pend) {             // the first survivor carries a copy of this ink
-                    const Corner2 Kf = gather_px<ROWSTRIDE, ORG>(G, fr, fc);
+                    const Corner2 Kf = gather_px(G, fr, fc, lay);
                     emit(fj, ink * Kf.gc, -(ink * Kf.gr));
                     segment(fr, fc, fj, e.r, e.c, j, fmaf(Kf.gink, sc, gsum));
                 }
@@ -398,7 +408,7 @@ __device__ __forceinline__ float warp_points_bwd(bool active, const CtrlSrc &src
             const PEval e = eval_pt(src, j, true);
             if (e.inb) { found = true; nr = e.r; nc = e.c; nj = j; break; }
         }
-        const Corner2 Kf = gather_px<ROWSTRIDE, ORG>(G, fr, fc);
+        const Corner2 Kf = gather_px(G, fr, fc, lay);
         if (found) {
             const float ink0 = ink_from(nr, nc, fr, fc, rc);
             if (DOT) {

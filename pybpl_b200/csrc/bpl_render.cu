@@ -414,7 +414,7 @@ __device__ __forceinline__ void affine_setup(const KArgs &a, const TokGeom &t, i
     block_sum<2>(v, ms->red);
     if (threadIdx.x == 0) {
         const double npts = (double)t.S * (double)a.neval;
-        const float cx = (float)(v[0] / npts), cy = (float)(v[1] / npts);
+        const float cx = npts > 0.0 ? (float)(v[0] / npts) : 0.0f, cy = npts > 0.0 ? (float)(v[1] / npts) : 0.0f;      // (no points: nothing depends on the warp)
         const float *A = a.affine + 4 * (size_t)p;
         ms->com[0] = cx; ms->com[1] = cy;
         ms->affB[0] = A[0]; ms->affB[1] = A[1];
@@ -1001,8 +1001,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) bpl_backward_kernel(const KArg
                 const float *Aa = a.affine + 4 * (size_t)p;
                 const double npts = (double)t.S * (double)a.neval;
                 b0 = ms->affB[0]; b1 = ms->affB[1];
-                gcx = (float)(-((double)Aa[0] - 1.0) * ms->aff_acc[2] / npts);
-                gcy = (float)(-((double)Aa[1] - 1.0) * ms->aff_acc[3] / npts);
+                gcx = npts > 0.0 ? (float)(-((double)Aa[0] - 1.0) * ms->aff_acc[2] / npts) : 0.0f;
+                gcy = npts > 0.0 ? (float)(-((double)Aa[1] - 1.0) * ms->aff_acc[3] / npts) : 0.0f;
                 if (threadIdx.x == 0 && a.g_affine) {
                     float *ga = a.g_affine + 4 * (size_t)p;
                     ga[0] = (float)(ms->aff_acc[0] - (double)ms->com[0] * ms->aff_acc[2]);
@@ -1076,6 +1076,12 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) bpl_backward_kernel(const KArg
 #endif
 }
 
+
+}  // namespace bpl
+
+#include "bpl_backward_teams.cuh"
+
+namespace bpl {
 
 // ------------------------------------------------------------------------------------------
 // Processing order for small batches: tokens by decreasing sub-stroke count (a counting sort in one CTA), so
@@ -1370,6 +1376,11 @@ int bpl_render_strokes(const bpl_params *ps, const bpl_stroke_batch *b, const bp
     return launch(bpl_forward_kernel<true>, FWD_THREADS, sizeof(FwdSmem), FWD_CTAS_PER_SM, ka, (cudaStream_t)stream);
 }
 
+#ifndef BPL_BWD_TEAMS_MIN
+#define BPL_BWD_TEAMS_MIN 2048
+#endif
+static constexpr int BWD_TEAMS_MIN = BPL_BWD_TEAMS_MIN;
+
 int bpl_score_tokens_grad(const bpl_params *ps, const bpl_token_batch *b, const bpl_targets *t,
                           const bpl_fwd_out *out, const bpl_grads *g, void *stream) {
     if (b && b->n_tokens == 0) return 0;
@@ -1380,9 +1391,21 @@ int bpl_score_tokens_grad(const bpl_params *ps, const bpl_token_batch *b, const 
     if (!g || !g->g_ctrl || !g->g_invscale || !g->g_position) { set_error("%s", "g_ctrl/g_invscale/g_position required"); return BPL_EINVAL; }
     if (ka.all_pairs) { set_error("%s", "all_pairs scoring is forward only"); return BPL_EINVAL; }
     if (!ka.image_bits && !ka.g_pimg) { set_error("%s", "need target images or a pimg cotangent"); return BPL_EINVAL; }
-    static const bool bwd_order = getenv("BPL_BWD_ORDER") != nullptr;      // A/B aid
-    if (!bwd_order) ka.order = nullptr;      // measured: the fused backward (one CTA per SM) is faster in index order
-    return launch(bpl_backward_kernel<false>, BWD_THREADS, sizeof(BwdSmem), 1, ka, (cudaStream_t)stream);
+    // Small batches: the full-canvas kernel, one 640-thread CTA per token and SM (shortest per-token latency, so the
+    // shortest tail of the launch).  From BWD_TEAMS_MIN tokens on: teams of one persistent CTA per SM share the SM's
+    // whole shared memory as a pool of box-sized arenas, expensive tokens first (bpl_backward_teams.cuh).
+    // BPL_BWD_CANVAS=1 / BPL_BWD_TEAMS=1 force one or the other (A/B aids); BPL_BWD_ORDER=1 lets the canvas kernel follow
+    // the processing order too (measured 2 % slower).
+    // (read per call, not cached: the parity tests switch kernels inside one process)
+    const bool bwd_order = getenv("BPL_BWD_ORDER") != nullptr;
+    const bool bwd_canvas = getenv("BPL_BWD_CANVAS") != nullptr;
+    const bool bwd_teams = getenv("BPL_BWD_TEAMS") != nullptr;
+    if (bwd_canvas || (!bwd_teams && ka.n_tokens < BWD_TEAMS_MIN)) {
+        if (!bwd_order) ka.order = nullptr;
+        return launch(bpl_backward_kernel<false>, BWD_THREADS, sizeof(BwdSmem), 1, ka, (cudaStream_t)stream);
+    }
+    return launch(bpl_backward_teams_kernel, BT_NT * BT_TT, (size_t)dev_info().smem_optin, 1, ka, (cudaStream_t)stream,
+                  (ka.n_tokens + BT_NT - 1) / BT_NT);
 }
 
 int bpl_token_points(const bpl_params *ps, const bpl_token_batch *b, float *motor, uint8_t *mask_out, int *fl, int *ce,

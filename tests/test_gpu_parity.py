@@ -21,6 +21,20 @@ def ops():
     return _ops
 
 
+@pytest.fixture(params=["canvas", "teams"])
+def bwd_kernel(request):
+    """Runs a gradient test once per fused backward kernel: the full-canvas kernel (small batches by default) and the
+    team kernel with box-sized arenas (bpl_backward_teams.cuh; batches of 2048 tokens and more by default)."""
+    import os
+    old = {k: os.environ.pop(k, None) for k in ("BPL_BWD_CANVAS", "BPL_BWD_TEAMS")}
+    os.environ["BPL_BWD_CANVAS" if request.param == "canvas" else "BPL_BWD_TEAMS"] = "1"
+    yield request.param
+    for k, v in old.items():
+        os.environ.pop(k, None)
+        if v is not None:
+            os.environ[k] = v
+
+
 def T(a, dtype=torch.float32):
     return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype, device=DEV)
 
@@ -224,7 +238,7 @@ def test_tokens_forward(ops):
             assert np.abs(pimg[i] - t["pimg"]).max() < 1e-5, t["name"]
 
 
-def test_tokens_gradients(ops):
+def test_tokens_gradients(ops, bwd_kernel):
     d, toks = token_cases()
     batch, imgs, idx, b = make_token_batch(ops, toks, grad=True)
     ll, _ = ops.score_tokens(batch, imgs, idx)
@@ -250,7 +264,7 @@ def test_tokens_gradients(ops):
     assert worst["gs"] < 1e-2 and worst["ge"] < 2e-3 and worst["ga"] < 2e-3
 
 
-def test_gradients_no_worse_than_reference_vs_fp64(ops):
+def test_gradients_no_worse_than_reference_vs_fp64(ops, bwd_kernel):
     """|g_cuda - g_fp64| <= |g_ref - g_fp64| (+ slack) per tensor: the build is as accurate as the reference."""
     from oracle import Oracle
     d, toks = token_cases()
@@ -274,7 +288,7 @@ def test_gradients_no_worse_than_reference_vs_fp64(ops):
     assert max(ours) <= max(3 * max(refs), 2e-4)
 
 
-def test_score_matches_oracle_on_random_batch(ops):
+def test_score_matches_oracle_on_random_batch(ops, bwd_kernel):
     """Seeded synthetic batch (the bench workload generator) against the CPU oracle, forward and backward."""
     from oracle import Oracle
     from pybpl_b200 import workload
@@ -299,6 +313,60 @@ def test_score_matches_oracle_on_random_batch(ops):
     assert relinf(pos.grad.cpu().numpy(), ref["g_position"]) < 2e-4
     assert relinf(eps.grad.cpu().numpy(), ref["g_eps"]) < 5e-4
     assert relinf(sig.grad.cpu().numpy(), ref["g_sigma"]) < 5e-3
+
+
+def test_backward_kernels_agree_on_every_mode(ops):
+    """The two fused backward kernels (full canvas / teams with box-sized arenas) on one mixed batch: affine warps,
+    blur_sigma <= 0, epsilon = 0, a token without strokes, a token that is entirely off the page, weighted scores
+    (g_ll) and the probability-map cotangent (get_pimg's backward).  Same algorithm, different summation orders."""
+    import os
+    from pybpl_b200 import workload
+    w = workload.synth_tokens(160, seed=77, sigma_mode="uniform")
+    rng = np.random.default_rng(5)
+    w["sigma"][::7] = 0.0
+    w["sigma"][3::11] = -1.0
+    w["eps"][::5] = 0.0
+    w["position"][w["tok_stroke_off"][10]:w["tok_stroke_off"][11]] += 400.0      # token 10: off the page
+    aff = np.tile(np.array([1, 1, 0, 0], np.float32), (160, 1))
+    aff[::3] = np.stack([rng.uniform(0.8, 1.25, 54), rng.uniform(0.8, 1.25, 54), rng.uniform(-6, 6, 54), rng.uniform(-6, 6, 54)], 1)
+    # a token without strokes in front
+    tso = np.concatenate([[0], w["tok_stroke_off"]]).astype(np.int64)
+    eps = np.concatenate([[1e-4], w["eps"]]).astype(np.float32); sig = np.concatenate([[2.0], w["sigma"]]).astype(np.float32)
+    aff = np.concatenate([[[1, 1, 0, 0]], aff]).astype(np.float32)
+    P = 161
+    img = (rng.random((3, 105, 105)) < 0.04).astype(np.uint8)
+    imgs = ops.pack_images(T(img, torch.uint8))
+    idx = T(rng.integers(0, 3, P), torch.int32)
+    g_ll = T(rng.standard_normal(P))
+    g_pimg = T(rng.standard_normal((P, 105, 105)) * (rng.random((P, 105, 105)) < 0.3))
+    res = {}
+    for kern in ("BPL_BWD_CANVAS", "BPL_BWD_TEAMS"):
+        os.environ.pop("BPL_BWD_CANVAS", None); os.environ.pop("BPL_BWD_TEAMS", None)
+        os.environ[kern] = "1"
+        try:
+            leaves = [T(w["ctrl"]), T(w["invscale"]), T(w["position"]), T(aff), T(eps), T(sig)]
+            for t in leaves:
+                t.requires_grad_(True)
+            batch = ops.TokenBatch(tso, w["stroke_sub_off"], leaves[0], leaves[1], leaves[2], leaves[4], leaves[5], affine=leaves[3])
+            ll, off = ops.score_tokens(batch, imgs, idx)
+            g1 = torch.autograd.grad((ll * g_ll).sum(), leaves)
+            pimg, off2 = ops.render_tokens(batch)
+            g2 = torch.autograd.grad((pimg * g_pimg).sum(), leaves)
+            res[kern] = (ll.detach().cpu().numpy(), off.cpu().numpy(), [g.cpu().numpy() for g in g1], [g.cpu().numpy() for g in g2])
+        finally:
+            os.environ.pop(kern, None)
+    a, b = res["BPL_BWD_CANVAS"], res["BPL_BWD_TEAMS"]
+    assert np.array_equal(a[1], b[1]) and bool(a[1][11]) and not bool(a[1][0])
+    assert np.allclose(a[0], b[0], rtol=2e-6, atol=0)
+    names = ("ctrl", "invscale", "position", "affine", "eps", "sigma")
+    for which, ga, gb in (("score", a[2], b[2]), ("pimg", a[3], b[3])):
+        for n, x, y in zip(names, ga, gb):
+            assert np.isfinite(x).all() and np.isfinite(y).all(), (which, n)
+            err = np.abs(x - y).max() / max(np.abs(x).max(), 1e-30)
+            print(which, n, "canvas vs teams inf-norm rel", err)
+            assert err < 1e-4, (which, n, err)      # half the bar of the oracle tests (summation order only)
+    # the token without strokes and the off-page token get exactly zero stroke gradients from both
+    assert not a[2][0][w["stroke_sub_off"][w["tok_stroke_off"][10]]:w["stroke_sub_off"][w["tok_stroke_off"][11]]].any()
 
 
 # ---------------------------------------------------------------------------------------------

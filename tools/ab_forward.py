@@ -64,3 +64,16 @@ for rep in range(5):
     e.record(); torch.cuda.synchronize()
     bestb = min(bestb, a.elapsed_time(e) / 20)
 print(f"{tag}: fwd+bwd kernel {bb.P / bestb / 1e3:.3f} M particles/s ({bestb * 1e3:.1f} us per launch)")
+# gradients of this build (compared across tags like the scores)
+leaves = [bb.ctrl, bb.invscale, bb.position, bb.eps, bb.sigma]
+gr = torch.autograd.grad(step().sum(), leaves)
+np.savez(os.path.join(ROOT, "gpurun_out", f"abg_{tag}.npz"), **{k: g.cpu().numpy() for k, g in zip(("ctrl", "invscale", "position", "eps", "sigma"), gr)})
+refg = None
+for f in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "abg_*.npz"))):
+    v = dict(np.load(f))
+    if v["eps"].shape != (bb.P,):
+        continue
+    if refg is None:
+        refg, rname = v, os.path.basename(f)
+        continue
+    print(f"  {os.path.basename(f)} vs {rname}: " + ", ".join(f"{k} {np.abs(v[k] - refg[k]).max() / np.abs(refg[k]).max():.1e}" for k in v))

@@ -19,4 +19,4 @@ for name, envs, so, pr in procs:
     for kv in filter(None, envs.split(",")):
         k, v = kv.split("=", 1); env[k] = v
     sys.stdout.flush()
-    subprocess.call([sys.executable, os.path.join(ROOT, "tools", "ab_forward.py"), name], env=env)
+    subprocess.call([sys.executable, os.path.join(ROOT, "tools", os.environ.get("VARIANT_SCRIPT", "ab_forward.py")), name] + os.environ.get("VARIANT_ARGS", "").split(), env=env)
