@@ -244,9 +244,11 @@ typedef struct {
 
 /* ll[P] <- log P(type): CharacterTypeDist.score_type (pybpl/model/type_dist.py:98-125; score_k :163-185,
  * score_part_type :507-531, score_relation_type :599-650).  The types are given as for bpl_score_token_prior (CSR
- * offsets + bpl_token_type; eval_spot and eval_spot_type only enter through a constant) plus the primitive id of
+ * offsets + bpl_token_type; eval_spot_type only enters through its support [2, ncpt + 1]) plus the primitive id of
  * every sub-stroke.  g_ctrl_type [S][5][2] / g_invscale_type [S]: gradients, or NULL.  -inf for a position outside
- * the histogram's range or an impossible count. */
+ * the histogram's range, an impossible count, an attachment index outside [0, i) / [0, nsub of the attached stroke)
+ * or a type-level spline coordinate outside [2, ncpt + 1] (the reference's Categorical / Uniform log_prob raises or
+ * returns -inf there, type_dist.py:636-647). */
 int bpl_score_type_prior(const bpl_type_lib *lib, const bpl_type_logtables *tabs, int n_types,
                          const int *tok_stroke_off, const int *stroke_sub_off, const int *subid,
                          const bpl_token_type *ty, float *ll, float *g_ctrl_type, float *g_invscale_type, void *stream);
@@ -277,6 +279,11 @@ int bpl_score_tokens_lse(const bpl_params *ps, const bpl_token_batch *b, const b
 /* order[P] <- the tokens by decreasing sub-stroke count (only the CSR offsets of b are read).  No reference
  * counterpart: the reference renders one token per Python call. */
 int bpl_order_tokens(const bpl_token_batch *b, int *order, void *stream);
+/* order[P] <- the tokens by decreasing ESTIMATED COST: the area of the box of the chained control polygons (a spline lies
+ * in the hull of its control points, pybpl/splines.py:72-93; chaining as objects/part.py:316-326) grown by the stencils'
+ * reach, and the sub-stroke count, in 256 cost classes.  keys[P]: scratch (receives the classes).  Reads the batch's
+ * geometry as it is now; an order made from earlier parameter values stays a valid (merely less sharp) order. */
+int bpl_order_tokens_by_cost(const bpl_params *ps, const bpl_token_batch *b, int *keys, int *order, void *stream);
 /* Same, plus the fused backward (autograd-equivalent gradients). */
 int bpl_score_tokens_grad(const bpl_params *ps, const bpl_token_batch *b, const bpl_targets *t,
                           const bpl_fwd_out *out, const bpl_grads *g, void *stream);

@@ -73,10 +73,18 @@ def score(d, tab, dtype=np.float64, grad=False):
                 else:
                     tot += f(tab["sp_logp"][h][xi * nb + yi]) - f(tab["sp_log_binarea"])
             else:
+                ai = int(d["attach_ix"][ki])
+                if not 0 <= ai < i:                       # Categorical(ones(nprev)).log_prob outside its support (:636-638)
+                    tot += f(-np.inf)
+                    continue
                 tot += -f(math.log(i))
                 if cat == 3:
-                    na = int(nsub[k0 + int(d["attach_ix"][ki])])
-                    tot += -f(math.log(na)) - f(math.log(4.0))                                 # Uniform(2, ncpt + 1)
+                    na = int(nsub[k0 + ai])
+                    es = float(d["eval_spot_type"][ki]) if "eval_spot_type" in d else 2.0
+                    if 0 <= int(d["attach_subix"][ki]) < na and 2.0 <= es <= 6.0:
+                        tot += -f(math.log(na)) - f(math.log(4.0))                             # Uniform(2, ncpt + 1) (:639-647)
+                    else:
+                        tot += f(-np.inf)
         ll[p] = tot
         k0 += k
     if grad:

@@ -105,6 +105,7 @@ EXPORTS = {
     "bpl_score_tokens_lse": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.POINTER(TokenBatchC), ctypes.POINTER(Targets),
                                             ctypes.POINTER(FwdOut), vp, vp, ctypes.c_int, vp]),
     "bpl_order_tokens": (ctypes.c_int, [ctypes.POINTER(TokenBatchC), vp, vp]),
+    "bpl_order_tokens_by_cost": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.POINTER(TokenBatchC), vp, vp, vp]),
     "bpl_score_tokens_grad": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.POINTER(TokenBatchC),
                                              ctypes.POINTER(Targets), ctypes.POINTER(FwdOut), ctypes.POINTER(Grads), vp]),
     "bpl_render_strokes": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.POINTER(StrokeBatchC),

@@ -921,6 +921,9 @@ __global__ void __launch_bounds__(BT_NT *BT_TT, 1) bpl_backward_teams_kernel(con
     int par = 0;
     while (p < a.n_tokens) {
         par ^= 1;
+#ifdef BPL_TOKEN_TIMING
+        const long long tt0 = clock64();      // cycles per token -> a.pt_buf[p] (tools/token_cost_fit.py)
+#endif
         const TokGeom t = token_geom<false>(a, p);
         if (tm.tid == 0) {
             item = a.sched ? (int)atomicAdd(&a.sched->next, 1u) + n_teams : item + n_teams;
@@ -949,6 +952,9 @@ __global__ void __launch_bounds__(BT_NT *BT_TT, 1) bpl_backward_teams_kernel(con
         bt_scalars(sh, acc);
         bt_gather(sh);
         bt_chain(sh);
+#ifdef BPL_TOKEN_TIMING
+        if (tm.tid == 0 && a.pt_buf) a.pt_buf[p] = (float)(clock64() - tt0);
+#endif
         p = tk->next[par];
     }
     if (tm.tid == 0) {

@@ -238,6 +238,9 @@ __global__ void __launch_bounds__(S_THREADS, S_CTAS_PER_SM) bpl_forward1s_kernel
     int p = a.order ? a.order[item] : item;                     // the token it stands for
     while (p < a.n_tokens) {
         int p_next = 0;
+#ifdef BPL_TOKEN_TIMING
+        const long long tt0 = clock64();      // cycles per token -> a.pt_buf[p] (tools/token_cost_fit.py)
+#endif
         if (threadIdx.x == 0) p_next = sched_next_token(a, item);      // consumed at the end of the iteration
         TokGeom t = token_geom<false>(a, p);
         const bool bad = t.S > MAXS || t.K > MAXK;
@@ -415,6 +418,9 @@ __global__ void __launch_bounds__(S_THREADS, S_CTAS_PER_SM) bpl_forward1s_kernel
             }
         }
         __syncthreads();
+#ifdef BPL_TOKEN_TIMING
+        if (threadIdx.x == 0 && a.pt_buf) a.pt_buf[p] = (float)(clock64() - tt0);
+#endif
         p = ms->next_item;      // rewritten only at the end of the next iteration, many barriers from here
         BPL_PT(5);
     }

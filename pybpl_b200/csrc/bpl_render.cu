@@ -1128,6 +1128,86 @@ __global__ void __launch_bounds__(1024) order_tokens_kernel(const int *__restric
 }
 
 // ------------------------------------------------------------------------------------------
+// Processing order by ESTIMATED COST.  The sub-stroke count explains a third of a token's cost (corr. 0.58 on the bench
+// workload); most of it is stencil work, proportional to the area of the ink's bounding box, which varies from 3 % to
+// 100 % of the canvas independently of the sub-stroke count.  A spline lies in the convex hull of its control points
+// (the rows of coefficient_mat are non-negative and sum to one, pybpl/splines.py:72-93), so the box of the chained
+// control polygons bounds the ink box: one thread per token walks its sub-strokes (first / last trajectory point from
+// rows 0 and neval-1 of the basis table, part.py:316-326) and turns (area, sub-strokes) into a key of 256 cost classes.
+// ------------------------------------------------------------------------------------------
+constexpr int COST_BINS = 256;
+
+__global__ void __launch_bounds__(128) token_cost_kernel(const bpl_token_batch b, int reach, float w_area, float w_sub,
+                                                         int *__restrict__ keys) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= b.n_tokens) return;
+    const int k0 = b.tok_stroke_off[p], k1 = b.tok_stroke_off[p + 1];
+    const float *r0 = b.basis, *r1 = b.basis + (size_t)(b.neval - 1) * NCPT;
+    float xmin = 1e30f, xmax = -1e30f, ymin = 1e30f, ymax = -1e30f;
+    int S = 0;
+    for (int k = k0; k < k1; ++k) {
+        float px = b.position[2 * k], py = b.position[2 * k + 1];
+        for (int s = b.stroke_sub_off[k]; s < b.stroke_sub_off[k + 1]; ++s, ++S) {
+            const float inv = b.invscale[s];
+            const float *cp = b.ctrl + (size_t)s * NCPT * 2;
+            float yx[NCPT], yy[NCPT], ax = 0.0f, ay = 0.0f, ex = 0.0f, ey = 0.0f;
+#pragma unroll
+            for (int q = 0; q < NCPT; ++q) {
+                yx[q] = inv * cp[2 * q]; yy[q] = inv * cp[2 * q + 1];
+                ax = fmaf(r0[q], yx[q], ax); ay = fmaf(r0[q], yy[q], ay);
+                ex = fmaf(r1[q], yx[q], ex); ey = fmaf(r1[q], yy[q], ey);
+            }
+            const float ox = ax - px, oy = ay - py;
+#pragma unroll
+            for (int q = 0; q < NCPT; ++q) {
+                xmin = fminf(xmin, yx[q] - ox); xmax = fmaxf(xmax, yx[q] - ox);
+                ymin = fminf(ymin, yy[q] - oy); ymax = fmaxf(ymax, yy[q] - oy);
+            }
+            px = ex - ox; py = ey - oy;
+        }
+    }
+    float area = 0.0f;
+    if (S > 0 && xmin <= xmax) {
+        if (b.affine) {      // scale about the box centre (the centre of mass is near it), then shift (affine.py:48-53)
+            const float *A = b.affine + 4 * (size_t)p;
+            const float cx = 0.5f * (xmin + xmax), cy = 0.5f * (ymin + ymax);
+            const float hx = 0.5f * (xmax - xmin) * fabsf(A[0]), hy = 0.5f * (ymax - ymin) * fabsf(A[1]);
+            xmin = cx + A[2] - hx; xmax = cx + A[2] + hx; ymin = cy + A[3] - hy; ymax = cy + A[3] + hy;
+        }
+        // image rows = -y, columns = x (rendering.py:52-53); grown by the stencils' reach, clipped to the canvas
+        const float c0 = fmaxf(0.0f, xmin - reach), c1 = fminf((float)(IMG - 1), xmax + reach);
+        const float q0 = fmaxf(0.0f, -ymax - reach), q1 = fminf((float)(IMG - 1), -ymin + reach);
+        area = fmaxf(0.0f, c1 - c0 + 1.0f) * fmaxf(0.0f, q1 - q0 + 1.0f);
+    }
+    // cost above the fixed part, in units of an average token's (area 4060 px, 5.2 sub-strokes); 256 classes over 0 .. 2
+    const float cost = w_area * area * (1.0f / 4060.0f) + w_sub * (float)S * (1.0f / 5.2f);
+    keys[p] = COST_BINS - 1 - min(COST_BINS - 1, max(0, (int)(cost * 128.0f)));                         // 0 = most expensive
+}
+
+// counting sort of the tokens by key (one CTA; keys < COST_BINS)
+__global__ void __launch_bounds__(1024) order_by_key_kernel(const int *__restrict__ keys, int n, int *__restrict__ order) {
+    __shared__ int hist[COST_BINS], start[COST_BINS];
+    for (int i = threadIdx.x; i < COST_BINS; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int p = threadIdx.x; p < n; p += blockDim.x) atomicAdd(&hist[keys[p]], 1);
+    __syncthreads();
+    if (threadIdx.x < 32) {                          // exclusive scan of the bins by one warp
+        int carry = 0;
+        for (int base = 0; base < COST_BINS; base += 32) {
+            const int i = base + (int)threadIdx.x;
+            const int v = hist[i];
+            int inc = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, inc, d); if ((int)threadIdx.x >= d) inc += o; }
+            start[i] = carry + inc - v;
+            carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < n; p += blockDim.x) order[atomicAdd(&start[keys[p]], 1)] = p;
+}
+
+// ------------------------------------------------------------------------------------------
 // Inspection kernel: the integer work of the path, per point, through the very same device
 // functions the fused kernels use (chain_offsets / affine_setup / CtrlSrc / walk_round):
 // motor-space points, out-of-bounds mask (rendering.py:27-31), floor/ceil pixel indices
@@ -1252,7 +1332,7 @@ static int launch(K kernel, int threads, size_t smem, int ctas_per_sm, const KAr
         }
         kb.sched = ring + (slot.fetch_add(1u) % SCHED_RING);
     }
-#ifdef BPL_PHASE_TIMING
+#if defined(BPL_PHASE_TIMING) || defined(BPL_TOKEN_TIMING)
     if (const char *pb = getenv("BPL_PT_BUF")) kb.pt_buf = reinterpret_cast<float *>(strtoull(pb, nullptr, 10));
 #endif
     kernel<<<grid, threads, smem, st>>>(kb);
@@ -1318,6 +1398,24 @@ int bpl_order_tokens(const bpl_token_batch *b, int *order, void *stream) {
     return 0;
 }
 
+int bpl_order_tokens_by_cost(const bpl_params *ps, const bpl_token_batch *b, int *keys, int *order, void *stream) {
+    if (!ps || !b || !order || !keys || !b->tok_stroke_off || !b->stroke_sub_off || !b->basis) {
+        set_error("%s", "bpl_order_tokens_by_cost: NULL argument"); return BPL_EINVAL;
+    }
+    if (b->ncpt != NCPT || b->neval < 1) { set_error("%s", "bpl_order_tokens_by_cost: fused path is built for ncpt=5"); return BPL_ELIMIT; }
+    if (b->n_tokens <= 0) return 0;
+    // weights fitted to measured cycles per token (tools/token_cost_fit.py, 4 096 bench tokens): forward 0.39 + 0.36 area
+    // + 0.19 sub-strokes, fused backward 0.53 + 0.30 area + 0.12 sub-strokes; one key serves both
+    float w_area = 0.34f, w_sub = 0.17f;
+    if (const char *wenv = getenv("BPL_COST_W")) sscanf(wenv, "%f,%f", &w_area, &w_sub);      // tuning aid
+    token_cost_kernel<<<(b->n_tokens + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*b, ps->ink_ncon + 2 * PAD, w_area, w_sub, keys);
+    order_by_key_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(keys, b->n_tokens, order);
+    count_launch(2);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("kernel launch: %s", cudaGetErrorString(e)); return (int)e; }
+    return 0;
+}
+
 int bpl_score_tokens(const bpl_params *ps, const bpl_token_batch *b, const bpl_targets *t, const bpl_fwd_out *out,
                      void *stream) {
     if (b && b->n_tokens == 0) return 0;
@@ -1377,7 +1475,7 @@ int bpl_render_strokes(const bpl_params *ps, const bpl_stroke_batch *b, const bp
 }
 
 #ifndef BPL_BWD_TEAMS_MIN
-#define BPL_BWD_TEAMS_MIN 2048
+#define BPL_BWD_TEAMS_MIN 1024
 #endif
 static constexpr int BWD_TEAMS_MIN = BPL_BWD_TEAMS_MIN;
 
@@ -1393,7 +1491,8 @@ int bpl_score_tokens_grad(const bpl_params *ps, const bpl_token_batch *b, const 
     if (!ka.image_bits && !ka.g_pimg) { set_error("%s", "need target images or a pimg cotangent"); return BPL_EINVAL; }
     // Small batches: the full-canvas kernel, one 640-thread CTA per token and SM (shortest per-token latency, so the
     // shortest tail of the launch).  From BWD_TEAMS_MIN tokens on: teams of one persistent CTA per SM share the SM's
-    // whole shared memory as a pool of box-sized arenas, expensive tokens first (bpl_backward_teams.cuh).
+    // whole shared memory as a pool of box-sized arenas, expensive tokens first (bpl_backward_teams.cuh).  Measured
+    // M particles/s, canvas / teams: 1 024 tokens 3.80 / 4.04, 2 048: 4.12 / 4.46, 8 192: 4.49 / 4.92, 32 768: 4.60 / 5.05.
     // BPL_BWD_CANVAS=1 / BPL_BWD_TEAMS=1 force one or the other (A/B aids); BPL_BWD_ORDER=1 lets the canvas kernel follow
     // the processing order too (measured 2 % slower).
     // (read per call, not cached: the parity tests switch kernels inside one process)

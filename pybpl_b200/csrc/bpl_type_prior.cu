@@ -96,11 +96,18 @@ __global__ void __launch_bounds__(256) type_prior_kernel(const TQArgs a) {
                 if (gy >= L.sp_ylab[0] && gy <= L.sp_ylab[nb]) { yi = 0; while (yi < nb - 1 && gy >= L.sp_ylab[yi + 1]) ++yi; }
                 acc += (xi >= 0 && yi >= 0) ? (double)a.T.sp_logp[(size_t)h * nb * nb + xi * nb + yi] - (double)a.T.sp_log_binarea : -INFINITY;
             } else {
-                acc += -log((double)i);                                                                             // :636-638
-                if (cat == BPL_REL_MID) {                                                                           // :639-647
-                    const int j = k0 + a.ty.attach_ix[kk];
+                // Outside the support the reference's Categorical / Uniform log_prob raises (validate_args) or returns
+                // -inf; here such a type scores -inf -- and an out-of-range index is never followed.
+                const int ai = a.ty.attach_ix[kk];
+                const bool ai_ok = ai >= 0 && ai < i;
+                acc += ai_ok ? -log((double)i) : -INFINITY;                                                          // :636-638
+                if (cat == BPL_REL_MID && ai_ok) {                                                                  // :639-647
+                    const int j = k0 + ai;
                     const int na = a.stroke_sub_off[j + 1] - a.stroke_sub_off[j];
-                    acc += -log((double)na) - log((double)(BPL_NCPT + 1) - 2.0);
+                    const int asub = a.ty.attach_subix ? a.ty.attach_subix[kk] : 0;
+                    const float es = a.ty.eval_spot_type ? a.ty.eval_spot_type[kk] : 2.0f;                          // (NULL: not checked)
+                    const bool in_support = asub >= 0 && asub < na && es >= 2.0f && es <= (float)(BPL_NCPT + 1);     // Uniform(lb = 2, ub = ncpt + 1)
+                    acc += in_support ? -log((double)na) - log((double)(BPL_NCPT + 1) - 2.0) : -INFINITY;
                 }
             }
         }

@@ -9,6 +9,7 @@ Patched names (each bound by-name in the reference, so both the defining module 
   pybpl.splines.get_stk_from_bspline (+ new alias pybpl.splines.bspline_eval),
   pybpl.objects.relation.get_stk_from_bspline                                 (splines.py:108, relation.py:9)
   pybpl.splines.fit_bspline_to_traj                                           (splines.py:141)
+  pybpl.bottomup.initialize.util.{fit_bspline_to_traj, get_stk_from_bspline}  (util.py:5; when that module imports)
   pybpl.objects.part.vanilla_to_motor                                         (part.py:290)
   CharacterImageDist.get_pimg / sample_image / score_image                    (image_dist.py:32-80)
   CharacterTokenDist.score_token                                              (token_dist.py:264-287)
@@ -16,7 +17,10 @@ Patched names (each bound by-name in the reference, so both the defining module 
                                                                                instance's library is the shipped one,
                                                                                Library(use_hist=True))
 """
+import functools
 import importlib
+import os
+import weakref
 
 from . import model, objects, rendering, splines
 
@@ -44,30 +48,69 @@ def install(pybpl_module=None):
     _patch(S, "bspline_eval", splines.bspline_eval)
     _patch(S, "fit_bspline_to_traj", splines.fit_bspline_to_traj)
     _patch(REL, "get_stk_from_bspline", splines.get_stk_from_bspline)
+    try:      # the bottom-up parser binds both by name (bottomup/initialize/util.py:5); it needs networkx/skimage to import
+        BU = importlib.import_module("pybpl.bottomup.initialize.util")
+        _patch(BU, "fit_bspline_to_traj", splines.fit_bspline_to_traj)
+        _patch(BU, "get_stk_from_bspline", splines.get_stk_from_bspline)
+    except Exception:
+        pass
     _patch(P, "vanilla_to_motor", objects.vanilla_to_motor)
     mirror = model.CharacterImageDist
     for meth in ("get_pimg", "sample_image", "score_image"):
         _patch(ID.CharacterImageDist, meth, getattr(mirror, meth))
     TD = importlib.import_module("pybpl.model.token_dist")
-    scorer = {}
+    scorer = weakref.WeakKeyDictionary()      # per reference instance (an id() can be reused after garbage collection)
 
     def score_token(self, ctype, ctoken):      # the reference's instance keeps its own lib constants
-        key = id(self)
-        if key not in scorer:
-            scorer[key] = model.CharacterTokenDist(_LibView(self))
-        return scorer[key].score_token(ctype, ctoken)
+        sc = scorer.get(self)
+        if sc is None:
+            sc = scorer[self] = model.CharacterTokenDist(_LibView(self))
+        return sc.score_token(ctype, ctoken)
     _patch(TD.CharacterTokenDist, "score_token", score_token)
     YD = importlib.import_module("pybpl.model.type_dist")
     ref_score_type = YD.CharacterTypeDist.score_type
     type_scorer = model.CharacterTypeDist()
 
+    shipped = weakref.WeakKeyDictionary()     # reference instance -> does it hold the shipped tables?
+
     def score_type(self, ctype):
-        # the shipped tables are Library(use_hist=True)'s: any other library keeps the reference's own code
-        hist = type(self.rdist.Spatial).__module__.endswith("spatial_OLD.spatial_model")
-        if not hist or self.pdist.shapes_mu.shape[0] != 1212:
+        # the shipped tables are Library(use_hist=True)'s: any other (re-fitted, modified, use_hist=False) library keeps
+        # the reference's own code.  Decided once per instance by comparing table values, not just shapes.
+        ok = shipped.get(self)
+        if ok is None:
+            ok = shipped[self] = _holds_shipped_tables(self, type_scorer)
+        if not ok:
             return ref_score_type(self, ctype)
         return type_scorer.score_type(ctype)
     _patch(YD.CharacterTypeDist, "score_type", score_type)
+
+
+@functools.lru_cache(maxsize=1)
+def _shipped_tables():
+    import numpy as np
+    return dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "type_lib.npz")))
+
+
+def _holds_shipped_tables(td, type_scorer):
+    """True when a reference CharacterTypeDist instance carries the very tables pybpl_b200/data/type_lib.npz was exported
+    from: histogram spatial model, 1212 primitives, and equal values in samples of the shape means, the Gamma
+    parameters, the start / transition / stroke-count tables."""
+    import numpy as np
+    try:
+        if not type(td.rdist.Spatial).__module__.endswith("spatial_OLD.spatial_model"):
+            return False
+        tab = _shipped_tables()
+        mu = td.pdist.shapes_mu.detach().cpu().numpy().reshape(-1, 10)
+        if mu.shape != tab["shape_mu"].reshape(-1, 10).shape:
+            return False
+        same = np.allclose(mu, tab["shape_mu"].reshape(-1, 10), rtol=1e-6, atol=0)
+        same = same and np.allclose(td.kappa.probs.detach().cpu().numpy()[:tab["logp_kappa"].shape[0]], np.exp(tab["logp_kappa"]), rtol=1e-5, atol=1e-12)
+        same = same and np.allclose(np.exp(td.pdist.logStart.detach().cpu().numpy()), np.exp(tab["logp_start"]), rtol=1e-5, atol=1e-6)
+        same = same and np.allclose(td.pdist.scales_con.detach().cpu().numpy(), tab["gamma_con"], rtol=1e-6, atol=0)
+        same = same and np.allclose(td.pdist.scales_rate.detach().cpu().numpy(), tab["gamma_rate"], rtol=1e-6, atol=0)
+        return bool(same)
+    except Exception:
+        return False      # an unfamiliar instance: the reference's own code scores it
 
 
 class _LibView:

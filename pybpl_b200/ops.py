@@ -176,22 +176,36 @@ class TokenBatch:
         self._sub_token = None
         self._stroke_token = None
         self._order = None
+        self._order_cost = None
         self.use_order = use_order      # False: index order (streamed chunks: the order kernel would cost more than it saves)
 
     # Processing order for the persistent kernels: expensive tokens first, so that a launch of a few thousand tokens
-    # (a few dozen per SM) does not end with one SM still busy on a large one.  It depends only on the CSR offsets,
-    # so it is computed once per batch (one small kernel); large batches keep index order.
-    ORDER_MAX_TOKENS = 65536      # measured gain: +6.7 % at 4 096 tokens, +2.5 % at 8 192, +1.2 % at 16 384
+    # (a few dozen per SM) does not end with one SM still busy on a large one.  Two keys, each computed once per batch
+    # and kept (an order is only a heuristic, results do not depend on it):
+    #   forward scoring  : the sub-stroke count (offsets only, one small kernel) -- measured best for that kernel
+    #   fused backward   : estimated cost, area of the box of the control polygons + sub-stroke count
+    #                      (bpl_order_tokens_by_cost, from the geometry at that time): 1 024 parses 3.67 -> 4.04 M/s
+    # Large batches keep index order.
+    ORDER_MAX_TOKENS = 65536      # measured gain of an order at all: +6.7 % at 4 096 tokens, +2.5 % at 8 192, +1.2 % at 16 384
 
-    def order_ptr(self):
+    def order_ptr(self, b=None):
+        """b: the batch's C struct (geometry filled in) for the cost order of the fused backward; None = by sub-stroke count."""
         if not self.use_order or self.P > self.ORDER_MAX_TOKENS or self.P < 2 or os.environ.get("BPL_NO_ORDER"):      # (env: A/B aid)
             return None
+        if b is not None and self.S > 0 and not os.environ.get("BPL_ORDER_BY_S"):      # (env: A/B aid)
+            if self._order_cost is None:
+                order = torch.empty(self.P, dtype=torch.int32, device=self.device)
+                self._keys = torch.empty(self.P, dtype=torch.int32, device=self.device)
+                check(lib().bpl_order_tokens_by_cost(ctypes.byref(make_params(None)), ctypes.byref(b), self._keys.data_ptr(),
+                                                     order.data_ptr(), _stream(self.device)))
+                self._order_cost = order
+            return self._order_cost.data_ptr()
         if self._order is None:
             order = torch.empty(self.P, dtype=torch.int32, device=self.device)
-            b = _lib.TokenBatchC()
-            b.n_tokens = self.P
-            b.tok_stroke_off = self.tok_stroke_off.data_ptr(); b.stroke_sub_off = self.stroke_sub_off.data_ptr()
-            check(lib().bpl_order_tokens(ctypes.byref(b), order.data_ptr(), _stream(self.device)))
+            o = _lib.TokenBatchC()
+            o.n_tokens = self.P
+            o.tok_stroke_off = self.tok_stroke_off.data_ptr(); o.stroke_sub_off = self.stroke_sub_off.data_ptr()
+            check(lib().bpl_order_tokens(ctypes.byref(o), order.data_ptr(), _stream(self.device)))
             self._order = order
         return self._order.data_ptr()
 
@@ -213,7 +227,7 @@ class TokenBatch:
                                                          tso[1:] - tso[:-1], output_size=self.K)
         return self._stroke_token
 
-    def c_struct(self, ctrl, invscale, position, affine, eps, sigma):
+    def c_struct(self, ctrl, invscale, position, affine, eps, sigma, cost_order=False):
         b = _lib.TokenBatchC()
         b.n_tokens = self.P; b.ncpt = NCPT; b.neval = self.neval
         b.tok_stroke_off = self.tok_stroke_off.data_ptr(); b.stroke_sub_off = self.stroke_sub_off.data_ptr()
@@ -221,7 +235,8 @@ class TokenBatch:
         b.affine = None if affine is None else affine.data_ptr()
         b.eps = eps.data_ptr(); b.sigma = sigma.data_ptr()
         b.basis = basis_table(NCPT, self.neval, self.device).data_ptr()
-        b.order = self.order_ptr()
+        b.order = None
+        b.order = self.order_ptr(b if cost_order else None)
         return b
 
 
@@ -380,11 +395,11 @@ class _ScoreTokens(torch.autograd.Function):
         ll = torch.empty(P, dtype=torch.float32, device=dev)
         off = torch.empty(P, dtype=torch.uint8, device=dev)
         out = _lib.FwdOut(ll.data_ptr(), off.data_ptr(), None)
-        b = batch.c_struct(ctrl_c, inv_c, pos_c, aff_c, eps_c, sig_c)
         t = _targets(images, img_idx)
         # grad_on = torch.is_grad_enabled() of the CALLER (inside forward() it is always off): leaves evaluated under
         # no_grad take the cheaper forward-only kernel
         need = grad_on and any(ctx.needs_input_grad[:6])
+        b = batch.c_struct(ctrl_c, inv_c, pos_c, aff_c, eps_c, sig_c, cost_order=need)
         if need:
             g_ctrl = torch.empty_like(ctrl_c); g_inv = torch.empty_like(inv_c); g_pos = torch.empty_like(pos_c)
             g_aff = None if aff_c is None else torch.empty_like(aff_c)
@@ -450,7 +465,7 @@ class _RenderTokens(torch.autograd.Function):
         g_eps = torch.empty(P, dtype=torch.float32, device=dev); g_sig = torch.empty_like(g_eps)
         g = _lib.Grads(None, gp.data_ptr(), g_ctrl.data_ptr(), g_inv.data_ptr(), g_pos.data_ptr(),
                        None if g_aff is None else g_aff.data_ptr(), None, g_eps.data_ptr(), g_sig.data_ptr())
-        b = batch.c_struct(ctrl, inv, pos, aff, eps, sig)
+        b = batch.c_struct(ctrl, inv, pos, aff, eps, sig, cost_order=True)
         t = _lib.Targets()
         out = _lib.FwdOut(None, None, None)
         check(lib().bpl_score_tokens_grad(ctypes.byref(ctx.ps), ctypes.byref(b), ctypes.byref(t), ctypes.byref(out),

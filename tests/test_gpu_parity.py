@@ -551,6 +551,45 @@ def test_token_order_is_a_permutation_by_decreasing_cost(ops):
     assert torch.allclose(ll1, ll2, rtol=2e-6, atol=0)
 
 
+def test_cost_order_for_the_fused_backward(ops):
+    """bpl_order_tokens_by_cost: a permutation, non-increasing in its own cost classes, and the classes track the true ink
+    box (the box of the control polygons bounds it); gradients do not depend on the order."""
+    from pybpl_b200 import workload
+    P = 1500
+    w = workload.synth_tokens(P, seed=9, sigma_mode="uniform")
+    b = workload.to_device(w, DEV, requires_grad=True)
+    cs = b.c_struct(b.ctrl.detach(), b.invscale.detach(), b.position.detach(), None, b.eps.detach(), b.sigma.detach(), cost_order=True)
+    assert cs.order is not None and b._order_cost is not None
+    order = b._order_cost.cpu().numpy(); keys = b._keys.cpu().numpy()
+    assert np.array_equal(np.sort(order), np.arange(P))
+    assert np.all(np.diff(keys[order]) >= 0)                     # class 0 = most expensive, first
+    pts = ops.token_points(workload.to_device(w, DEV))
+    mask = pts["mask_out"].cpu().numpy().astype(bool); fl = pts["floor"].cpu().numpy(); ce = pts["ceil"].cpu().numpy()
+    tso, sso = w["tok_stroke_off"], w["stroke_sub_off"]
+    area = np.zeros(P)
+    for p in range(P):
+        s0, s1 = sso[tso[p]], sso[tso[p + 1]]
+        m = ~mask[s0:s1].reshape(-1)
+        if m.any():
+            f = fl[s0:s1].reshape(-1, 2)[m]; c = ce[s0:s1].reshape(-1, 2)[m]
+            h = min(104, c[:, 0].max() + 12) - max(0, f[:, 0].min() - 12) + 1
+            wd = min(104, c[:, 1].max() + 12) - max(0, f[:, 1].min() - 12) + 1
+            area[p] = h * wd
+    S = np.diff(sso[tso])
+    cost = 0.34 * area / 4060.0 + 0.17 * S / 5.2
+    r = np.corrcoef(cost, -keys.astype(np.float64))[0, 1]
+    print("corr(true-box cost, cost class)", r)
+    assert r > 0.9
+    pimg, _ = ops.render_tokens(workload.to_device(workload.permute(w, np.arange(1)), DEV))
+    imgs = ops.pack_images((pimg[0] > 0.5).to(torch.uint8))
+    leaves = [b.ctrl, b.invscale, b.position, b.eps, b.sigma]
+    g1 = torch.autograd.grad(ops.score_tokens(b, imgs)[0].sum(), leaves)
+    b._order_cost = torch.arange(P, dtype=torch.int32, device=DEV)
+    g2 = torch.autograd.grad(ops.score_tokens(b, imgs)[0].sum(), leaves)
+    for x, y in zip(g1, g2):
+        assert (x - y).abs().max() <= 2e-5 * x.abs().max()
+
+
 # ---------------------------------------------------------------------------------------------
 # the benchmarked kernel (bpl_forward1s_kernel<false>, forward only) on the bench workloads, against the oracle
 # ---------------------------------------------------------------------------------------------

@@ -185,6 +185,34 @@ def test_type_score_matches_reference():
     assert np.max(np.abs(got[fin] - o[fin]) / np.abs(o[fin])) < 2e-6
 
 
+def test_type_score_outside_the_support_is_minus_inf():
+    """A 'mid' relation whose spline coordinate lies outside Uniform(2, ncpt + 1), or whose attachment indices are out
+    of range, has no finite score: the reference's Uniform / Categorical log_prob returns -inf or raises there
+    (type_dist.py:636-647).  The kernel gives -inf (and never follows the bad index); the numpy oracle states the rule."""
+    from oracle import type_prior as tp
+    from pybpl_b200 import ops
+    d = dict(load("type_prior"))
+    mids = np.flatnonzero(d["rel_cat"] == ops.REL_CODES["mid"])
+    later = np.flatnonzero((d["rel_cat"] != ops.REL_CODES["unihist"]))
+    assert len(mids) >= 3 and len(later) >= 2
+    d["eval_spot_type"] = d["eval_spot_type"].copy(); d["attach_ix"] = d["attach_ix"].copy(); d["attach_subix"] = d["attach_subix"].copy()
+    d["eval_spot_type"][mids[0]] = 1.5            # below lb = 2
+    d["eval_spot_type"][mids[1]] = 6.25           # above ub = ncpt + 1
+    d["attach_subix"][mids[2]] = 99               # no such sub-stroke
+    d["attach_ix"][later[-1]] = 31                # no such stroke
+    stroke_type = np.repeat(np.arange(len(d["K"])), d["K"])
+    hit = np.zeros(len(d["K"]), bool); hit[stroke_type[[mids[0], mids[1], mids[2], later[-1]]]] = True
+    lib = ops.TypeLibrary(DEV)
+    tso, sso, types, subid = _type_inputs(ops, d)
+    got = ops.score_type_prior(lib, tso, sso, types, subid).cpu().numpy()
+    tab = dict(np.load(os.path.join(ROOT, "pybpl_b200", "data", "type_lib.npz")))
+    o = tp.score(d, tab, np.float64)
+    assert np.all(got[hit] == -np.inf) and np.all(o[hit] == -np.inf)
+    fin = np.isfinite(o)
+    assert np.array_equal(np.isfinite(got), fin)
+    assert np.max(np.abs(got[fin] - o[fin]) / np.abs(o[fin])) < 2e-6
+
+
 def test_type_score_of_sampled_types_is_the_negative_entropy_rate(draw):
     """Consistency of sampler and scorer on 200 000 draws: every drawn type has a finite score, and the mean score of
     types with exactly one stroke and one sub-stroke matches the mean score of the reference's own such draws."""
