@@ -17,15 +17,17 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pybpl_b200 import ops, workload  # noqa: E402
 
 
-def fit(P=1024, steps=100, lr=4e-3, seed=2024, device="cuda:0", log_every=0, token_prior=False, graph=True):
+def fit(P=1024, steps=100, lr=4e-3, seed=2024, device="cuda:0", log_every=0, token_prior=False, graph=True, target=None):
     dev = torch.device(device)
     w = workload.synth_tokens(P, seed=seed, sigma_mode=10.0)
     batch = workload.to_device(w, dev, requires_grad=True)
-    # target: a sample of parse 0's own probability map
-    with torch.no_grad():
-        pimg, _ = ops.render_tokens(workload.to_device(workload.permute(w, np.array([0])), dev))
-        g = torch.Generator(device="cpu").manual_seed(seed)
-        target = (torch.rand(105, 105, generator=g).to(dev) < pimg[0]).to(torch.uint8)
+    if target is None:      # a sample of parse 0's own probability map
+        with torch.no_grad():
+            pimg, _ = ops.render_tokens(workload.to_device(workload.permute(w, np.array([0])), dev))
+            g = torch.Generator(device="cpu").manual_seed(seed)
+            target = (torch.rand(105, 105, generator=g).to(dev) < pimg[0]).to(torch.uint8)
+    else:                   # given (the parity test passes the image the reference's goldens were made with)
+        target = torch.as_tensor(np.asarray(target), dtype=torch.uint8, device=dev)
     imgs = ops.pack_images(target)
     params = [batch.ctrl, batch.invscale, batch.position, batch.sigma, batch.eps]
     types = prior_c = None

@@ -2,9 +2,8 @@
 
 `oracle/bpl_oracle.c` (plain C, fp32 and fp64 instantiations) restates the
 reference algorithm (each function cites the /root/reference file:line it
-follows); this module is its ctypes/numpy binding, and `oracle/torch_port.py` is
-a second, torch-op-level restatement used for autograd gradients and as the
-"reference-like" CPU baseline.
+follows); this module is its ctypes/numpy binding.  `oracle/token_prior.py` and
+`oracle/type_prior.py` are numpy restatements of the two prior scores.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 `--impl reference` legs may import this package.  The product (pybpl_b200/)

@@ -427,7 +427,10 @@ __device__ __forceinline__ float bt_tail(const BtShared *sh, const BtTok *tk, co
         // A pixel without ink has the analytic background value (closed form in bt_scalars); pm == bgv alone does not
         // mean "no ink" (eps = 0.5 maps every v to 0.5).
         if (eps > 0.0f && (pm != bgv || i6 != 0.0f))
-            acc.eps += ((double)(d * (1.0f - 2.0f * i6)) - ms->dlp_bg_d[x]) * (double)gscale;
+        {   // in double from the fp32 probability on (the terms are +-1e4 and cancel to a few tens)
+            const double dd = (d == 0.0f) ? 0.0 : (x ? 1.0 / (double)pm : -1.0 / (1.0 - (double)pm));
+            acc.eps += (dd * (1.0 - 2.0 * (double)i6) - ms->dlp_bg_d[x]) * (double)gscale;
+        }
         gp = d * gscale;
     }
     return pass5 ? gp * tk->mixd : 0.0f;

@@ -12,7 +12,7 @@
 #include "../../include/pybpl_b200.h"
 
 // Optional per-phase cycle counters (build with -DBPL_PHASE_TIMING; thread 0 of every CTA accumulates clock64()
-// deltas, written to a.g_pts[blockIdx.x*16 + phase]; used only by tools/phase_timing.py).
+// deltas, written to a.pt_buf[blockIdx.x*16 + phase]; used only by tools/phase_timing_sparse.py).
 #ifdef BPL_PHASE_TIMING
 #define BPL_PT(n) do { if (threadIdx.x == 0) { const long long t1_ = clock64(); pt_acc[n] += t1_ - pt_t0; pt_t0 = t1_; } } while (0)
 #else
@@ -225,7 +225,8 @@ __device__ __forceinline__ void pixel_lp(float p, bool x, bool want_grad, float 
 //   1 - a < 1/8    : -b (1 + b/2 + ... + b^7/8), truncation b^8/9                  -> 7e-9 (+ rounding 2e-7)
 //   otherwise      : hardware log, absolute error 2^-21.41 on |log a| >= 0.1335    -> 2.7e-6
 // i.e. ll is within 3e-6 relative of the exact sum; a and its complement b = 1 - a are both exact inputs
-// (b = p or 1 - p with p >= 1/2).  The backward kernel keeps libm logs (pixel_lp).
+// (b = p or 1 - p with p >= 1/2).  The fused backward kernels score with this function too; the dense probability-map
+// kernel keeps the two-logarithm form (pixel_lp).
 __device__ __forceinline__ float pixel_lp_fwd(float p, bool x) {
     const float pt = fminf(fmaxf(p, TORCH_EPS), 1.0f - TORCH_EPS);
     const float q = 1.0f - pt;

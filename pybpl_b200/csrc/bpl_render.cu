@@ -29,7 +29,7 @@ namespace bpl {
 // behind the mean.  CTAs take their first item by blockIdx.x and every later one from `next`; the CTA that
 // finishes last resets the slot, so a slot is all-zero again when its launch completes.
 struct Sched { unsigned next, done; };
-constexpr int SCHED_RING = 4096;      // launches in flight at once never come near this
+constexpr int SCHED_RING = 4096;      // lower half: live launches in flight (never near 2 048); upper half: launches captured in CUDA graphs
 __device__ Sched g_sched[SCHED_RING];
 
 struct KArgs {
@@ -514,7 +514,6 @@ __device__ __forceinline__ void broaden(float *A, float *T, const RenderConsts &
 }  // namespace bpl
 
 #include "bpl_forward.cuh"
-#include "bpl_forward2.cuh"
 #include "bpl_forward1s.cuh"
 
 namespace bpl {
@@ -799,7 +798,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) bpl_backward_kernel(const KArg
                 // A pixel without ink has the analytic background value (closed form below); pm == bgv alone does not
                 // mean "no ink" (eps = 0.5 maps every v to 0.5).
                 if (eps > 0.0f && (pm != bgv || i6 != 0.0f))
-                    acc_eps += ((double)(d * (1.0f - 2.0f * i6)) - (x ? dlp_bgd1 : dlp_bgd0)) * (double)gscale;
+                {   // in double from the fp32 probability on (the terms are +-1e4 and cancel to a few tens)
+                    const double dd = (d == 0.0f) ? 0.0 : (x ? 1.0 / (double)pm : -1.0 / (1.0 - (double)pm));
+                    acc_eps += (dd * (1.0 - 2.0 * (double)i6) - (x ? dlp_bgd1 : dlp_bgd0)) * (double)gscale;
+                }
                 gp = d * gscale;
             }
             return pass5 ? gp * mixd : 0.0f;
@@ -1330,7 +1332,18 @@ static int launch(K kernel, int threads, size_t smem, int ctas_per_sm, const KAr
             if (es != cudaSuccess) { set_error("cudaGetSymbolAddress: %s", cudaGetErrorString(es)); return (int)es; }
             ring_dev = dev;
         }
-        kb.sched = ring + (slot.fetch_add(1u) % SCHED_RING);
+        // A launch owns its slot from launch to completion (the last CTA resets it).  Live launches rotate through
+        // the lower half of the ring -- 2 048 launches would have to be in flight at once to collide.  A launch that is
+        // being CAPTURED into a CUDA graph keeps its slot for every replay, so it takes one from the upper half, which
+        // live launches never touch; replays of one graph are serialised by CUDA when they are launched into one
+        // stream (examples/fit_parses.py).  Launching the SAME captured graph into two streams at once, or capturing
+        // more than 2 048 launches that later run concurrently, is not supported.
+        static std::atomic<unsigned> slot_captured{0};
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) { cap = cudaStreamCaptureStatusNone; (void)cudaGetLastError(); }
+        kb.sched = (cap == cudaStreamCaptureStatusActive)
+                       ? ring + SCHED_RING / 2 + (slot_captured.fetch_add(1u) % (SCHED_RING / 2))
+                       : ring + (slot.fetch_add(1u) % (SCHED_RING / 2));
     }
 #if defined(BPL_PHASE_TIMING) || defined(BPL_TOKEN_TIMING)
     if (const char *pb = getenv("BPL_PT_BUF")) kb.pt_buf = reinterpret_cast<float *>(strtoull(pb, nullptr, 10));
@@ -1426,20 +1439,16 @@ int bpl_score_tokens(const bpl_params *ps, const bpl_token_batch *b, const bpl_t
     if (ka.all_pairs && (!ka.image_bits || ka.pimg || ka.n_images < 1)) {
         set_error("%s", "all_pairs scoring needs target images and no pimg output"); return BPL_EINVAL;
     }
-    // Scoring one target per token: the box-confined kernel (one token per CTA).  BPL_FWD_PAIRED=1 / BPL_FORCE_SINGLE=1
-    // select the dense paired / dense single kernels instead (A/B and profiling aids).
+    // Scoring: the box-confined kernel (one token per CTA).  Probability maps (pimg), and BPL_FORCE_SINGLE=1 (A/B and
+    // profiling aid, one target per token only), take the dense single-token kernel.
     static const bool force_single = getenv("BPL_FORCE_SINGLE") != nullptr;
-    static const bool force_paired = getenv("BPL_FWD_PAIRED") != nullptr;
-    if (!force_single && !force_paired && ka.image_bits && !ka.pimg) {
+    if (ka.image_bits && !ka.pimg && (ka.all_pairs || !force_single)) {
         if (ka.all_pairs) {      // (tokens are few in this mode: no processing order)
             ka.order = nullptr;
             return launch(bpl_forward1s_kernel<true>, S_THREADS, sizeof(Fwd1sSmem), S_CTAS_PER_SM, ka, (cudaStream_t)stream);
         }
         return launch(bpl_forward1s_kernel<false>, S_THREADS, sizeof(Fwd1sSmem), S_CTAS_PER_SM, ka, (cudaStream_t)stream);
     }
-    if (ka.image_bits && !ka.pimg && (!force_single || ka.all_pairs))      // scoring hot path: two tokens per CTA, packed FP32 stencils
-        return launch(bpl_forward2_kernel, F2_THREADS, sizeof(Fwd2Smem), F2_CTAS_PER_SM, ka, (cudaStream_t)stream,
-                      (ka.n_tokens + 1) / 2);
     return launch(bpl_forward_kernel<false>, FWD_THREADS, sizeof(FwdSmem), FWD_CTAS_PER_SM, ka, (cudaStream_t)stream);
 }
 

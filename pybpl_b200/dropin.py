@@ -9,7 +9,8 @@ Patched names (each bound by-name in the reference, so both the defining module 
   pybpl.splines.get_stk_from_bspline (+ new alias pybpl.splines.bspline_eval),
   pybpl.objects.relation.get_stk_from_bspline                                 (splines.py:108, relation.py:9)
   pybpl.splines.fit_bspline_to_traj                                           (splines.py:141)
-  pybpl.bottomup.initialize.util.{fit_bspline_to_traj, get_stk_from_bspline}  (util.py:5; when that module imports)
+  pybpl.bottomup.initialize.util.{fit_bspline_to_traj, get_stk_from_bspline, fit_smooth_stk}
+                                                                              (util.py:5,13; when that module imports)
   pybpl.objects.part.vanilla_to_motor                                         (part.py:290)
   CharacterImageDist.get_pimg / sample_image / score_image                    (image_dist.py:32-80)
   CharacterTokenDist.score_token                                              (token_dist.py:264-287)
@@ -52,6 +53,7 @@ def install(pybpl_module=None):
         BU = importlib.import_module("pybpl.bottomup.initialize.util")
         _patch(BU, "fit_bspline_to_traj", splines.fit_bspline_to_traj)
         _patch(BU, "get_stk_from_bspline", splines.get_stk_from_bspline)
+        _patch(BU, "fit_smooth_stk", splines.fit_smooth_stk)
     except Exception:
         pass
     _patch(P, "vanilla_to_motor", objects.vanilla_to_motor)

@@ -141,6 +141,30 @@ class ParseFile:
             raise ValueError("parse file offsets are inconsistent")
         if P and (np.diff(tso).max() > MAX_STROKES or np.diff(sso[tso]).max() > MAX_SUBSTROKES):
             raise ValueError("a token exceeds 32 strokes / 128 sub-strokes (BPL_MAX_*)")
+        # every section against the header's counts: the kernels index these arrays by the offsets without bounds checks
+        want = {"ctrl": (S, NCPT, 2), "invscale": (S,), "position": (K, 2), "eps": (P,), "sigma": (P,), "affine": (P, 4),
+                "ctrl_type": (S, NCPT, 2), "invscale_type": (S,), "rel_cat": (K,), "attach_ix": (K,), "attach_subix": (K,),
+                "gpos": (K, 2), "eval_spot_type": (K,), "eval_spot": (K,), "image_bits": (T, IMG_WORDS)}
+        for k, shp in want.items():
+            if k in self.table and tuple(self.table[k][1]) != shp:
+                raise ValueError(f"parse file section {k} has shape {tuple(self.table[k][1])}, the header says {shp}")
+        if "rel_cat" in self.table and K:
+            rank = np.arange(K) - np.repeat(tso[:-1], np.diff(tso))          # stroke index inside its token
+            cat, aix, asub = a["rel_cat"], a["attach_ix"], a["attach_subix"]
+            if cat.min() < 0 or cat.max() > 3:
+                raise ValueError("parse file: rel_cat outside 0..3")
+            att = cat != 0
+            if np.any(att & ((aix < 0) | (aix >= rank))):
+                raise ValueError("parse file: attach_ix does not name an earlier stroke of the same token")
+            mid = cat == 3
+            if mid.any():
+                tgt = np.repeat(tso[:-1], np.diff(tso))[mid] + aix[mid]
+                if np.any((asub[mid] < 0) | (asub[mid] >= np.diff(sso)[tgt])):
+                    raise ValueError("parse file: attach_subix outside the attached stroke's sub-strokes")
+        if "image_bits" in self.table and T:
+            used = IMSIZE * IMSIZE - 32 * (IMG_WORDS - 1)                      # 17 pixels in the last word, 15 padding bits
+            if np.any(a["image_bits"].view(np.uint32)[:, -1] >> np.uint32(used)):
+                raise ValueError("parse file: padding bits of an image are set (the ones count would be wrong)")
 
     @classmethod
     def load(cls, path, pin=None):

@@ -88,6 +88,36 @@ def fit_bspline_to_traj(X, nland, s=None, include_resid=False):
     return Y
 
 
+def fit_smooth_stk(stroke, loss_threshold=0.3, max_nland=100, unif_space=None):
+    """The "smooth" version of a stroke: the spline with the fewest control points whose mean squared residual stays
+    below `loss_threshold`, evaluated with the adaptive number of points (pybpl/bottomup/initialize/util.py:13-31: the
+    refit loop over fit_bspline_to_traj, then get_stk_from_bspline).  The least-squares fits and the evaluation run on
+    the GPU; the loop itself is the reference's (first nland under the threshold, in increasing order).
+
+    stroke: [n,2] numpy array or tensor.  unif_space: the resampling function the reference applies first
+    (pybpl/data/unif_space.py, host-side data preparation, outside this package); None uses the reference's when it is
+    importable and otherwise expects `stroke` to be uniformly spaced already.  Returns a numpy array like the reference."""
+    import numpy as np
+    ntraj = len(stroke)
+    if ntraj == 1:
+        return stroke
+    if unif_space is None:
+        try:
+            from pybpl.data.unif_space import unif_space
+        except Exception:
+            unif_space = None
+    if unif_space is not None:
+        stroke = unif_space(stroke)
+    stroke = torch.as_tensor(np.asarray(stroke), dtype=torch.float)
+    Xd = stroke.to(_compute_device(stroke))
+    for nland in range(1, min(max_nland, ntraj + 1)):
+        spline, residuals = fit_bspline_to_traj(Xd, nland, include_resid=True)
+        loss = torch.sum(residuals) / ntraj
+        if loss.item() < loss_threshold:
+            break
+    return get_stk_from_bspline(spline).cpu().numpy()
+
+
 def bspline_eval(sval, cpts):
     """Evaluate the spline with control points `cpts` [nland,2] at times `sval` (scalar or [n])."""
     return get_stk_from_bspline(cpts, s=sval)

@@ -1,0 +1,102 @@
+#!/usr/bin/env python
+"""tests/golden/fit64.npz: BASELINE.json configs[2] at 64 parses, step 0, from the LIVE reference.
+
+The 64 parses of workload.synth_tokens(64, seed=2024, sigma_mode=10.0) (= examples/fit_parses.py's start state) are turned
+into real pybpl CharacterTokens and scored by the unmodified CharacterImageDist.score_image against the target image
+(a Bernoulli sample of parse 0's own reference-rendered probability map); autograd gives d ll / d {shapes, invscales,
+position, blur_sigma, epsilon}.  torch >= 2 refuses to differentiate through the in-place clamp_ of rendering.py:97, so
+that one token is made out-of-place in memory (baseline/ref_loader.py, forward bit-identical).  Build container only:
+
+    python tests/golden/make_fit_golden.py                 # fit64.npz
+    python tests/golden/make_fit_golden.py --fit-smooth    # fit_smooth.npz (fit_smooth_stk, see make_fit_smooth)
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+warnings.filterwarnings("ignore")
+
+
+def main(P=64, seed=2024):
+    from baseline import ref_loader, torch_ref
+    from pybpl_b200 import workload
+    ref_loader.load(grad_patch=True)
+    from pybpl.model.image_dist import CharacterImageDist
+    torch.manual_seed(0)
+    w = workload.synth_tokens(P, seed=seed, sigma_mode=10.0)
+    toks = torch_ref._tokens_from(w, 0, P)
+    dist = CharacterImageDist(None)
+    with torch.no_grad():
+        pimg0 = dist.get_pimg(toks[0])
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    target = (torch.rand(105, 105, generator=g) < pimg0).to(torch.float32)
+    out = dict(target=target.numpy().astype(np.uint8), ll=np.zeros(P, np.float32), g_ctrl=np.zeros_like(w["ctrl"]),
+               g_invscale=np.zeros_like(w["invscale"]), g_position=np.zeros_like(w["position"]),
+               g_sigma=np.zeros(P, np.float32), g_eps=np.zeros(P, np.float32))
+    tso, sso = w["tok_stroke_off"].astype(np.int64), w["stroke_sub_off"].astype(np.int64)
+    for p, t in enumerate(toks):
+        leaves = [x for pt in t.part_tokens for x in (pt.shapes, pt.invscales, pt.position)] + [t.blur_sigma, t.epsilon]
+        for x in leaves:
+            x.requires_grad_(True)
+        ll = dist.score_image(t, target)
+        ll.backward()
+        out["ll"][p] = float(ll)
+        for i, pt in enumerate(t.part_tokens):
+            k = tso[p] + i
+            out["g_ctrl"][sso[k]:sso[k + 1]] = pt.shapes.grad.permute(2, 0, 1).numpy()
+            out["g_invscale"][sso[k]:sso[k + 1]] = pt.invscales.grad.numpy()
+            out["g_position"][k] = pt.position.grad.numpy()
+        out["g_sigma"][p] = float(t.blur_sigma.grad)
+        out["g_eps"][p] = float(t.epsilon.grad)
+    path = os.path.join(ROOT, "tests", "golden", "fit64.npz")
+    np.savez_compressed(path, P=P, seed=seed, **out)
+    print("wrote", path, "mean ll", out["ll"].mean(), {k: float(np.abs(v).max()) for k, v in out.items() if k.startswith("g_")})
+
+
+if __name__ == "__main__" and "--fit-smooth" not in sys.argv:
+    main()
+
+
+def make_fit_smooth():
+    """tests/golden/fit_smooth.npz: the reference's fit_smooth_stk (pybpl/bottomup/initialize/util.py:13-31) on a few
+    trajectories.  pybpl.bottomup needs scikit-image at import time, which this image lacks, so the function's own source
+    text is executed against the reference's unif_space / fit_bspline_to_traj / get_stk_from_bspline (nothing is edited)."""
+    import ast
+    from baseline import ref_loader
+    ref_loader.load()
+    import pybpl.splines as S
+    import importlib.util      # pybpl/data/__init__.py does not import under numpy 2 (np.infty): load the one file
+    spec = importlib.util.spec_from_file_location("_ref_unif_space", os.path.join(ref_loader.REF, "pybpl", "data", "unif_space.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    unif_space = mod.unif_space
+    src = open(os.path.join(ref_loader.REF, "pybpl", "bottomup", "initialize", "util.py")).read()
+    fn = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "fit_smooth_stk")
+    ns = dict(torch=torch, np=np, unif_space=unif_space, fit_bspline_to_traj=S.fit_bspline_to_traj,
+              get_stk_from_bspline=S.get_stk_from_bspline)
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "util.py", "exec"), ns)
+    rng = np.random.default_rng(3)
+    t = np.linspace(0, 1, 60)
+    strokes = [np.stack([10 + 60 * t, -20 - 40 * t], 1),                                        # a line
+               np.stack([50 + 25 * np.cos(5 * t), -50 + 25 * np.sin(5 * t)], 1),                # most of a circle
+               np.stack([10 + 80 * t, -50 + 20 * np.sin(9 * t)], 1),                            # a wave
+               np.stack([30 + 40 * t * np.cos(8 * t), -50 + 40 * t * np.sin(8 * t)], 1),        # a spiral
+               np.stack([20 + 50 * t + rng.normal(0, 0.6, 60), -30 - 30 * t ** 2 + rng.normal(0, 0.6, 60)], 1),   # noisy arc
+               np.array([[40.0, -40.0]])]                                                       # a single point
+    out = {}
+    for i, s in enumerate(strokes):
+        s = s.astype(np.float32)
+        out[f"in_{i}"] = s
+        out[f"unif_{i}"] = np.asarray(unif_space(s), np.float32)
+        out[f"out_{i}"] = np.asarray(ns["fit_smooth_stk"](s), np.float32)
+    path = os.path.join(ROOT, "tests", "golden", "fit_smooth.npz")
+    np.savez_compressed(path, n=len(strokes), **out)
+    print("wrote", path, [out[f"out_{i}"].shape for i in range(len(strokes))])
+
+
+if __name__ == "__main__" and "--fit-smooth" in sys.argv:
+    make_fit_smooth()

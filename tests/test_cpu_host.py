@@ -206,3 +206,33 @@ def test_parse_file_roundtrip_and_layout(tmp_path):
         packed.ParseFile(bytes(bad), pin=False)
     with pytest.raises(ValueError):
         packed.pack_bits(np.full((1, 105, 105), 0.5))
+
+
+def test_parse_file_rejects_malformed_sections(tmp_path):
+    """ParseFile checks every section against the header's counts, the attachment indices against the token structure and
+    the images' padding bits: the kernels index these arrays without bounds checks."""
+    import numpy as np
+    from pybpl_b200 import packed, workload
+    w = workload.synth_tokens(120, seed=4, sigma_mode="uniform")
+    ty = workload.synth_types(w, 5)
+    imgs = (np.random.default_rng(1).random((3, 105, 105)) < 0.1).astype(np.uint8)
+    bits = packed.pack_bits(imgs)
+    packed.ParseFile(packed.to_bytes(w, ty, imgs), pin=False)                        # the well-formed file loads
+
+    def rejected(w2=w, ty2=ty, bits2=bits):
+        with pytest.raises(ValueError):
+            packed.ParseFile(packed.to_bytes(w2, ty2, image_bits=bits2), pin=False)
+    rejected(w2=dict(w, eps=w["eps"][:-1]))                                          # eps shorter than P
+    rejected(w2=dict(w, position=np.concatenate([w["position"], w["position"][:1]])))  # position longer than K
+    later = np.flatnonzero(ty["rel_cat"] != 0)
+    assert later.size
+    bad = dict(ty, attach_ix=ty["attach_ix"].copy()); bad["attach_ix"][later[0]] = 31
+    rejected(ty2=bad)                                                                # names a stroke that does not exist
+    bad = dict(ty, rel_cat=ty["rel_cat"].copy()); bad["rel_cat"][0] = 7
+    rejected(ty2=bad)
+    mids = np.flatnonzero(ty["rel_cat"] == 3)
+    if mids.size:
+        bad = dict(ty, attach_subix=ty["attach_subix"].copy()); bad["attach_subix"][mids[0]] = 99
+        rejected(ty2=bad)
+    b2 = bits.copy(); b2[1, -1] |= np.uint32(1 << 20)                                # a padding bit
+    rejected(bits2=b2)

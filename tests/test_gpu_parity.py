@@ -4,6 +4,8 @@ live reference and against the CPU oracle on the same seeded inputs.
 Bars (BASELINE.json north_star): integer work bit-exact; fp32 pimg / ll within 1e-5 relative;
 gradients per tensor in inf-norm-relative terms, stated below next to the reference's own fp32 noise
 (the reference's autograd is 7e-5 (points) .. 5e-3 (d/d sigma) from fp64)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -265,27 +267,45 @@ def test_tokens_gradients(ops, bwd_kernel):
 
 
 def test_gradients_no_worse_than_reference_vs_fp64(ops, bwd_kernel):
-    """|g_cuda - g_fp64| <= |g_ref - g_fp64| (+ slack) per tensor: the build is as accurate as the reference."""
+    """Per gradient tensor, the distance to the fp64 oracle: max over tokens of |g_cuda - g_fp64| must not exceed the same
+    figure for the reference's own fp32 autograd, max |g_ref - g_fp64| (factor 1.0, plus an absolute slack of 1e-6 of
+    the tensor's scale; 1.5 for epsilon, see below), and the median token is within 5 % of the reference's -- the build
+    is as accurate as the reference for every leaf: control points, scales, positions, blur_sigma, epsilon."""
     from oracle import Oracle
     d, toks = token_cases()
     sel = [t for t in toks if not t["has_affine"]][:24]
     batch, imgs, idx, b = make_token_batch(ops, sel, grad=True, with_affine=False)
     ll, _ = ops.score_tokens(batch, imgs, idx)
     ll.sum().backward()
-    gc = batch.ctrl.grad.cpu().numpy(); gs = batch.sigma.grad.cpu().numpy()
+    got = dict(ctrl=batch.ctrl.grad.cpu().numpy(), invscale=batch.invscale.grad.cpu().numpy(),
+               position=batch.position.grad.cpu().numpy(), sigma=batch.sigma.grad.cpu().numpy(), eps=batch.eps.grad.cpu().numpy())
     o64 = Oracle(np.float64)
     C64 = d["basis_5_200"].astype(np.float64)
-    s0 = 0
-    ours, refs = [], []
+    s0 = k0 = 0
+    ours = {k: [] for k in got}; refs = {k: [] for k in got}
     for i, t in enumerate(sel):
-        S = len(t["invscale"])
+        S, K = len(t["invscale"]), len(t["nsub"])
         r = o64.token(C64, t["nsub"], t["ctrl"], t["invscale"], t["position"], t["eps"], t["sigma"],
                       image=t["image"], grad=True)
-        ours.append(relinf(gc[s0:s0 + S], r["g_ctrl"])); refs.append(relinf(t["g_ctrl"], r["g_ctrl"]))
-        s0 += S
-    print("g_ctrl vs fp64: ours max %.2e median %.2e | reference max %.2e median %.2e" %
-          (max(ours), np.median(ours), max(refs), np.median(refs)))
-    assert max(ours) <= max(3 * max(refs), 2e-4)
+        for name, mine, ref, tru in (("ctrl", got["ctrl"][s0:s0 + S], t["g_ctrl"], r["g_ctrl"]),
+                                     ("invscale", got["invscale"][s0:s0 + S], t["g_invscale"], r["g_invscale"]),
+                                     ("position", got["position"][k0:k0 + K], t["g_position"], r["g_position"]),
+                                     ("sigma", got["sigma"][i:i + 1], np.atleast_1d(t["g_sigma"]), np.atleast_1d(r["g_sigma"])),
+                                     ("eps", got["eps"][i:i + 1], np.atleast_1d(t["g_eps"]), np.atleast_1d(r["g_eps"]))):
+            scale = max(np.abs(tru).max(), 1.0 if name in ("sigma", "eps") else 1e-30)
+            ours[name].append(np.abs(mine - tru).max() / scale); refs[name].append(np.abs(np.asarray(ref) - tru).max() / scale)
+        s0 += S; k0 += K
+    for name in got:
+        print("g_%s vs fp64 (%s kernel): ours max %.2e median %.2e | reference max %.2e median %.2e" %
+              (name, bwd_kernel, max(ours[name]), np.median(ours[name]), max(refs[name]), np.median(refs[name])))
+    # factor 1.0 on the worst token for every leaf but epsilon: its worst token is one whose target has zeros under
+    # p ~ 0.9996 ink, where d lp / d p = -1 / (1 - p) turns the 6e-8 rounding of the fp32 probability itself into
+    # 1.5e-4 per term -- conditioning both implementations share; the kernel sums those terms in double and is the
+    # more accurate of the two on the median token (1.7e-7 vs 3.9e-7), on the worst one it may land either side.
+    for name in got:
+        factor = 1.5 if name == "eps" else 1.0
+        assert max(ours[name]) <= factor * max(refs[name]) + 1e-6, (name, max(ours[name]), max(refs[name]))
+        assert np.median(ours[name]) <= 1.05 * np.median(refs[name]) + 1e-7, (name, np.median(ours[name]), np.median(refs[name]))
 
 
 def test_score_matches_oracle_on_random_batch(ops, bwd_kernel):
@@ -527,6 +547,23 @@ def test_fit_bspline_to_traj(ops):
     assert relinf(xg.grad.numpy(), d["gX_fit"]) < 1e-4
 
 
+def test_fit_smooth_stk_matches_reference(ops):
+    """fit_smooth_stk (pybpl/bottomup/initialize/util.py:13-31), the adaptive refit loop over fit_bspline_to_traj: same
+    number of control points chosen (an integer decision: same output length through the adaptive neval) and the same
+    smooth trajectory as the reference on the golden strokes (tests/golden/fit_smooth.npz; inputs already resampled by
+    the reference's unif_space, which is host-side data preparation outside this package)."""
+    from pybpl_b200 import splines
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fit_smooth.npz"))
+    for i in range(int(d["n"])):
+        ref = d[f"out_{i}"]
+        got = splines.fit_smooth_stk(d[f"in_{i}"], unif_space=lambda s, u=d[f"unif_{i}"]: u)
+        got = np.asarray(got)
+        assert got.shape == ref.shape, (i, got.shape, ref.shape)
+        err = np.abs(got - ref).max()
+        print("fit_smooth_stk stroke", i, "points", ref.shape[0], "max abs difference", err)
+        assert err < 2e-4          # pixels (measured 3e-5: the fp32 least-squares solutions of gels and the Householder QR)
+
+
 def test_token_order_is_a_permutation_by_decreasing_cost(ops):
     """bpl_order_tokens: the processing order handed to the persistent kernels (results do not depend on it)."""
     from pybpl_b200 import workload
@@ -549,6 +586,48 @@ def test_token_order_is_a_permutation_by_decreasing_cost(ops):
     b._order = torch.arange(512, dtype=torch.int32, device=DEV)
     ll2, _ = ops.score_tokens(b, imgs)
     assert torch.allclose(ll1, ll2, rtol=2e-6, atol=0)
+
+
+def test_work_queue_under_concurrent_streams_and_graph_replay(ops):
+    """Every launch of a persistent kernel owns one slot of the work-queue ring (g_sched) until its last CTA resets it.
+    Two streams launching back to back at the same time, and a CUDA graph replayed while live launches run on another
+    stream, must give exactly the scores of serial launches (a shared or stale slot would skip or repeat tokens)."""
+    from pybpl_b200 import workload
+    wa = workload.synth_tokens(3000, seed=21, sigma_mode="uniform")
+    wb = workload.synth_tokens(2500, seed=22, sigma_mode="uniform")
+    ba, bb = workload.to_device(wa, DEV), workload.to_device(wb, DEV)
+    pimg, _ = ops.render_tokens(workload.to_device(workload.permute(wa, np.arange(1)), DEV))
+    imgs = ops.pack_images((pimg[0] > 0.5).to(torch.uint8))
+    with torch.no_grad():
+        ra, rb = ops.score_tokens(ba, imgs)[0].clone(), ops.score_tokens(bb, imgs)[0].clone()
+        torch.cuda.synchronize()
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+        outs_a, outs_b = [], []
+        for _ in range(12):
+            with torch.cuda.stream(s1):
+                outs_a.append(ops.score_tokens(ba, imgs)[0])
+            with torch.cuda.stream(s2):
+                outs_b.append(ops.score_tokens(bb, imgs)[0])
+        torch.cuda.synchronize()
+        for o in outs_a:
+            assert torch.allclose(o, ra, rtol=2e-6, atol=0)
+        for o in outs_b:
+            assert torch.allclose(o, rb, rtol=2e-6, atol=0)
+        # a captured launch replayed on s1 while live launches run on s2
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(s1):
+            ops.score_tokens(ba, imgs)                       # warm-up on the capture stream
+            with torch.cuda.graph(g, stream=s1):
+                ga = ops.score_tokens(ba, imgs)[0]
+        torch.cuda.synchronize()
+        for _ in range(8):
+            with torch.cuda.stream(s1):
+                g.replay()
+            with torch.cuda.stream(s2):
+                ob = ops.score_tokens(bb, imgs)[0]
+            torch.cuda.synchronize()
+            assert torch.allclose(ga, ra, rtol=2e-6, atol=0) and torch.allclose(ob, rb, rtol=2e-6, atol=0)
+            ga.zero_()
 
 
 def test_cost_order_for_the_fused_backward(ops):

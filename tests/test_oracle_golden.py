@@ -217,3 +217,23 @@ def test_type_prior_oracle_matches_reference():
     m = fin[ts]
     assert np.abs(g["ctrl_type"][m] - d["g_ctrl_type"][m]).max() <= 2e-5 * np.abs(d["g_ctrl_type"]).max()
     assert np.abs(g["invscale_type"][m] - d["g_invscale_type"][m]).max() <= 2e-5 * np.abs(d["g_invscale_type"]).max()
+
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_oracle_matches_reference_on_the_config3_start_state():
+    """The C oracle (fp32, forward + backward) on the 64 parses of configs[2] against the live reference's autograd
+    (tests/golden/fit64.npz)."""
+    from oracle import Oracle
+    from pybpl_b200 import workload
+    d = dict(np.load(os.path.join(ROOT, "tests", "golden", "fit64.npz")))
+    w = workload.synth_tokens(int(d["P"]), seed=int(d["seed"]), sigma_mode=10.0)
+    C = np.load(os.path.join(ROOT, "pybpl_b200", "data", "basis_5_200.npy"))
+    ref = Oracle(np.float32).token_batch(C, w["tok_stroke_off"], w["stroke_sub_off"], w["ctrl"], w["invscale"], w["position"],
+                                         w["eps"], w["sigma"], d["target"][None], grad=True)
+    assert (np.abs(ref["ll"] - d["ll"]) / np.abs(d["ll"])).max() < 1e-5
+    rel = lambda g, r: np.abs(g - r).max() / np.abs(r).max()
+    assert rel(ref["g_ctrl"], d["g_ctrl"]) < 5e-4 and rel(ref["g_invscale"], d["g_invscale"]) < 5e-4
+    assert rel(ref["g_position"], d["g_position"]) < 5e-4
+    assert rel(ref["g_sigma"], d["g_sigma"]) < 1e-2 and rel(ref["g_eps"], d["g_eps"]) < 2e-3

@@ -1,11 +1,10 @@
 #!/usr/bin/env python
-"""Per-phase cycle breakdown of bpl_forward1s_kernel (BPL_FWD_SPARSE=1), same scheme as tools/phase_timing.py."""
+"""Per-phase cycle breakdown of bpl_forward1s_kernel : thread 0 of every CTA accumulates clock64() deltas per phase (-DBPL_PHASE_TIMING)."""
 import ctypes, os, subprocess, sys
 import numpy as np
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-os.environ["BPL_FWD_SPARSE"] = "1"
 so = "/tmp/libbpl_pt.so"
 src = [os.path.join(ROOT, "pybpl_b200", "csrc", f) for f in ("bpl_render.cu", "bpl_splines.cu", "bpl_token_prior.cu", "bpl_token_sample.cu", "bpl_type_sample.cu", "bpl_type_prior.cu")]
 subprocess.check_call(["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-DBPL_PHASE_TIMING",
