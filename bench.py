@@ -16,10 +16,13 @@ and wall clock; nothing is untimed between steps); the collective is on the crit
 `config1` : configs[1], the 4,096-token step on one GPU (kernel time, roofline)       \\
 `fwd_bwd` : configs[2] shape, 1,024 parses/step through the fused forward+backward     > secondary objects
 `config2` : configs[2], 1,024 parses x 100 Adam steps, total seconds                   /
-`cpu_baseline` (C oracle port, all cores) and `cpu_baseline_torch` (the reference's own torch code from
-baseline/_ref, one single-thread process per core) are timed on rank 0 at N=1 on a bounded sample of the same particles.
+`config4` : configs[4], cross-scoring of 40,000 tokens x 20 images, tokens sharded over the ranks, blocks all-gathered
+`cpu_baseline` = the reference's own torch code (unmodified pybpl from baseline/_ref, one single-thread process per
+core; `cpu_baseline_torch` repeats it) and `cpu_baseline_port` (C oracle port, OpenMP over all cores) are timed on rank 0
+at N=1 on a bounded sample of the same particles.
 
-`--impl reference` times the CPU arm alone (same config; rank 0 only under torchrun).
+`--impl reference` times the CPU arm alone (same config; rank 0 only under torchrun): its `value` is the reference's
+own torch code when baseline/_ref is present (kind "reference"), else the port.
 """
 import argparse
 import json
@@ -128,6 +131,9 @@ def cpu_sample():
 
 
 def run_reference(args):
+    """The CPU arm: the reference's OWN torch code (unmodified pybpl from baseline/_ref: CharacterImageDist.score_image,
+    one single-thread process per host core) on a bounded sample of the sweep's particles; the C
+    oracle port (OpenMP, all cores) is timed beside it and stands in when baseline/_ref is absent."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -144,15 +150,23 @@ def run_reference(args):
     for _ in range(args.steps):
         call()
     t_tot = time.perf_counter() - t0
-    value = w["P"] * args.steps / t_tot
-    sample = (f"{CPU_SAMPLE} particles of sweep block 0 per step (of the 1,000,000), C oracle port (fp32) with OpenMP over "
-              f"tokens on {cores} cores")
+    port_value = w["P"] * args.steps / t_tot
+    port = {"value": port_value, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{CPU_SAMPLE} particles of sweep block 0 per step (of the 1,000,000) x {args.steps} steps, C oracle port "
+                      f"(fp32) with OpenMP over tokens on {cores} cores"}
+    # each step of the torch arm = CPU_SAMPLE particles shared by the worker processes; all steps in one set of workers
+    # (a worker's start-up -- importing torch and the reference -- is outside its own clock)
+    torch_ref = torch_reference_rate(w, img, budget_s=max(4.0, min(args.cpu_budget, 1.5 * args.steps)))
+    if torch_ref and "value" in torch_ref:
+        value, baseline = torch_ref["value"], torch_ref
+    else:
+        value, baseline = port_value, port
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * CPU_SAMPLE / value,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": sweep_config(args.gpus),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-            "cpu_baseline_torch": torch_reference_rate(w, img, budget_s=args.cpu_budget),
+            "cpu_baseline": baseline, "cpu_baseline_port": port,
+            "cpu_baseline_torch": torch_ref,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -402,6 +416,24 @@ def run_gpu(args):
     bwd_h2d = hb.nbytes
     bwd_d2h = sum(t.numel() * 4 for t in g_host.values())
 
+    # ---- configs[4]: cross-scoring, tokens sharded over the ranks, packed images replicated, blocks all-gathered ----
+    X_TYPES, X_PER_TYPE, X_IMAGES = 20, 2000, 20
+    xw = workload.synth_tokens(X_TYPES * X_PER_TYPE, seed=5, max_strokes=10, kappa="prior", sigma_mode="fixed")
+    xlo, xhi = sweep.shard_bounds(xw["P"], rank, world)
+    xown = np.arange(0, xw["P"], xw["P"] // X_IMAGES)[:X_IMAGES]
+    with torch.no_grad():
+        xp, _ = ops.render_tokens(workload.to_device(workload.permute(xw, xown), dev))      # seeded: identical on every rank
+    ximgs = ops.pack_images((torch.from_numpy(np.random.default_rng(7).random((X_IMAGES, 105, 105))).to(dev) < xp).to(torch.uint8))
+    xs = sweep.CrossScore(workload.to_device(workload.permute(xw, np.arange(xlo, xhi)), dev), ximgs, xw["P"])
+    n_x = max(steps, 10)
+    ms_x, wall_x_ms, _ = timed(xs.step, n_x, 3)
+    x_sum = float(xs.ll.double().sum().item())
+    config4 = {"workload": f"configs[4]: cross-scoring, {X_TYPES} types x {X_PER_TYPE} tokens x {X_IMAGES} target images (all pairs, "
+                           f"max 10 strokes), tokens sharded over the ranks, [tokens, images] blocks all-gathered every pass",
+               "value": xw["P"] * X_IMAGES * n_x / (wall_x_ms * 1e-3), "unit": "scored (token, image) pairs/s", "timing": "wall clock",
+               "ms_per_pass": wall_x_ms / n_x, "tokens_per_s": xw["P"] * n_x / (wall_x_ms * 1e-3), "checksum": x_sum,
+               "scaling": "strong"}
+
     # ---- live FP32 FMA peak (roofline denominator): best of 5 timed launches of the FFMA probe ----
     scratch = torch.zeros(1, device=dev)
     iters, blocks = 16384, 148 * 8
@@ -498,7 +530,9 @@ def run_gpu(args):
             "dtype": "f32", "data": "synthetic", "config": sweep_config(world),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "timing": "wall clock around all steps", "chunk": E2E_CHUNK},
-            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "cpu_baseline_torch": cpu_torch,
+            "gpu_launches": int(launches), "roofline": roofline,
+            "cpu_baseline": cpu_torch if (cpu_torch and "value" in cpu_torch) else cpu, "cpu_baseline_port": cpu,
+            "cpu_baseline_torch": cpu_torch, "config4": config4,
             "clocks": clocks, "wall_s": wall_dev_ms * 1e-3, "logsumexp": {"device": lse_dev, "e2e": lse_e2e},
             "particles_per_rank": P_rank, "fwd_bwd": fwd_bwd, "config1": config1, "config2": config2}
     emit(line)

@@ -69,3 +69,55 @@ class Sweep:
             parts = self.state.partial
         self.total = ops.logsumexp_combine(parts)
         return self.total
+
+
+# ---------------------------------------------------------------------------------------------
+# Cross-scoring across ranks (BASELINE.json configs[4]): every token against every target image.
+# ---------------------------------------------------------------------------------------------
+def shard_bounds(n, rank, world):
+    """Contiguous shard [lo, hi) of n items for `rank` of `world` (the first n % world ranks hold one item more)."""
+    q, r = divmod(n, world)
+    lo = rank * q + min(rank, r)
+    return lo, lo + q + (1 if rank < r else 0)
+
+
+def gather_rows(block, n_total, group=None):
+    """All-gather row blocks of a [n_total, T] matrix whose rows are sharded contiguously (shard_bounds) over the ranks:
+    every rank passes its [n_r, T] block and receives the whole matrix.  Blocks are padded to the largest shard so that
+    ONE all_gather_into_tensor moves everything (NCCL on GPU tensors, gloo on CPU tensors in the tests)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return block
+    world = dist.get_world_size(group)
+    T = block.shape[1]
+    rows = -(-n_total // world)
+    pad = torch.zeros((rows, T), dtype=block.dtype, device=block.device)
+    pad[:block.shape[0]] = block
+    out = torch.empty((world * rows, T), dtype=block.dtype, device=block.device)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    parts = []
+    for r in range(world):
+        lo, hi = shard_bounds(n_total, r, world)
+        parts.append(out[r * rows:r * rows + (hi - lo)])
+    return torch.cat(parts)
+
+
+class CrossScore:
+    """One rank of a cross-scoring job: the rank's contiguous shard of the tokens is resident on its GPU, the packed target
+    images are replicated (1 380 B each).  step() renders every local token ONCE and scores it against all images
+    (bpl_forward1s_kernel<true>: per-pixel score differences gathered at each image's set bits -- the per-pair value
+    is CharacterImageDist.score_image, pybpl/model/image_dist.py:60-80), then all-gathers the [tokens, images] blocks:
+    the only exchange, 4 bytes per pair."""
+
+    def __init__(self, batch, images, n_tokens_total, group=None, ps=None):
+        from . import ops
+        self.batch, self.images, self.n_total, self.group = batch, images, int(n_tokens_total), group
+        self.ps = ops.make_params(ps)
+        self.ll = None
+
+    def step(self):
+        from . import ops
+        with torch.no_grad():
+            block, self.off_page = ops.score_tokens_all_images(self.batch, self.images, ps=self.ps)
+        self.ll = gather_rows(block, self.n_total, self.group)
+        return self.ll

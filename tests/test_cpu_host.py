@@ -110,6 +110,13 @@ assert abs(tot - want) < 1e-6 * abs(want), (tot, want)
 tot2 = sweep.combine_partials(sweep.partial_from_scores(mine if rank == 0 else mine[:0]), group=None)
 want2 = torch.logsumexp(ll[:per].double(), 0).item()
 assert abs(tot2 - want2) < 1e-6 * abs(want2)
+# cross-scoring (configs[4]): contiguous row shards of a [tokens, images] matrix, uneven (1001 = 501 + 500), one gather
+full = torch.arange(1001 * 7, dtype=torch.float32).view(1001, 7)
+lo, hi = sweep.shard_bounds(1001, rank, world)
+assert (lo, hi) == ((0, 501) if rank == 0 else (501, 1001))
+got = sweep.gather_rows(full[lo:hi].clone(), 1001)
+assert got.shape == full.shape and torch.equal(got, full)
+assert sum(sweep.shard_bounds(10, r, 4)[1] - sweep.shard_bounds(10, r, 4)[0] for r in range(4)) == 10
 dist.destroy_process_group()
 print("rank", rank, "ok")
 '''
@@ -132,7 +139,10 @@ def test_bench_reference_arm_runs():
     assert r.returncode == 0, r.stderr[-2000:]
     import json
     line = json.loads(r.stdout.strip().splitlines()[-1])
-    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["impl"] == "reference" and line["value"] > 0
+    # the reference's own torch code when baseline/_ref is installed (kind "reference"), else the C oracle port
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline_port"]["kind"] == "port"
+    assert line["value"] == line["cpu_baseline"]["value"] == line["e2e"]["value"]
 
 
 def test_dropin_rebinds_reference_call_sites():
