@@ -48,7 +48,7 @@ BWD_BATCH = 1024
 CPU_SAMPLE = 8192            # particles per step of the CPU arm (first tokens of sweep block 0)
 # dram__bytes_read.sum + dram__bytes_write.sum of one scoring launch, from the ncu --set full capture summarised under
 # profiles/ (filled in from the round's capture; None until one exists for the current kernel)
-NCU_DRAM_BYTES_PER_PARTICLE = None
+NCU_DRAM_BYTES_PER_PARTICLE = 295.69      # profiles/r02_fwd1s_sweep.raw.txt: (283.65 MB read + 12.04 MB written) / 1,000,000 particles
 
 
 def flops_fwd(S):      # algorithmic work per particle, separable minimal algorithm
