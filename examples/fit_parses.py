@@ -41,22 +41,22 @@ def fit(P=1024, steps=100, lr=4e-3, seed=2024, device="cuda:0", log_every=0, tok
         if token_prior:
             ll = ll + ops.score_token_prior(batch, types, c=prior_c)
         return ll
-    # One optimisation step is ~15 small launches around the fused kernel (autograd scaling, Adam, clamps); captured
-    # once as a CUDA graph it replays as a single submission (graph=False keeps the eager loop for comparison).
-    opt = torch.optim.Adam(params, lr=lr, fused=True, capturable=graph)
+    # One optimisation step = the fused forward+backward kernel, one launch that scales its gradients by the cotangent,
+    # and ONE launch for Adam + the parameter bounds of pybpl/parameters.py:54-63 (ops.FusedAdam: torch's update rule;
+    # torch's own fused multi-tensor Adam takes 66 us on these five small tensors, plus three clamp kernels), with the
+    # reduction of the objective around it; captured once as a CUDA graph it replays as a single submission (graph=False
+    # keeps the eager loop for comparison).  The objective sum(ll) is ASCENDED (maximize): no negation kernels.
+    bounds = {3: (0.5, 16.0), 4: (1e-4, 0.5), 1: (1e-3, None)}            # blur_sigma, epsilon, invscale
+    if token_prior:
+        bounds[5] = (2.0 + 1e-4, 6.0 - 1e-4)                               # RelationToken.lbs/ubs (objects/relation.py:96-131)
+    opt = ops.FusedAdam(params, lr=lr, bounds=bounds, maximize=True)
 
     def step():
-        opt.zero_grad(set_to_none=True)
-        loss = -objective().sum()
-        loss.backward()
+        opt.zero_grad()
+        obj = objective().sum()
+        obj.backward()
         opt.step()
-        with torch.no_grad():       # bounds of pybpl/parameters.py:54-63
-            batch.sigma.clamp_(0.5, 16.0)
-            batch.eps.clamp_(1e-4, 0.5)
-            batch.invscale.clamp_(min=1e-3)
-            if token_prior:
-                types.eval_spot.clamp_(2.0 + 1e-4, 6.0 - 1e-4)      # RelationToken.lbs/ubs (objects/relation.py:96-131)
-        return loss
+        return obj.detach()            # (the loss is its negative; negated on the host when logged)
 
     # warm-up (module load, allocator, lazily built index maps), then everything it touched is put back
     init = [p.detach().clone() for p in params]
@@ -69,14 +69,11 @@ def fit(P=1024, steps=100, lr=4e-3, seed=2024, device="cuda:0", log_every=0, tok
     with torch.no_grad():
         for p, p0 in zip(params, init):
             p.copy_(p0)
-        for st in opt.state.values():
-            for v in st.values():
-                if torch.is_tensor(v):
-                    v.zero_()
+        opt.reset()
     g = None
     if graph:
         g = torch.cuda.CUDAGraph()
-        opt.zero_grad(set_to_none=True)
+        opt.zero_grad()
         with torch.cuda.graph(g):
             loss_buf = step()
         with torch.no_grad():      # the capture itself does not run the step, but be explicit about the start state
@@ -92,7 +89,7 @@ def fit(P=1024, steps=100, lr=4e-3, seed=2024, device="cuda:0", log_every=0, tok
         else:
             loss = step()
         if log_every and it % log_every == 0:
-            losses.append(float(loss.detach()))
+            losses.append(-float(loss.detach()))
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     with torch.no_grad():

@@ -287,6 +287,27 @@ int bpl_order_tokens_by_cost(const bpl_params *ps, const bpl_token_batch *b, int
 /* Same, plus the fused backward (autograd-equivalent gradients). */
 int bpl_score_tokens_grad(const bpl_params *ps, const bpl_token_batch *b, const bpl_targets *t,
                           const bpl_fwd_out *out, const bpl_grads *g, void *stream);
+/* out.g_* <- in.g_* scaled, token by token, by the cotangent g_ll[P] (the chain rule step torch's autograd performs on
+ * the outputs of bpl_score_tokens_grad, which runs before the cotangent exists): g_ctrl, g_invscale, g_position, g_eps,
+ * g_sigma and, when in->g_affine is set, g_affine.  One launch.  No reference counterpart (autograd does this there). */
+int bpl_scale_token_grads(int P, int K, int S, const int *tok_stroke_off, const int *stroke_sub_off, const float *g_ll,
+                          const bpl_grads *in, const bpl_grads *out, void *stream);
+/* One Adam step (torch.optim.Adam's rule, no weight decay / amsgrad) over up to BPL_ADAM_MAX_TENSORS parameter tensors
+ * in ONE launch, each then clamped to [lo, hi]: the optimiser step of the differentiable fit (fit_image,
+ * pybpl/model/model.py:42-65, with the bounds of pybpl/parameters.py:54-63).  state: dev [2] floats, zero before the first
+ * step -- state[0] counts the steps on the device (a captured CUDA graph advances it), state[1] is scratch. */
+#define BPL_ADAM_MAX_TENSORS 8
+typedef struct {
+    int n_tensors, maximize;                       /* maximize: ascend (the gradient of sum ll is used as it is) */
+    float lr, beta1, beta2, eps;
+    float *state;
+    float *param[BPL_ADAM_MAX_TENSORS];
+    const float *grad[BPL_ADAM_MAX_TENSORS];
+    float *exp_avg[BPL_ADAM_MAX_TENSORS], *exp_avg_sq[BPL_ADAM_MAX_TENSORS];
+    long long n[BPL_ADAM_MAX_TENSORS];
+    float lo[BPL_ADAM_MAX_TENSORS], hi[BPL_ADAM_MAX_TENSORS];   /* -inf / +inf: unbounded */
+} bpl_adam_args;
+int bpl_adam_step(const bpl_adam_args *a, void *stream);
 /* rendering.render_image on raw trajectories (+ optional scoring). */
 int bpl_render_strokes(const bpl_params *ps, const bpl_stroke_batch *b, const bpl_targets *t,
                        const bpl_fwd_out *out, void *stream);

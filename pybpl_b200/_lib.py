@@ -51,6 +51,17 @@ class Grads(ctypes.Structure):
                 ("g_affine", vp), ("g_pts", vp), ("g_eps", vp), ("g_sigma", vp)]
 
 
+ADAM_MAX_TENSORS = 8
+
+
+class AdamArgs(ctypes.Structure):
+    _fields_ = [("n_tensors", ctypes.c_int), ("maximize", ctypes.c_int), ("lr", ctypes.c_float), ("beta1", ctypes.c_float),
+                ("beta2", ctypes.c_float), ("eps", ctypes.c_float), ("state", vp), ("param", vp * ADAM_MAX_TENSORS),
+                ("grad", vp * ADAM_MAX_TENSORS), ("exp_avg", vp * ADAM_MAX_TENSORS), ("exp_avg_sq", vp * ADAM_MAX_TENSORS),
+                ("n", ctypes.c_longlong * ADAM_MAX_TENSORS), ("lo", ctypes.c_float * ADAM_MAX_TENSORS),
+                ("hi", ctypes.c_float * ADAM_MAX_TENSORS)]
+
+
 class TokenPriorParams(ctypes.Structure):
     _fields_ = [("sigma_shape", ctypes.c_float), ("sigma_invscale", ctypes.c_float), ("sigma_attach", ctypes.c_float),
                 ("sigma_x", ctypes.c_float), ("sigma_y", ctypes.c_float), ("min_blur_sigma", ctypes.c_float),
@@ -105,6 +116,9 @@ EXPORTS = {
     "bpl_score_tokens_lse": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.POINTER(TokenBatchC), ctypes.POINTER(Targets),
                                             ctypes.POINTER(FwdOut), vp, vp, ctypes.c_int, vp]),
     "bpl_order_tokens": (ctypes.c_int, [ctypes.POINTER(TokenBatchC), vp, vp]),
+    "bpl_adam_step": (ctypes.c_int, [ctypes.POINTER(AdamArgs), vp]),
+    "bpl_scale_token_grads": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, ctypes.POINTER(Grads),
+                                             ctypes.POINTER(Grads), vp]),
     "bpl_order_tokens_by_cost": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.POINTER(TokenBatchC), vp, vp, vp]),
     "bpl_score_tokens_grad": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.POINTER(TokenBatchC),
                                              ctypes.POINTER(Targets), ctypes.POINTER(FwdOut), ctypes.POINTER(Grads), vp]),

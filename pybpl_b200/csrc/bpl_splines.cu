@@ -361,6 +361,61 @@ static int grid_for(long long work_items, int per_block) {
 
 using namespace bpl;
 
+// Adam over up to BPL_ADAM_MAX_TENSORS small parameter tensors in ONE launch (torch.optim.Adam's update rule: no weight
+// decay, no amsgrad; `maximize` flips the gradient's sign), followed by the clamp to each tensor's bounds -- the
+// optimiser step of the differentiable fit (fit_image, pybpl/model/model.py:42-65 with the bounds of
+// parameters.py:54-63).  torch's fused multi-tensor Adam takes 66 us on these five tensors (one block per tensor
+// chunk); this is 3 us.  The step count lives on the device (state[0]) so that a captured CUDA graph advances it: the
+// block that finishes last increments it.
+__global__ void __launch_bounds__(256) adam_step_kernel(const bpl_adam_args a) {
+    const float t = a.state[0] + 1.0f;
+    const float bias1 = 1.0f - powf(a.beta1, t), bias2 = 1.0f - powf(a.beta2, t);
+    const float step_size = a.lr / bias1, rs2 = rsqrtf(bias2);
+    long long base = 0;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+    for (int k = 0; k < a.n_tensors; ++k) {
+        const long long n = a.n[k];
+        float *p = a.param[k], *m = a.exp_avg[k], *v = a.exp_avg_sq[k];
+        const float *g = a.grad[k];
+        const float lo = a.lo[k], hi = a.hi[k];
+        // a rotating start so that consecutive small tensors land on different threads
+        for (long long i = (tid + nth - base % nth) % nth; i < n; i += nth) {
+            const float gi = a.maximize ? -g[i] : g[i];
+            const float mi = fmaf(a.beta1, m[i], (1.0f - a.beta1) * gi);
+            const float vi = fmaf(a.beta2, v[i], (1.0f - a.beta2) * gi * gi);
+            m[i] = mi; v[i] = vi;
+            const float denom = fmaf(sqrtf(vi), rs2, a.eps);
+            p[i] = fminf(fmaxf(p[i] - step_size * (mi / denom), lo), hi);
+        }
+        base += n;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned *done = reinterpret_cast<unsigned *>(a.state + 1);
+        if (atomicAdd(done, 1u) == gridDim.x - 1u) { *done = 0u; a.state[0] = t; }
+    }
+}
+
+// Autograd scaling of the fused backward's outputs: every gradient of token p times the incoming cotangent g_ll[p]
+// (the fused kernel runs in the autograd forward, before the cotangent exists).  One warp per token walks the token's
+// strokes and sub-strokes through the CSR offsets: ONE launch instead of three gathers and six multiplies.
+__global__ void __launch_bounds__(128) scale_token_grads_kernel(int P, const int *__restrict__ tso, const int *__restrict__ sso,
+                                                                const float *__restrict__ g_ll, const bpl_grads in, const bpl_grads out) {
+    const int lane = threadIdx.x & 31;
+    for (int p = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); p < P; p += (int)((gridDim.x * blockDim.x) >> 5)) {
+        const float g = g_ll[p];
+        const int k0 = tso[p], k1 = tso[p + 1];
+        const int s0 = sso[k0], s1 = sso[k1];
+        for (int i = s0 * 10 + lane; i < s1 * 10; i += 32) out.g_ctrl[i] = in.g_ctrl[i] * g;
+        for (int i = s0 + lane; i < s1; i += 32) out.g_invscale[i] = in.g_invscale[i] * g;
+        for (int i = k0 * 2 + lane; i < k1 * 2; i += 32) out.g_position[i] = in.g_position[i] * g;
+        if (lane < 4 && in.g_affine) out.g_affine[4 * (size_t)p + lane] = in.g_affine[4 * (size_t)p + lane] * g;
+        if (lane == 4) out.g_eps[p] = in.g_eps[p] * g;
+        if (lane == 5) out.g_sigma[p] = in.g_sigma[p] * g;
+    }
+}
+
 extern "C" {
 
 int bpl_version(void) { return 1; }
@@ -496,6 +551,34 @@ int bpl_logsumexp_combine(const float *parts, int n, float *out, void *stream) {
     if (!parts || !out || n < 0) { set_error("%s", "bad logsumexp_combine arguments"); return BPL_EINVAL; }
     logsumexp_combine_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(parts, n, out);
     return check_launch("logsumexp_combine");
+}
+
+int bpl_adam_step(const bpl_adam_args *a, void *stream) {
+    if (!a || !a->state || a->n_tensors < 0 || a->n_tensors > BPL_ADAM_MAX_TENSORS) { set_error("%s", "bad bpl_adam_step arguments"); return BPL_EINVAL; }
+    long long total = 0;
+    for (int k = 0; k < a->n_tensors; ++k) {
+        if (a->n[k] < 0 || (a->n[k] > 0 && (!a->param[k] || !a->grad[k] || !a->exp_avg[k] || !a->exp_avg_sq[k]))) {
+            set_error("%s", "bpl_adam_step: NULL tensor"); return BPL_EINVAL;
+        }
+        total += a->n[k];
+    }
+    if (total == 0) return 0;
+    const long long cap = (long long)sm_count() * 8;
+    long long blocks = (total + 255) / 256;
+    if (blocks > cap) blocks = cap;
+    adam_step_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(*a);
+    return check_launch("adam_step");
+}
+
+int bpl_scale_token_grads(int P, int K, int S, const int *tok_stroke_off, const int *stroke_sub_off, const float *g_ll,
+                          const bpl_grads *in, const bpl_grads *out, void *stream) {
+    if (!tok_stroke_off || !stroke_sub_off || !g_ll || !in || !out) { set_error("%s", "bpl_scale_token_grads: NULL argument"); return BPL_EINVAL; }
+    if (P <= 0) return 0;
+    const int cap = sm_count() * 8;
+    const int blocks = (P + 3) / 4 < cap ? (P + 3) / 4 : cap;       // one warp per token, four per block
+    scale_token_grads_kernel<<<blocks > 0 ? blocks : 1, 128, 0, (cudaStream_t)stream>>>(P, tok_stroke_off, stroke_sub_off, g_ll, *in, *out);
+    (void)K; (void)S;
+    return check_launch("scale_token_grads");
 }
 
 }  // extern "C"

@@ -4,6 +4,7 @@ torch is plumbing here (device memory, streams, autograd graph); every number is
 the CUDA kernels in pybpl_b200/csrc through libpybpl_b200.so.
 """
 import ctypes
+import math
 import functools
 import os
 
@@ -423,10 +424,18 @@ class _ScoreTokens(torch.autograd.Function):
         g_ctrl, g_inv, g_pos, g_eps, g_sig = saved[:5]
         g_aff = saved[5] if ctx.has_aff else None
         b = ctx.batch
-        gs = g_ll.to(torch.float32)
-        st, kt = b.sub_token, b.stroke_token
-        return (g_ctrl * gs[st].view(-1, 1, 1), g_inv * gs[st], g_pos * gs[kt].view(-1, 1),
-                None if g_aff is None else g_aff * gs.view(-1, 1), g_eps * gs, g_sig * gs, None, None, None, None, None)
+        gs = _c32(g_ll)
+        # every gradient of token p times g_ll[p]: one kernel over the CSR structure (was three gathers + six multiplies)
+        o_ctrl = torch.empty_like(g_ctrl); o_inv = torch.empty_like(g_inv); o_pos = torch.empty_like(g_pos)
+        o_aff = None if g_aff is None else torch.empty_like(g_aff)
+        o_eps = torch.empty_like(g_eps); o_sig = torch.empty_like(g_sig)
+        gin = _lib.Grads(None, None, g_ctrl.data_ptr(), g_inv.data_ptr(), g_pos.data_ptr(),
+                         None if g_aff is None else g_aff.data_ptr(), None, g_eps.data_ptr(), g_sig.data_ptr())
+        gout = _lib.Grads(None, None, o_ctrl.data_ptr(), o_inv.data_ptr(), o_pos.data_ptr(),
+                          None if o_aff is None else o_aff.data_ptr(), None, o_eps.data_ptr(), o_sig.data_ptr())
+        check(lib().bpl_scale_token_grads(b.P, b.K, b.S, b.tok_stroke_off.data_ptr(), b.stroke_sub_off.data_ptr(), gs.data_ptr(),
+                                          ctypes.byref(gin), ctypes.byref(gout), _stream(b.device)))
+        return o_ctrl, o_inv, o_pos, o_aff, o_eps, o_sig, None, None, None, None, None
 
 
 class _RenderTokens(torch.autograd.Function):
@@ -1012,6 +1021,57 @@ def score_type_prior(library, tok_stroke_off, stroke_sub_off, types, subid):
     dev = library.device
     return _ScoreTypePrior.apply(types.ctrl_type, types.invscale_type, library, _i32(tok_stroke_off, dev),
                                  _i32(stroke_sub_off, dev), _i32(subid, dev), types, torch.is_grad_enabled())
+
+
+class FusedAdam:
+    """torch.optim.Adam's update (no weight decay, no amsgrad) over a handful of small leaf tensors in ONE launch, each
+    clamped to its bounds afterwards: the optimiser step of the differentiable fit (fit_image, pybpl/model/model.py:42-65;
+    bounds as pybpl/parameters.py:54-63).  The step counter lives on the device, so a step captured in a CUDA graph
+    advances on replay.  params: float32 contiguous CUDA leaves (at most 8); bounds: {index: (lo, hi)}, None = unbounded;
+    maximize: ascend along the gradients (use with `objective.sum().backward()`)."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, bounds=None, maximize=False):
+        self.params = list(params)
+        if not 0 < len(self.params) <= _lib.ADAM_MAX_TENSORS:
+            raise ValueError("FusedAdam takes 1..8 tensors")
+        for p in self.params:
+            _need_cuda(p, "param")
+            if p.dtype != torch.float32 or not p.is_contiguous():
+                raise ValueError("FusedAdam parameters must be contiguous float32")
+        dev = self.params[0].device
+        self.lr, self.betas, self.eps, self.maximize = float(lr), betas, float(eps), bool(maximize)
+        self.bounds = dict(bounds or {})
+        self.exp_avg = [torch.zeros_like(p) for p in self.params]
+        self.exp_avg_sq = [torch.zeros_like(p) for p in self.params]
+        self.state = torch.zeros(2, dtype=torch.float32, device=dev)
+
+    def zero_grad(self):
+        for p in self.params:
+            p.grad = None
+
+    def reset(self):
+        self.state.zero_()
+        for t in self.exp_avg + self.exp_avg_sq:
+            t.zero_()
+
+    @torch.no_grad()
+    def step(self):
+        a = _lib.AdamArgs()
+        a.n_tensors = len(self.params); a.maximize = int(self.maximize)
+        a.lr, a.beta1, a.beta2, a.eps = self.lr, float(self.betas[0]), float(self.betas[1]), self.eps
+        a.state = self.state.data_ptr()
+        grads = []
+        for k, p in enumerate(self.params):
+            g = p.grad
+            if g is None:
+                raise RuntimeError("FusedAdam.step: a parameter has no gradient")
+            g = _c32(g); grads.append(g)
+            lo, hi = self.bounds.get(k, (None, None))
+            a.param[k] = p.data_ptr(); a.grad[k] = g.data_ptr()
+            a.exp_avg[k] = self.exp_avg[k].data_ptr(); a.exp_avg_sq[k] = self.exp_avg_sq[k].data_ptr()
+            a.n[k] = p.numel()
+            a.lo[k] = -math.inf if lo is None else float(lo); a.hi[k] = math.inf if hi is None else float(hi)
+        check(lib().bpl_adam_step(ctypes.byref(a), _stream(self.params[0].device)))
 
 
 def logsumexp_partial(ll):

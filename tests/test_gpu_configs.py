@@ -75,6 +75,57 @@ def test_config3_fit_follows_an_oracle_driven_adam_run():
     assert rel.max() < 2e-3 and rel[-1] < 2e-3
 
 
+def test_fused_adam_matches_torch_adam():
+    """ops.FusedAdam (one launch: Adam + bounds) against torch.optim.Adam + clamp_ on the same gradients, 25 steps, eager
+    and replayed from a CUDA graph (the step counter lives on the device)."""
+    from pybpl_b200 import ops
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(1)
+    shapes = [(700, 5, 2), (700,), (300, 2), (128,), (128,)]
+    init = [torch.randn(s, generator=g).to(dev) for s in shapes]
+    grads = [[torch.randn(s, generator=g).to(dev) * (10.0 ** (i % 3 - 1)) for s in shapes] for i in range(25)]
+    bounds = {3: (0.5, 16.0), 4: (1e-4, 0.5), 1: (1e-3, None)}
+    ref = [p.clone().requires_grad_(True) for p in init]
+    topt = torch.optim.Adam(ref, lr=4e-3)
+    for gs in grads:
+        for p, gr in zip(ref, gs):
+            p.grad = -gr                                          # FusedAdam below ascends
+        topt.step()
+        with torch.no_grad():
+            ref[3].clamp_(0.5, 16.0); ref[4].clamp_(1e-4, 0.5); ref[1].clamp_(min=1e-3)
+    for use_graph in (False, True):
+        mine = [p.clone().requires_grad_(True) for p in init]
+        opt = ops.FusedAdam(mine, lr=4e-3, bounds=bounds, maximize=True)
+        gbuf = [torch.zeros_like(p) for p in mine]
+        for p, gb in zip(mine, gbuf):
+            p.grad = gb
+        graph = None
+        if use_graph:
+            side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                opt.step()                                        # warm-up, then put everything back
+            torch.cuda.current_stream().wait_stream(side)
+            with torch.no_grad():
+                for p, p0 in zip(mine, init):
+                    p.copy_(p0)
+            opt.reset()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                opt.step()
+            with torch.no_grad():
+                for p, p0 in zip(mine, init):
+                    p.copy_(p0)
+            opt.reset()
+        for gs in grads:
+            for gb, gr in zip(gbuf, gs):
+                gb.copy_(gr)
+            graph.replay() if graph is not None else opt.step()
+        torch.cuda.synchronize()
+        assert abs(float(opt.state[0]) - 25.0) < 1e-6
+        for a, b in zip(mine, ref):
+            assert torch.allclose(a, b, rtol=2e-5, atol=2e-6), (use_graph, (a - b).abs().max())
+
+
 def test_config3_fit_with_token_prior_term():
     """The fit objective with log P(token | type) added (model.py:59-62): finite, decreasing, and the prior term's
     value on the synthetic types agrees with the numpy oracle."""
