@@ -180,6 +180,7 @@ __device__ __forceinline__ void chain_offsets_t(const TeamCtx &tm, const KArgs &
             const float ox = __fsub_rn(v.x, px), oy = __fsub_rn(v.y, py);
             px = __fsub_rn(v.z, ox); py = __fsub_rn(v.w, oy);
             ms->sub[s] = make_float4(ox, oy, 0.0f, 0.0f);
+            ms->ink64[s] = 0ull;
         }
     }
     tm.sync();
@@ -427,10 +428,7 @@ __device__ __forceinline__ float bt_tail(const BtShared *sh, const BtTok *tk, co
         // A pixel without ink has the analytic background value (closed form in bt_scalars); pm == bgv alone does not
         // mean "no ink" (eps = 0.5 maps every v to 0.5).
         if (eps > 0.0f && (pm != bgv || i6 != 0.0f))
-        {   // in double from the fp32 probability on (the terms are +-1e4 and cancel to a few tens)
-            const double dd = (d == 0.0f) ? 0.0 : (x ? 1.0 / (double)pm : -1.0 / (1.0 - (double)pm));
-            acc.eps += (dd * (1.0 - 2.0 * (double)i6) - ms->dlp_bg_d[x]) * (double)gscale;
-        }
+            acc.eps += ((double)(d * (1.0f - 2.0f * i6)) - ms->dlp_bg_d[x]) * (double)gscale;
         gp = d * gscale;
     }
     return pass5 ? gp * tk->mixd : 0.0f;
@@ -651,12 +649,13 @@ __device__ __noinline__ void bt_splat(BtShared *sh) {
         if (active) src = make_ctrl_src(a, t, s, tab, ms, aff);
         const LaneAcc acc = warp_points<false, 1, IMG, 0, BT_PPL, LayD>(active, src, tab, s, a.neval, active ? it - s * QN : 0,
                                                                        tm.lane, a.rc, A, 0.0f, 0, nullptr, lay);
-        reduce_by_substroke(active, s, acc.sum, acc.cnt, ms->sub, tm.lane);
+        reduce_by_substroke(active, s, acc.sum, acc.cnt, ms->sub, ms->ink64, tm.lane);
     }
     tm.sync();
     bool need_fix = false;
     for (int s = 0; s < t.S; ++s) {
-        const float4 v = ms->sub[s];
+        float4 v = ms->sub[s];
+        v.z = ink_sum(ms, s);
         need_fix |= (__float_as_int(v.w) >= 2 && v.z < a.rc.ink_pp);
     }
     if (need_fix) bt_splat_fix(sh);

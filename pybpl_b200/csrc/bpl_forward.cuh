@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) bpl_forward_kern
                 const LaneAcc acc = warp_points<false, 1>(active, src, sm.tab, s, a.neval, active ? item - s * QN : 0, lane,
                                                           a.rc, A, 0.0f, 0);
                 any_out |= acc.any_out;
-                reduce_by_substroke(active, s, acc.sum, acc.cnt, ms->sub, lane);
+                reduce_by_substroke(active, s, acc.sum, acc.cnt, ms->sub, ms->ink64, lane);
             }
             any_out = __any_sync(0xffffffffu, any_out);
             if (any_out && lane == 0) atomicOr(&ms->off_page, 1);
@@ -230,7 +230,8 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) bpl_forward_kern
             // min-ink branches (rendering.py:104-107): every thread reaches the same verdict from the totals
             bool need_fix = false;
             for (int s = 0; s < t.S; ++s) {
-                const float4 v = ms->sub[s];
+                float4 v = ms->sub[s];
+                v.z = ink_sum(ms, s);
                 need_fix |= (__float_as_int(v.w) >= 2 && v.z < a.rc.ink_pp);
             }
             if (need_fix) {

@@ -21,11 +21,23 @@
 #ifndef BPL_S_CTAS
 #define BPL_S_CTAS 3
 #endif
+#ifndef BPL_S_THREADS_LARGE
+#define BPL_S_THREADS_LARGE 256
+#endif
+#ifndef BPL_S_CTAS_LARGE
+#define BPL_S_CTAS_LARGE 4
+#endif
+#ifndef BPL_S_LARGE_MIN
+#define BPL_S_LARGE_MIN 2048
+#endif
 
 namespace bpl {
 
 constexpr int S_THREADS = BPL_S_THREADS;
 constexpr int S_CTAS_PER_SM = BPL_S_CTAS;
+constexpr int S_THREADS_LARGE = BPL_S_THREADS_LARGE;      // launch shape for batches of S_LARGE_MIN tokens and more
+constexpr int S_CTAS_LARGE = BPL_S_CTAS_LARGE;
+constexpr int S_LARGE_MIN = BPL_S_LARGE_MIN;
 
 struct BBox {
     int r0, r1, c0, c1;     // inclusive; empty when r0 > r1
@@ -99,7 +111,7 @@ __device__ BPL_GAUSS_ATTR void gauss_inplace_s(float *buf, const G6 gg, int l0, 
 #ifndef BPL_GAUSS_BANDS
 #define BPL_GAUSS_BANDS 1
 #endif
-template <bool VERT>
+template <bool VERT, int S_THREADS>
 __device__ __forceinline__ void gauss_box(float *buf, const G6 &g, int l0, int l1, int a0, int a1) {
     const int nl = l1 - l0 + 1;
 #if BPL_GAUSS_BANDS >= 5
@@ -137,6 +149,7 @@ __device__ __forceinline__ void gauss_box(float *buf, const G6 &g, int l0, int l
 #else
 #define BPL_BROADEN_ATTR __noinline__
 #endif
+template <int S_THREADS>
 __device__ BPL_BROADEN_ATTR void broaden_box(float *A, float *side, const RenderConsts rc, BBox bb) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int nw = S_THREADS / 32;             // (compile time: the divisions below become multiplications)
@@ -214,9 +227,15 @@ struct Fwd1sSmem {
     Misc ms;
 };
 
+// four CTAs of the large-batch shape must fit an SM (228 KB, 1 KB reserved per CTA)
+static_assert((sizeof(Fwd1sSmem) + 1024) * S_CTAS_LARGE <= 233472, "Fwd1sSmem too large for the large-batch launch shape");
+
 // AP: all-pairs mode (bpl_targets.all_pairs): the token is rendered once and scored against every target image.
-template <bool AP>
-__global__ void __launch_bounds__(S_THREADS, S_CTAS_PER_SM) bpl_forward1s_kernel(const KArgs a) {
+// Launch shape: 320 threads x 3 CTAs per SM below 2 048 tokens (fewer, faster CTAs: a shorter tail of the launch), 256 x 4
+// from there on (measured M particles/s, 320x3 / 256x4: 1 024 tokens 10.9 / 10.6, 2 048: 14.2 / 14.8, 4 096: 16.2 / 17.0,
+// 32 768: 18.0 / 19.2, 131 072: 18.3 / 19.2).
+template <bool AP, int S_THREADS, int S_CTAS>
+__global__ void __launch_bounds__(S_THREADS, S_CTAS) bpl_forward1s_kernel(const KArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Fwd1sSmem &sm = *reinterpret_cast<Fwd1sSmem *>(smem_raw);
     float *A = sm.A;
@@ -270,7 +289,7 @@ __global__ void __launch_bounds__(S_THREADS, S_CTAS_PER_SM) bpl_forward1s_kernel
             const LaneAcc acc = warp_points<false, 1>(active, src, sm.tab, s, a.neval, active ? item - s * QN : 0, lane,
                                                       a.rc, A, 0.0f, 0, sm.bbox);
             any_out |= acc.any_out;
-            reduce_by_substroke(active, s, acc.sum, acc.cnt, ms->sub, lane);
+            reduce_by_substroke(active, s, acc.sum, acc.cnt, ms->sub, ms->ink64, lane);
         }
         BPL_PT(6);
         any_out = __any_sync(0xffffffffu, any_out);
@@ -279,7 +298,8 @@ __global__ void __launch_bounds__(S_THREADS, S_CTAS_PER_SM) bpl_forward1s_kernel
         BPL_PT(7);
         bool need_fix = false;
         for (int s = 0; s < t.S; ++s) {
-            const float4 v = ms->sub[s];
+            float4 v = ms->sub[s];
+            v.z = ink_sum(ms, s);
             need_fix |= (__float_as_int(v.w) >= 2 && v.z < a.rc.ink_pp);
         }
         if (need_fix) {
@@ -302,7 +322,7 @@ __global__ void __launch_bounds__(S_THREADS, S_CTAS_PER_SM) bpl_forward1s_kernel
 
         // ---- broaden + clamp, blur: only where the image can be non-zero ----
         if (!bb.empty()) {
-            broaden_box(A, sm.side, a.rc, bb);
+            broaden_box<S_THREADS>(A, sm.side, a.rc, bb);
             bb.grow_rows(a.rc.ink_ncon); bb.grow_cols(a.rc.ink_ncon);
             if (a.rc.ink_ncon == 0) {
                 for (int i = threadIdx.x; i < NPIX; i += blockDim.x) A[i] = fminf(A[i], 1.0f);
@@ -317,10 +337,10 @@ __global__ void __launch_bounds__(S_THREADS, S_CTAS_PER_SM) bpl_forward1s_kernel
                 for (int rep = 0; rep < 2; ++rep) {
                     // vertical: lines = the box's columns, bands = those holding output rows [r0-5, r1+5]
                     bb.grow_rows(PAD);
-                    gauss_box<true>(A, g, bb.c0, bb.c1, bb.r0, bb.r1);
+                    gauss_box<true, S_THREADS>(A, g, bb.c0, bb.c1, bb.r0, bb.r1);
                     __syncthreads();
                     bb.grow_cols(PAD);
-                    gauss_box<false>(A, g, bb.r0, bb.r1, bb.c0, bb.c1);
+                    gauss_box<false, S_THREADS>(A, g, bb.r0, bb.r1, bb.c0, bb.c1);
                     __syncthreads();
                 }
             }

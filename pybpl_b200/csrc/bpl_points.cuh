@@ -425,9 +425,13 @@ __device__ __forceinline__ float warp_points_bwd(bool active, const CtrlSrc &src
     return dot;
 }
 
-// Add each lane's (sum, cnt) into rec[sid].z / .w, combining the lanes of a warp that share a sub-stroke
-// first (a warp spans at most a few sub-strokes).  All 32 lanes must call this.
-__device__ __forceinline__ void reduce_by_substroke(bool active, int sid, float sum, int cnt, float4 *rec, int lane) {
+// Add each lane's (sum, cnt) into ink64[sid] / rec[sid].w, combining the lanes of a warp that share a sub-stroke first (a
+// warp spans at most a few sub-strokes).  All 32 lanes must call this.  The sum is kept as 16.40 fixed point in two
+// 32-bit words (whole multiples of 2^-16, and the remainder in units of 2^-40): integer atomics are native on shared
+// memory and add in any order to the same bits, and a warp's partial is a float reduced in a fixed order, so the total
+// is reproducible bit for bit (a float atomicAdd is a compare-and-swap loop whose result depends on arrival order).
+__device__ __forceinline__ void reduce_by_substroke(bool active, int sid, float sum, int cnt, float4 *rec,
+                                                    unsigned long long *ink64, int lane) {
     unsigned todo = __ballot_sync(0xffffffffu, active);
     while (todo) {
         const int leader = __ffs(todo) - 1;
@@ -436,7 +440,10 @@ __device__ __forceinline__ void reduce_by_substroke(bool active, int sid, float 
         const float v = warp_sum(mine ? sum : 0.0f);
         const int c = __reduce_add_sync(0xffffffffu, mine ? cnt : 0);
         if (lane == leader) {
-            atomicAdd(&rec[cur].z, v);
+            const float t = v * 65536.0f, whole = floorf(t);                  // exact scaling; t < 2^25 (ink of a sub-stroke < 400)
+            unsigned *w = reinterpret_cast<unsigned *>(ink64 + cur);
+            atomicAdd(w + 1, (unsigned)whole);
+            atomicAdd(w, (unsigned)((t - whole) * 16777216.0f));
             atomicAdd(reinterpret_cast<int *>(&rec[cur].w), c);
         }
         todo &= ~__ballot_sync(0xffffffffu, mine);

@@ -120,6 +120,10 @@ __device__ __forceinline__ void lse_finish(const KArgs &a, float m, float s, int
 struct Misc {
     double red[4 * 32];      // block_sum scratch
     float4 sub[MAXS];        // per sub-stroke: (t0x,t0y,tlastx,tlasty) then (offx, offy, sum ink, survivors)
+    unsigned long long ink64[MAXS];   // the sum of ink accumulated as fixed point (high word: multiples of 2^-16, low word:
+                             // units of 2^-40): integer atomics add in any order to the same bits, so the min-ink
+                             // branch taken for a borderline sub-stroke (rendering.py:104-107) does not depend on
+                             // which warp's atomic lands first
     float dot[MAXS];         // rescale branch: sum_k gink[k] ink0[k] (backward)
     float g[8], ht[8];       // Gaussian half kernel g[d], and h~[d] = (d^2 - mu2) g[d]
     float lp_bg[2], dlp_bg[2];
@@ -136,6 +140,15 @@ struct Misc {
     int ones_acc;            // accumulator for n_ones while a new image is loaded
     uint32_t bits[IMG_WORDS + 1];
 };
+
+// The sub-stroke's total ink after the point stage's barrier: every thread converts the fixed-point sum and stores it
+// in the record (all threads store the same bits, so later readers of sub[s].z need no further barrier).
+__device__ __forceinline__ float ink_sum(Misc *ms, int s) {
+    const unsigned long long w = ms->ink64[s];
+    const float v = fmaf((float)(unsigned)(w >> 32), 1.0f / 65536.0f, (float)(unsigned)w * (1.0f / 1099511627776.0f));
+    ms->sub[s].z = v;
+    return v;
+}
 
 enum : int { BR_NONE = 0, BR_SINGLE = 1, BR_FILL = 2, BR_RESCALE = 3, BR_NORMAL = 4 };
 
@@ -358,6 +371,7 @@ __device__ __forceinline__ void chain_offsets(const KArgs &a, const TokGeom &t, 
             const float ox = __fsub_rn(v.x, px), oy = __fsub_rn(v.y, py);
             px = __fsub_rn(v.z, ox); py = __fsub_rn(v.w, oy);
             ms->sub[s] = make_float4(ox, oy, 0.0f, 0.0f);
+            ms->ink64[s] = 0ull;
         }
     }
     __syncthreads();
@@ -713,14 +727,15 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) bpl_backward_kernel(const KArg
                                                                           active ? item - s * QN : 0, lane, a.rc, A, 0.0f, 0,
                                                                           ms->bbox);
                 any_out |= acc.any_out;
-                reduce_by_substroke(active, s, acc.sum, acc.cnt, ms->sub, lane);
+                reduce_by_substroke(active, s, acc.sum, acc.cnt, ms->sub, ms->ink64, lane);
             }
             any_out = __any_sync(0xffffffffu, any_out);
             if (any_out && lane == 0) atomicOr(&ms->off_page, 1);
             __syncthreads();
             bool need_fix = false;
             for (int s = 0; s < t.S; ++s) {
-                const float4 v = ms->sub[s];
+                float4 v = ms->sub[s];
+                v.z = ink_sum(ms, s);
                 need_fix |= (__float_as_int(v.w) >= 2 && v.z < a.rc.ink_pp);
             }
             if (need_fix) {
@@ -798,10 +813,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) bpl_backward_kernel(const KArg
                 // A pixel without ink has the analytic background value (closed form below); pm == bgv alone does not
                 // mean "no ink" (eps = 0.5 maps every v to 0.5).
                 if (eps > 0.0f && (pm != bgv || i6 != 0.0f))
-                {   // in double from the fp32 probability on (the terms are +-1e4 and cancel to a few tens)
-                    const double dd = (d == 0.0f) ? 0.0 : (x ? 1.0 / (double)pm : -1.0 / (1.0 - (double)pm));
-                    acc_eps += (dd * (1.0 - 2.0 * (double)i6) - (x ? dlp_bgd1 : dlp_bgd0)) * (double)gscale;
-                }
+                    acc_eps += ((double)(d * (1.0f - 2.0f * i6)) - (x ? dlp_bgd1 : dlp_bgd0)) * (double)gscale;
                 gp = d * gscale;
             }
             return pass5 ? gp * mixd : 0.0f;
@@ -1411,6 +1423,13 @@ int bpl_order_tokens(const bpl_token_batch *b, int *order, void *stream) {
     return 0;
 }
 
+// launch shape of the scoring kernel: see bpl_forward1s.cuh (BPL_FWD_SHAPE=small|large forces one, an A/B aid)
+static bool large_shape(int n_tokens) {
+    static const char *force = getenv("BPL_FWD_SHAPE");
+    if (force) return force[0] == 'l';
+    return n_tokens >= S_LARGE_MIN;
+}
+
 int bpl_order_tokens_by_cost(const bpl_params *ps, const bpl_token_batch *b, int *keys, int *order, void *stream) {
     if (!ps || !b || !order || !keys || !b->tok_stroke_off || !b->stroke_sub_off || !b->basis) {
         set_error("%s", "bpl_order_tokens_by_cost: NULL argument"); return BPL_EINVAL;
@@ -1443,11 +1462,15 @@ int bpl_score_tokens(const bpl_params *ps, const bpl_token_batch *b, const bpl_t
     // profiling aid, one target per token only), take the dense single-token kernel.
     static const bool force_single = getenv("BPL_FORCE_SINGLE") != nullptr;
     if (ka.image_bits && !ka.pimg && (ka.all_pairs || !force_single)) {
-        if (ka.all_pairs) {      // (tokens are few in this mode: no processing order)
+        if (ka.all_pairs) {      // (no processing order in this mode)
             ka.order = nullptr;
-            return launch(bpl_forward1s_kernel<true>, S_THREADS, sizeof(Fwd1sSmem), S_CTAS_PER_SM, ka, (cudaStream_t)stream);
+            if (large_shape(ka.n_tokens))
+                return launch(bpl_forward1s_kernel<true, S_THREADS_LARGE, S_CTAS_LARGE>, S_THREADS_LARGE, sizeof(Fwd1sSmem), S_CTAS_LARGE, ka, (cudaStream_t)stream);
+            return launch(bpl_forward1s_kernel<true, S_THREADS, S_CTAS_PER_SM>, S_THREADS, sizeof(Fwd1sSmem), S_CTAS_PER_SM, ka, (cudaStream_t)stream);
         }
-        return launch(bpl_forward1s_kernel<false>, S_THREADS, sizeof(Fwd1sSmem), S_CTAS_PER_SM, ka, (cudaStream_t)stream);
+        if (large_shape(ka.n_tokens))
+            return launch(bpl_forward1s_kernel<false, S_THREADS_LARGE, S_CTAS_LARGE>, S_THREADS_LARGE, sizeof(Fwd1sSmem), S_CTAS_LARGE, ka, (cudaStream_t)stream);
+        return launch(bpl_forward1s_kernel<false, S_THREADS, S_CTAS_PER_SM>, S_THREADS, sizeof(Fwd1sSmem), S_CTAS_PER_SM, ka, (cudaStream_t)stream);
     }
     return launch(bpl_forward_kernel<false>, FWD_THREADS, sizeof(FwdSmem), FWD_CTAS_PER_SM, ka, (cudaStream_t)stream);
 }
@@ -1470,7 +1493,9 @@ int bpl_score_tokens_lse(const bpl_params *ps, const bpl_token_batch *b, const b
         return 0;
     }
     ka.lse = lse; ka.lse_scratch = lse_scratch; ka.lse_accumulate = accumulate;
-    return launch(bpl_forward1s_kernel<false>, S_THREADS, sizeof(Fwd1sSmem), S_CTAS_PER_SM, ka, (cudaStream_t)stream, -1, true);
+    if (large_shape(ka.n_tokens))
+        return launch(bpl_forward1s_kernel<false, S_THREADS_LARGE, S_CTAS_LARGE>, S_THREADS_LARGE, sizeof(Fwd1sSmem), S_CTAS_LARGE, ka, (cudaStream_t)stream, -1, true);
+    return launch(bpl_forward1s_kernel<false, S_THREADS, S_CTAS_PER_SM>, S_THREADS, sizeof(Fwd1sSmem), S_CTAS_PER_SM, ka, (cudaStream_t)stream, -1, true);
 }
 
 int bpl_render_strokes(const bpl_params *ps, const bpl_stroke_batch *b, const bpl_targets *t, const bpl_fwd_out *out,
