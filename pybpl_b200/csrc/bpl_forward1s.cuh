@@ -106,6 +106,46 @@ __device__ BPL_GAUSS_ATTR void gauss_inplace_s(float *buf, const G6 gg, int l0, 
     block(q);
 }
 
+// One run per line, exactly the 7-blocks that hold rows [a0, a1]: nobody else touches the line, so the pass needs no
+// halo exchange and no barrier of its own (the in-place window reads ahead of what it writes).  Only `nl` threads work
+// (a third of the CTA), but with four CTAs on the SM the others' warps fill the issue slots, and the saved barrier and
+// halo loads are worth +4 % at 4 096 tokens, +6 % on 131 072 (19.1 -> 20.3 M particles/s).  Measured alternatives under
+// the same launch shape: the banded variants below (35-row runs, halos taken before a barrier; -DBPL_GAUSS_BANDED), the
+// box in two groups of whole lines (-6 %), and the same idea for the broaden -- one warp for all rows of a box up to 64
+// columns wide, no barriers between its passes -- which was 11 % slower (too serial: 2 x 45 rows by one warp).
+template <bool VERT>
+__device__ BPL_GAUSS_ATTR void gauss_run(float *buf, const G6 gg, int l0, int nl, int a0, int a1) {
+    const float (&g)[PAD + 1] = gg.v;
+    constexpr int SA = VERT ? IMG : 1;
+    constexpr int SL = VERT ? 1 : IMG;
+    constexpr int GU = 7;
+    if ((int)threadIdx.x >= nl) return;
+    const int s0 = a0 / GU * GU, nblk = a1 / GU - a0 / GU + 1;
+    float *p = buf + s0 * SA + (l0 + (int)threadIdx.x) * SL;
+    float W[GU + 2 * PAD];
+#pragma unroll
+    for (int i = 0; i < PAD; ++i) {
+        W[i] = (s0 > 0) ? p[(i - PAD) * SA] : 0.0f;
+        W[PAD + i] = p[i * SA];
+    }
+#pragma unroll 1
+    for (int blk = 0; blk < nblk; ++blk) {
+        float *q = p + blk * GU * SA;
+        const int pos = s0 + blk * GU + PAD;          // canvas position of the first new input
+#pragma unroll
+        for (int u = 0; u < GU; ++u) W[2 * PAD + u] = (pos + u < IMG) ? q[(u + PAD) * SA] : 0.0f;
+#pragma unroll
+        for (int u = 0; u < GU; ++u) {
+            float acc = g[0] * W[u + PAD];
+#pragma unroll
+            for (int d = 1; d <= PAD; ++d) acc = fmaf(g[d], W[u + PAD - d] + W[u + PAD + d], acc);
+            q[u * SA] = acc;
+        }
+#pragma unroll
+        for (int k = 0; k < 2 * PAD; ++k) W[k] = W[k + GU];
+    }
+}
+
 // Band size: the shortest runs whose items still fit one thread each.  Short runs spread a small box over more
 // threads (a 58 x 70 box is 133 items with 35-row bands but 290 with 15-row bands), at the price of more halo loads.
 #ifndef BPL_GAUSS_BANDS
@@ -114,6 +154,10 @@ __device__ BPL_GAUSS_ATTR void gauss_inplace_s(float *buf, const G6 gg, int l0, 
 template <bool VERT, int S_THREADS>
 __device__ __forceinline__ void gauss_box(float *buf, const G6 &g, int l0, int l1, int a0, int a1) {
     const int nl = l1 - l0 + 1;
+#ifndef BPL_GAUSS_BANDED
+    gauss_run<VERT>(buf, g, l0, nl, a0, a1);
+    return;
+#endif
 #if BPL_GAUSS_BANDS >= 5
     // One band size (15 or 21 rows) for every box: lines are independent, so a box with more (line, band) items than
     // threads is taken in groups of whole lines, one after the other (each group with its own halo-load barrier).
