@@ -48,7 +48,9 @@ BWD_BATCH = 1024
 CPU_SAMPLE = 8192            # particles per step of the CPU arm (first tokens of sweep block 0)
 # dram__bytes_read.sum + dram__bytes_write.sum of one scoring launch, from the ncu --set full capture summarised under
 # profiles/ (filled in from the round's capture; None until one exists for the current kernel)
-NCU_DRAM_BYTES_PER_PARTICLE = 295.69      # profiles/r02_fwd1s_sweep.raw.txt: (283.65 MB read + 12.04 MB written) / 1,000,000 particles
+NCU_SMEM_WAVEFRONTS_PER_PARTICLE = 5126.7   # profiles/r02_fwd1s_sweep_final.raw.txt: l1tex__data_pipe_lsu_wavefronts_mem_shared.sum
+                                            # / 1,000,000 particles; one wavefront moves up to 128 bytes
+NCU_DRAM_BYTES_PER_PARTICLE = 293.60        # profiles/r02_fwd1s_sweep_final.raw.txt: (282.36 MB read + 11.24 MB written) / 1,000,000 particles
 
 
 def flops_fwd(S):      # algorithmic work per particle, separable minimal algorithm
@@ -447,6 +449,18 @@ def run_gpu(args):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); probe(); b.record(); torch.cuda.synchronize()
         fp32_peak = max(fp32_peak, (blocks * 1024.0 * iters * 8 * 2) / (a.elapsed_time(b) * 1e-3) / 1e12)
+    # ---- live shared-memory bandwidth (second roofline of SURVEY.md 8(d)): best of 5 launches of the LDS.128 probe ----
+    s_iters, s_blocks = 8192, 148 * 2
+    sprobe = lambda: _lib.check(_lib.lib().bpl_smem_probe(ctypes.c_void_p(scratch.data_ptr()), s_iters, s_blocks,
+                                                          ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    for _ in range(2):
+        sprobe()
+    torch.cuda.synchronize()
+    smem_peak = 0.0
+    for _ in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); sprobe(); b.record(); torch.cuda.synchronize()
+        smem_peak = max(smem_peak, (s_blocks * 1024.0 * s_iters * 64) / (a.elapsed_time(b) * 1e-3) / 1e9)
     clocks = sampler.stop() if sampler else None
 
     # ---- secondary single-GPU objects (N=1 only) ----
@@ -497,6 +511,10 @@ def run_gpu(args):
                 "traffic": None if NCU_DRAM_BYTES_PER_PARTICLE is None else NCU_DRAM_BYTES_PER_PARTICLE * P_rank,
                 "kernel": "bpl_forward1s_kernel<false>", "kernel_ms": k_ms, "particles_per_launch": P_rank,
                 "flop_per_particle": flops_fwd(Sbar), "mean_substrokes": Sbar, "mean_strokes": Kbar, "peak_source": peak_note,
+                "smem": {"achieved": k_rate * NCU_SMEM_WAVEFRONTS_PER_PARTICLE * 128.0 / 1e9, "peak": smem_peak, "unit": "GB/s",
+                         "frac": k_rate * NCU_SMEM_WAVEFRONTS_PER_PARTICLE * 128.0 / 1e9 / smem_peak,
+                         "note": "achieved = shared-memory wavefronts per particle (ncu, profiles/) x 128 B x particles/s; peak = live "
+                                 "LDS.128 probe (bpl_smem_probe); nominal 148 SMs x 128 B/clk x 1.965 GHz = 37.2 TB/s"},
                 "hbm": {"achieved": k_rate * hbm_bytes(Sbar, Kbar) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": k_rate * hbm_bytes(Sbar, Kbar) / 1e9 / hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}

@@ -330,6 +330,9 @@ int bpl_logsumexp_combine(const float *parts, int n, float *out, void *stream);
 
 /* Roofline probe: `blocks` CTAs x 1024 threads x `iters` x 8 FFMA (2 flop each); scratch = 1 dev float. */
 int bpl_fp32_probe(float *scratch, int iters, int blocks, void *stream);
+/* Shared-memory bandwidth probe: blocks x 1024 threads, each streaming iters x 4 conflict-free 128-bit loads
+ * (= blocks * 1024 * iters * 64 bytes) -- the measured peak the kernels' shared-memory traffic is put against. */
+int bpl_smem_probe(float *scratch, int iters, int blocks, void *stream);
 
 /* number of kernel launches issued by this library in this process (bench.py gpu_launches) */
 long long bpl_launch_count(void);

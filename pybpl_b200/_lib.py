@@ -138,6 +138,7 @@ EXPORTS = {
     "bpl_logsumexp_partial": (ctypes.c_int, [vp, ctypes.c_int, vp, vp]),
     "bpl_logsumexp_combine": (ctypes.c_int, [vp, ctypes.c_int, vp, vp]),
     "bpl_fp32_probe": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, vp]),
+    "bpl_smem_probe": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, vp]),
     "bpl_launch_count": (ctypes.c_longlong, []),
 }
 

@@ -397,6 +397,26 @@ __global__ void __launch_bounds__(256) adam_step_kernel(const bpl_adam_args a) {
     }
 }
 
+// Shared-memory bandwidth probe (the second roofline SURVEY.md 8(d) names): every thread streams conflict-free 128-bit
+// loads from a 32 KB shared array, four independent accumulators; bytes moved = blocks * threads * iters * 4 loads * 16 B.
+__global__ void __launch_bounds__(1024) smem_probe_kernel(float *scratch, int iters) {
+    __shared__ float4 buf[2048];
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) buf[i] = make_float4((float)i, 1.0f, 2.0f, 3.0f);
+    __syncthreads();
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+    int j = threadIdx.x;
+    for (int it = 0; it < iters; ++it) {
+        const float4 v0 = buf[j & 2047], v1 = buf[(j + 512) & 2047], v2 = buf[(j + 1024) & 2047], v3 = buf[(j + 1536) & 2047];
+        a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+        a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
+        a2.x += v2.x; a2.y += v2.y; a2.z += v2.z; a2.w += v2.w;
+        a3.x += v3.x; a3.y += v3.y; a3.z += v3.z; a3.w += v3.w;
+        j += 32;
+    }
+    const float r = a0.x + a0.y + a0.z + a0.w + a1.x + a1.y + a1.z + a1.w + a2.x + a2.y + a2.z + a2.w + a3.x + a3.y + a3.z + a3.w;
+    if (r == -1.0f) scratch[0] = r;      // never true: keeps the loads alive
+}
+
 // Autograd scaling of the fused backward's outputs: every gradient of token p times the incoming cotangent g_ll[p]
 // (the fused kernel runs in the autograd forward, before the cotangent exists).  One warp per token walks the token's
 // strokes and sub-strokes through the CSR offsets: ONE launch instead of three gathers and six multiplies.
@@ -525,6 +545,12 @@ int bpl_fp32_probe(float *scratch, int iters, int blocks, void *stream) {
     if (!scratch || iters < 1 || blocks < 1) { set_error("%s", "bad fp32_probe arguments"); return BPL_EINVAL; }
     fp32_probe_kernel<<<blocks, 1024, 0, (cudaStream_t)stream>>>(scratch, iters, 0.999f, 0.001f);
     return check_launch("fp32_probe");
+}
+
+int bpl_smem_probe(float *scratch, int iters, int blocks, void *stream) {
+    if (!scratch || iters < 1 || blocks < 1) { set_error("%s", "bad smem_probe arguments"); return BPL_EINVAL; }
+    smem_probe_kernel<<<blocks, 1024, 0, (cudaStream_t)stream>>>(scratch, iters);
+    return check_launch("smem_probe");
 }
 
 int bpl_logsumexp_partial(const float *ll, int n, float *out2, void *stream) {
