@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """A/B of the forward scoring kernels on the bench workload (4096 tokens, device-resident, back to back):
-    python tools/ab_forward.py TAG          # kernel choice comes from the environment (BPL_FWD_SPARSE / BPL_FORCE_SINGLE)
+    python tools/ab_forward.py TAG          # kernel choice comes from the environment (BPL_FORCE_SINGLE, BPL_FWD_SHAPE=small|large)
 writes gpurun_out/ab_TAG.npy (the scores) and prints particles/s; with two or more earlier tags it also prints the
 largest relative difference between their scores."""
 import glob, os, sys
