@@ -214,6 +214,27 @@ def test_all_images_scoring_equals_pairwise():
     assert ((ll2 - ll_all).abs() <= 2e-5 * ll_all.abs()).all()
 
 
+def test_all_images_scoring_large_batch_shape():
+    """From 2 048 tokens on the scoring kernel runs as 256 threads x 4 CTAs per SM (below: 320 x 3), in all-pairs mode too
+    (the cross-scoring bench, configs[4], runs there): all-images scores of 2 300 tokens equal their pairwise scores, and
+    the first 40 tokens scored alone (the small shape) give the same numbers."""
+    from pybpl_b200 import ops, workload
+    dev = torch.device("cuda:0")
+    w = workload.synth_tokens(2300, seed=19, max_strokes=10, kappa="prior", sigma_mode="fixed")
+    batch = workload.to_device(w, dev)
+    g = torch.Generator().manual_seed(4)
+    images = (torch.rand((3, 105, 105), generator=g) < 0.05).to(torch.uint8).to(dev)
+    packed = ops.pack_images(images)
+    with torch.no_grad():
+        ll_all, off_all = ops.score_tokens_all_images(batch, packed)
+        for m in range(3):
+            ll_m, off_m = ops.score_tokens(batch, ops.pack_images(images[m]))
+            assert torch.equal(off_m, off_all)
+            assert ((ll_all[:, m] - ll_m).abs() <= 2e-5 * ll_m.abs()).all()
+        small, _ = ops.score_tokens_all_images(workload.to_device(workload.permute(w, np.arange(40)), dev), packed)
+        assert ((small - ll_all[:40]).abs() <= 2e-5 * small.abs()).all()
+
+
 def test_parse_file_upload_scores_like_the_original(tmp_path):
     """a batch + types + image set written to a parse file, loaded with ONE host->device copy, gives the
     scores of the original tensors; the host bit packing equals bpl_pack_images_u8."""
