@@ -598,6 +598,53 @@ def test_token_order_is_a_permutation_by_decreasing_cost(ops):
     assert torch.allclose(ll1, ll2, rtol=2e-6, atol=0)
 
 
+def test_team_backward_with_arenas_that_do_not_fit_side_by_side(ops):
+    """Tokens whose boxes cover the whole canvas and that carry many sub-strokes need 3 x 105 x 105 floats + their
+    per-sub-stroke sums each: two such arenas exceed the shared-memory pool, so one team of every CTA has to wait for the
+    other to finish (the `waiting` hand-over of the arena allocator).  Scores and gradients must equal the full-canvas
+    kernel's; a token beyond the per-CTA limits (129 sub-strokes) is flagged NaN / 255 by both."""
+    import os
+    rng = np.random.default_rng(11)
+    P, K, NS = 40, 10, 10                                   # 100 sub-strokes per token, spread over the canvas
+    S = P * K * NS
+    ctrl = np.zeros((S, 5, 2), np.float32)
+    t = np.linspace(0, 1, 5)
+    for s in range(S):
+        a, b = rng.uniform(-1, 1, 2), rng.uniform(-1, 1, 2)
+        ctrl[s] = 12.0 * (np.outer(t, a) + np.outer(t * t, b))
+    inv = rng.uniform(0.5, 1.5, S).astype(np.float32)
+    pos = np.stack([rng.uniform(5, 100, P * K), -rng.uniform(5, 100, P * K)], 1).astype(np.float32)
+    tso = np.arange(0, P * K + 1, K); sso = np.arange(0, S + 1, NS)
+    # one token more with 129 sub-strokes in a single stroke (beyond BPL_MAX_SUBSTROKES)
+    ctrl = np.concatenate([ctrl, ctrl[:129]]); inv = np.concatenate([inv, inv[:129]])
+    pos = np.concatenate([pos, pos[:1]]); tso = np.concatenate([tso, [P * K + 1]]); sso = np.concatenate([sso, [S + 129]])
+    eps = np.full(P + 1, 1e-4, np.float32); sig = rng.uniform(0.5, 8.0, P + 1).astype(np.float32)
+    img = (rng.random((105, 105)) < 0.2).astype(np.uint8)
+    imgs = ops.pack_images(T(img, torch.uint8))
+    res = {}
+    for kern in ("BPL_BWD_CANVAS", "BPL_BWD_TEAMS"):
+        os.environ.pop("BPL_BWD_CANVAS", None); os.environ.pop("BPL_BWD_TEAMS", None)
+        os.environ[kern] = "1"
+        try:
+            leaves = [T(ctrl), T(inv), T(pos), T(eps), T(sig)]
+            for x in leaves:
+                x.requires_grad_(True)
+            batch = ops.TokenBatch(tso, sso, *leaves, check_limits=False)
+            ll, off = ops.score_tokens(batch, imgs)
+            g = torch.autograd.grad(ll[:P].sum(), leaves)
+            res[kern] = (ll.detach().cpu().numpy(), off.cpu().numpy(), [x.cpu().numpy() for x in g])
+        finally:
+            os.environ.pop(kern, None)
+    a, b = res["BPL_BWD_CANVAS"], res["BPL_BWD_TEAMS"]
+    for r in (a, b):
+        assert np.isnan(r[0][P]) and r[1].view(np.uint8)[P] != 0 and np.isfinite(r[0][:P]).all()
+    assert np.allclose(a[0][:P], b[0][:P], rtol=2e-6, atol=0) and np.array_equal(a[1][:P], b[1][:P])
+    for n, x, y in zip(("ctrl", "invscale", "position", "eps", "sigma"), a[2], b[2]):
+        err = np.abs(x - y).max() / np.abs(x).max()
+        print("full-canvas tokens:", n, "canvas vs teams", err)
+        assert np.isfinite(y).all() and err < 1e-4, (n, err)
+
+
 def test_work_queue_under_concurrent_streams_and_graph_replay(ops):
     """Every launch of a persistent kernel owns one slot of the work-queue ring (g_sched) until its last CTA resets it.
     Two streams launching back to back at the same time, and a CUDA graph replayed while live launches run on another
