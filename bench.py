@@ -509,7 +509,8 @@ def run_gpu(args):
                  "SURVEY.md 8(d) shows the path is FP32-issue/shared-memory bound, not HBM")
     roofline = {"bound": "fp32", "achieved": ach_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach_tf / fp32_peak,
                 "traffic": None if NCU_DRAM_BYTES_PER_PARTICLE is None else NCU_DRAM_BYTES_PER_PARTICLE * P_rank,
-                "kernel": "bpl_forward1s_kernel<false>", "kernel_ms": k_ms, "particles_per_launch": P_rank,
+                "peak_nominal": 74.45, "frac_of_nominal": ach_tf / 74.45,      # 148 SMs x 128 FMA/clk x 2 x 1.965 GHz
+                "kernel": "bpl_forward1s_kernel<false, 256, 4>", "kernel_ms": k_ms, "particles_per_launch": P_rank,
                 "flop_per_particle": flops_fwd(Sbar), "mean_substrokes": Sbar, "mean_strokes": Kbar, "peak_source": peak_note,
                 "smem": {"achieved": k_rate * NCU_SMEM_WAVEFRONTS_PER_PARTICLE * 128.0 / 1e9, "peak": smem_peak, "unit": "GB/s",
                          "frac": k_rate * NCU_SMEM_WAVEFRONTS_PER_PARTICLE * 128.0 / 1e9 / smem_peak,
