@@ -507,6 +507,44 @@ __device__ __noinline__ void bt_pass3_update(const float *in, float *A, Axis ax,
         A[q] = fmaf(c1, acc[0], c2 * A[q]); });
 }
 
+// One broaden pass as ONE two-dimensional sweep, out of place: out = c1 * (1,2,1)x(1,2,1) * in + c2 * in over the region.
+// A thread owns a run of rows of one column and slides down it: per row it loads the three horizontal neighbours (lanes
+// hold adjacent columns: conflict free), forms the row's (1,2,1) sum and combines the sums of three consecutive rows.
+// Half the passes, barriers and per-pass set-up of the separable form (which is kept below for A/B: -DBPL_BT_BROADEN_SEP).
+__device__ __noinline__ void bt_pass_broaden2d(const float *__restrict__ in, float *__restrict__ out, int stride, int H, int W,
+                                               Reg g, float c1, float c2) {
+    const TeamCtx tm = team_ctx();
+    constexpr int GU = BT_GU;
+    const float rnl = __frcp_rn((float)g.nl);
+    const int NB = min(g.nblk, small_div(BT_TT, rnl));
+    const int qb = small_div(g.nblk, __frcp_rn((float)NB)), rem = g.nblk - qb * NB;
+    const int bi = small_div(tm.tid, rnl), col = g.l0 + tm.tid - bi * g.nl;
+    if (bi >= NB) return;
+    const int nb = qb + (bi < rem ? 1 : 0);
+    const int a0 = g.s0 + (bi * qb + min(bi, rem)) * GU, a1 = a0 + nb * GU;      // rows [a0, a1)
+    const bool okl = col > 0, okr = col < W - 1;
+    const float *p = in + a0 * stride + col;
+    float *o = out + a0 * stride + col;
+    auto hsum = [&](const float *q, float &xc) {      // (1,2,1) sum of one row at this column; zero outside the box
+        xc = q[0];
+        const float xl = okl ? q[-1] : 0.0f, xr = okr ? q[1] : 0.0f;
+        return xl + 2.0f * xc + xr;
+    };
+    float xc, xn, dummy;
+    float hp = (a0 > 0) ? hsum(p - stride, dummy) : 0.0f;
+    float hc = hsum(p, xc);
+#pragma unroll 1
+    for (int r = a0; r < a1; r += GU) {
+#pragma unroll
+        for (int u = 0; u < GU; ++u) {
+            const float hn = (r + u + 1 < H) ? hsum(p + stride, xn) : 0.0f;
+            *o = fmaf(c1, hp + 2.0f * hc + hn, c2 * xc);
+            hp = hc; hc = hn; xc = xn;
+            p += stride; o += stride;
+        }
+    }
+}
+
 // broaden (rendering.py:160-168): ncon x [ c1 * S_h S_v + c2 ]; A holds the image and receives the result, B is scratch.
 // m: margin (around the ink box) up to which the input is non-zero (forward, dm = +1: the image grows by one pixel per
 // pass) or the adjoint's input is valid (dm = -1: the region in which the result is still needed shrinks).
@@ -515,9 +553,31 @@ __device__ __noinline__ void bt_broaden(BtShared *sh, int m, int dm) {
     const BtTok *tk = &sh->tok[tm.id];
     const LBox bx = tk->bx;
     float *A = bt_pool(sh) + tk->arena, *T = A + bx.area();
-    const Axis V = make_axis(bx, true), H = make_axis(bx, false);
     const float c1 = sh->ka.rc.c1, c2 = sh->ka.rc.c2;
-    for (int it = 0; it < sh->ka.rc.ink_ncon; ++it) {
+    const int ncon = sh->ka.rc.ink_ncon;
+#ifndef BPL_BT_BROADEN_SEP
+    // ping-pong A -> T -> A ...: a pass reads its input one pixel beyond its output region; there the input holds either
+    // what the previous pass wrote (adjoint: the regions shrink) or the zeros nothing has written yet (forward: T is
+    // first used here, and the true image is zero beyond the previous region)
+    for (int it = 0; it < ncon; ++it) {
+        const int mo = m + dm;
+        bt_pass_broaden2d((it & 1) ? T : A, (it & 1) ? A : T, bx.stride, bx.H, bx.W, make_reg(tk, true, mo, mo), c1, c2);
+        tm.sync();
+        m = mo;
+    }
+    if (ncon & 1) {      // an odd number of passes leaves the result in T
+        const Reg g = make_reg(tk, false, m, m);
+        const int wn = g.nblk * BT_GU, bn = wn * g.nl;
+        const float rw = __frcp_rn((float)wn);
+        for (int i = tm.tid; i < bn; i += BT_TT) {
+            const int rr = small_div(i, rw), q = (g.l0 + rr) * bx.stride + g.s0 + i - rr * wn;
+            A[q] = T[q];
+        }
+        tm.sync();
+    }
+#else
+    const Axis V = make_axis(bx, true), H = make_axis(bx, false);
+    for (int it = 0; it < ncon; ++it) {
         const int mo = m + dm;
         bt_pass3_store(A, T, V, make_reg(tk, true, mo, max(m, mo)));      // rows of the result, columns the row pass reads
         tm.sync();
@@ -525,6 +585,7 @@ __device__ __noinline__ void bt_broaden(BtShared *sh, int m, int dm) {
         tm.sync();
         m = mo;
     }
+#endif
 }
 
 // Per-token set-up: target bits, chain offsets, affine, constants, the ink box and the team's arena (zeroed).
