@@ -335,6 +335,39 @@ def test_score_matches_oracle_on_random_batch(ops, bwd_kernel):
     assert relinf(sig.grad.cpu().numpy(), ref["g_sigma"]) < 5e-3
 
 
+def test_other_neval_against_oracle(ops, bwd_kernel):
+    """The fused kernels take any number of evaluation points per sub-stroke (neval * 5 <= 1024 table entries), not only
+    the reference's default 200 (objects/part.py:290): 64 points, scoring kernel and both backward kernels against the
+    oracle with the basis table coefficient_mat(5, 64)."""
+    from oracle import Oracle
+    from pybpl_b200 import workload
+    import oracle as _oracle
+    w = workload.synth_tokens(80, seed=31, sigma_mode="uniform", neval=64)
+    o = Oracle(np.float32)
+    C = ops.basis_table(5, 64, DEV).cpu().numpy()
+    img = _oracle.target_image_for(w, o, C)
+    ref = o.token_batch(C, w["tok_stroke_off"], w["stroke_sub_off"], w["ctrl"], w["invscale"], w["position"],
+                        w["eps"], w["sigma"], img[None], grad=True)
+    imgs = ops.pack_images(T(img, torch.uint8))
+    leaves = [T(w["ctrl"]), T(w["invscale"]), T(w["position"]), T(w["eps"]), T(w["sigma"])]
+    with torch.no_grad():
+        ll0, off0 = ops.score_tokens(ops.TokenBatch(w["tok_stroke_off"], w["stroke_sub_off"], *leaves, neval=64), imgs)
+    for x in leaves:
+        x.requires_grad_(True)
+    ll, off = ops.score_tokens(ops.TokenBatch(w["tok_stroke_off"], w["stroke_sub_off"], *leaves, neval=64), imgs)
+    g = torch.autograd.grad(ll.sum(), leaves)
+    for got in (ll0, ll.detach()):
+        assert (np.abs(got.cpu().numpy() - ref["ll"]) / np.abs(ref["ll"])).max() < 1e-5
+    assert np.array_equal(off0.cpu().numpy(), ref["off_page"]) and np.array_equal(off.cpu().numpy(), ref["off_page"])
+    # Gradients against the fp64 oracle: with 64 points the segments are three times longer, fewer and larger terms carry
+    # the gradient, and the fp32 ORACLE's own noise grows to 4e-4 ... 7e-4 of fp64 (measured), the kernels stay below 1e-4.
+    r64 = Oracle(np.float64).token_batch(C.astype(np.float64), w["tok_stroke_off"], w["stroke_sub_off"], w["ctrl"], w["invscale"],
+                                         w["position"], w["eps"], w["sigma"], img[None], grad=True)
+    errs = [relinf(x.cpu().numpy(), r64[k]) for x, k in zip(g, ("g_ctrl", "g_invscale", "g_position", "g_eps", "g_sigma"))]
+    print("neval 64,", bwd_kernel, "kernel: gradient errors vs fp64 oracle (ctrl, invscale, position, eps, sigma)", errs)
+    assert errs[0] < 2e-4 and errs[1] < 2e-4 and errs[2] < 2e-4 and errs[3] < 5e-4 and errs[4] < 5e-3, errs
+
+
 def test_backward_kernels_agree_on_every_mode(ops):
     """The two fused backward kernels (full canvas / teams with box-sized arenas) on one mixed batch: affine warps,
     blur_sigma <= 0, epsilon = 0, a token without strokes, a token that is entirely off the page, weighted scores
