@@ -38,7 +38,7 @@ namespace bpl {
 #define BPL_BT_TEAMS 2
 #endif
 #ifndef BPL_BT_THREADS
-#define BPL_BT_THREADS 384
+#define BPL_BT_THREADS 320
 #endif
 #ifndef BPL_BT_PPL
 #define BPL_BT_PPL 4

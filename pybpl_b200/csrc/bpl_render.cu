@@ -1526,7 +1526,7 @@ int bpl_score_tokens_grad(const bpl_params *ps, const bpl_token_batch *b, const 
     // Small batches: the full-canvas kernel, one 640-thread CTA per token and SM (shortest per-token latency, so the
     // shortest tail of the launch).  From BWD_TEAMS_MIN tokens on: teams of one persistent CTA per SM share the SM's
     // whole shared memory as a pool of box-sized arenas, expensive tokens first (bpl_backward_teams.cuh).  Measured
-    // M particles/s, canvas / teams: 1 024 tokens 3.80 / 4.04, 2 048: 4.12 / 4.46, 8 192: 4.49 / 4.92, 32 768: 4.60 / 5.05.
+    // M particles/s, canvas / teams: 1 024 tokens 3.80 / 4.12, 2 048: 4.12 / 4.46, 8 192: 4.49 / 4.85, 32 768: 4.60 / 4.95.
     // BPL_BWD_CANVAS=1 / BPL_BWD_TEAMS=1 force one or the other (A/B aids); BPL_BWD_ORDER=1 lets the canvas kernel follow
     // the processing order too (measured 2 % slower).
     // (read per call, not cached: the parity tests switch kernels inside one process)
