@@ -183,9 +183,11 @@ class TokenBatch:
     # Processing order for the persistent kernels: expensive tokens first, so that a launch of a few thousand tokens
     # (a few dozen per SM) does not end with one SM still busy on a large one.  Two keys, each computed once per batch
     # and kept (an order is only a heuristic, results do not depend on it):
-    #   forward scoring  : the sub-stroke count (offsets only, one small kernel) -- measured best for that kernel
-    #   fused backward   : estimated cost, area of the box of the control polygons + sub-stroke count
-    #                      (bpl_order_tokens_by_cost, from the geometry at that time): 1 024 parses 3.67 -> 4.04 M/s
+    #   estimated cost   : area of the box of the control polygons + sub-stroke count (bpl_order_tokens_by_cost, from the
+    #                      geometry at that time) -- the scoring calls and the fused backward: 1 024 parses 3.67 -> 4.04 M/s
+    #                      fwd+bwd; 4 096 tokens forward 16.5 M/s in index order, 17.6 by sub-stroke count, 17.9 by this key
+    #                      (18.2 when ordered by MEASURED cycles per token, tools/order_upper_bound.py)
+    #   sub-stroke count : offsets only, one small kernel -- callers without the geometry at hand (token_points, staging)
     # Large batches keep index order.
     ORDER_MAX_TOKENS = 65536      # measured gain of an order at all: +6.7 % at 4 096 tokens, +2.5 % at 8 192, +1.2 % at 16 384
 
@@ -400,7 +402,7 @@ class _ScoreTokens(torch.autograd.Function):
         # grad_on = torch.is_grad_enabled() of the CALLER (inside forward() it is always off): leaves evaluated under
         # no_grad take the cheaper forward-only kernel
         need = grad_on and any(ctx.needs_input_grad[:6])
-        b = batch.c_struct(ctrl_c, inv_c, pos_c, aff_c, eps_c, sig_c, cost_order=need)
+        b = batch.c_struct(ctrl_c, inv_c, pos_c, aff_c, eps_c, sig_c, cost_order=True)
         if need:
             g_ctrl = torch.empty_like(ctrl_c); g_inv = torch.empty_like(inv_c); g_pos = torch.empty_like(pos_c)
             g_aff = None if aff_c is None else torch.empty_like(aff_c)
@@ -529,7 +531,7 @@ def score_tokens_lse(batch, images, state, accumulate=False, want_ll=True, ps=No
             None if batch.affine is None else _c32(batch.affine), _c32(batch.eps), _c32(batch.sigma)]
     ll = torch.empty(P, dtype=torch.float32, device=dev) if want_ll else None
     off = torch.empty(P, dtype=torch.uint8, device=dev)
-    b = batch.c_struct(*tens)
+    b = batch.c_struct(*tens, cost_order=True)
     t = _targets(images, None)
     out = _lib.FwdOut(None if ll is None else ll.data_ptr(), off.data_ptr(), None)
     check(lib().bpl_score_tokens_lse(ctypes.byref(ps), ctypes.byref(b), ctypes.byref(t), ctypes.byref(out),

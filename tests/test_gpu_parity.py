@@ -626,7 +626,7 @@ def test_token_order_is_a_permutation_by_decreasing_cost(ops):
     pimg, _ = ops.render_tokens(workload.to_device(workload.permute(w, np.arange(1)), DEV))
     imgs = ops.pack_images((pimg[0] > 0.5).to(torch.uint8))
     ll1, _ = ops.score_tokens(b, imgs)
-    b._order = torch.arange(512, dtype=torch.int32, device=DEV)
+    b._order = b._order_cost = torch.arange(512, dtype=torch.int32, device=DEV)
     ll2, _ = ops.score_tokens(b, imgs)
     assert torch.allclose(ll1, ll2, rtol=2e-6, atol=0)
 

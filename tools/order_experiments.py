@@ -39,7 +39,7 @@ ext = np.array([np.ptp(pos[tso[i]:tso[i + 1], 0]) + np.ptp(pos[tso[i]:tso[i + 1]
 cands["by S + extent/20"] = np.argsort(-(S + ext / 20.0), kind="stable")
 cands["by S + extent/10"] = np.argsort(-(S + ext / 10.0), kind="stable")
 for name, order in cands.items():
-    b._order = torch.from_numpy(order.astype(np.int32)).to(dev)
+    b._order = b._order_cost = torch.from_numpy(order.astype(np.int32)).to(dev)
     for _ in range(5):
         ops.score_tokens(b, imgs)
     torch.cuda.synchronize()
