@@ -237,7 +237,7 @@ __device__ __forceinline__ void load_image_bits_t(const TeamCtx &tm, const KArgs
 __device__ __forceinline__ bool warp_bbox(bool active, const CtrlSrc &src, int n, int q, int lane, int *bbox) {
     int rmin = IMG, rmax = -1, cmin = IMG, cmax = -1;
     bool any_out = false;
-#pragma unroll
+    BPL_UNROLL_A
     for (int k = 0; k < BT_PPL; ++k) {
         const int j = q * BT_PPL + k;
         const bool valid = active && j < n;
@@ -838,25 +838,27 @@ __device__ __noinline__ void bt_gather(BtShared *sh) {
                 ax = fmaf(gx, px, ax); ay = fmaf(gy, py, ay);
             }
         }, lay);
-        // combine the lanes of a warp that share a sub-stroke, then one set of atomics per (warp, sub-stroke)
+        // combine the lanes of a warp that share a sub-stroke: the 12 (+ 2 affine) sums are reduced together
+        // (warp_reduce16: lanes 2i, 2i+1 end up with sum i), then the even lanes add their sum to the sub-stroke's record
         unsigned todo = __ballot_sync(0xffffffffu, active);
         while (todo) {
             const int leader = __ffs(todo) - 1;
             const int cur = __shfl_sync(0xffffffffu, s, leader);
             const bool mine = active && s == cur;
-            float *o = accs + cur * NACC;
+            float v[16];
 #pragma unroll
-            for (int k = 0; k < NCPT; ++k) {
-                const float a0 = warp_sum(mine ? wx[k] : 0.0f), a1 = warp_sum(mine ? wy[k] : 0.0f);
-                if (tm.lane == leader) { atomicAdd(o + 2 * k, a0); atomicAdd(o + 2 * k + 1, a1); }
-            }
-            const float tsx = warp_sum(mine ? sx : 0.0f), tsy = warp_sum(mine ? sy : 0.0f);
-            if (tm.lane == leader) { atomicAdd(o + 2 * NCPT, tsx); atomicAdd(o + 2 * NCPT + 1, tsy); }
-            if (aff) {
-                const float tax = warp_sum(mine ? ax : 0.0f), tay = warp_sum(mine ? ay : 0.0f);
-                if (tm.lane == leader) {
-                    atomicAdd(&ms->aff_acc[0], (double)tax); atomicAdd(&ms->aff_acc[1], (double)tay);
-                    atomicAdd(&ms->aff_acc[2], (double)tsx); atomicAdd(&ms->aff_acc[3], (double)tsy);
+            for (int k = 0; k < NCPT; ++k) { v[2 * k] = mine ? wx[k] : 0.0f; v[2 * k + 1] = mine ? wy[k] : 0.0f; }
+            v[2 * NCPT] = mine ? sx : 0.0f; v[2 * NCPT + 1] = mine ? sy : 0.0f;
+            v[12] = mine ? ax : 0.0f; v[13] = mine ? ay : 0.0f; v[14] = 0.0f; v[15] = 0.0f;
+            const float tot = warp_reduce16(v, tm.lane);
+            const int idx = tm.lane >> 1;
+            if (!(tm.lane & 1)) {
+                if (idx < NACC) atomicAdd(accs + cur * NACC + idx, tot);
+                if (aff) {
+                    if (idx == 12) atomicAdd(&ms->aff_acc[0], (double)tot);
+                    else if (idx == 13) atomicAdd(&ms->aff_acc[1], (double)tot);
+                    else if (idx == 2 * NCPT) atomicAdd(&ms->aff_acc[2], (double)tot);
+                    else if (idx == 2 * NCPT + 1) atomicAdd(&ms->aff_acc[3], (double)tot);
                 }
             }
             todo &= ~__ballot_sync(0xffffffffu, mine);

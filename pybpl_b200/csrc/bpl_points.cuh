@@ -14,6 +14,14 @@
 // FIX = true that adds (final - common) ink.
 #pragma once
 
+// Phase A of the point stages (a lane evaluates its PPL points once to see which are on the page): unrolled by default;
+// -DBPL_ROLL_PHASE_A keeps one copy of the point evaluation per stage (instruction-cache footprint A/B).
+#ifdef BPL_ROLL_PHASE_A
+#define BPL_UNROLL_A _Pragma("unroll 1")
+#else
+#define BPL_UNROLL_A _Pragma("unroll")
+#endif
+
 namespace bpl {
 
 #ifndef BPL_PPL
@@ -111,7 +119,7 @@ __device__ __forceinline__ LaneAcc warp_points(bool active, const CtrlSrc &src, 
     unsigned inbm = 0u;
     bool hv = false;
     float lr = 0.0f, lc = 0.0f;
-#pragma unroll
+    BPL_UNROLL_A
     for (int k = 0; k < PPL; ++k) {
         const int j = j0 + k;
         const PEval e = eval_pt(src, j, active && j < n);
@@ -296,7 +304,7 @@ __device__ __forceinline__ float warp_points_bwd(bool active, const CtrlSrc &src
     bool hv = false;
     float lr = 0.0f, lc = 0.0f;
     int lj = 0;
-#pragma unroll
+    BPL_UNROLL_A
     for (int k = 0; k < PPL; ++k) {
         const int j = j0 + k;
         const PEval e = eval_pt(src, j, active && j < n);
@@ -423,6 +431,22 @@ __device__ __forceinline__ float warp_points_bwd(bool active, const CtrlSrc &src
         }
     }
     return dot;
+}
+
+// Sixteen sums over the warp for the price of sixteen shuffles (sixteen butterfly reductions take eighty): at every
+// stage a lane hands half of the values it still holds to its partner and keeps the other half, so the number of
+// values per lane halves as the partner distance does.  Afterwards lanes 2i and 2i+1 both hold the total of value i.
+__device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
+#pragma unroll
+    for (int half = 8, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+        const bool up = (lane & bit) != 0;
+#pragma unroll
+        for (int k = 0; k < half; ++k) {
+            const float send = up ? v[k] : v[k + half], keep = up ? v[k + half] : v[k];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+        }
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
 // Add each lane's (sum, cnt) into ink64[sid] / rec[sid].w, combining the lanes of a warp that share a sub-stroke first (a

@@ -980,25 +980,27 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) bpl_backward_kernel(const KArg
                         ax = fmaf(gx, px, ax); ay = fmaf(gy, py, ay);
                     }
                 });
-                // combine the lanes of a warp that share a sub-stroke, then one set of atomics per (warp, sub-stroke)
+                // combine the lanes of a warp that share a sub-stroke: the 12 (+ 2 affine) sums are reduced together
+                // (warp_reduce16: lanes 2i, 2i+1 end up with sum i), then the even lanes add their sum to the record
                 unsigned todo = __ballot_sync(0xffffffffu, active);
                 while (todo) {
                     const int leader = __ffs(todo) - 1;
                     const int cur = __shfl_sync(0xffffffffu, s, leader);
                     const bool mine = active && s == cur;
-                    float *o = accs + ORIGIN + cur * NACC;
+                    float v[16];
 #pragma unroll
-                    for (int k = 0; k < NCPT; ++k) {
-                        const float a0 = warp_sum(mine ? wx[k] : 0.0f), a1 = warp_sum(mine ? wy[k] : 0.0f);
-                        if (lane == leader) { atomicAdd(o + 2 * k, a0); atomicAdd(o + 2 * k + 1, a1); }
-                    }
-                    const float tsx = warp_sum(mine ? sx : 0.0f), tsy = warp_sum(mine ? sy : 0.0f);
-                    if (lane == leader) { atomicAdd(o + 2 * NCPT, tsx); atomicAdd(o + 2 * NCPT + 1, tsy); }
-                    if (aff) {
-                        const float tax = warp_sum(mine ? ax : 0.0f), tay = warp_sum(mine ? ay : 0.0f);
-                        if (lane == leader) {
-                            atomicAdd(&ms->aff_acc[0], (double)tax); atomicAdd(&ms->aff_acc[1], (double)tay);
-                            atomicAdd(&ms->aff_acc[2], (double)tsx); atomicAdd(&ms->aff_acc[3], (double)tsy);
+                    for (int k = 0; k < NCPT; ++k) { v[2 * k] = mine ? wx[k] : 0.0f; v[2 * k + 1] = mine ? wy[k] : 0.0f; }
+                    v[2 * NCPT] = mine ? sx : 0.0f; v[2 * NCPT + 1] = mine ? sy : 0.0f;
+                    v[12] = mine ? ax : 0.0f; v[13] = mine ? ay : 0.0f; v[14] = 0.0f; v[15] = 0.0f;
+                    const float tot = warp_reduce16(v, lane);
+                    const int idx = lane >> 1;
+                    if (!(lane & 1)) {
+                        if (idx < NACC) atomicAdd(accs + ORIGIN + cur * NACC + idx, tot);
+                        if (aff) {
+                            if (idx == 12) atomicAdd(&ms->aff_acc[0], (double)tot);
+                            else if (idx == 13) atomicAdd(&ms->aff_acc[1], (double)tot);
+                            else if (idx == 2 * NCPT) atomicAdd(&ms->aff_acc[2], (double)tot);
+                            else if (idx == 2 * NCPT + 1) atomicAdd(&ms->aff_acc[3], (double)tot);
                         }
                     }
                     todo &= ~__ballot_sync(0xffffffffu, mine);
