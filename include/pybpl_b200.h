@@ -35,7 +35,7 @@ extern "C" {
 /* Rendering constants: pybpl/parameters.py:19-41 (class Parameters). */
 typedef struct {
     int imsize;          /* must be 105 */
-    int fsize;           /* must be 11 */
+    int fsize;           /* odd, 1..11 (the reference default is 11; smaller filters run as 11-tap passes with zero outer taps) */
     int ink_ncon;        /* :31 */
     float ink_pp;        /* :25 */
     float ink_max_dist;  /* :27 */

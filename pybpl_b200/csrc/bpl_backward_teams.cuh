@@ -210,12 +210,12 @@ __device__ __forceinline__ void affine_setup_t(const TeamCtx &tm, const KArgs &a
     tm.sync();
 }
 
-__device__ __forceinline__ void token_consts_t(const TeamCtx &tm, float eps, float sigma, Misc *ms) {
+__device__ __forceinline__ void token_consts_t(const TeamCtx &tm, float eps, float sigma, int fhalf, Misc *ms) {
     if (tm.warp != TeamCtx::NW - 1) return;      // the team's last warp; only it reads or writes c_eps / c_sigma
     const bool same_eps = (eps == ms->c_eps), same_sigma = (sigma == ms->c_sigma);
     __syncwarp();
     if (tm.lane == 0) { ms->c_eps = eps; ms->c_sigma = sigma; }
-    if (!same_sigma) token_consts_sigma(sigma, tm.lane, ms);
+    if (!same_sigma) token_consts_sigma(sigma, tm.lane, fhalf, ms);
     if (!same_eps && (tm.lane == 8 || tm.lane == 9)) token_consts_eps(eps, tm.lane == 9, ms);
 }
 
@@ -606,7 +606,7 @@ __device__ __noinline__ void bt_setup(BtShared *sh) {
     }
     chain_offsets_t(tm, a, t, tab, ms);
     if (aff) affine_setup_t(tm, a, t, p, tab, ms);
-    token_consts_t(tm, a.eps[p], a.sigma[p], ms);      // double-precision constants by one warp, hidden behind the point stage
+    token_consts_t(tm, a.eps[p], a.sigma[p], a.rc.fhalf, ms);      // double-precision constants by one warp, hidden behind the point stage
     if (tm.tid == 0 && a.image_bits) {
         const int img = a.img_idx ? a.img_idx[p] : 0;
         if (img != ms->cur_img) { ms->n_ones = ms->ones_acc; ms->cur_img = img; }      // a new image was loaded above

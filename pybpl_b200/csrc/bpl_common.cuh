@@ -42,6 +42,7 @@ struct RenderConsts {
     float ink_f;     // ink_pp / ink_max_dist (d ink / d dist)
     float inv_max_dist;   // 1 / ink_max_dist when that is exact (a power of two), else 0: x / 2 == x * 0.5 bit for bit
     float c1, c2;    // H_broaden = c1 * (1,2,1)x(1,2,1) + c2 * delta
+    int fhalf;       // half-width of the Gaussian, fsize / 2 <= PAD: taps beyond it are zero (parameters.py:41, general.py:196-207)
 };
 
 __device__ __forceinline__ float warp_sum(float v) {

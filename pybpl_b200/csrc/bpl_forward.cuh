@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) bpl_forward_kern
         const bool aff = !RAW && a.affine != nullptr;
         zero_floats(A, FBUF);
         load_image_bits(a, p, ms);
-        token_consts(eps, sigma, false, ms);
+        token_consts(eps, sigma, false, ms, a.rc.fhalf);
         if (threadIdx.x == 0) ms->off_page = 0;
         if (!RAW) {
             chain_offsets(a, t, sm.tab, ms);

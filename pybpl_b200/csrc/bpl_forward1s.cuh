@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(S_THREADS, S_CTAS) bpl_forward1s_kernel(const 
         BPL_PT(0);
         chain_offsets(a, t, sm.tab, ms);
         if (aff) affine_setup(a, t, p, sm.tab, ms);
-        token_consts(eps, sigma, false, ms);
+        token_consts(eps, sigma, false, ms, a.rc.fhalf);
         if (threadIdx.x == 0) {
             const int img = a.img_idx ? a.img_idx[p] : 0;
             if (img != ms->cur_img) { ms->n_ones = ms->ones_acc; ms->cur_img = img; }      // a new image was loaded above

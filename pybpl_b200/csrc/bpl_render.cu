@@ -442,8 +442,8 @@ __device__ __forceinline__ void affine_setup(const KArgs &a, const TokGeom &t, i
 // the 1-D Gaussian g (K = g (x) g exactly: fspecial normalises by sum(E) = (sum e)^2,
 // util/general.py:196-207), h~ for d/dsigma, and the background log-prob constants.
 __device__ __noinline__ void token_consts_eps(float eps, bool x, Misc *ms);
-__device__ __noinline__ void token_consts_sigma(float sigma, int lane, Misc *ms);
-__device__ __forceinline__ void token_consts(float eps, float sigma, bool grad, Misc *ms, int wsel = 0) {
+__device__ __noinline__ void token_consts_sigma(float sigma, int lane, int fhalf, Misc *ms);
+__device__ __forceinline__ void token_consts(float eps, float sigma, bool grad, Misc *ms, int fhalf, int wsel = 0) {
     const int lane = threadIdx.x & 31;
     if ((int)(threadIdx.x >> 5) != (int)(blockDim.x >> 5) - 1 - wsel) return;     // wsel-th warp from the end
     // Both sets of constants are kept from one token to the next (only this warp reads or writes c_eps / c_sigma):
@@ -452,7 +452,7 @@ __device__ __forceinline__ void token_consts(float eps, float sigma, bool grad, 
     const bool same_eps = (eps == ms->c_eps), same_sigma = (sigma == ms->c_sigma);
     __syncwarp();
     if (lane == 0) { ms->c_eps = eps; ms->c_sigma = sigma; }
-    if (!same_sigma) token_consts_sigma(sigma, lane, ms);
+    if (!same_sigma) token_consts_sigma(sigma, lane, fhalf, ms);
     if (!same_eps && (lane == 8 || lane == 9)) token_consts_eps(eps, lane == 9, ms);
     (void)grad;
 }
@@ -467,10 +467,11 @@ __device__ __noinline__ void token_consts_eps(float eps, bool x, Misc *ms) {
     ms->dlp_bg_d[x] = (bg < TORCH_EPS || bg > 1.0f - TORCH_EPS) ? 0.0 : (x ? 1.0 / (double)bg : -1.0 / (1.0 - (double)bg));
 }
 
-__device__ __noinline__ void token_consts_sigma(float sigma, int lane, Misc *ms) {
-    // lanes 0..5: e[d] = exp(-0.5 (d/sigma)^2)
+__device__ __noinline__ void token_consts_sigma(float sigma, int lane, int fhalf, Misc *ms) {
+    // lanes 0..fhalf: e[d] = exp(-0.5 (d/sigma)^2); the taps beyond the filter's half-width (fsize < 11) are zero, so the
+    // 11-tap passes compute the fsize-tap filter exactly (fspecial normalises over its own fsize x fsize support)
     double e = 0.0;
-    if (lane <= PAD && sigma > 0.0f) {
+    if (lane <= fhalf && sigma > 0.0f) {
         const double q = (double)lane / (double)sigma;
         e = exp(-0.5 * q * q);
     }
@@ -694,7 +695,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) bpl_backward_kernel(const KArg
         } else {
             __syncthreads();
         }
-        token_consts(eps, sigma, true, ms);      // double-precision constants by one warp, hidden behind the splat
+        token_consts(eps, sigma, true, ms, a.rc.fhalf);      // double-precision constants by one warp, hidden behind the splat
         if (threadIdx.x == 0 && a.image_bits) {
             const int img = a.img_idx ? a.img_idx[p] : 0;
             if (img != ms->cur_img) { ms->n_ones = ms->ones_acc; ms->cur_img = img; }      // a new image was loaded above
@@ -1281,8 +1282,8 @@ long long launch_count() { return g_launches.load(); }
 
 static int make_consts(const bpl_params *ps, RenderConsts *rc) {
     if (!ps) { set_error("%s", "params is NULL"); return BPL_EINVAL; }
-    if (ps->imsize != BPL_IMSIZE || ps->fsize != BPL_FSIZE) {
-        set_error("%s", "only imsize=105 and fsize=11 are built (pybpl/parameters.py:21,41)");
+    if (ps->imsize != BPL_IMSIZE || ps->fsize < 1 || ps->fsize > BPL_FSIZE || !(ps->fsize & 1)) {
+        set_error("%s", "imsize must be 105 and fsize an odd number <= 11 (pybpl/parameters.py:21,41)");
         return BPL_EINVAL;
     }
     if (ps->ink_ncon < 0 || ps->ink_ncon > 16) { set_error("%s", "ink_ncon out of range"); return BPL_EINVAL; }
@@ -1297,6 +1298,7 @@ static int make_consts(const bpl_params *ps, RenderConsts *rc) {
         const float mant = frexpf(ps->ink_max_dist, &ex);
         rc->inv_max_dist = (mant == 0.5f && ex > -100 && ex < 100) ? 1.0f / ps->ink_max_dist : 0.0f;
     }
+    rc->fhalf = ps->fsize / 2;
     rc->c1 = (float)(hs * a / 12.0);
     rc->c2 = (float)(hs * (1.0 - 4.0 * a / 3.0));
     return 0;

@@ -48,8 +48,10 @@ def make_params(ps=None):
     p = _lib.default_params()
     if ps is not None:
         imsize = tuple(int(v) for v in getattr(ps, "imsize", (IMSIZE, IMSIZE)))
-        if imsize != (IMSIZE, IMSIZE) or int(getattr(ps, "fsize", 11)) != 11:
-            raise NotImplementedError("pybpl_b200 kernels are built for imsize=(105,105), fsize=11")
+        fsize = int(getattr(ps, "fsize", 11))
+        if imsize != (IMSIZE, IMSIZE) or not (1 <= fsize <= 11 and fsize % 2 == 1):
+            raise NotImplementedError("pybpl_b200 kernels are built for imsize=(105,105) and odd fsize <= 11")
+        p.fsize = fsize
         p.ink_ncon = int(getattr(ps, "ink_ncon", p.ink_ncon))
         p.ink_pp = float(getattr(ps, "ink_pp", p.ink_pp))
         p.ink_max_dist = float(getattr(ps, "ink_max_dist", p.ink_max_dist))

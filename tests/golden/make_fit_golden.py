@@ -9,6 +9,7 @@ that one token is made out-of-place in memory (baseline/ref_loader.py, forward b
 
     python tests/golden/make_fit_golden.py                 # fit64.npz
     python tests/golden/make_fit_golden.py --fit-smooth    # fit_smooth.npz (fit_smooth_stk, see make_fit_smooth)
+    python tests/golden/make_fit_golden.py --fsize         # fsize.npz (render_image with Parameters.fsize = 7, 5, 3)
 """
 import os
 import sys
@@ -58,7 +59,7 @@ def main(P=64, seed=2024):
     print("wrote", path, "mean ll", out["ll"].mean(), {k: float(np.abs(v).max()) for k, v in out.items() if k.startswith("g_")})
 
 
-if __name__ == "__main__" and "--fit-smooth" not in sys.argv:
+if __name__ == "__main__" and "--fit-smooth" not in sys.argv and "--fsize" not in sys.argv:
     main()
 
 
@@ -100,3 +101,40 @@ def make_fit_smooth():
 
 if __name__ == "__main__" and "--fit-smooth" in sys.argv:
     make_fit_smooth()
+
+
+def make_fsize():
+    """tests/golden/fsize.npz: render_image with a smaller Gaussian (Parameters.fsize = 7, 5, 3; pybpl/parameters.py:41)
+    from the live reference: probability maps and autograd gradients for a cotangent, three stroke sets per size."""
+    from baseline import ref_loader
+    ref_loader.load(grad_patch=True)
+    from pybpl.parameters import Parameters
+    from pybpl.rendering import render_image
+    rng = np.random.default_rng(17)
+    t = np.linspace(0, 1, 40)
+    sets = [[np.stack([20 + 60 * t, -30 - 30 * t], 1)],
+            [np.stack([50 + 30 * np.cos(6 * t), -50 + 30 * np.sin(6 * t)], 1), np.stack([10 + 85 * t, -90 + 5 * np.sin(9 * t)], 1)],
+            [np.stack([2 + 100 * t, -3 - 99 * t], 1), np.stack([100 - 40 * t, -10 - 20 * t ** 2], 1), np.stack([55 + 0 * t, -5 - 95 * t], 1)]]
+    out = {"n_sets": len(sets)}
+    for fsize in (7, 5, 3):
+        ps = Parameters(); ps.fsize = fsize
+        for i, strokes in enumerate(sets):
+            st = [torch.tensor(s, dtype=torch.float32, requires_grad=True) for s in strokes]
+            eps = torch.tensor(1e-3, requires_grad=True); sig = torch.tensor(0.5 + 1.3 * i, requires_grad=True)
+            pimg, off = render_image(st, eps, sig, ps)
+            ct = torch.from_numpy(rng.standard_normal((105, 105)).astype(np.float32))
+            (pimg * ct).sum().backward()
+            key = f"f{fsize}_s{i}"
+            out[key + "_pimg"] = pimg.detach().numpy(); out[key + "_ct"] = ct.numpy()
+            out[key + "_off"] = bool(off); out[key + "_eps"] = float(eps); out[key + "_sigma"] = float(sig)
+            out[key + "_g_eps"] = float(eps.grad); out[key + "_g_sigma"] = float(sig.grad)
+            for j, s in enumerate(st):
+                out[f"{key}_stroke{j}"] = s.detach().numpy(); out[f"{key}_g_stroke{j}"] = s.grad.numpy()
+            out[key + "_n"] = len(st)
+    path = os.path.join(ROOT, "tests", "golden", "fsize.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path)
+
+
+if __name__ == "__main__" and "--fsize" in sys.argv:
+    make_fsize()

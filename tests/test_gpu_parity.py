@@ -368,6 +368,58 @@ def test_other_neval_against_oracle(ops, bwd_kernel):
     assert errs[0] < 2e-4 and errs[1] < 2e-4 and errs[2] < 2e-4 and errs[3] < 5e-4 and errs[4] < 5e-3, errs
 
 
+def test_smaller_gaussian_filter(ops, bwd_kernel):
+    """Parameters.fsize (pybpl/parameters.py:41) below its default 11: the 11-tap passes run with zero outer taps.
+    render_image against the live reference's goldens (fsize 7, 5, 3: probability maps and autograd gradients,
+    tests/golden/fsize.npz); the token kernels (scoring, both backward kernels) against the oracle at fsize = 7."""
+    from types import SimpleNamespace as NS
+    from oracle import Oracle
+    import oracle as _oracle
+    from pybpl_b200 import rendering, workload
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fsize.npz"))
+    for fsize in (7, 5, 3):
+        ps = NS(imsize=(105, 105), fsize=fsize, ink_ncon=2, ink_pp=2.0, ink_max_dist=2.0, ink_a=0.5, ink_b=6.0, broaden_mode="Lake")
+        for i in range(int(d["n_sets"])):
+            key = f"f{fsize}_s{i}"
+            st = [torch.from_numpy(d[f"{key}_stroke{j}"].copy()).requires_grad_(True) for j in range(int(d[key + "_n"]))]
+            eps = torch.tensor(float(d[key + "_eps"]), requires_grad=True); sig = torch.tensor(float(d[key + "_sigma"]), requires_grad=True)
+            pimg, off = rendering.render_image(st, eps, sig, ps)
+            assert bool(off) == bool(d[key + "_off"])
+            assert (pimg.detach().numpy() - d[key + "_pimg"]).__abs__().max() < 1e-5, (fsize, i)
+            (pimg * torch.from_numpy(d[key + "_ct"])).sum().backward()
+            for j, s in enumerate(st):
+                assert relinf(s.grad.numpy(), d[f"{key}_g_stroke{j}"]) < 5e-4, (fsize, i, j)
+            assert abs(sig.grad.item() - float(d[key + "_g_sigma"])) <= 1e-2 * max(1.0, abs(float(d[key + "_g_sigma"])))
+            assert abs(eps.grad.item() - float(d[key + "_g_eps"])) <= 2e-3 * max(1.0, abs(float(d[key + "_g_eps"])))
+    # tokens at fsize = 7 against the oracle
+    w = workload.synth_tokens(64, seed=41, sigma_mode="uniform")
+    ops_ps = ops.make_params(NS(imsize=(105, 105), fsize=7))
+    ops7 = _oracle.default_params(); ops7.fsize = 7
+    C = ops.basis_table(5, 200, DEV).cpu().numpy()
+    o = Oracle(np.float32, ops7)
+    img = _oracle.target_image_for(w, o, C)
+    # (the fp32 oracle: it takes the same branch decisions as the kernels -- one token of this batch sits on a
+    #  discontinuity where fp64 arithmetic decides differently, at any filter size)
+    ref = o.token_batch(C, w["tok_stroke_off"], w["stroke_sub_off"], w["ctrl"], w["invscale"], w["position"], w["eps"], w["sigma"],
+                        img[None], grad=True)
+    imgs = ops.pack_images(T(img, torch.uint8))
+    leaves = [T(w["ctrl"]), T(w["invscale"]), T(w["position"]), T(w["eps"]), T(w["sigma"])]
+    with torch.no_grad():
+        ll0, _ = ops.score_tokens(ops.TokenBatch(w["tok_stroke_off"], w["stroke_sub_off"], *leaves), imgs, ps=ops_ps)
+    for x in leaves:
+        x.requires_grad_(True)
+    ll, _ = ops.score_tokens(ops.TokenBatch(w["tok_stroke_off"], w["stroke_sub_off"], *leaves), imgs, ps=ops_ps)
+    g = torch.autograd.grad(ll.sum(), leaves)
+    for got in (ll0, ll.detach()):
+        assert (np.abs(got.cpu().numpy() - ref["ll"]) / np.abs(ref["ll"])).max() < 1e-5
+    errs = [relinf(x.cpu().numpy(), ref[k]) for x, k in zip(g, ("g_ctrl", "g_invscale", "g_position", "g_eps", "g_sigma"))]
+    print("fsize 7,", bwd_kernel, "kernel: gradient errors vs the fp32 oracle", errs)
+    assert errs[0] < 2e-4 and errs[1] < 2e-4 and errs[2] < 2e-4 and errs[3] < 5e-4 and errs[4] < 5e-3, errs
+    # and a filter the kernels are not built for raises
+    with pytest.raises(NotImplementedError):
+        ops.make_params(NS(imsize=(105, 105), fsize=13))
+
+
 def test_backward_kernels_agree_on_every_mode(ops):
     """The two fused backward kernels (full canvas / teams with box-sized arenas) on one mixed batch: affine warps,
     blur_sigma <= 0, epsilon = 0, a token without strokes, a token that is entirely off the page, weighted scores

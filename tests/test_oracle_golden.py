@@ -237,3 +237,18 @@ def test_oracle_matches_reference_on_the_config3_start_state():
     assert rel(ref["g_ctrl"], d["g_ctrl"]) < 5e-4 and rel(ref["g_invscale"], d["g_invscale"]) < 5e-4
     assert rel(ref["g_position"], d["g_position"]) < 5e-4
     assert rel(ref["g_sigma"], d["g_sigma"]) < 1e-2 and rel(ref["g_eps"], d["g_eps"]) < 2e-3
+
+
+def test_oracle_smaller_gaussian_matches_reference():
+    """Parameters.fsize = 7, 5, 3 (pybpl/parameters.py:41): the oracle's probability maps against the live reference's
+    (tests/golden/fsize.npz, made by tests/golden/make_fit_golden.py --fsize)."""
+    d = np.load(os.path.join(ROOT, "tests", "golden", "fsize.npz"))
+    for fsize in (7, 5, 3):
+        ps = O.default_params(); ps.fsize = fsize
+        o = Oracle(np.float32, ps)
+        for i in range(int(d["n_sets"])):
+            key = f"f{fsize}_s{i}"
+            strokes = [d[f"{key}_stroke{j}"] for j in range(int(d[key + "_n"]))]
+            pimg, off = o.render(strokes, float(d[key + "_eps"]), float(d[key + "_sigma"]))
+            assert off == bool(d[key + "_off"])
+            assert np.abs(pimg - d[key + "_pimg"]).max() < 1e-5, (fsize, i)
