@@ -46,7 +46,10 @@ namespace bpl {
 constexpr int BT_NT = BPL_BT_TEAMS;        // teams per CTA
 constexpr int BT_TT = BPL_BT_THREADS;      // threads per team
 constexpr int BT_PPL = BPL_BT_PPL;         // points per lane in the point stages
-constexpr int BT_GU = 5;                   // outputs per unrolled block = granularity of the box
+#ifndef BPL_BT_GU
+#define BPL_BT_GU 5
+#endif
+constexpr int BT_GU = BPL_BT_GU;           // outputs per unrolled block = granularity of the box (5 or 7: 105 = 21 * 5 = 15 * 7)
 static_assert(BT_TT % 32 == 0 && BT_TT >= IMG, "a team needs one thread per line of the widest box");
 static_assert(BT_NT >= 1 && BT_NT <= 8 && BT_NT * BT_TT <= 1024, "team shape");
 static_assert(IMG % BT_GU == 0 && BT_GU >= PAD, "block structure");
