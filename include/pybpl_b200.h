@@ -62,6 +62,9 @@ typedef struct {
     const int *order;           /* dev [P] or NULL: a permutation of 0..P-1, the order in which the persistent kernels
                                  * take the tokens (results do not depend on it; bpl_order_tokens gives the order that
                                  * ends a small launch on its cheapest tokens) */
+    unsigned *cycles_out;       /* dev [P] or NULL: bpl_score_tokens_grad (team kernel) stores the SM cycles every token took.
+                                 * A fit evaluates the same parses a hundred times: the cycles of one evaluation order the
+                                 * next (bpl_order_tokens_by_cycles) -- the measured cost, not an estimate of it. */
 } bpl_token_batch;
 
 /* A ragged batch of characters given as raw motor-space trajectories = the `strokes`
@@ -284,6 +287,9 @@ int bpl_order_tokens(const bpl_token_batch *b, int *order, void *stream);
  * reach, and the sub-stroke count, in 256 cost classes.  keys[P]: scratch (receives the classes).  Reads the batch's
  * geometry as it is now; an order made from earlier parameter values stays a valid (merely less sharp) order. */
 int bpl_order_tokens_by_cost(const bpl_params *ps, const bpl_token_batch *b, int *keys, int *order, void *stream);
+/* order[P] <- the tokens by decreasing measured cost: cycles[P] as written through bpl_token_batch.cycles_out by an earlier
+ * evaluation of the same batch (2 048-cycle classes).  keys[P]: scratch. */
+int bpl_order_tokens_by_cycles(const unsigned *cycles, int n, int *keys, int *order, void *stream);
 /* Same, plus the fused backward (autograd-equivalent gradients). */
 int bpl_score_tokens_grad(const bpl_params *ps, const bpl_token_batch *b, const bpl_targets *t,
                           const bpl_fwd_out *out, const bpl_grads *g, void *stream);

@@ -30,7 +30,7 @@ class Params(ctypes.Structure):
 class TokenBatchC(ctypes.Structure):
     _fields_ = [("n_tokens", ctypes.c_int), ("ncpt", ctypes.c_int), ("neval", ctypes.c_int),
                 ("tok_stroke_off", vp), ("stroke_sub_off", vp), ("ctrl", vp), ("invscale", vp), ("position", vp),
-                ("affine", vp), ("eps", vp), ("sigma", vp), ("basis", vp), ("order", vp)]
+                ("affine", vp), ("eps", vp), ("sigma", vp), ("basis", vp), ("order", vp), ("cycles_out", vp)]
 
 
 class StrokeBatchC(ctypes.Structure):
@@ -116,6 +116,7 @@ EXPORTS = {
     "bpl_score_tokens_lse": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.POINTER(TokenBatchC), ctypes.POINTER(Targets),
                                             ctypes.POINTER(FwdOut), vp, vp, ctypes.c_int, vp]),
     "bpl_order_tokens": (ctypes.c_int, [ctypes.POINTER(TokenBatchC), vp, vp]),
+    "bpl_order_tokens_by_cycles": (ctypes.c_int, [vp, ctypes.c_int, vp, vp, vp]),
     "bpl_adam_step": (ctypes.c_int, [ctypes.POINTER(AdamArgs), vp]),
     "bpl_scale_token_grads": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, ctypes.POINTER(Grads),
                                              ctypes.POINTER(Grads), vp]),

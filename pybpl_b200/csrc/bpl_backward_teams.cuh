@@ -989,6 +989,7 @@ __global__ void __launch_bounds__(BT_NT *BT_TT, 1) bpl_backward_teams_kernel(con
     int par = 0;
     while (p < a.n_tokens) {
         par ^= 1;
+        const long long tc0 = (a.cycles_out && tm.tid == 0) ? clock64() : 0;      // measured cost, fed back into the next order
 #ifdef BPL_TOKEN_TIMING
         const long long tt0 = clock64();      // cycles per token -> a.pt_buf[p] (tools/token_cost_fit.py)
 #endif
@@ -1020,6 +1021,7 @@ __global__ void __launch_bounds__(BT_NT *BT_TT, 1) bpl_backward_teams_kernel(con
         bt_scalars(sh, acc);
         bt_gather(sh);
         bt_chain(sh);
+        if (a.cycles_out && tm.tid == 0) a.cycles_out[p] = (unsigned)min(clock64() - tc0, 0xffffffffll);
 #ifdef BPL_TOKEN_TIMING
         if (tm.tid == 0 && a.pt_buf) a.pt_buf[p] = (float)(clock64() - tt0);
 #endif

@@ -40,6 +40,7 @@ struct KArgs {
     const int *tok_stroke_off, *stroke_sub_off;
     const float *ctrl, *invscale, *position, *affine, *basis;
     const int *order;        // optional processing order of the tokens (bpl_order_tokens); NULL = index order
+    unsigned *cycles_out;    // optional: cycles every token took (team backward), fed back into the next launch's order
     // raw stroke mode
     const int *tok_sub_off, *sub_pt_off;
     const float *pts;
@@ -1201,6 +1202,11 @@ __global__ void __launch_bounds__(128) token_cost_kernel(const bpl_token_batch b
     keys[p] = COST_BINS - 1 - min(COST_BINS - 1, max(0, (int)(cost * 128.0f)));                         // 0 = most expensive
 }
 
+__global__ void __launch_bounds__(256) cycles_key_kernel(const unsigned *__restrict__ cycles, int n, int *__restrict__ keys) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) keys[p] = COST_BINS - 1 - min(COST_BINS - 1, (int)(cycles[p] >> 11));      // 0 = most expensive
+}
+
 // counting sort of the tokens by key (one CTA; keys < COST_BINS)
 __global__ void __launch_bounds__(1024) order_by_key_kernel(const int *__restrict__ keys, int n, int *__restrict__ order) {
     __shared__ int hist[COST_BINS], start[COST_BINS];
@@ -1397,6 +1403,7 @@ static int fill_tokens(KArgs &ka, const bpl_token_batch *b) {
     ka.ctrl = b->ctrl; ka.invscale = b->invscale; ka.position = b->position; ka.affine = b->affine;
     ka.basis = b->basis; ka.eps = b->eps; ka.sigma = b->sigma;
     ka.order = b->order;
+    ka.cycles_out = b->cycles_out;
     return 0;
 }
 
@@ -1446,6 +1453,17 @@ int bpl_order_tokens_by_cost(const bpl_params *ps, const bpl_token_batch *b, int
     if (const char *wenv = getenv("BPL_COST_W")) sscanf(wenv, "%f,%f", &w_area, &w_sub);      // tuning aid
     token_cost_kernel<<<(b->n_tokens + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*b, ps->ink_ncon + 2 * PAD, w_area, w_sub, keys);
     order_by_key_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(keys, b->n_tokens, order);
+    count_launch(2);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("kernel launch: %s", cudaGetErrorString(e)); return (int)e; }
+    return 0;
+}
+
+int bpl_order_tokens_by_cycles(const unsigned *cycles, int n, int *keys, int *order, void *stream) {
+    if (!cycles || !keys || !order) { set_error("%s", "bpl_order_tokens_by_cycles: NULL argument"); return BPL_EINVAL; }
+    if (n <= 0) return 0;
+    cycles_key_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(cycles, n, keys);
+    order_by_key_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(keys, n, order);
     count_launch(2);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("kernel launch: %s", cudaGetErrorString(e)); return (int)e; }

@@ -180,6 +180,8 @@ class TokenBatch:
         self._stroke_token = None
         self._order = None
         self._order_cost = None
+        self._cycles = None             # cycles per token of the last fused backward (team kernel), see order_ptr
+        self._cycles_valid = False
         self.use_order = use_order      # False: index order (streamed chunks: the order kernel would cost more than it saves)
 
     # Processing order for the persistent kernels: expensive tokens first, so that a launch of a few thousand tokens
@@ -198,6 +200,15 @@ class TokenBatch:
         if not self.use_order or self.P > self.ORDER_MAX_TOKENS or self.P < 2 or os.environ.get("BPL_NO_ORDER"):      # (env: A/B aid)
             return None
         if b is not None and self.S > 0 and not os.environ.get("BPL_ORDER_BY_S"):      # (env: A/B aid)
+            if self._cycles_valid and not os.environ.get("BPL_NO_CYCLE_FEEDBACK"):
+                # the batch has been through the fused backward before: its tokens' MEASURED cycles order this launch
+                # (a fit evaluates the same parses a hundred times; +5 % over the estimate at 1 024 parses)
+                if self._order_cost is None:
+                    self._order_cost = torch.empty(self.P, dtype=torch.int32, device=self.device)
+                    self._keys = torch.empty(self.P, dtype=torch.int32, device=self.device)
+                check(lib().bpl_order_tokens_by_cycles(self._cycles.data_ptr(), self.P, self._keys.data_ptr(),
+                                                       self._order_cost.data_ptr(), _stream(self.device)))
+                return self._order_cost.data_ptr()
             if self._order_cost is None:
                 order = torch.empty(self.P, dtype=torch.int32, device=self.device)
                 self._keys = torch.empty(self.P, dtype=torch.int32, device=self.device)
@@ -241,8 +252,18 @@ class TokenBatch:
         b.eps = eps.data_ptr(); b.sigma = sigma.data_ptr()
         b.basis = basis_table(NCPT, self.neval, self.device).data_ptr()
         b.order = None
+        b.cycles_out = None
         b.order = self.order_ptr(b if cost_order else None)
         return b
+
+    def cycles_ptr(self):
+        """Device buffer the team backward writes every token's cycles to (small batches only: the feedback pays where a
+        launch is a few tokens per team deep)."""
+        if not self.use_order or self.P > self.ORDER_MAX_TOKENS or self.P < 1024:
+            return None
+        if self._cycles is None:
+            self._cycles = torch.zeros(self.P, dtype=torch.int32, device=self.device)
+        return self._cycles.data_ptr()
 
 
 class HostStagedBatch:
@@ -411,8 +432,10 @@ class _ScoreTokens(torch.autograd.Function):
             g_eps = torch.empty(P, dtype=torch.float32, device=dev); g_sig = torch.empty_like(g_eps)
             g = _lib.Grads(None, None, g_ctrl.data_ptr(), g_inv.data_ptr(), g_pos.data_ptr(),
                            None if g_aff is None else g_aff.data_ptr(), None, g_eps.data_ptr(), g_sig.data_ptr())
+            b.cycles_out = batch.cycles_ptr()
             check(lib().bpl_score_tokens_grad(ctypes.byref(ps), ctypes.byref(b), ctypes.byref(t), ctypes.byref(out),
                                               ctypes.byref(g), _stream(dev)))
+            batch._cycles_valid = b.cycles_out is not None and not os.environ.get("BPL_BWD_CANVAS")      # (the full-canvas kernel does not report cycles)
             ctx.batch = batch
             ctx.has_aff = g_aff is not None
             ctx.save_for_backward(g_ctrl, g_inv, g_pos, g_eps, g_sig, *([g_aff] if g_aff is not None else []))

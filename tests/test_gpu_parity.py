@@ -811,6 +811,33 @@ def test_cost_order_for_the_fused_backward(ops):
         assert (x - y).abs().max() <= 2e-5 * x.abs().max()
 
 
+def test_cycle_feedback_orders_the_next_backward(ops):
+    """A batch that has been through the fused backward (team kernel) carries every token's measured cycles; the next
+    evaluation is ordered by them (bpl_order_tokens_by_cycles): a permutation, most expensive class first, and the
+    gradients are those of the first evaluation."""
+    import os
+    from pybpl_b200 import workload
+    os.environ.pop("BPL_BWD_CANVAS", None); os.environ.pop("BPL_BWD_TEAMS", None)
+    P = 1200                                               # >= 1024: the team kernel, and the feedback buffer is kept
+    w = workload.synth_tokens(P, seed=13, sigma_mode=10.0)
+    b = workload.to_device(w, DEV, requires_grad=True)
+    pimg, _ = ops.render_tokens(workload.to_device(workload.permute(w, np.arange(1)), DEV))
+    imgs = ops.pack_images((pimg[0] > 0.5).to(torch.uint8))
+    leaves = [b.ctrl, b.invscale, b.position, b.eps, b.sigma]
+    g1 = torch.autograd.grad(ops.score_tokens(b, imgs)[0].sum(), leaves)
+    assert b._cycles_valid
+    first_order = b._order_cost.clone()
+    cyc = b._cycles.cpu().numpy().astype(np.int64)
+    assert (cyc > 0).all()                                 # every token reported
+    g2 = torch.autograd.grad(ops.score_tokens(b, imgs)[0].sum(), leaves)
+    order = b._order_cost.cpu().numpy()
+    assert np.array_equal(np.sort(order), np.arange(P))
+    assert np.all(np.diff(cyc[order] >> 11) <= 0)          # 2 048-cycle classes, non-increasing
+    assert not torch.equal(first_order, b._order_cost)     # (the estimate's order has been replaced)
+    for x, y in zip(g1, g2):
+        assert (x - y).abs().max() <= 2e-5 * x.abs().max()
+
+
 # ---------------------------------------------------------------------------------------------
 # the benchmarked kernel (bpl_forward1s_kernel<false>, forward only) on the bench workloads, against the oracle
 # ---------------------------------------------------------------------------------------------

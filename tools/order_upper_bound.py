@@ -7,6 +7,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 P = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+BWD = len(sys.argv) > 2 and sys.argv[2] == "bwd"      # the fused backward (teams kernel) instead of the scoring kernel
 so = "/tmp/libbpl_tt.so"
 src = [os.path.join(ROOT, "pybpl_b200", "csrc", f) for f in ("bpl_render.cu", "bpl_splines.cu", "bpl_token_prior.cu", "bpl_token_sample.cu", "bpl_type_sample.cu", "bpl_type_prior.cu")]
 subprocess.check_call(["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-w", "-Xcompiler", "-fPIC,-ffp-contract=off",
@@ -16,18 +17,20 @@ from pybpl_b200 import _lib
 _lib.SO_PATH = so
 from pybpl_b200 import ops, workload
 dev = torch.device("cuda", 0)
-w = workload.synth_tokens(P, seed=1234, sigma_mode="uniform")
+w = workload.synth_tokens(P, seed=2024 if BWD else 1234, sigma_mode=10.0 if BWD else "uniform")
+if BWD:
+    os.environ["BPL_BWD_TEAMS"] = "1"
 p0, _ = ops.render_tokens(workload.to_device(workload.permute(w, np.arange(1)), dev))
 imgs = ops.pack_images((torch.from_numpy(np.random.default_rng(99).random((105, 105))).to(dev) < p0[0]).to(torch.uint8))
 buf = torch.zeros(P + 148 * 64, device=dev)
 os.environ["BPL_PT_BUF"] = str(buf.data_ptr())
-b = workload.to_device(w, dev)
+b = workload.to_device(w, dev, requires_grad=BWD)
 
 
 def rate(order):
     b._order = b._order_cost = None if order is None else torch.as_tensor(order, dtype=torch.int32, device=dev)
     b.use_order = order is not None
-    with torch.no_grad():
+    with torch.set_grad_enabled(BWD):
         for _ in range(5):
             ops.score_tokens(b, imgs)
         torch.cuda.synchronize()
