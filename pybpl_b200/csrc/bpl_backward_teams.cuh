@@ -28,6 +28,7 @@
 //   P4 B = G5 = tail(g_h U); dsigma += G5 . (h~_h U)   (in place)      P5 B = t = g_h G5; dsigma += t . W  (in place)
 //   P6 C = G4 = g_v t        P7 B = t1 = g_h G4, C = t1' = h~_h G4     (in place on C)
 //   P9 dsigma += min(A,1) . (g_v t1')                  P8 dsigma += min(A,1) . (h~_v t1); A = [A <= 1] g_v t1
+//   (P9 and P8 run as one sweep with two windows, bt_pass_mask2)
 // (sigma^3 dK/dsigma = h~ (x) g + g (x) h~ with h~[u] = (u^2 - mu2) g[u]; all filters symmetric, so every adjoint pass
 // is the same zero-padded convolution.)
 #pragma once
@@ -404,6 +405,62 @@ __device__ __noinline__ float bt_pass_mask(const float *in, float *I2, Axis ax, 
     return s;
 }
 
+// P9 and P8 of the blur chain in ONE pass (same orientation, same region): two windows slide together,
+//   sig += min(I2,1) . (f1 * inB + f0 * inC);   I2 = [I2 <= 1] (f0 * inB)
+// -- one pass set-up, one item mapping and one loop instead of two.
+__device__ __noinline__ float bt_pass_mask2(const float *__restrict__ inB, const float *__restrict__ inC, float *I2, Axis ax, Reg g,
+                                            const float *w0p, const float *w1p) {
+    const TeamCtx tm = team_ctx();
+    constexpr int HALF = PAD, GU = BT_GU;
+    float w0[HALF + 1], w1[HALF + 1];
+#pragma unroll
+    for (int d = 0; d <= HALF; ++d) { w0[d] = w0p[d]; w1[d] = w1p[d]; }
+    const float rnl = __frcp_rn((float)g.nl);
+    const int NB = min(g.nblk, small_div(BT_TT, rnl));
+    const int qb = small_div(g.nblk, __frcp_rn((float)NB)), rem = g.nblk - qb * NB;
+    const int bi = small_div(tm.tid, rnl), line = g.l0 + tm.tid - bi * g.nl;
+    if (bi >= NB) return 0.0f;
+    const int nb = qb + (bi < rem ? 1 : 0);
+    const int a0 = g.s0 + (bi * qb + min(bi, rem)) * GU, len = nb * GU;
+    const int SA = ax.SA;
+    const int q0 = a0 * SA + line * ax.SL;
+    const float *pb = inB + q0, *pc = inC + q0;
+    const bool more = a0 + len < ax.L;
+    float xb[GU + 2 * HALF], xc[GU + 2 * HALF];
+#pragma unroll
+    for (int i = 0; i < HALF; ++i) {
+        xb[i] = (a0 > 0) ? pb[(i - HALF) * SA] : 0.0f; xc[i] = (a0 > 0) ? pc[(i - HALF) * SA] : 0.0f;
+        xb[HALF + i] = pb[i * SA]; xc[HALF + i] = pc[i * SA];
+    }
+    float s = 0.0f;
+#pragma unroll 1
+    for (int blk = 0; blk < nb; ++blk) {
+        const int o = blk * GU * SA;
+        const bool live = blk < nb - 1 || more;      // inputs beyond the last block: the box's zero padding
+#pragma unroll
+        for (int u = 0; u < GU; ++u) {
+            xb[2 * HALF + u] = live ? pb[o + (u + HALF) * SA] : 0.0f;
+            xc[2 * HALF + u] = live ? pc[o + (u + HALF) * SA] : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < GU; ++u) {
+            float g3 = w0[0] * xb[u + HALF], sB = w1[0] * xb[u + HALF], sC = w0[0] * xc[u + HALF];
+#pragma unroll
+            for (int d = 1; d <= HALF; ++d) {
+                const float tb = xb[u + HALF - d] + xb[u + HALF + d], tc = xc[u + HALF - d] + xc[u + HALF + d];
+                g3 = fmaf(w0[d], tb, g3); sB = fmaf(w1[d], tb, sB); sC = fmaf(w0[d], tc, sC);
+            }
+            const int q = q0 + o + u * SA;
+            const float i2 = I2[q];
+            s = fmaf(fminf(i2, 1.0f), sB + sC, s);
+            I2[q] = (i2 <= 1.0f) ? g3 : 0.0f;
+        }
+#pragma unroll
+        for (int k = 0; k < 2 * HALF; ++k) { xb[k] = xb[k + GU]; xc[k] = xc[k + GU]; }
+    }
+    return s;
+}
+
 struct TailAcc { float ll, sig; double eps; };
 
 // pointwise tail of the forward + head of the backward for LOCAL pixel (r,c) with blurred value v: returns d L / d I5
@@ -478,9 +535,13 @@ __device__ __noinline__ TailAcc bt_blur(BtShared *sh) {
         tm.sync();
         bt_pass_split(C, B, H, make_reg(tk, false, nc + PAD, nc), wg, wh);                         // P7: B = t1 = g_h G4, C = t1' = h~_h G4
         tm.sync();
+#ifdef BPL_BT_SPLIT_P98
         const Reg g8 = make_reg(tk, true, nc, nc);
         acc.sig += bt_pass_reduce(C, A, V, g8, wg);                                                // P9: sig += I3 . (g_v t1')
         acc.sig += bt_pass_mask(B, A, V, g8, wg, wh);                                              // P8: sig += I3 . (h~_v t1); A = G3
+#else
+        acc.sig += bt_pass_mask2(B, C, A, V, make_reg(tk, true, nc, nc), wg, wh);                  // P9 + P8 in one pass
+#endif
         tm.sync();
     } else {
         const Reg g0 = make_reg(tk, false, nc, nc);      // rows l0.., columns s0.. (whole 5-blocks)
