@@ -34,7 +34,7 @@ extern "C" {
 
 /* Rendering constants: pybpl/parameters.py:19-41 (class Parameters). */
 typedef struct {
-    int imsize;          /* must be 105 */
+    int imsize;          /* must be 105 (any H x W: bpl_render_strokes_any, which ignores this field) */
     int fsize;           /* odd, 1..11 (the reference default is 11; smaller filters run as 11-tap passes with zero outer taps) */
     int ink_ncon;        /* :31 */
     float ink_pp;        /* :25 */
@@ -319,6 +319,25 @@ int bpl_render_strokes(const bpl_params *ps, const bpl_stroke_batch *b, const bp
                        const bpl_fwd_out *out, void *stream);
 int bpl_render_strokes_grad(const bpl_params *ps, const bpl_stroke_batch *b, const bpl_targets *t,
                             const bpl_fwd_out *out, const bpl_grads *g, void *stream);
+
+/* rendering.render_image for ANY Parameters.imsize (pybpl/parameters.py:21; rendering.py:185-229 with ps.imsize = (H, W):
+ * the map is H x W, rows bounded by imsize[0], columns by imsize[1], rendering.py:27-31,214), with the Bernoulli score
+ * of model/image_dist.py:75-78 and the fused backward.  ps->imsize is ignored here.  The fused kernels above are built
+ * for the reference's default 105 x 105; these run the same pipeline with run-time geometry, one CTA per character,
+ * on dense canvases in a caller-provided workspace.  Outputs / cotangents as bpl_render_strokes[_grad] with
+ * [P][H][W] maps; target images are plain float maps (the caller checks they are exactly 0 / 1). */
+typedef struct {
+    int H, W;                   /* imsize[0] (rows), imsize[1] (columns); H * W <= 2^24 */
+    const float *images;        /* dev [T][H][W], every value exactly 0 or 1; NULL => no scoring */
+    const int *img_idx;         /* dev [P] image per character, or NULL => image 0 */
+    float *workspace;           /* dev, at least bpl_render_any_workspace(...) floats, private to the call while it runs */
+    long long workspace_floats;
+} bpl_any_geom;
+long long bpl_render_any_workspace(int H, int W, int n_tokens, int with_grad);      /* floats; < 0: bad argument */
+int bpl_render_strokes_any(const bpl_params *ps, const bpl_any_geom *geo, const bpl_stroke_batch *b, const bpl_fwd_out *out,
+                           void *stream);
+int bpl_render_strokes_any_grad(const bpl_params *ps, const bpl_any_geom *geo, const bpl_stroke_batch *b,
+                                const bpl_fwd_out *out, const bpl_grads *g, void *stream);
 
 /* Inspection: the path's integer work per point, computed by the same device code as the fused
  * kernels: motor [S][neval][2] (post-warp motor space = torch.cat(motor) in image_dist.py:34-38),

@@ -46,6 +46,11 @@ class FwdOut(ctypes.Structure):
     _fields_ = [("ll", vp), ("off_page", vp), ("pimg", vp)]
 
 
+class AnyGeomC(ctypes.Structure):       # bpl_any_geom: rendering for any Parameters.imsize
+    _fields_ = [("H", ctypes.c_int), ("W", ctypes.c_int), ("images", vp), ("img_idx", vp), ("workspace", vp),
+                ("workspace_floats", ctypes.c_longlong)]
+
+
 class Grads(ctypes.Structure):
     _fields_ = [("g_ll", vp), ("g_pimg", vp), ("g_ctrl", vp), ("g_invscale", vp), ("g_position", vp),
                 ("g_affine", vp), ("g_pts", vp), ("g_eps", vp), ("g_sigma", vp)]
@@ -127,6 +132,12 @@ EXPORTS = {
                                           ctypes.POINTER(Targets), ctypes.POINTER(FwdOut), vp]),
     "bpl_render_strokes_grad": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.POINTER(StrokeBatchC),
                                                ctypes.POINTER(Targets), ctypes.POINTER(FwdOut), ctypes.POINTER(Grads), vp]),
+    "bpl_render_any_workspace": (ctypes.c_longlong, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "bpl_render_strokes_any": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.POINTER(AnyGeomC), ctypes.POINTER(StrokeBatchC),
+                                              ctypes.POINTER(FwdOut), vp]),
+    "bpl_render_strokes_any_grad": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.POINTER(AnyGeomC),
+                                                   ctypes.POINTER(StrokeBatchC), ctypes.POINTER(FwdOut),
+                                                   ctypes.POINTER(Grads), vp]),
     "bpl_token_points": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.POINTER(TokenBatchC), vp, vp, vp, vp, vp, vp]),
     "bpl_score_token_prior": (ctypes.c_int, [ctypes.POINTER(TokenPriorParams), ctypes.POINTER(TokenBatchC),
                                              ctypes.POINTER(TokenTypeC), vp, ctypes.POINTER(TokenPriorGrads), vp]),

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libpybpl_b200.so")
 SOURCES = ["bpl_render.cu", "bpl_splines.cu", "bpl_token_prior.cu", "bpl_token_sample.cu", "bpl_type_sample.cu", "bpl_type_prior.cu"]
-HEADERS = [os.path.join(CSRC, "bpl_common.cuh"), os.path.join(CSRC, "bpl_forward.cuh"), os.path.join(CSRC, "bpl_forward1s.cuh"), os.path.join(CSRC, "bpl_backward_teams.cuh"), os.path.join(CSRC, "bpl_points.cuh"), os.path.join(CSRC, "bpl_token_common.cuh"), os.path.join(os.path.dirname(HERE), "include", "pybpl_b200.h")]
+HEADERS = [os.path.join(CSRC, "bpl_common.cuh"), os.path.join(CSRC, "bpl_forward.cuh"), os.path.join(CSRC, "bpl_forward1s.cuh"), os.path.join(CSRC, "bpl_backward_teams.cuh"), os.path.join(CSRC, "bpl_anysize.cuh"), os.path.join(CSRC, "bpl_points.cuh"), os.path.join(CSRC, "bpl_token_common.cuh"), os.path.join(os.path.dirname(HERE), "include", "pybpl_b200.h")]
 
 
 def nvcc_path():

@@ -43,6 +43,8 @@ struct RenderConsts {
     float inv_max_dist;   // 1 / ink_max_dist when that is exact (a power of two), else 0: x / 2 == x * 0.5 bit for bit
     float c1, c2;    // H_broaden = c1 * (1,2,1)x(1,2,1) + c2 * delta
     int fhalf;       // half-width of the Gaussian, fsize / 2 <= PAD: taps beyond it are zero (parameters.py:41, general.py:196-207)
+    float rmax, cmax; // largest in-bounds row / column coordinate, imsize - 1 (rendering.py:27-31); read by the raw-trajectory
+                      // walk only (the any-size kernels set them to H - 1, W - 1), the control-point stages keep IMG - 1
 };
 
 __device__ __forceinline__ float warp_sum(float v) {

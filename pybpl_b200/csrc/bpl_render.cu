@@ -221,7 +221,7 @@ __device__ __forceinline__ Pt walk_round(const Src &src, int n, int base, int la
     p.r = -y;   // space_motor_to_img (rendering.py:52-53): flip, times (-1, 1)
     p.c = x;
     // check_bounds (rendering.py:27-31): floor<0 | ceil>=105  <=>  not (0 <= v <= 104)
-    p.inb = p.valid && (p.r >= 0.0f) && (p.r <= (float)(IMG - 1)) && (p.c >= 0.0f) && (p.c <= (float)(IMG - 1));
+    p.inb = p.valid && (p.r >= 0.0f) && (p.r <= rc.rmax) && (p.c >= 0.0f) && (p.c <= rc.cmax);
     const unsigned m = __ballot_sync(0xffffffffu, p.inb);
     const unsigned lower = m & ((1u << lane) - 1u);
     const int srcl = lower ? (31 - __clz(lower)) : 0;
@@ -566,12 +566,14 @@ struct BwdSmem {
 struct Corner {
     float gink, gr, gc;     // d/d ink, d/d row, d/d col (for ink weight 1)
 };
-__device__ __forceinline__ Corner gather_corners(const float *G, float r, float c) {
+using LayPadded = LayS<1, STRIDE, ORIGIN>;      // the full-canvas backward's padded buffers
+template <class Lay = LayPadded>
+__device__ __forceinline__ Corner gather_corners(const float *G, float r, float c, const Lay lay = Lay()) {
     const float rf = floorf(r), cf = floorf(c), rce = ceilf(r), cce = ceilf(c);
     const float fr = r - rf, fc = c - cf, gr = 1.0f - fr, gc = 1.0f - fc;
     const int r0 = (int)rf, c0 = (int)cf, r1 = (int)rce, c1 = (int)cce;
-    const float G00 = G[ORIGIN + r0 * STRIDE + c0], G10 = G[ORIGIN + r1 * STRIDE + c0];
-    const float G01 = G[ORIGIN + r0 * STRIDE + c1], G11 = G[ORIGIN + r1 * STRIDE + c1];
+    const float G00 = G[lay(r0, c0)], G10 = G[lay(r1, c0)];
+    const float G01 = G[lay(r0, c1)], G11 = G[lay(r1, c1)];
     Corner k;
     k.gink = gr * gc * G00 + fr * gc * G10 + gr * fc * G01 + fr * fc * G11;
     k.gr = gc * (G10 - G00) + fc * (G11 - G01);
@@ -581,9 +583,9 @@ __device__ __forceinline__ Corner gather_corners(const float *G, float r, float 
 
 // Backward of add_stroke for one sub-stroke.  `emit(j, gx, gy)` receives motor-space (post-warp)
 // point gradients; a point may be emitted more than once (own splat, own segment, next segment).
-template <class Src, class Emit>
+template <class Src, class Emit, class Lay = LayPadded>
 __device__ __forceinline__ void substroke_backward(const Src &src, int n, int lane, const RenderConsts &rc,
-                                                   const Stats &st, const float *G, Emit emit) {
+                                                   const Stats &st, const float *G, Emit emit, const Lay lay = Lay()) {
     if (st.cnt == 0) return;
     const bool use_dist = (st.branch == BR_NORMAL || st.branch == BR_RESCALE);
     float sc = 1.0f, gsum = 0.0f;
@@ -593,7 +595,7 @@ __device__ __forceinline__ void substroke_backward(const Src &src, int n, int la
         for (int base = 0; base < n; base += 32) {
             const Pt p = walk_round(src, n, base, lane, rc, w);
             if (p.inb) {
-                const Corner k = gather_corners(G, p.r, p.c);
+                const Corner k = gather_corners(G, p.r, p.c, lay);
                 dot += k.gink * ((p.idx == 0) ? st.first : p.ink0);
             }
         }
@@ -607,7 +609,7 @@ __device__ __forceinline__ void substroke_backward(const Src &src, int n, int la
         const Pt p = walk_round(src, n, base, lane, rc, w);
         float ginkp = 0.0f, g_r = 0.0f, g_c = 0.0f;
         if (p.inb) {
-            const Corner k = gather_corners(G, p.r, p.c);
+            const Corner k = gather_corners(G, p.r, p.c, lay);
             const float ink = final_ink(p, st);
             g_r = ink * k.gr;
             g_c = ink * k.gc;
@@ -1098,6 +1100,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) bpl_backward_kernel(const KArg
 }  // namespace bpl
 
 #include "bpl_backward_teams.cuh"
+#include "bpl_anysize.cuh"
 
 namespace bpl {
 
@@ -1286,10 +1289,10 @@ const char *last_error() { return g_err; }
 void count_launch(int n) { g_launches += n; }
 long long launch_count() { return g_launches.load(); }
 
-static int make_consts(const bpl_params *ps, RenderConsts *rc) {
+static int make_consts(const bpl_params *ps, RenderConsts *rc, bool any_size = false) {
     if (!ps) { set_error("%s", "params is NULL"); return BPL_EINVAL; }
-    if (ps->imsize != BPL_IMSIZE || ps->fsize < 1 || ps->fsize > BPL_FSIZE || !(ps->fsize & 1)) {
-        set_error("%s", "imsize must be 105 and fsize an odd number <= 11 (pybpl/parameters.py:21,41)");
+    if ((!any_size && ps->imsize != BPL_IMSIZE) || ps->fsize < 1 || ps->fsize > BPL_FSIZE || !(ps->fsize & 1)) {
+        set_error("%s", "imsize must be 105 (other sizes: bpl_render_strokes_any) and fsize an odd number <= 11 (pybpl/parameters.py:21,41)");
         return BPL_EINVAL;
     }
     if (ps->ink_ncon < 0 || ps->ink_ncon > 16) { set_error("%s", "ink_ncon out of range"); return BPL_EINVAL; }
@@ -1305,6 +1308,7 @@ static int make_consts(const bpl_params *ps, RenderConsts *rc) {
         rc->inv_max_dist = (mant == 0.5f && ex > -100 && ex < 100) ? 1.0f / ps->ink_max_dist : 0.0f;
     }
     rc->fhalf = ps->fsize / 2;
+    rc->rmax = rc->cmax = (float)(IMG - 1);
     rc->c1 = (float)(hs * a / 12.0);
     rc->c2 = (float)(hs * (1.0 - 4.0 * a / 3.0));
     return 0;
@@ -1590,6 +1594,66 @@ int bpl_render_strokes_grad(const bpl_params *ps, const bpl_stroke_batch *b, con
     if (!g || !g->g_pts) { set_error("%s", "g_pts required"); return BPL_EINVAL; }
     if (!ka.image_bits && !ka.g_pimg) { set_error("%s", "need target images or a pimg cotangent"); return BPL_EINVAL; }
     return launch(bpl_backward_kernel<true>, BWD_THREADS, sizeof(BwdSmem), 1, ka, (cudaStream_t)stream);
+}
+
+
+// ---- any image size -----------------------------------------------------------------------------------
+static int any_grid(int n_tokens) {
+    const DevInfo di = dev_info();
+    if (!di.ok) return 0;
+    const int g = di.sm_count * 4;
+    return n_tokens < g ? n_tokens : g;
+}
+
+long long bpl_render_any_workspace(int H, int W, int n_tokens, int with_grad) {
+    if (H < 1 || W < 1 || n_tokens < 0) return -1;
+    const int grid = any_grid(n_tokens);
+    return (long long)grid * (with_grad ? ANY_BWD_BUFS : ANY_FWD_BUFS) * H * W;
+}
+
+static int any_launch(const bpl_params *ps, const bpl_any_geom *geo, const bpl_stroke_batch *b, const bpl_fwd_out *out,
+                      const bpl_grads *g, bool grad, cudaStream_t st) {
+    if (b && b->n_tokens == 0) return 0;
+    if (!geo) { set_error("%s", "geometry is NULL"); return BPL_EINVAL; }
+    if (geo->H < 1 || geo->W < 1 || (long long)geo->H * geo->W > (1ll << 24)) {
+        set_error("%s", "imsize out of range (1 <= H, W and H * W <= 2^24)"); return BPL_EINVAL;
+    }
+    KArgs ka{};
+    int r = make_consts(ps, &ka.rc, true);
+    if (r) return r;
+    ka.rc.rmax = (float)(geo->H - 1);
+    ka.rc.cmax = (float)(geo->W - 1);
+    if ((r = fill_strokes(ka, b))) return r;
+    ka.img_idx = geo->img_idx;
+    if (out) { ka.ll = out->ll; ka.off_page = out->off_page; ka.pimg = out->pimg; }
+    if (grad) {
+        if (!g || !g->g_pts) { set_error("%s", "g_pts required"); return BPL_EINVAL; }
+        if (!geo->images && !g->g_pimg) { set_error("%s", "need target images or a pimg cotangent"); return BPL_EINVAL; }
+        ka.g_ll = g->g_ll; ka.g_pimg = g->g_pimg; ka.g_pts = g->g_pts; ka.g_eps = g->g_eps; ka.g_sigma = g->g_sigma;
+    }
+    const int grid = any_grid(ka.n_tokens);
+    if (grid <= 0) { set_error("%s", "no CUDA device"); return BPL_ENODEV; }
+    const long long need = bpl_render_any_workspace(geo->H, geo->W, ka.n_tokens, grad);
+    if (!geo->workspace || geo->workspace_floats < need) {
+        set_error("%s", "workspace too small (bpl_render_any_workspace)"); return BPL_EINVAL;
+    }
+    AnyGeom gm{geo->H, geo->W, geo->workspace, geo->images};
+    if (grad) bpl_render_any_grad_kernel<<<grid, ANY_THREADS, 0, st>>>(ka, gm);
+    else bpl_render_any_kernel<<<grid, ANY_THREADS, 0, st>>>(ka, gm);
+    count_launch(1);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("kernel launch: %s", cudaGetErrorString(e)); return (int)e; }
+    return 0;
+}
+
+int bpl_render_strokes_any(const bpl_params *ps, const bpl_any_geom *geo, const bpl_stroke_batch *b, const bpl_fwd_out *out,
+                           void *stream) {
+    return any_launch(ps, geo, b, out, nullptr, false, (cudaStream_t)stream);
+}
+
+int bpl_render_strokes_any_grad(const bpl_params *ps, const bpl_any_geom *geo, const bpl_stroke_batch *b,
+                                const bpl_fwd_out *out, const bpl_grads *g, void *stream) {
+    return any_launch(ps, geo, b, out, g, true, (cudaStream_t)stream);
 }
 
 }  // extern "C"

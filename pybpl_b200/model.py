@@ -63,8 +63,12 @@ class CharacterImageDist:
         """Log-likelihood of a binary image (image_dist.py:60-80): 0-d float32 tensor."""
         src = ctoken.part_tokens[0].shapes.device
         batch = token_batch_from([ctoken])
-        imgs = ops.pack_images(image.detach().to(batch.device), validate=True)
-        ll, _ = ops.score_tokens(batch, imgs, ps=self.ps)
+        ps = ops.make_params(self.ps)
+        if ops.image_size(ps) != (ops.IMSIZE, ops.IMSIZE):       # self.ps.imsize was changed: run-time-geometry kernels
+            imgs = ops.binary_images(image.detach(), ps, batch.device)
+        else:
+            imgs = ops.pack_images(image.detach().to(batch.device), validate=True)
+        ll, _ = ops.score_tokens(batch, imgs, ps=ps)
         return ll[0].to(src)
 
 

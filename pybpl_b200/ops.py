@@ -49,8 +49,15 @@ def make_params(ps=None):
     if ps is not None:
         imsize = tuple(int(v) for v in getattr(ps, "imsize", (IMSIZE, IMSIZE)))
         fsize = int(getattr(ps, "fsize", 11))
-        if imsize != (IMSIZE, IMSIZE) or not (1 <= fsize <= 11 and fsize % 2 == 1):
-            raise NotImplementedError("pybpl_b200 kernels are built for imsize=(105,105) and odd fsize <= 11")
+        if not (1 <= fsize <= 11 and fsize % 2 == 1):
+            raise NotImplementedError("pybpl_b200 kernels are built for odd fsize <= 11")
+        if imsize != (IMSIZE, IMSIZE):
+            # Any other size runs through the run-time-geometry kernels (render_strokes / rendering.render_image /
+            # CharacterImageDist); the fused 105 x 105 entry points refuse a Params with imsize != 105.
+            if len(imsize) != 2 or min(imsize) < 1 or imsize[0] * imsize[1] > (1 << 24):
+                raise ValueError(f"imsize must be (H, W) with H, W >= 1 and H * W <= 2^24; got {imsize}")
+            p.imsize = 0
+            p.hw = imsize
         p.fsize = fsize
         p.ink_ncon = int(getattr(ps, "ink_ncon", p.ink_ncon))
         p.ink_pp = float(getattr(ps, "ink_pp", p.ink_pp))
@@ -509,12 +516,38 @@ class _RenderTokens(torch.autograd.Function):
         return g_ctrl, g_inv, g_pos, g_aff, g_eps, g_sig, None, None
 
 
+def tokens_as_strokes(batch):
+    """A TokenBatch as raw motor-space trajectories, what CharacterImageDist.get_pimg hands to render_image
+    (model/image_dist.py:34-40): vanilla_to_motor (objects/part.py:290-328) by its kernel, then apply_warp
+    (util/affine.py:29-55: com_char = mean of all the character's points, util/stroke.py:119-136) as a few elementwise
+    tensor operations on the device.  Only the non-default-imsize path goes this way (the fused 105 x 105 kernels evaluate
+    the splines themselves); differentiable in every leaf of the batch."""
+    motor, _ = vanilla_to_motor_batch(batch.ctrl, batch.invscale, batch.position, batch.stroke_sub_off, batch.neval)
+    S, n = motor.shape[0], motor.shape[1]
+    sub_tok = batch.sub_token.long()
+    if batch.affine is not None:
+        A = batch.affine.to(torch.float32)
+        cnt = torch.zeros(batch.P, dtype=torch.float32, device=batch.device).index_add_(
+            0, sub_tok, torch.full((S,), float(n), device=batch.device))
+        com = torch.zeros(batch.P, 2, dtype=torch.float32, device=batch.device).index_add(0, sub_tok, motor.sum(1))
+        com = com / cnt.clamp(min=1.0).unsqueeze(1)
+        B = torch.stack([A[:, 0], A[:, 1], A[:, 2] - (A[:, 0] - 1) * com[:, 0], A[:, 3] - (A[:, 1] - 1) * com[:, 1]], 1)
+        Bs = B[sub_tok]
+        motor = motor * Bs[:, None, :2] + Bs[:, None, 2:]
+    tso = batch.stroke_sub_off.long()[batch.tok_stroke_off.long()]              # token -> sub-strokes
+    spo = torch.arange(S + 1, device=batch.device, dtype=torch.int32) * n
+    return StrokeBatch(tso.to(torch.int32), spo, motor.reshape(-1, 2), batch.eps, batch.sigma)
+
+
 def score_tokens(batch, images, img_idx=None, ps=None):
     """Render and score a TokenBatch.  images: PackedImages; img_idx: int32 [P] or None (image 0).
     Returns (ll [P] float32, ink_off_page [P] bool).  Differentiable w.r.t. batch.ctrl / invscale /
-    position / affine / eps / sigma."""
+    position / affine / eps / sigma.  (A non-default Parameters.imsize: images from binary_images.)"""
     if not isinstance(ps, _lib.Params):
         ps = make_params(ps)
+    if image_size(ps) != (IMSIZE, IMSIZE):
+        _, ll, off = render_strokes(tokens_as_strokes(batch), images, img_idx, want_pimg=False, ps=ps)
+        return ll, off
     if img_idx is not None:
         img_idx = _i32(img_idx, batch.device)
         _check_img_idx(img_idx, images)
@@ -583,9 +616,12 @@ def score_tokens_all_images(batch, images, ps=None):
 
 
 def render_tokens(batch, ps=None):
-    """Probability maps of a TokenBatch: (pimg [P,105,105], ink_off_page [P] bool)."""
+    """Probability maps of a TokenBatch: (pimg [P,H,W], ink_off_page [P] bool); H x W = Parameters.imsize."""
     if not isinstance(ps, _lib.Params):
         ps = make_params(ps)
+    if image_size(ps) != (IMSIZE, IMSIZE):
+        pimg, _, off = render_strokes(tokens_as_strokes(batch), want_pimg=True, ps=ps)
+        return pimg, off
     pimg, off = _RenderTokens.apply(batch.ctrl, batch.invscale, batch.position, batch.affine, batch.eps, batch.sigma,
                                     batch, ps)
     return pimg, off.bool()
@@ -690,12 +726,107 @@ class _RenderStrokes(torch.autograd.Function):
         return tot[0], tot[1], tot[2], None, None, None, None, None
 
 
+def image_size(ps):
+    """(H, W) a Params stands for: (105, 105) unless make_params saw another Parameters.imsize."""
+    return getattr(ps, "hw", (IMSIZE, IMSIZE))
+
+
+class _RenderStrokesAny(torch.autograd.Function):
+    """render_image (+ Bernoulli score) for any Parameters.imsize: bpl_render_strokes_any[_grad].  images: float32
+    [T,H,W] of exact 0 / 1 values or None."""
+
+    @staticmethod
+    def _geom(ps, images, img_idx, P, grad, dev):
+        H, W = image_size(ps)
+        n = int(lib().bpl_render_any_workspace(H, W, P, int(grad)))
+        if n < 0:
+            raise _lib.BplError("bpl_render_any_workspace: bad argument")
+        ws = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+        g = _lib.AnyGeomC(H, W, None if images is None else images.data_ptr(),
+                          None if img_idx is None else img_idx.data_ptr(), ws.data_ptr(), n)
+        return g, ws
+
+    @staticmethod
+    def forward(ctx, pts, eps, sigma, batch, images, img_idx, want_pimg, ps):
+        dev = batch.device
+        P = batch.P
+        H, W = image_size(ps)
+        pts_c, eps_c, sig_c = _c32(pts), _c32(eps), _c32(sigma)
+        pimg = torch.empty((P, H, W), dtype=torch.float32, device=dev) if want_pimg else None
+        ll = torch.empty(P, dtype=torch.float32, device=dev) if images is not None else None
+        off = torch.empty(P, dtype=torch.uint8, device=dev)
+        out = _lib.FwdOut(None if ll is None else ll.data_ptr(), off.data_ptr(), None if pimg is None else pimg.data_ptr())
+        b = batch.c_struct(pts_c, eps_c, sig_c)
+        g, ws = _RenderStrokesAny._geom(ps, images, img_idx, P, False, dev)
+        check(lib().bpl_render_strokes_any(ctypes.byref(ps), ctypes.byref(g), ctypes.byref(b), ctypes.byref(out),
+                                           _stream(dev)))
+        ctx.batch = batch; ctx.ps = ps; ctx.images = images; ctx.img_idx = img_idx
+        ctx.save_for_backward(pts_c, eps_c, sig_c)
+        ctx.mark_non_differentiable(off)
+        if pimg is None:
+            pimg = torch.empty(0, device=dev)
+        if ll is None:
+            ll = torch.zeros(P, dtype=torch.float32, device=dev)
+        return pimg, ll, off
+
+    @staticmethod
+    def backward(ctx, g_pimg, g_ll, _g_off):
+        pts, eps, sig = ctx.saved_tensors
+        batch = ctx.batch
+        dev = batch.device
+        P = batch.P
+
+        def run(gp, gl, images):
+            g_pts = torch.zeros_like(pts)
+            g_eps = torch.empty(P, dtype=torch.float32, device=dev); g_sig = torch.empty_like(g_eps)
+            gr = _lib.Grads(None if gl is None else gl.data_ptr(), None if gp is None else gp.data_ptr(), None, None,
+                            None, None, g_pts.data_ptr(), g_eps.data_ptr(), g_sig.data_ptr())
+            b = batch.c_struct(pts, eps, sig)
+            geo, ws = _RenderStrokesAny._geom(ctx.ps, images, ctx.img_idx, P, True, dev)
+            out = _lib.FwdOut(None, None, None)
+            check(lib().bpl_render_strokes_any_grad(ctypes.byref(ctx.ps), ctypes.byref(geo), ctypes.byref(b),
+                                                    ctypes.byref(out), ctypes.byref(gr), _stream(dev)))
+            return g_pts, g_eps, g_sig
+
+        tot = None
+        if g_pimg is not None and g_pimg.numel() > 0:
+            tot = run(g_pimg.to(torch.float32).contiguous(), None, None)
+        if ctx.images is not None and g_ll is not None:
+            r = run(None, g_ll.to(torch.float32).contiguous(), ctx.images)
+            tot = r if tot is None else tuple(a + b for a, b in zip(tot, r))
+        if tot is None:
+            tot = (torch.zeros_like(pts), torch.zeros(P, device=dev), torch.zeros(P, device=dev))
+        return tot[0], tot[1], tot[2], None, None, None, None, None
+
+
+def binary_images(images, ps, device):
+    """Target images for a non-default imsize: float32 [T,H,W] on `device`, checked to be exactly 0 / 1 the way torch's
+    Bernoulli.log_prob checks its argument (model/image_dist.py:76-77).  (105 x 105 targets are bit-packed: pack_images.)"""
+    H, W = image_size(ps)
+    t = torch.as_tensor(images).to(device, torch.float32)
+    if t.dim() == 2:
+        t = t.unsqueeze(0)
+    if tuple(t.shape[1:]) != (H, W):
+        raise ValueError(f"images must be [T,{H},{W}]; got {tuple(t.shape)}")
+    if not bool(((t == 0) | (t == 1)).all()):
+        raise ValueError("Expected value argument to be within the support (Boolean()) of the "
+                         "distribution Bernoulli(), but found invalid values")
+    return t.contiguous()
+
+
 def render_strokes(batch, images=None, img_idx=None, want_pimg=True, ps=None):
-    """render_image over a StrokeBatch: returns (pimg [P,105,105] or None, ll [P] or None, off_page [P] bool)."""
+    """render_image over a StrokeBatch: returns (pimg [P,H,W] or None, ll [P] or None, off_page [P] bool).  H x W is
+    Parameters.imsize: 105 x 105 runs the fused kernels (images: PackedImages), any other size the run-time-geometry
+    kernels (images: float32 [T,H,W] from binary_images)."""
     if not isinstance(ps, _lib.Params):
         ps = make_params(ps)
     if img_idx is not None:
         img_idx = _i32(img_idx, batch.device)
+    if image_size(ps) != (IMSIZE, IMSIZE):
+        if images is not None and not torch.is_tensor(images):
+            raise TypeError("a non-default imsize takes its target images from ops.binary_images, not pack_images")
+        pimg, ll, off = _RenderStrokesAny.apply(batch.pts, batch.eps, batch.sigma, batch, images, img_idx, want_pimg, ps)
+        return (pimg if want_pimg else None), (ll if images is not None else None), off.bool()
     pimg, ll, off = _RenderStrokes.apply(batch.pts, batch.eps, batch.sigma, batch, images, img_idx, want_pimg, ps)
     return (pimg if want_pimg else None), (ll if images is not None else None), off.bool()
 

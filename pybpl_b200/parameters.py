@@ -4,7 +4,7 @@ Only the attributes the render+score path reads are mirrored."""
 
 class Parameters:
     def __init__(self):
-        self.imsize = (105, 105)        # parameters.py:21
+        self.imsize = (105, 105)        # parameters.py:21 (any (H, W): other sizes run the run-time-geometry kernels)
         self.ink_pp = 2.                # :25
         self.ink_max_dist = 2.          # :27
         self.ink_ncon = 2               # :31

@@ -1,5 +1,6 @@
 """Drop-in for pybpl/rendering.py:render_image (and the helpers it exposes), computed by the fused CUDA
-kernels.  Same signature and return convention: (pimg [105,105] float32 on strokes' device, ink_off_page)."""
+kernels.  Same signature and return convention: (pimg [H,W] float32 on strokes' device, ink_off_page), H x W =
+ps.imsize (105 x 105 by default: the fused kernels; any other size: the run-time-geometry kernels)."""
 import torch
 
 from . import ops

@@ -10,6 +10,7 @@ that one token is made out-of-place in memory (baseline/ref_loader.py, forward b
     python tests/golden/make_fit_golden.py                 # fit64.npz
     python tests/golden/make_fit_golden.py --fit-smooth    # fit_smooth.npz (fit_smooth_stk, see make_fit_smooth)
     python tests/golden/make_fit_golden.py --fsize         # fsize.npz (render_image with Parameters.fsize = 7, 5, 3)
+    python tests/golden/make_fit_golden.py --imsize        # imsize.npz (render_image with Parameters.imsize = 64x80, 150x130, 33x47)
 """
 import os
 import sys
@@ -59,7 +60,7 @@ def main(P=64, seed=2024):
     print("wrote", path, "mean ll", out["ll"].mean(), {k: float(np.abs(v).max()) for k, v in out.items() if k.startswith("g_")})
 
 
-if __name__ == "__main__" and "--fit-smooth" not in sys.argv and "--fsize" not in sys.argv:
+if __name__ == "__main__" and "--fit-smooth" not in sys.argv and "--fsize" not in sys.argv and "--imsize" not in sys.argv:
     main()
 
 
@@ -138,3 +139,73 @@ def make_fsize():
 
 if __name__ == "__main__" and "--fsize" in sys.argv:
     make_fsize()
+
+
+def make_imsize():
+    """tests/golden/imsize.npz: render_image with Parameters.imsize other than 105 x 105 (pybpl/parameters.py:21; the image
+    is H x W = imsize[0] x imsize[1], rows bounded by imsize[0], rendering.py:27-31,214) from the live reference:
+    probability maps, the off-page flag, autograd gradients for a random cotangent, and -- against a Bernoulli sample of
+    the map -- the log-likelihood with its gradients (model/image_dist.py:75-78)."""
+    from baseline import ref_loader
+    ref_loader.load(grad_patch=True)
+    from pybpl.parameters import Parameters
+    from pybpl.rendering import render_image
+    rng = np.random.default_rng(23)
+    t = np.linspace(0, 1, 60)
+
+    def sets(H, W):
+        # x runs over columns [0, W-1], -y over rows [0, H-1]
+        a = [np.stack([0.2 * W + 0.6 * W * t, -(0.25 * H + 0.5 * H * t)], 1)]
+        b = [np.stack([0.5 * W + 0.3 * W * np.cos(6 * t), -(0.5 * H + 0.3 * H * np.sin(6 * t))], 1),
+             np.stack([0.05 * W + 1.05 * W * t, -(0.8 * H + 0.1 * H * np.sin(9 * t))], 1)]           # runs off the right edge
+        c = [np.stack([(W - 1) * t, -(H - 1) * t], 1),                                                # corner to corner, ends exactly on the border
+             np.stack([(W - 1) + 0 * t[:20], -(H - 1) * t[:20]], 1),                                   # along the last column
+             np.array([[W - 1.0, -(H - 1.0)], [np.nextafter(np.float32(W - 1), np.float32(1e9)), -1.0], [3.0, -2.0]], np.float64),
+             np.stack([0.3 * W + 0.6 * t[:12] / t[11], -(0.3 * H + 0.35 * t[:12] / t[11])], 1)]       # 0.7 px long: rescale branch
+        return [a, b, c]
+
+    out = {}
+    cases = []
+    for (H, W, hinton) in ((64, 80, False), (150, 130, False), (33, 47, True)):
+        ps = Parameters(); ps.imsize = torch.Size([H, W])
+        if hinton:
+            ps.broaden_mode = 'Hinton'
+        for i, strokes in enumerate(sets(H, W)):
+            key = f"h{H}w{W}_s{i}"
+            cases.append(key)
+            eps_v = (1e-3, 1e-4, 0.0)[i]; sig_v = (0.5, 2.5, 6.0)[i] if not (hinton and i == 0) else 0.0
+            mk = lambda: ([torch.tensor(s, dtype=torch.float32, requires_grad=True) for s in strokes],
+                          torch.tensor(eps_v, requires_grad=eps_v > 0), torch.tensor(sig_v, requires_grad=sig_v > 0))
+            st, eps, sig = mk()
+            pimg, off = render_image(st, eps, sig, ps)
+            assert tuple(pimg.shape) == (H, W)
+            ct = torch.from_numpy(rng.standard_normal((H, W)).astype(np.float32))
+            (pimg * ct).sum().backward()
+            out[key + "_H"] = H; out[key + "_W"] = W; out[key + "_hinton"] = int(hinton)
+            out[key + "_pimg"] = pimg.detach().numpy(); out[key + "_ct"] = ct.numpy()
+            out[key + "_off"] = bool(off); out[key + "_eps"] = np.float32(eps_v); out[key + "_sigma"] = np.float32(sig_v)
+            out[key + "_g_eps"] = float(eps.grad) if eps.grad is not None else 0.0
+            out[key + "_g_sigma"] = float(sig.grad) if sig.grad is not None else 0.0
+            for j, s in enumerate(st):
+                out[f"{key}_stroke{j}"] = s.detach().numpy(); out[f"{key}_g_stroke{j}"] = s.grad.numpy()
+            out[key + "_n"] = len(st)
+            # score against a sample of the map
+            g = torch.Generator().manual_seed(100 + len(cases))
+            image = (torch.rand(H, W, generator=g) < pimg.detach()).float()
+            st2, eps2, sig2 = mk()
+            pimg2, _ = render_image(st2, eps2, sig2, ps)
+            ll = torch.distributions.Bernoulli(pimg2).log_prob(image).sum()
+            ll.backward()
+            out[key + "_image"] = image.numpy().astype(np.uint8); out[key + "_ll"] = np.float32(ll.item())
+            out[key + "_gll_eps"] = float(eps2.grad) if eps2.grad is not None else 0.0
+            out[key + "_gll_sigma"] = float(sig2.grad) if sig2.grad is not None else 0.0
+            for j, s in enumerate(st2):
+                out[f"{key}_gll_stroke{j}"] = s.grad.numpy()
+    out["cases"] = np.array(cases)
+    path = os.path.join(ROOT, "tests", "golden", "imsize.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB", cases)
+
+
+if __name__ == "__main__" and "--imsize" in sys.argv:
+    make_imsize()

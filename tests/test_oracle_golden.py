@@ -252,3 +252,30 @@ def test_oracle_smaller_gaussian_matches_reference():
             pimg, off = o.render(strokes, float(d[key + "_eps"]), float(d[key + "_sigma"]))
             assert off == bool(d[key + "_off"])
             assert np.abs(pimg - d[key + "_pimg"]).max() < 1e-5, (fsize, i)
+
+
+def test_oracle_other_image_sizes_match_reference():
+    """Parameters.imsize other than 105 x 105 (pybpl/parameters.py:21; H x W = imsize[0] x imsize[1]): the oracle's
+    probability maps, off-page flags, log-likelihoods and gradients against the live reference's (tests/golden/imsize.npz,
+    made by tests/golden/make_fit_golden.py --imsize: 64 x 80, 150 x 130 and 33 x 47 with the Hinton broaden)."""
+    d = np.load(os.path.join(ROOT, "tests", "golden", "imsize.npz"))
+    rel = lambda g, r: np.abs(g - r).max() / max(np.abs(r).max(), 1e-12)
+    for key in d["cases"]:
+        ps = O.default_params(hinton=bool(d[key + "_hinton"])); ps.H = int(d[key + "_H"]); ps.W = int(d[key + "_W"])
+        o = Oracle(np.float32, ps)
+        strokes = [d[f"{key}_stroke{j}"] for j in range(int(d[key + "_n"]))]
+        eps, sigma = float(d[key + "_eps"]), float(d[key + "_sigma"])
+        pimg, off = o.render(strokes, eps, sigma)
+        assert pimg.shape == (ps.H, ps.W) and off == bool(d[key + "_off"])
+        assert np.abs(pimg - d[key + "_pimg"]).max() < 1e-5, key
+        r = o.render_grad(strokes, eps, sigma, gP=d[key + "_ct"])
+        g_ref = np.concatenate([d[f"{key}_g_stroke{j}"] for j in range(len(strokes))])
+        assert rel(r["g_pts"], g_ref) < 5e-4, key
+        assert abs(r["g_sigma"] - float(d[key + "_g_sigma"])) <= 1e-2 * max(1.0, abs(float(d[key + "_g_sigma"])))
+        assert abs(r["g_eps"] - float(d[key + "_g_eps"])) <= 2e-3 * max(1.0, abs(float(d[key + "_g_eps"])))
+        r = o.render_grad(strokes, eps, sigma, image=d[key + "_image"])
+        assert abs(r["ll"] - float(d[key + "_ll"])) <= 1e-5 * abs(float(d[key + "_ll"])), key
+        g_ref = np.concatenate([d[f"{key}_gll_stroke{j}"] for j in range(len(strokes))])
+        assert rel(r["g_pts"], g_ref) < 5e-4, key
+        assert abs(r["g_sigma"] - float(d[key + "_gll_sigma"])) <= 1e-2 * max(1.0, abs(float(d[key + "_gll_sigma"])))
+        assert abs(r["g_eps"] - float(d[key + "_gll_eps"])) <= 2e-3 * max(1.0, abs(float(d[key + "_gll_eps"])))
