@@ -149,3 +149,41 @@ def test_render_image_and_spline_call_sites_on_reference_tokens(ref):
         assert float((Xs - want_Xs).abs().max()) <= 1e-5 * float(want_Xs.abs().max())
     finally:
         dropin.uninstall()
+
+
+def test_changed_imsize_under_the_real_reference(ref):
+    """Parameters.imsize other than 105 x 105 with the reference's own objects: render_image(strokes, eps, sigma, ps) with
+    ps.imsize = (72, 90) (rendering.py:214), and a CharacterImageDist whose ps.imsize was changed (image_dist.py:30), the
+    un-patched reference against the installed drop-in (which routes these sizes to bpl_render_strokes_any)."""
+    from pybpl_b200 import dropin
+    import pybpl.rendering as R
+    from pybpl.parameters import Parameters
+    model, tokens = ref["model"], ref["tokens"]
+    tok = tokens[2]
+    ps = Parameters(); ps.imsize = torch.Size([72, 90])
+    motor = torch.cat([p.motor for p in tok.part_tokens]) * 0.8           # keep most of the ink on the smaller page
+    want_p, want_off = R.render_image(motor, 1e-3, 1.5, ps)
+    old_ps = model.image_dist.ps
+    model.image_dist.ps = ps
+    try:
+        want_pimg = model.get_pimg(tok).clone()
+        torch.manual_seed(3)
+        img = torch.bernoulli(want_pimg)
+        want_ll, want_g = _score_with_grads(model, tok, img)
+        dropin.install()
+        try:
+            p, off = R.render_image(motor, 1e-3, 1.5, ps)
+            assert p.shape == (72, 90) and float((p - want_p).abs().max()) <= 1e-5 and bool(off) == bool(want_off)
+            pimg = model.get_pimg(tok)
+            assert pimg.shape == (72, 90) and float((pimg - want_pimg).abs().max()) <= 1e-5
+            ll, g = _score_with_grads(model, tok, img)
+            assert abs(float(ll) - float(want_ll)) <= 1e-5 * abs(float(want_ll))
+            bars = [5e-4] * (3 * len(tok.part_tokens)) + [1e-2]
+            for a, b, bar in zip(g, want_g, bars):
+                assert _relinf(a, b) <= bar, (_relinf(a, b), bar)
+            with pytest.raises(ValueError):
+                model.score_image(tok, img * 0.5)
+        finally:
+            dropin.uninstall()
+    finally:
+        model.image_dist.ps = old_ps
