@@ -3,16 +3,14 @@
 // A token's ink touches about a third of the 105x105 canvas (34 % including the 12-pixel reach of two
 // broaden and two blur passes, measured on the bench workload); everything outside is exactly zero
 // before the epsilon mix and exactly epsilon after it.  The point phase records the bounding box of the
-// splatted pixels; every later phase maps its threads onto the lines and bands that can be non-zero:
-//   broaden    a warp skips its 21-row band when the band cannot hold ink yet
-//   Gaussian   items = (band, line) only for lines inside the box and bands that reach it (threads are
-//              re-packed, so whole warps drop out instead of lanes idling)
-//   Gaussian   ... with the shortest bands (15, 21 or 35 rows) whose items still fit one thread each
+// splatted pixels; every later phase maps its threads onto the lines and rows that can be non-zero:
+//   broaden    the warps split the box's rows, the lanes hold column pairs of the box (broaden_box)
+//   Gaussian   ONE run per line of the box over the 7-pixel blocks that hold its rows: no halo exchange, no barrier
+//              inside the pass (gauss_run; the banded round-1 variant gauss_inplace_s is kept behind -DBPL_GAUSS_BANDED)
 //   tail       ll = [score of an all-background render: lp_bg[1] * ones(target) + lp_bg[0] * zeros(target)]
-//              + sum over the box's pixels of (lp - background lp); one warp per row of the box
+//              + sum over the box's pixels of (lp - background lp), the box's pixels flattened over the CTA
 // The box grows by 1 per broaden pass and by 5 along the filtered axis per Gaussian pass.
-// Scalar FP32 (one token cannot use the packed float2 trick), 64 registers, 56 KB shared memory,
-// three CTAs per SM.
+// Scalar FP32, 64 registers, 55 KB shared memory; 256 threads x 4 CTAs per SM from 2 048 tokens on, 320 x 3 below.
 #pragma once
 
 #ifndef BPL_S_THREADS
@@ -402,10 +400,22 @@ __global__ void __launch_bounds__(S_THREADS, S_CTAS) bpl_forward1s_kernel(const 
         if (!AP) {
             if (!bb.empty()) {
                 const int wbox = bb.c1 - bb.c0 + 1;
+#ifndef BPL_TAIL_ROWS
+                // the box's pixels flattened over the CTA: no lanes idle at the ends of rows (a 65-pixel row costs a warp
+                // three rounds, the third for one pixel), at the price of a reciprocal multiplication per pixel: +1.0 % at 4 096
+                // tokens, +1.4 % at 131 072 (20.24 -> 20.52 M particles/s); -DBPL_TAIL_ROWS keeps one warp per row
+                const int nbox = wbox * (bb.r1 - bb.r0 + 1);
+                const float rw = __frcp_rn((float)wbox);
+                for (int k = threadIdx.x; k < nbox; k += blockDim.x) {
+                    const int rr = __float2int_rd(((float)k + 0.5f) * rw);      // k / wbox (exact: see small_div)
+                    {
+                        const int i = (bb.r0 + rr) * IMG + bb.c0 + (k - rr * wbox);
+#else
                 const int nw_ = blockDim.x >> 5, warp_ = threadIdx.x >> 5;
                 for (int r = bb.r0 + warp_; r <= bb.r1; r += nw_) {            // one warp per row of the box
                     for (int cc = lane; cc < wbox; cc += 32) {
                         const int i = r * IMG + bb.c0 + cc;
+#endif
                         float v = fminf(fmaxf(A[i], 0.0f), 1.0f);                                          // clamp_(0,1) (:180)
                         A[i] = 0.0f;                                            // the buffer is all zero again afterwards
                         if (eps > 0.0f) v = __fadd_rn(__fmul_rn(om, v), __fmul_rn(eps, __fsub_rn(1.0f, v)));   // (:227)
@@ -433,10 +443,19 @@ __global__ void __launch_bounds__(S_THREADS, S_CTAS) bpl_forward1s_kernel(const 
             const float dbg = l1 - l0;
             if (!bb.empty()) {
                 const int wbox = bb.c1 - bb.c0 + 1;
+#ifndef BPL_TAIL_ROWS
+                const int nbox = wbox * (bb.r1 - bb.r0 + 1);
+                const float rw = __frcp_rn((float)wbox);
+                for (int k = threadIdx.x; k < nbox; k += blockDim.x) {
+                    const int rr = __float2int_rd(((float)k + 0.5f) * rw);
+                    {
+                        const int i = (bb.r0 + rr) * IMG + bb.c0 + (k - rr * wbox);
+#else
                 const int nw_ = blockDim.x >> 5, warp_ = threadIdx.x >> 5;
                 for (int r = bb.r0 + warp_; r <= bb.r1; r += nw_) {
                     for (int cc = lane; cc < wbox; cc += 32) {
                         const int i = r * IMG + bb.c0 + cc;
+#endif
                         float v = fminf(fmaxf(A[i], 0.0f), 1.0f);
                         if (eps > 0.0f) v = __fadd_rn(__fmul_rn(om, v), __fmul_rn(eps, __fsub_rn(1.0f, v)));
                         float dl = 0.0f;
