@@ -523,8 +523,11 @@ def run_gpu(args):
     fwd_bwd = {"value": world * BWD_BATCH * n_bwd / (ms_bwd * 1e-3), "unit": UNIT, "batch_per_gpu": BWD_BATCH, "steps": n_bwd,
                "scaling": "weak", "ms_per_step": ms_bwd / n_bwd,
                "roofline": {"bound": "fp32", "achieved": bwd_rate * flops_fwd_bwd(Sb) / 1e12, "peak": fp32_peak,
-                            "unit": "TFLOP/s", "frac": bwd_rate * flops_fwd_bwd(Sb) / 1e12 / fp32_peak, "traffic": None,
-                            "kernel": "bpl_backward_kernel<false>", "kernel_ms": kb_ms, "flop_per_particle": flops_fwd_bwd(Sb),
+                            "unit": "TFLOP/s", "frac": bwd_rate * flops_fwd_bwd(Sb) / 1e12 / fp32_peak,
+                            # ncu (profiles/r02_backward_teams_final.raw.txt, 8 192 parses): 3.12 MB read + 0.19 MB written per
+                            # launch = 405 B per parse (the gradient stores stay in L2 for the length of the launch)
+                            "traffic": 405.0 * BWD_BATCH,
+                            "kernel": "bpl_backward_teams_kernel" if BWD_BATCH >= 1024 else "bpl_backward_kernel<false>", "kernel_ms": kb_ms, "flop_per_particle": flops_fwd_bwd(Sb),
                             "mean_substrokes": Sb},
                "e2e": {"value": world * BWD_BATCH * n_bwd / (wall_bwd_e2e_ms * 1e-3), "unit": UNIT,
                        "h2d_bytes_per_step": int(bwd_h2d), "d2h_bytes_per_step": int(bwd_d2h)}}
