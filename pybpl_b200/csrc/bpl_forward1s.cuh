@@ -219,6 +219,29 @@ __device__ BPL_BROADEN_ATTR void broaden_box(float *A, float *side, const Render
                 side[sidx * IMG + r] = (cb - 1 + sidx < IMG) ? A[r * IMG + cb - 1 + sidx] : 0.0f;
             }
         // horizontal (1,2,1) sums of a row.  DIRECT: before the barrier the boundary neighbours are still intact in A
+#ifndef BPL_BROADEN_BRANCHY
+        // What lies left of lane 0 / right of lane 31 comes through a pointer chosen once per pass -- the side copies for
+        // the inner edge of a two-warp row, a column of zeros otherwise -- so the row loop has two predicated loads
+        // instead of a nest of lane- and shape-dependent branches (the nest was a quarter of the loop's instructions).
+        const bool inL = nhalf == 2 && half == 1, inR = nhalf == 2 && half == 0 && cb < IMG;
+        const float *pl = inL ? sideL : side + 2 * IMG + 2, *pr = inR ? sideR : side + 2 * IMG + 2;
+        auto hrow = [&](int r, bool direct, float &x0, float &x1, float &h0, float &h1) {
+            const float *row = A + r * IMG;
+            x0 = ok0 ? row[c0] : 0.0f;
+            x1 = ok1 ? row[c1] : 0.0f;
+            float xl = __shfl_up_sync(0xffffffffu, x1, 1);
+            float xr = __shfl_down_sync(0xffffffffu, x0, 1);
+            if (direct) {
+                if (lane == 0) xl = inL ? row[cb - 1] : 0.0f;
+                if (lane == 31) xr = inR ? row[cb] : 0.0f;
+            } else {
+                if (lane == 0) xl = pl[r];
+                if (lane == 31) xr = pr[r];
+            }
+            h0 = xl + 2.0f * x0 + x1;
+            h1 = x0 + 2.0f * x1 + xr;
+        };
+#else
         auto hrow = [&](int r, bool direct, float &x0, float &x1, float &h0, float &h1) {
             const float *row = A + r * IMG;
             x0 = ok0 ? row[c0] : 0.0f;
@@ -235,6 +258,7 @@ __device__ BPL_BROADEN_ATTR void broaden_box(float *A, float *side, const Render
             h0 = xl + 2.0f * x0 + x1;
             h1 = x0 + 2.0f * x1 + xr;
         };
+#endif
         float hp0 = 0.0f, hp1 = 0.0f, ht0 = 0.0f, ht1 = 0.0f, d0, d1;
         if (live) {
             if (a0 > 0) hrow(a0 - 1, true, d0, d1, hp0, hp1);
@@ -244,6 +268,24 @@ __device__ BPL_BROADEN_ATTR void broaden_box(float *A, float *side, const Render
         if (live) {
             float xc0, xc1, hc0, hc1;
             hrow(a0, false, xc0, xc1, hc0, hc1);
+#ifndef BPL_BROADEN_BRANCHY
+            const float vmax = last ? 1.0f : 3.0e38f;                          // clamp_(max=1) in the last pass only (:171)
+            auto put = [&](int r, float hn0, float hn1) {
+                const float v0 = fminf(fmaf(c1w, hp0 + 2.0f * hc0 + hn0, c2w * xc0), vmax);
+                const float v1 = fminf(fmaf(c1w, hp1 + 2.0f * hc1 + hn1, c2w * xc1), vmax);
+                float *row = A + r * IMG;
+                if (ok0) row[c0] = v0;
+                if (ok1) row[c1] = v1;
+            };
+#pragma unroll 2
+            for (int r = a0; r < a1; ++r) {                                     // every row but the band's last: the next row is the band's own
+                float xn0, xn1, hn0, hn1;
+                hrow(r + 1, false, xn0, xn1, hn0, hn1);
+                put(r, hn0, hn1);
+                hp0 = hc0; hp1 = hc1; hc0 = hn0; hc1 = hn1; xc0 = xn0; xc1 = xn1;
+            }
+            put(a1, ht0, ht1);                                                  // below the last row: the halo taken before the barrier
+#else
 #pragma unroll 2
             for (int r = a0; r <= a1; ++r) {
                 float xn0 = 0.0f, xn1 = 0.0f, hn0 = ht0, hn1 = ht1;
@@ -256,6 +298,7 @@ __device__ BPL_BROADEN_ATTR void broaden_box(float *A, float *side, const Render
                 if (ok1) row[c1] = v1;
                 hp0 = hc0; hp1 = hc1; hc0 = hn0; hc1 = hn1; xc0 = xn0; xc1 = xn1;
             }
+#endif
         }
         __syncthreads();
     }
@@ -263,7 +306,7 @@ __device__ BPL_BROADEN_ATTR void broaden_box(float *A, float *side, const Render
 
 struct Fwd1sSmem {
     float A[FBUF];
-    float side[2 * IMG + 2];
+    float side[2 * IMG + 2 + IMG];      // two boundary columns (broaden_box), then a column of zeros
     float tab[MAX_TABLE];
     int bbox[4];
     Misc ms;
@@ -288,6 +331,7 @@ __global__ void __launch_bounds__(S_THREADS, S_CTAS) bpl_forward1s_kernel(const 
     for (int i = threadIdx.x; i < a.neval * NCPT; i += blockDim.x) sm.tab[i] = a.basis[i];
     if (threadIdx.x == 0) { ms->cur_img = -1; ms->c_eps = ms->c_sigma = nanf(""); ms->n_ones = 0; ms->ones_acc = 0; }
     zero_floats(A, FBUF);              // afterwards the tail re-zeroes exactly the rows it touched
+    for (int i = threadIdx.x; i < IMG; i += blockDim.x) sm.side[2 * IMG + 2 + i] = 0.0f;
     __syncthreads();
 #ifdef BPL_PHASE_TIMING
     long long pt_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
