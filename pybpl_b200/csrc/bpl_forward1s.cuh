@@ -126,6 +126,39 @@ __device__ BPL_GAUSS_ATTR void gauss_run(float *buf, const G6 gg, int l0, int nl
         W[i] = (s0 > 0) ? p[(i - PAD) * SA] : 0.0f;
         W[PAD + i] = p[i * SA];
     }
+#ifndef BPL_GAUSS_PREDICATED
+    // Only the canvas's LAST 7-block reads beyond the canvas (its new inputs are positions 103..109, of which two
+    // exist), so it is peeled off: the loop's loads need no bounds predicate (7 compares and 7 zero-moves per block, a
+    // ninth of the loop's instructions), and the peeled block knows at compile time which inputs are zero.
+    static_assert(IMG % GU == 0, "block structure");
+    constexpr int BLAST = IMG / GU - 1, NV = IMG - (BLAST * GU + PAD);      // 14; 2
+    auto block = [&](float *q) {
+#pragma unroll
+        for (int u = 0; u < GU; ++u) {
+            float acc = g[0] * W[u + PAD];
+#pragma unroll
+            for (int d = 1; d <= PAD; ++d) acc = fmaf(g[d], W[u + PAD - d] + W[u + PAD + d], acc);
+            q[u * SA] = acc;
+        }
+#pragma unroll
+        for (int k = 0; k < 2 * PAD; ++k) W[k] = W[k + GU];
+    };
+    const bool to_end = (a1 / GU == BLAST);
+    const int nfull = nblk - (to_end ? 1 : 0);
+#pragma unroll 1
+    for (int blk = 0; blk < nfull; ++blk) {
+        float *q = p + blk * GU * SA;
+#pragma unroll
+        for (int u = 0; u < GU; ++u) W[2 * PAD + u] = q[(u + PAD) * SA];
+        block(q);
+    }
+    if (to_end) {
+        float *q = p + nfull * GU * SA;
+#pragma unroll
+        for (int u = 0; u < GU; ++u) W[2 * PAD + u] = (u < NV) ? q[(u + PAD) * SA] : 0.0f;
+        block(q);
+    }
+#else
 #pragma unroll 1
     for (int blk = 0; blk < nblk; ++blk) {
         float *q = p + blk * GU * SA;
@@ -142,6 +175,7 @@ __device__ BPL_GAUSS_ATTR void gauss_run(float *buf, const G6 gg, int l0, int nl
 #pragma unroll
         for (int k = 0; k < 2 * PAD; ++k) W[k] = W[k + GU];
     }
+#endif
 }
 
 // Band size: the shortest runs whose items still fit one thread each.  Short runs spread a small box over more
