@@ -477,17 +477,22 @@ __global__ void __launch_bounds__(S_THREADS, S_CTAS) bpl_forward1s_kernel(const 
         float acc_ll = 0.0f;
         if (!AP) {
             if (!bb.empty()) {
-                const int wbox = bb.c1 - bb.c0 + 1;
+                int wbox = bb.c1 - bb.c0 + 1, c0t = bb.c0;
+                if (wbox == 1) { wbox = 2; c0t = max(c0t - 1, 0); }            // (a one-column box takes a background column along:
+                                                                                //  the multiply-high division needs wbox >= 2)
 #ifndef BPL_TAIL_ROWS
                 // the box's pixels flattened over the CTA: no lanes idle at the ends of rows (a 65-pixel row costs a warp
                 // three rounds, the third for one pixel), at the price of a reciprocal multiplication per pixel: +1.0 % at 4 096
                 // tokens, +1.4 % at 131 072 (20.24 -> 20.52 M particles/s); -DBPL_TAIL_ROWS keeps one warp per row
                 const int nbox = wbox * (bb.r1 - bb.r0 + 1);
-                const float rw = __frcp_rn((float)wbox);
+                // row of box pixel k = k / wbox = umulhi(k, ceil(2^32 / wbox)), exact while k * wbox < 2^32; one integer
+                // multiply-high instead of two conversions through the special-function pipe
+                const unsigned mw = 0xffffffffu / (unsigned)wbox + 1u;         // (wbox >= 2: see below)
+                const int skip = IMG - wbox, base0 = bb.r0 * IMG + c0t;
                 for (int k = threadIdx.x; k < nbox; k += blockDim.x) {
-                    const int rr = __float2int_rd(((float)k + 0.5f) * rw);      // k / wbox (exact: see small_div)
+                    const int rr = (int)__umulhi((unsigned)k, mw);
                     {
-                        const int i = (bb.r0 + rr) * IMG + bb.c0 + (k - rr * wbox);
+                        const int i = rr * skip + (k + base0);                  // (r0 + rr) * IMG + c0 + (k - rr * wbox)
 #else
                 const int nw_ = blockDim.x >> 5, warp_ = threadIdx.x >> 5;
                 for (int r = bb.r0 + warp_; r <= bb.r1; r += nw_) {            // one warp per row of the box
@@ -520,14 +525,17 @@ __global__ void __launch_bounds__(S_THREADS, S_CTAS) bpl_forward1s_kernel(const 
             // and (delta - delta_bg) is zero outside the box and at background pixels, i.e. wherever the buffer holds zero.
             const float dbg = l1 - l0;
             if (!bb.empty()) {
-                const int wbox = bb.c1 - bb.c0 + 1;
+                int wbox = bb.c1 - bb.c0 + 1, c0t = bb.c0;
+                if (wbox == 1) { wbox = 2; c0t = max(c0t - 1, 0); }            // (a one-column box takes a background column along:
+                                                                                //  the multiply-high division needs wbox >= 2)
 #ifndef BPL_TAIL_ROWS
                 const int nbox = wbox * (bb.r1 - bb.r0 + 1);
-                const float rw = __frcp_rn((float)wbox);
+                const unsigned mw = 0xffffffffu / (unsigned)wbox + 1u;
+                const int skip = IMG - wbox, base0 = bb.r0 * IMG + c0t;
                 for (int k = threadIdx.x; k < nbox; k += blockDim.x) {
-                    const int rr = __float2int_rd(((float)k + 0.5f) * rw);
+                    const int rr = (int)__umulhi((unsigned)k, mw);
                     {
-                        const int i = (bb.r0 + rr) * IMG + bb.c0 + (k - rr * wbox);
+                        const int i = rr * skip + (k + base0);
 #else
                 const int nw_ = blockDim.x >> 5, warp_ = threadIdx.x >> 5;
                 for (int r = bb.r0 + warp_; r <= bb.r1; r += nw_) {
