@@ -29,8 +29,21 @@
 #define BPL_S_LARGE_MIN 2048
 #endif
 
+#ifndef BPL_BROADEN_UNROLL
+#define BPL_BROADEN_UNROLL 2      // rows per trip of the broaden loop (A/B: 3 and 6 remove the register rotation)
+#endif
+#ifndef BPL_GAUSS_UNROLL
+#define BPL_GAUSS_UNROLL 1        // 7-blocks per trip of the Gaussian run loop
+#endif
+
 namespace bpl {
 
+constexpr int BROADEN_UNROLL = BPL_BROADEN_UNROLL, GAUSS_UNROLL = BPL_GAUSS_UNROLL;
+#ifdef BPL_S_UNROLL_A
+constexpr bool S_ROLL_A = false;      // A/B: phase A of the point stage unrolled, as in the backward kernels
+#else
+constexpr bool S_ROLL_A = true;
+#endif
 constexpr int S_THREADS = BPL_S_THREADS;
 constexpr int S_CTAS_PER_SM = BPL_S_CTAS;
 constexpr int S_THREADS_LARGE = BPL_S_THREADS_LARGE;      // launch shape for batches of S_LARGE_MIN tokens and more
@@ -145,7 +158,7 @@ __device__ BPL_GAUSS_ATTR void gauss_run(float *buf, const G6 gg, int l0, int nl
     };
     const bool to_end = (a1 / GU == BLAST);
     const int nfull = nblk - (to_end ? 1 : 0);
-#pragma unroll 1
+#pragma unroll GAUSS_UNROLL
     for (int blk = 0; blk < nfull; ++blk) {
         float *q = p + blk * GU * SA;
 #pragma unroll
@@ -311,7 +324,7 @@ __device__ BPL_BROADEN_ATTR void broaden_box(float *A, float *side, const Render
                 if (ok0) row[c0] = v0;
                 if (ok1) row[c1] = v1;
             };
-#pragma unroll 2
+#pragma unroll BROADEN_UNROLL
             for (int r = a0; r < a1; ++r) {                                     // every row but the band's last: the next row is the band's own
                 float xn0, xn1, hn0, hn1;
                 hrow(r + 1, false, xn0, xn1, hn0, hn1);
@@ -406,7 +419,7 @@ __global__ void __launch_bounds__(S_THREADS, S_CTAS) bpl_forward1s_kernel(const 
             const int s = active ? item / QN : 0x7fffffff;
             CtrlSrc src{};
             if (active) src = make_ctrl_src(a, t, s, sm.tab, ms, aff);
-            const LaneAcc acc = warp_points<false, 1>(active, src, sm.tab, s, a.neval, active ? item - s * QN : 0, lane,
+            const LaneAcc acc = warp_points<false, 1, IMG, 0, PPL, LayS<1, IMG, 0>, S_ROLL_A>(active, src, sm.tab, s, a.neval, active ? item - s * QN : 0, lane,
                                                       a.rc, A, 0.0f, 0, sm.bbox);
             any_out |= acc.any_out;
             reduce_by_substroke(active, s, acc.sum, acc.cnt, ms->sub, ms->ink64, lane);
@@ -432,7 +445,7 @@ __global__ void __launch_bounds__(S_THREADS, S_CTAS) bpl_forward1s_kernel(const 
                 active = active && (__float_as_int(v.w) >= 2 && v.z < a.rc.ink_pp);
                 CtrlSrc src{};
                 if (active) src = make_ctrl_src(a, t, s, sm.tab, ms, aff);
-                warp_points<true, 1>(active, src, sm.tab, s, a.neval, item < items ? item - s * QN : 0, lane, a.rc, A, v.z,
+                warp_points<true, 1, IMG, 0, PPL, LayS<1, IMG, 0>, S_ROLL_A>(active, src, sm.tab, s, a.neval, item < items ? item - s * QN : 0, lane, a.rc, A, v.z,
                                      __float_as_int(v.w));
             }
             __syncthreads();

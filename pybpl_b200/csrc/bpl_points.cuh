@@ -104,8 +104,11 @@ __device__ __forceinline__ CtrlSrc shfl_src(const CtrlSrc &s, int from, const fl
 //  C. every lane walks its points: ink from the distance to the previous survivor, splat.
 // FIX: fix_sum / fix_cnt are the sub-stroke totals; ink becomes fill or scale*ink and only the
 // difference to the common-branch ink is splatted.
+// ROLL_A: phase A as a rolled loop (one copy of the point evaluation instead of PPL).  The box-confined scoring kernel
+// takes it: with its loop bodies trimmed instruction fetch weighs more than the loop overhead,
+// +1.4 % on 131 072 tokens, +0.9 % on 4 096; the backward kernels keep the unrolled form (-2 % at 1 024 parses rolled).
 template <bool FIX, int PIXSTRIDE, int ROWSTRIDE = IMG, int ORG = 0, int PPL = PPL_DEFAULT,
-          class Lay = LayS<PIXSTRIDE, ROWSTRIDE, ORG>>
+          class Lay = LayS<PIXSTRIDE, ROWSTRIDE, ORG>, bool ROLL_A = false>
 __device__ __forceinline__ LaneAcc warp_points(bool active, const CtrlSrc &src, const float *tab, int sid, int n, int q,
                                                int lane, const RenderConsts &rc, float *img, float fix_sum, int fix_cnt,
                                                int *bbox = nullptr, Lay lay = Lay()) {
@@ -119,7 +122,11 @@ __device__ __forceinline__ LaneAcc warp_points(bool active, const CtrlSrc &src, 
     unsigned inbm = 0u;
     bool hv = false;
     float lr = 0.0f, lc = 0.0f;
-    BPL_UNROLL_A
+#ifdef BPL_ROLL_PHASE_A
+#pragma unroll 1
+#else
+#pragma unroll (ROLL_A ? 1 : PPL)
+#endif
     for (int k = 0; k < PPL; ++k) {
         const int j = j0 + k;
         const PEval e = eval_pt(src, j, active && j < n);
