@@ -48,9 +48,9 @@ BWD_BATCH = 1024
 CPU_SAMPLE = 8192            # particles per step of the CPU arm (first tokens of sweep block 0)
 # dram__bytes_read.sum + dram__bytes_write.sum of one scoring launch, from the ncu --set full capture summarised under
 # profiles/ (filled in from the round's capture; None until one exists for the current kernel)
-NCU_SMEM_WAVEFRONTS_PER_PARTICLE = 5126.7   # profiles/r02_fwd1s_sweep_final.raw.txt: l1tex__data_pipe_lsu_wavefronts_mem_shared.sum
+NCU_SMEM_WAVEFRONTS_PER_PARTICLE = 5848.0   # profiles/r02_fwd1s_sweep_final4.raw.txt: l1tex__data_pipe_lsu_wavefronts_mem_shared.sum
                                             # / 1,000,000 particles; one wavefront moves up to 128 bytes
-NCU_DRAM_BYTES_PER_PARTICLE = 293.60        # profiles/r02_fwd1s_sweep_final.raw.txt: (282.36 MB read + 11.24 MB written) / 1,000,000 particles
+NCU_DRAM_BYTES_PER_PARTICLE = 291.24        # profiles/r02_fwd1s_sweep_final4.raw.txt: (280.92 MB read + 10.32 MB written) / 1,000,000 particles
 
 
 def flops_fwd(S):      # algorithmic work per particle, separable minimal algorithm
