@@ -47,6 +47,11 @@ namespace bpl {
 constexpr int BT_NT = BPL_BT_TEAMS;        // teams per CTA
 constexpr int BT_TT = BPL_BT_THREADS;      // threads per team
 constexpr int BT_PPL = BPL_BT_PPL;         // points per lane in the point stages
+#ifdef BPL_UNROLL_PHASE_A_BWD
+constexpr bool BT_ROLL_SPLAT = false;       // A/B: phase A of the point stages unrolled
+#else
+constexpr bool BT_ROLL_SPLAT = true;        // phase A of the splat as a rolled loop (as in the scoring kernel; see bpl_points.cuh)
+#endif
 #ifndef BPL_BT_GU
 #define BPL_BT_GU 5
 #endif
@@ -241,7 +246,7 @@ __device__ __forceinline__ void load_image_bits_t(const TeamCtx &tm, const KArgs
 __device__ __forceinline__ bool warp_bbox(bool active, const CtrlSrc &src, int n, int q, int lane, int *bbox) {
     int rmin = IMG, rmax = -1, cmin = IMG, cmax = -1;
     bool any_out = false;
-    BPL_UNROLL_A
+    BPL_UNROLL_A_BBOX
     for (int k = 0; k < BT_PPL; ++k) {
         const int j = q * BT_PPL + k;
         const bool valid = active && j < n;
@@ -747,7 +752,7 @@ __device__ __noinline__ void bt_splat_fix(BtShared *sh) {
         active = active && (__float_as_int(v.w) >= 2 && v.z < a.rc.ink_pp);
         CtrlSrc src{};
         if (active) src = make_ctrl_src(a, t, s, tab, ms, aff);
-        warp_points<true, 1, IMG, 0, BT_PPL, LayD>(active, src, tab, s, a.neval, it < items ? it - s * QN : 0, tm.lane,
+        warp_points<true, 1, IMG, 0, BT_PPL, LayD, BT_ROLL_SPLAT>(active, src, tab, s, a.neval, it < items ? it - s * QN : 0, tm.lane,
                                                   a.rc, A, v.z, __float_as_int(v.w), nullptr, lay);
     }
     tm.sync();
@@ -772,7 +777,7 @@ __device__ __noinline__ void bt_splat(BtShared *sh) {
         const int s = active ? it / QN : 0x7fffffff;
         CtrlSrc src{};
         if (active) src = make_ctrl_src(a, t, s, tab, ms, aff);
-        const LaneAcc acc = warp_points<false, 1, IMG, 0, BT_PPL, LayD>(active, src, tab, s, a.neval, active ? it - s * QN : 0,
+        const LaneAcc acc = warp_points<false, 1, IMG, 0, BT_PPL, LayD, BT_ROLL_SPLAT>(active, src, tab, s, a.neval, active ? it - s * QN : 0,
                                                                        tm.lane, a.rc, A, 0.0f, 0, nullptr, lay);
         reduce_by_substroke(active, s, acc.sum, acc.cnt, ms->sub, ms->ink64, tm.lane);
     }

@@ -21,6 +21,17 @@
 #else
 #define BPL_UNROLL_A _Pragma("unroll")
 #endif
+// The gather stage (warp_points_bwd) and the team kernel's bounding-box pass (warp_bbox) take phase A ROLLED by default:
+// together with the rolled splat of the team kernel (BT_ROLL_SPLAT) it is +4.5 % at 8 192 parses (5.09 -> 5.33 M/s) and
+// within the noise at 1 024 -- the team kernel is bound by instruction fetch (253 KB of SASS), see DESIGN.md.
+// -DBPL_UNROLL_PHASE_A_BWD restores the unrolled form.
+#if !defined(BPL_UNROLL_PHASE_A_BWD)
+#define BPL_UNROLL_A_BWD _Pragma("unroll 1")
+#define BPL_UNROLL_A_BBOX _Pragma("unroll 1")
+#else
+#define BPL_UNROLL_A_BWD _Pragma("unroll")
+#define BPL_UNROLL_A_BBOX _Pragma("unroll")
+#endif
 
 namespace bpl {
 
@@ -311,7 +322,7 @@ __device__ __forceinline__ float warp_points_bwd(bool active, const CtrlSrc &src
     bool hv = false;
     float lr = 0.0f, lc = 0.0f;
     int lj = 0;
-    BPL_UNROLL_A
+    BPL_UNROLL_A_BWD
     for (int k = 0; k < PPL; ++k) {
         const int j = j0 + k;
         const PEval e = eval_pt(src, j, active && j < n);
@@ -378,15 +389,20 @@ __device__ __forceinline__ float warp_points_bwd(bool active, const CtrlSrc &src
     bool pend = false;
     float fr = 0.0f, fc = 0.0f;
     int fj = 0;
-    // one segment (earlier point e, later point l): ink0 of the point(s) whose ink it defines, with d L / d ink0 = gi
-    auto segment = [&](float er, float ec, int ej, float lr_, float lc_, int lj_, float gi) {
+    // One segment (earlier point e, later point l) defines ink0 of the later point -- and of the sub-stroke's first
+    // survivor when e is that survivor (dist[:1], rendering.py:98) -- with d L / d ink0 = gi in total.  Returns the
+    // gradient (ur, uc) the segment puts on the later point (the earlier one gets its negative); (0, 0) where the
+    // clamp or the norm's zero gradient cuts it.
+    // Every point receives ONE emit per walk step with all its contributions summed (own splat + own segment; the
+    // previous survivor: its end of the segment + its splat when it is the first survivor, whose ink this segment also
+    // defines): four inlined copies of the caller's emit instead of ten, and half as many emits executed.
+    auto segment = [&](float er, float ec, float lr_, float lc_, float gi, float &ur, float &uc) {
         const float dr = __fsub_rn(lr_, er), dc = __fsub_rn(lc_, ec);
         const float dist = __fsqrt_rn(__fadd_rn(__fmul_rn(dr, dr), __fmul_rn(dc, dc)));
+        ur = 0.0f; uc = 0.0f;
         if (!fill && dist <= rc.ink_max_dist && dist != 0.0f) {         // clamp passes at the bound; norm' = 0 at 0
             const float gd = rc.ink_f * gi;
-            const float ur = gd * (dr / dist), uc = gd * (dc / dist);
-            emit(lj_, uc, -ur);        // un-flip: row = -y, col = x
-            emit(ej, -uc, ur);
+            ur = gd * (dr / dist); uc = gd * (dc / dist);
         }
     };
 #pragma unroll 1
@@ -401,13 +417,18 @@ __device__ __forceinline__ float warp_points_bwd(bool active, const CtrlSrc &src
                 if (pend) dot = fmaf(gather_px(G, fr, fc, lay).gink, ink0, dot);
             } else {
                 const float ink = fill ? fillv : __fmul_rn(sc, ink0);
-                emit(j, ink * K.gc, -(ink * K.gr));
-                segment(pr, pc, pj, e.r, e.c, j, fmaf(K.gink, sc, gsum));
-                if (pend) {             // the first survivor carries a copy of this ink
+                float gi = fmaf(K.gink, sc, gsum);
+                float gpc = 0.0f, gpr = 0.0f;                  // splat gradient of the previous survivor (col, row)
+                if (pend) {             // the previous survivor is the first one (pj == fj): it carries a copy of this ink
                     const Corner2 Kf = gather_px(G, fr, fc, lay);
-                    emit(fj, ink * Kf.gc, -(ink * Kf.gr));
-                    segment(fr, fc, fj, e.r, e.c, j, fmaf(Kf.gink, sc, gsum));
+                    gpc = ink * Kf.gc; gpr = ink * Kf.gr;
+                    gi += fmaf(Kf.gink, sc, gsum);
                 }
+                float ur, uc;
+                segment(pr, pc, e.r, e.c, gi, ur, uc);
+                emit(j, fmaf(ink, K.gc, uc), -fmaf(ink, K.gr, ur));        // un-flip: row = -y, col = x
+                gpc -= uc; gpr -= ur;
+                if (gpc != 0.0f || gpr != 0.0f) emit(pj, gpc, -gpr);
             }
             pend = false;
         } else {
@@ -424,17 +445,17 @@ __device__ __forceinline__ float warp_points_bwd(bool active, const CtrlSrc &src
             if (e.inb) { found = true; nr = e.r; nc = e.c; nj = j; break; }
         }
         const Corner2 Kf = gather_px(G, fr, fc, lay);
-        if (found) {
-            const float ink0 = ink_from(nr, nc, fr, fc, rc);
-            if (DOT) {
-                dot = fmaf(Kf.gink, ink0, dot);
-            } else {
-                const float ink = fill ? fillv : __fmul_rn(sc, ink0);
-                emit(fj, ink * Kf.gc, -(ink * Kf.gr));
-                segment(fr, fc, fj, nr, nc, nj, fmaf(Kf.gink, sc, gsum));
+        if (DOT) {
+            if (found) dot = fmaf(Kf.gink, ink_from(nr, nc, fr, fc, rc), dot);
+        } else {
+            float ink = rc.ink_pp, ur = 0.0f, uc = 0.0f;
+            if (found) {
+                const float ink0 = ink_from(nr, nc, fr, fc, rc);
+                ink = fill ? fillv : __fmul_rn(sc, ink0);
+                segment(fr, fc, nr, nc, fmaf(Kf.gink, sc, gsum), ur, uc);
+                if (ur != 0.0f || uc != 0.0f) emit(nj, uc, -ur);
             }
-        } else if (!DOT) {
-            emit(fj, rc.ink_pp * Kf.gc, -(rc.ink_pp * Kf.gr));
+            emit(fj, fmaf(ink, Kf.gc, -uc), -fmaf(ink, Kf.gr, -ur));
         }
     }
     return dot;
