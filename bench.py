@@ -524,9 +524,9 @@ def run_gpu(args):
                "scaling": "weak", "ms_per_step": ms_bwd / n_bwd,
                "roofline": {"bound": "fp32", "achieved": bwd_rate * flops_fwd_bwd(Sb) / 1e12, "peak": fp32_peak,
                             "unit": "TFLOP/s", "frac": bwd_rate * flops_fwd_bwd(Sb) / 1e12 / fp32_peak,
-                            # ncu (profiles/r02_backward_teams_final.raw.txt, 8 192 parses): 3.12 MB read + 0.19 MB written per
-                            # launch = 405 B per parse (the gradient stores stay in L2 for the length of the launch)
-                            "traffic": 405.0 * BWD_BATCH,
+                            # ncu (profiles/r02_backward_teams_final2_1024.raw.txt, one launch of 1 024 parses): 591.9 KB read +
+                            # 4.9 KB written (the gradient stores stay in L2 for the length of the launch; 8 192 parses: 327 B each)
+                            "traffic": 596.7e3 if BWD_BATCH == 1024 else 327.0 * BWD_BATCH,
                             "kernel": "bpl_backward_teams_kernel" if BWD_BATCH >= 1024 else "bpl_backward_kernel<false>", "kernel_ms": kb_ms, "flop_per_particle": flops_fwd_bwd(Sb),
                             "mean_substrokes": Sb},
                "e2e": {"value": world * BWD_BATCH * n_bwd / (wall_bwd_e2e_ms * 1e-3), "unit": UNIT,
