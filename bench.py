@@ -322,7 +322,9 @@ def run_gpu(args):
     lse_dev = float(sw.total.item())
 
     # ---- end to end: the same sweep from host numpy arrays ----
-    stager = ops.HostSweepStager(w, dev, chunk=E2E_CHUNK)
+    # at least four chunks per step and rank, so that packing / copying chunk c+1 overlaps the kernel of chunk c
+    e2e_chunk = int(min(E2E_CHUNK, max(16384, -(-P_rank // 4))))
+    stager = ops.HostSweepStager(w, dev, chunk=e2e_chunk)
     nchunks = len(stager.chunks)
     host_ll = torch.empty(P_rank, dtype=torch.float32).pin_memory()
     host_total = torch.empty(1, dtype=torch.float32).pin_memory()
@@ -551,7 +553,7 @@ def run_gpu(args):
             "ms_per_step": ms_dev / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": sweep_config(world),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "timing": "wall clock around all steps", "chunk": E2E_CHUNK},
+                    "timing": "wall clock around all steps", "chunk": e2e_chunk, "pack_threads": stager.threads},
             "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu_torch if (cpu_torch and "value" in cpu_torch) else cpu, "cpu_baseline_port": cpu,
             "cpu_baseline_torch": cpu_torch, "config4": config4,
