@@ -246,3 +246,23 @@ def test_parse_file_rejects_malformed_sections(tmp_path):
         rejected(ty2=bad)
     b2 = bits.copy(); b2[1, -1] |= np.uint32(1 << 20)                                # a padding bit
     rejected(bits2=b2)
+
+
+def test_host_stager_packs_the_same_bytes_with_any_number_of_threads():
+    """ops.HostSweepStager: the ragged packing of a chunk (offsets rebased, the chunk's slices copied into one staging
+    buffer) gives the same sections whether the control-point copy runs on one thread or is split over a pool."""
+    import numpy as np
+    from pybpl_b200 import ops, workload
+    w = workload.synth_tokens(20000, seed=3, sigma_mode="uniform")
+    a = ops.HostSweepStager(w, "cpu", chunk=8192, pin=False, threads=1)
+    b = ops.HostSweepStager(w, "cpu", chunk=8192, pin=False, threads=4)
+    assert len(a.chunks) == 3 and b.threads == 4
+    for c in range(len(a.chunks)):
+        a.pack(c, 0); b.pack(c, 1)
+        c0, c1, k0, k1, s0, s1 = a.chunks[c]
+        rows = dict(tok_stroke_off=c1 - c0 + 1, stroke_sub_off=k1 - k0 + 1, ctrl=s1 - s0, invscale=s1 - s0, position=k1 - k0,
+                    eps=c1 - c0, sigma=c1 - c0)
+        for name, n in rows.items():
+            assert np.array_equal(a._host_view(0, name, n), b._host_view(1, name, n)), (c, name)
+        assert np.array_equal(b._host_view(1, "ctrl", s1 - s0), w["ctrl"][s0:s1].reshape(-1, 10))
+        assert b._host_view(1, "tok_stroke_off", c1 - c0 + 1)[0] == 0 and b._host_view(1, "stroke_sub_off", k1 - k0 + 1)[0] == 0
