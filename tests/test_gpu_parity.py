@@ -929,3 +929,40 @@ def test_logsumexp_partial_and_combine(ops):
         assert part[0].item() == x[ok].max().item()
     empty = ops.logsumexp_combine(torch.tensor([float("-inf"), 0.0], device=DEV))
     assert empty.item() == float("-inf")
+
+
+def test_one_column_box_through_the_scoring_kernel(ops):
+    """A token whose ink falls on ONE pixel column (control points with x = 0 exactly, so every trajectory point has the
+    stroke position's integer x) with ink_ncon = 0 and blur_sigma = 0: nothing widens the box, and the scoring kernel's
+    flattened tail runs on a box one pixel wide (it takes a background column along).  Scores against the oracle; a second
+    token hugs the canvas's first column."""
+    from types import SimpleNamespace as NS
+    from oracle import Oracle
+    import oracle as _oracle
+    rng = np.random.default_rng(11)
+    P = 3
+    ctrl = np.zeros((P, 5, 2), np.float32)
+    ctrl[:, :, 1] = -np.sort(rng.uniform(0, 60, (P, 5)), axis=1)            # straight down, x stays 0
+    w = dict(P=P, tok_stroke_off=np.arange(P + 1, dtype=np.int32), stroke_sub_off=np.arange(P + 1, dtype=np.int32),
+             ctrl=ctrl, invscale=np.ones(P, np.float32), position=np.array([[40.0, -10.0], [0.0, -20.0], [104.0, -5.0]], np.float32),
+             eps=np.full(P, 1e-3, np.float32), sigma=np.zeros(P, np.float32))
+    ops_ps = _oracle.default_params(); ops_ps.ink_ncon = 0
+    o = Oracle(np.float32, ops_ps)
+    C = load("tokens")["basis_5_200"]
+    img = (rng.random((105, 105)) < 0.05).astype(np.uint8)
+    img[10:60, 40] = 1
+    ref = o.token_batch(C, w["tok_stroke_off"], w["stroke_sub_off"], w["ctrl"], w["invscale"], w["position"], w["eps"],
+                        w["sigma"], img[None], want_pimg=True)
+    assert [(ref["pimg"][p] > 2e-3).any(0).sum() for p in range(P)] == [1, 1, 1]      # one ink column each
+    ps = ops.make_params(NS(imsize=(105, 105), fsize=11, ink_ncon=0))
+    batch = ops.TokenBatch(w["tok_stroke_off"], w["stroke_sub_off"], T(w["ctrl"]), T(w["invscale"]), T(w["position"]),
+                           T(w["eps"]), T(w["sigma"]))
+    imgs = ops.pack_images(T(img, torch.uint8))
+    with torch.no_grad():
+        ll, off = ops.score_tokens(batch, imgs, ps=ps)
+        ll2, _ = ops.score_tokens(batch, imgs, ps=ps)                           # the buffer is clean again after the first pass
+        ll_all = ops.score_tokens_all_images(batch, imgs, ps=ps)[0][:, 0]
+    assert np.array_equal(off.cpu().numpy(), ref["off_page"])
+    for got in (ll, ll2, ll_all):
+        rel = np.abs(got.cpu().numpy() - ref["ll"]) / np.abs(ref["ll"])
+        assert rel.max() < 1e-5, rel
