@@ -6,7 +6,7 @@
 // splatted pixels; every later phase maps its threads onto the lines and rows that can be non-zero:
 //   broaden    the warps split the box's rows, the lanes hold column pairs of the box (broaden_box)
 //   Gaussian   ONE run per line of the box over the 7-pixel blocks that hold its rows: no halo exchange, no barrier
-//              inside the pass (gauss_run; the banded round-1 variant gauss_inplace_s is kept behind -DBPL_GAUSS_BANDED)
+//              inside the pass (gauss_run; round 1's banded variant with halo exchange is in the history: 631856b)
 //   tail       ll = [score of an all-background render: lp_bg[1] * ones(target) + lp_bg[0] * zeros(target)]
 //              + sum over the box's pixels of (lp - background lp), the box's pixels flattened over the CTA
 // The box grows by 1 per broaden pass and by 5 along the filtered axis per Gaussian pass.
@@ -57,71 +57,19 @@ struct BBox {
     __device__ __forceinline__ void grow_cols(int d) { if (!empty()) { c0 = max(0, c0 - d); c1 = min(IMG - 1, c1 + d); } }
 };
 
-// in-place 11-tap pass over lines [l0, l0+nl) and bands [b0, b0+nb); see gauss_inplace for the scheme
 struct G6 { float v[PAD + 1]; };      // the half kernel by value: the pass is a real (non-inlined) function so that
-                                       // its six instantiations do not add to the register pressure of the kernel body
+                                       // its instantiations do not add to the register pressure of the kernel body
 #ifdef BPL_GAUSS_INLINE
 #define BPL_GAUSS_ATTR __forceinline__
 #else
 #define BPL_GAUSS_ATTR __noinline__
 #endif
-template <bool VERT, int GR, int GU>
-__device__ BPL_GAUSS_ATTR void gauss_inplace_s(float *buf, const G6 gg, int l0, int nl, int b0, int nb) {
-    static_assert(IMG % GR == 0 && GR % GU == 0 && GU >= PAD, "band structure");
-    const float (&g)[PAD + 1] = gg.v;
-    constexpr int GNB = IMG / GR;
-    constexpr int SA = VERT ? IMG : 1;
-    constexpr int SL = VERT ? 1 : IMG;
-    const int item = threadIdx.x;
-    const bool active = item < nl * nb;
-    int bi = 0;                          // item / nl without a division: a line has at most IMG / GR bands
-#pragma unroll
-    for (int k = 1; k < GNB; ++k) bi += (item >= k * nl);
-    const int band = b0 + bi;
-    const int line = l0 + (item - bi * nl);
-    float *p = buf + band * GR * SA + line * SL;
-    float W[GU + 2 * PAD];
-    float trail[PAD];
-    if (active) {
-#pragma unroll
-        for (int i = 0; i < PAD; ++i) {
-            W[i] = (band > 0) ? p[(i - PAD) * SA] : 0.0f;
-            trail[i] = (band < GNB - 1) ? p[(GR + i) * SA] : 0.0f;
-        }
-    }
-    __syncthreads();
-    if (!active) return;
-#pragma unroll
-    for (int i = 0; i < PAD; ++i) W[PAD + i] = p[i * SA];
-    auto block = [&](float *q) {
-#pragma unroll
-        for (int u = 0; u < GU; ++u) {
-            float acc = g[0] * W[u + PAD];
-#pragma unroll
-            for (int d = 1; d <= PAD; ++d) acc = fmaf(g[d], W[u + PAD - d] + W[u + PAD + d], acc);
-            q[u * SA] = acc;
-        }
-    };
-#pragma unroll 1
-    for (int ob = 0; ob < GR - GU; ob += GU) {
-        float *q = p + ob * SA;
-#pragma unroll
-        for (int u = 0; u < GU; ++u) W[2 * PAD + u] = q[(u + PAD) * SA];
-        block(q);
-#pragma unroll
-        for (int k = 0; k < 2 * PAD; ++k) W[k] = W[k + GU];
-    }
-    float *q = p + (GR - GU) * SA;
-#pragma unroll
-    for (int u = 0; u < GU; ++u) W[2 * PAD + u] = (u + PAD < GU) ? q[(u + PAD) * SA] : trail[u + PAD - GU];
-    block(q);
-}
 
 // One run per line, exactly the 7-blocks that hold rows [a0, a1]: nobody else touches the line, so the pass needs no
 // halo exchange and no barrier of its own (the in-place window reads ahead of what it writes).  Only `nl` threads work
 // (a third of the CTA), but with four CTAs on the SM the others' warps fill the issue slots, and the saved barrier and
 // halo loads are worth +4 % at 4 096 tokens, +6 % on 131 072 (19.1 -> 20.3 M particles/s).  Measured alternatives under
-// the same launch shape: the banded variants below (35-row runs, halos taken before a barrier; -DBPL_GAUSS_BANDED), the
+// the same launch shape: round 1's banded variants (35-row runs, halos taken before a barrier), the
 // box in two groups of whole lines (-6 %), and the same idea for the broaden -- one warp for all rows of a box up to 64
 // columns wide, no barriers between its passes -- which was 11 % slower (too serial: 2 x 45 rows by one warp).
 template <bool VERT>
@@ -191,40 +139,9 @@ __device__ BPL_GAUSS_ATTR void gauss_run(float *buf, const G6 gg, int l0, int nl
 #endif
 }
 
-// Band size: the shortest runs whose items still fit one thread each.  Short runs spread a small box over more
-// threads (a 58 x 70 box is 133 items with 35-row bands but 290 with 15-row bands), at the price of more halo loads.
-#ifndef BPL_GAUSS_BANDS
-#define BPL_GAUSS_BANDS 1
-#endif
 template <bool VERT, int S_THREADS>
 __device__ __forceinline__ void gauss_box(float *buf, const G6 &g, int l0, int l1, int a0, int a1) {
-    const int nl = l1 - l0 + 1;
-#ifndef BPL_GAUSS_BANDED
-    gauss_run<VERT>(buf, g, l0, nl, a0, a1);
-    return;
-#endif
-#if BPL_GAUSS_BANDS >= 5
-    // One band size (15 or 21 rows) for every box: lines are independent, so a box with more (line, band) items than
-    // threads is taken in groups of whole lines, one after the other (each group with its own halo-load barrier).
-    constexpr int GB = (BPL_GAUSS_BANDS == 5) ? 15 : 21, GBU = (BPL_GAUSS_BANDS == 5) ? 5 : 7;
-    const int b0 = a0 / GB, nb = a1 / GB - b0 + 1;
-    const int per = (int)blockDim.x / nb;               // lines per group
-    for (int l = l0; l <= l1; l += per) {
-        gauss_inplace_s<VERT, GB, GBU>(buf, g, l, min(per, l1 - l + 1), b0, nb);
-        if (l + per <= l1) __syncthreads();
-    }
-    return;
-#endif
-    if (BPL_GAUSS_BANDS >= 3 && nl * (a1 / 15 - a0 / 15 + 1) <= (int)blockDim.x)
-        gauss_inplace_s<VERT, 15, 5>(buf, g, l0, nl, a0 / 15, a1 / 15 - a0 / 15 + 1);
-#if BPL_GAUSS_BANDS == 2 || BPL_GAUSS_BANDS == 4
-    else if (nl * (a1 / 21 - a0 / 21 + 1) <= (int)blockDim.x)
-        gauss_inplace_s<VERT, 21, 7>(buf, g, l0, nl, a0 / 21, a1 / 21 - a0 / 21 + 1);
-#endif
-    else if (S_THREADS >= 3 * IMG || nl * (a1 / 35 - a0 / 35 + 1) <= (int)blockDim.x)
-        gauss_inplace_s<VERT, 35, 7>(buf, g, l0, nl, a0 / 35, a1 / 35 - a0 / 35 + 1);
-    else if (S_THREADS < 3 * IMG)
-        gauss_inplace_s<VERT, 105, 7>(buf, g, l0, nl, 0, 1);      // whole lines: always fits (nl <= 105 <= threads)
+    gauss_run<VERT>(buf, g, l0, l1 - l0 + 1, a0, a1);
 }
 
 // In-place 3x3 broaden confined to the box.  The lanes of a warp hold column pairs of the box, the warps split
